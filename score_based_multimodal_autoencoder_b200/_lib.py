@@ -1,0 +1,78 @@
+"""ctypes binding of libsbmae_b200.so (the C ABI declared in include/sbmae_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is
+raised.  PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsbmae_b200.so")
+
+_lib = None
+
+
+class SbmError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SbmError(
+                f"{LIB_PATH} is missing: build it with `python -m score_based_multimodal_autoencoder_b200.build` "
+                "(there is no CPU / eager fallback for the B200 path)"
+            )
+        _lib = C.CDLL(LIB_PATH)
+        _lib.sbm_last_error.restype = C.c_char_p
+        _lib.sbm_launch_count.restype = C.c_ulonglong
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise SbmError(f"{what} failed (rc={rc}): {lib().sbm_last_error().decode()}")
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: torch.Tensor | None) -> C.c_void_p:
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise SbmError("libsbmae_b200 operates on CUDA tensors only (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def launch_count() -> int:
+    return int(lib().sbm_launch_count())
+
+
+# ------------------------------------------------------------------ enums (mirror sbmae_b200.h)
+CONV_S1, CONV_S2, CONVT_4X4_S2 = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+F32, BF16 = 0, 1
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32),
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("wpk", C.c_void_p), ("cin_pad", C.c_int32), ("act", C.c_int32),
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("ldr", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("out_dtype", C.c_int32), ("out_nchw", C.c_int32),
+        ("res_dtype", C.c_int32), ("reserved", C.c_int32),
+        ("stats", C.c_void_p),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64),
+    ]

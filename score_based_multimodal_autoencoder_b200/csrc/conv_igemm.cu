@@ -1,0 +1,559 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   out[b, oh, ow, n] = epilogue( sum_{tap, c} X[b, ih(tap), iw(tap), c] * Wpk[tap][n][c] )
+//
+// GEMM view: M = batch*OH*OW output pixels (128 per CTA), N = cout (BN per CTA),
+// K = taps * cin walked in 64-channel blocks.  There is no im2col buffer: for every
+// (tap, channel block) one TMA box load fetches the 128 shifted input pixels x 64 channels
+// straight from the channels-last activation tensor; pixels that fall in the zero padding
+// are outside the tensor-map extent and TMA fills them with zeros.  Taps that only ever see
+// padding (e.g. 8 of the 9 taps of a 3x3 convolution on a 1x1 map) are dropped from the K loop.
+//
+// One generic 5-D activation view serves every layer type:
+//     (c, wv, q, hv, b)  with element strides (1, sw, sq, sh, sb)
+//   stride-1 conv / linear : wv=w, hv=h, q unused
+//   stride-2 conv          : wv=w/2, hv=h/2, q = (h parity)*W + (w parity)   (space-to-depth by strides)
+//   ConvTranspose 4x4 s2   : four output-parity phases (grid.z), each a 2x2-tap stride-1 conv
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> bias/act/residual -> global).
+//
+// Replaces: nn.Conv2d / nn.ConvTranspose2d / nn.Linear in unet_model.py:30,33,107,110,113,132-133,
+// 157-159,208,224,226,272 and unet_openai.py:185,207,253-268,322-324,421-425.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+
+#include "../../include/sbmae_b200.h"
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace sbm {
+
+std::atomic<unsigned long long> g_launches{0};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kMaxTaps = 16;
+
+struct TapTable {
+  int32_t ntaps;
+  int32_t out_off;          // element offset of this phase inside the output tensor
+  int8_t dh[kMaxTaps];      // added to the tile's hv origin
+  int8_t dw[kMaxTaps];      // wv coordinate of the box start
+  int16_t q[kMaxTaps];      // coordinate in the parity dimension
+  int16_t wtap[kMaxTaps];   // tap index inside the packed weight tensor
+};
+
+struct ConvKernelParams {
+  int32_t batch;
+  int32_t log_ow, log_th;   // tile = nb images x 2^log_th rows x 2^log_ow columns = 128 pixels
+  int32_t log_oh;
+  int32_t cin, cout;
+  int32_t cblocks;          // ceil(cin / 64)
+  int64_t o_sb, o_sh, o_sw, o_sc;  // output element strides (batch, row, col, channel)
+  int64_t r_sb, r_sh, r_sw;        // residual element strides
+  int64_t o2_sb, o2_sh, o2_sw;     // optional second (bf16) output
+  const float* bias;
+  const void* residual;
+  void* out;
+  void* out2;
+  double* stats;
+  int32_t act, out_dtype, res_dtype, vec_ok;
+  TapTable taps[4];
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ ConvKernelParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const TapTable& tt = p.taps[blockIdx.z];
+
+  // ---- tile origin
+  const int log_ohw = p.log_oh + p.log_ow;
+  int b0, oh0;
+  if (log_ohw >= 7) {
+    const int tiles_per_img = 1 << (log_ohw - 7);
+    b0 = blockIdx.x / tiles_per_img;
+    oh0 = (blockIdx.x % tiles_per_img) << p.log_th;
+  } else {
+    b0 = blockIdx.x << (7 - log_ohw);
+    oh0 = 0;
+  }
+  const int n0 = blockIdx.y * BN;
+  const int num_kb = tt.ntaps * p.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<(BN < 32 ? 32 : BN)>(tmem_slot);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int tap = kb / p.cblocks;
+        const int cb = kb - tap * p.cblocks;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes;
+        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+        ptx::tma_load_5d(sa, &tmA, &full_bar[stage], cb * kBK, tt.dw[tap], tt.q[tap], oh0 + tt.dh[tap], b0);
+        ptx::tma_load_3d(sb, &tmB, &full_bar[stage], cb * kBK, n0, tt.wtap[tap]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+        const uint64_t adesc = ptx::make_desc_k_sw128(sa);
+        const uint64_t bdesc = ptx::make_desc_k_sw128(sa + L::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the 16-byte address field
+          ptx::umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: one output pixel (row) per thread
+    const int ew = warp & 3;  // TMEM lane quarter this warp may read
+    const int r = ew * 32 + lane;
+    const int ow_mask = (1 << p.log_ow) - 1;
+    const int j = r & ow_mask;
+    const int i = (r >> p.log_ow) & ((1 << p.log_th) - 1);
+    const int bl = r >> (p.log_ow + p.log_th);
+    const int b = b0 + bl;
+    const int oh = oh0 + i;
+    const bool row_ok = b < p.batch;
+    const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw + tt.out_off;
+    const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
+    const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw;
+    float s1 = 0.f, s2 = 0.f;
+
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after_sync();
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld16(tmem_base + (uint32_t(ew * 32) << 16) + c0, v);
+      ptx::tmem_ld_wait();
+      const int n = n0 + c0;
+      if (n >= p.cout) continue;  // warp-uniform
+      float f[16];
+      const bool full = (n + 16 <= p.cout);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        float x = __uint_as_float(v[e]);
+        if (p.bias != nullptr && (full || n + e < p.cout)) x += __ldg(p.bias + n + e);
+        if (p.act == SBM_ACT_GELU) x = gelu_exact(x);
+        else if (p.act == SBM_ACT_SILU) x = silu(x);
+        f[e] = x;
+      }
+      if (row_ok) {
+        if (p.residual != nullptr) {
+          if (p.res_dtype == SBM_F32) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + r_base + n;
+            if (full && p.vec_ok) {
+#pragma unroll
+              for (int e = 0; e < 16; e += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(rp + e);
+                f[e] += t.x; f[e + 1] += t.y; f[e + 2] += t.z; f[e + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (n + e < p.cout) f[e] += rp[e];
+            }
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_base + n;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (n + e < p.cout) f[e] += __bfloat162float(rp[e]);
+          }
+        }
+        if (p.out_dtype == SBM_BF16) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+        }
+        if (p.stats != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (full || n + e < p.cout) { s1 += f[e]; s2 += f[e] * f[e]; }
+        }
+        if (p.out_dtype == SBM_F32) {
+          float* op = reinterpret_cast<float*>(p.out) + o_base;
+          if (full && p.vec_ok && p.o_sc == 1) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4)
+              *reinterpret_cast<float4*>(op + n + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (n + e < p.cout) op[(int64_t)(n + e) * p.o_sc] = f[e];
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + o_base + n;
+          if (full && p.vec_ok) {
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              w[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
+          }
+        }
+        if (p.out2 != nullptr) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + o2_base + n;
+          if (full && p.vec_ok) {
+            uint32_t w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              w[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
+          }
+        }
+      }
+    }
+
+    if (p.stats != nullptr) {
+      // rows of one warp are 32 consecutive pixels: they belong to one sample when OH*OW >= 32,
+      // otherwise to 32/(OH*OW) samples -> segmented butterfly over groups of OH*OW lanes.
+      if (!row_ok) { s1 = 0.f; s2 = 0.f; }
+      const int seg = log_ohw >= 5 ? 32 : (1 << log_ohw);
+      for (int o = seg >> 1; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if ((lane & (seg - 1)) == 0 && row_ok) {
+        atomicAdd(p.stats + 2 * (int64_t)b, (double)s1);
+        atomicAdd(p.stats + 2 * (int64_t)b + 1, (double)s2);
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return ((1 << l) == v) ? l : -1;
+}
+
+template <int BN, int STAGES>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, dim3 grid,
+                       cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     L::kTotal));
+    configured = true;
+  }
+  conv_igemm_kernel<BN, STAGES><<<grid, 256, L::kTotal, stream>>>(tmA, tmB, p);
+  SBM_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
+  SBM_CHECK_ARG(a != nullptr, "sbm_conv_igemm: null args");
+  SBM_CHECK_ARG(a->x && a->wpk && a->out, "sbm_conv_igemm: null operand pointer");
+  SBM_CHECK_ARG(a->batch > 0 && a->cin > 0 && a->cout > 0, "sbm_conv_igemm: bad sizes");
+  const int lh = ilog2_exact(a->h), lw = ilog2_exact(a->w);
+  SBM_CHECK_ARG(lh >= 0 && lw >= 0 && a->h <= 128 && a->w <= 128,
+                "sbm_conv_igemm: spatial extent %dx%d must be powers of two <= 128", a->h, a->w);
+  SBM_CHECK_ARG(a->ldx % 8 == 0 && a->ldx >= a->cin, "sbm_conv_igemm: ldx=%lld must be a multiple of 8 and >= cin",
+                (long long)a->ldx);
+  SBM_CHECK_ARG(a->cin_pad % 8 == 0 && a->cin_pad >= a->cin, "sbm_conv_igemm: cin_pad must be a multiple of 8");
+  SBM_CHECK_ARG((reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->wpk) & 15) == 0,
+                "sbm_conv_igemm: x / wpk must be 16-byte aligned");
+  auto encode = get_encode_fn();
+  SBM_CHECK_ARG(encode != nullptr, "sbm_conv_igemm: cuTensorMapEncodeTiled entry point not available");
+
+  ConvKernelParams p;
+  memset(&p, 0, sizeof(p));
+  int oh, ow, nphase = 1;
+  // activation view (c, wv, q, hv, b)
+  cuuint64_t adim[5];
+  cuuint64_t astr[4];
+  const int64_t ld = a->ldx;
+  if (a->kind == SBM_CONV_S1) {
+    SBM_CHECK_ARG(a->kh >= 1 && a->kw >= 1 && (a->kh & 1) && (a->kw & 1) && a->kh * a->kw <= kMaxTaps,
+                  "sbm_conv_igemm: stride-1 kernel %dx%d unsupported (odd, <= 16 taps)", a->kh, a->kw);
+    oh = a->h; ow = a->w;
+    adim[0] = a->cin; adim[1] = a->w; adim[2] = 1; adim[3] = a->h; adim[4] = a->batch;
+    astr[0] = ld * 2; astr[1] = (cuuint64_t)a->w * ld * 2; astr[2] = (cuuint64_t)a->w * ld * 2;
+    astr[3] = (cuuint64_t)a->h * a->w * ld * 2;
+    TapTable& t = p.taps[0];
+    const int ph = a->kh / 2, pw = a->kw / 2;
+    for (int kh = 0; kh < a->kh; ++kh)
+      for (int kw = 0; kw < a->kw; ++kw) {
+        const int dh = kh - ph, dw = kw - pw;
+        if (abs(dh) >= a->h || abs(dw) >= a->w) continue;  // tap only ever reads zero padding
+        t.dh[t.ntaps] = (int8_t)dh; t.dw[t.ntaps] = (int8_t)dw; t.q[t.ntaps] = 0;
+        t.wtap[t.ntaps] = (int16_t)(kh * a->kw + kw);
+        ++t.ntaps;
+      }
+  } else if (a->kind == SBM_CONV_S2) {
+    SBM_CHECK_ARG((a->kh == 4 && a->kw == 4) || (a->kh == 3 && a->kw == 3),
+                  "sbm_conv_igemm: stride-2 kernel must be 4x4 or 3x3");
+    SBM_CHECK_ARG(a->h >= 2 && a->w >= 2, "sbm_conv_igemm: stride-2 needs h,w >= 2");
+    oh = a->h / 2; ow = a->w / 2;
+    adim[0] = a->cin; adim[1] = ow; adim[2] = a->w + 2; adim[3] = oh; adim[4] = a->batch;
+    astr[0] = 2 * ld * 2; astr[1] = ld * 2; astr[2] = (cuuint64_t)2 * a->w * ld * 2;
+    astr[3] = (cuuint64_t)a->h * a->w * ld * 2;
+    TapTable& t = p.taps[0];
+    for (int kh = 0; kh < a->kh; ++kh)
+      for (int kw = 0; kw < a->kw; ++kw) {
+        // input row = 2*oh - 1 + kh = 2*(oh + dh) + parity
+        const int rh = kh - 1, rw = kw - 1;
+        const int dh = (rh < 0) ? -1 : rh / 2, par_h = (rh < 0) ? 1 : (rh & 1);
+        const int dw = (rw < 0) ? -1 : rw / 2, par_w = (rw < 0) ? 1 : (rw & 1);
+        if (abs(dh) >= oh && dh != 0) continue;
+        if (abs(dw) >= ow && dw != 0) continue;
+        t.dh[t.ntaps] = (int8_t)dh; t.dw[t.ntaps] = (int8_t)dw;
+        t.q[t.ntaps] = (int16_t)(par_h * a->w + par_w);
+        t.wtap[t.ntaps] = (int16_t)(kh * a->kw + kw);
+        ++t.ntaps;
+      }
+  } else if (a->kind == SBM_CONVT_4X4_S2) {
+    SBM_CHECK_ARG(a->kh == 4 && a->kw == 4, "sbm_conv_igemm: transposed conv must be 4x4");
+    SBM_CHECK_ARG(a->h <= 64 && a->w <= 64, "sbm_conv_igemm: transposed conv input must be <= 64x64");
+    oh = a->h; ow = a->w;  // per-phase output grid; full output is 2h x 2w
+    nphase = 4;
+    adim[0] = a->cin; adim[1] = a->w; adim[2] = 1; adim[3] = a->h; adim[4] = a->batch;
+    astr[0] = ld * 2; astr[1] = (cuuint64_t)a->w * ld * 2; astr[2] = (cuuint64_t)a->w * ld * 2;
+    astr[3] = (cuuint64_t)a->h * a->w * ld * 2;
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        TapTable& t = p.taps[ph * 2 + pw];
+        // out[2i+ph, 2j+pw] += in[i+dh, j+dw] * W[kh][kw] with 2(i+dh) = 2i + ph + 1 - kh
+        for (int kh = 0; kh < 4; ++kh) {
+          if (((ph + 1 - kh) & 1) != 0) continue;
+          const int dh = (ph + 1 - kh) / 2;
+          for (int kw = 0; kw < 4; ++kw) {
+            if (((pw + 1 - kw) & 1) != 0) continue;
+            const int dw = (pw + 1 - kw) / 2;
+            if (abs(dh) >= a->h || abs(dw) >= a->w) continue;
+            t.dh[t.ntaps] = (int8_t)dh; t.dw[t.ntaps] = (int8_t)dw; t.q[t.ntaps] = 0;
+            t.wtap[t.ntaps] = (int16_t)(kh * 4 + kw);
+            ++t.ntaps;
+          }
+        }
+      }
+  } else {
+    SBM_CHECK_ARG(false, "sbm_conv_igemm: unknown kind %d", a->kind);
+  }
+
+  const int log_oh = ilog2_exact(oh), log_ow = ilog2_exact(ow);
+  const int log_ohw = log_oh + log_ow;
+  const int log_th = (log_ohw >= 7) ? (7 - log_ow) : log_oh;
+  const int nb = (log_ohw >= 7) ? 1 : (1 << (7 - log_ohw));
+  p.batch = a->batch;
+  p.log_ow = log_ow; p.log_th = log_th; p.log_oh = log_oh;
+  p.cin = a->cin; p.cout = a->cout;
+  p.cblocks = (a->cin + kBK - 1) / kBK;
+  p.bias = a->bias; p.residual = a->residual; p.out = a->out; p.out2 = a->out2; p.stats = a->stats;
+  p.act = a->act; p.out_dtype = a->out_dtype; p.res_dtype = a->res_dtype;
+
+  // output addressing
+  const int64_t OHf = (a->kind == SBM_CONVT_4X4_S2) ? 2 * oh : oh;
+  const int64_t OWf = (a->kind == SBM_CONVT_4X4_S2) ? 2 * ow : ow;
+  const int64_t sp = (a->kind == SBM_CONVT_4X4_S2) ? 2 : 1;  // spatial step between a phase's neighbours
+  if (a->out_nchw) {
+    SBM_CHECK_ARG(a->out_dtype == SBM_F32 && a->residual == nullptr && a->out2 == nullptr,
+                  "sbm_conv_igemm: NCHW output is fp32 without residual");
+    p.o_sc = OHf * OWf; p.o_sw = sp; p.o_sh = sp * OWf; p.o_sb = (int64_t)a->cout * OHf * OWf;
+  } else {
+    SBM_CHECK_ARG(a->ldo >= a->cout, "sbm_conv_igemm: ldo < cout");
+    p.o_sc = 1; p.o_sw = sp * a->ldo; p.o_sh = sp * OWf * a->ldo; p.o_sb = OHf * OWf * a->ldo;
+  }
+  p.r_sw = sp * a->ldr; p.r_sh = sp * OWf * a->ldr; p.r_sb = OHf * OWf * a->ldr;
+  p.o2_sw = sp * a->ldo2; p.o2_sh = sp * OWf * a->ldo2; p.o2_sb = OHf * OWf * a->ldo2;
+  for (int ph = 0; ph < nphase; ++ph) {
+    const int64_t phh = ph >> 1, pww = ph & 1;
+    int64_t off = 0;
+    if (a->kind == SBM_CONVT_4X4_S2) {
+      off = a->out_nchw ? (phh * OWf + pww) : (phh * OWf + pww) * a->ldo;
+      SBM_CHECK_ARG(a->residual == nullptr && a->out2 == nullptr,
+                    "sbm_conv_igemm: transposed conv does not take residual/out2");
+    }
+    SBM_CHECK_ARG(off < (int64_t(1) << 31), "sbm_conv_igemm: phase offset overflow");
+    p.taps[ph].out_off = (int32_t)off;
+    SBM_CHECK_ARG(p.taps[ph].ntaps > 0, "sbm_conv_igemm: empty tap table");
+  }
+  // 16-byte vector access is legal when every row start and channel chunk is 16-byte aligned
+  const int esz = (a->out_dtype == SBM_F32) ? 4 : 2;
+  bool vec = !a->out_nchw && ((a->ldo * esz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0);
+  if (a->residual) {
+    const int rsz = (a->res_dtype == SBM_F32) ? 4 : 2;
+    vec = vec && ((a->ldr * rsz) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
+  }
+  if (a->out2) vec = vec && ((a->ldo2 * 2) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
+  p.vec_ok = vec ? 1 : 0;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  const cuuint32_t abox[5] = {(cuuint32_t)kBK, (cuuint32_t)ow, 1u, (cuuint32_t)(1 << log_th), (cuuint32_t)nb};
+  const cuuint32_t ones5[5] = {1, 1, 1, 1, 1};
+  CUresult cr = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->x), adim, astr, abox, ones5,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_igemm: activation tensor map encode failed (CUresult %d)", (int)cr);
+
+  int BN;
+  if (a->cout <= 32) BN = 32;
+  else if (a->cout <= 64) BN = 64;
+  else if (a->cout <= 128) BN = 128;
+  else if (a->cout % 256 == 0 || a->cout > 512) BN = 256;
+  else BN = (a->cout % 128 == 0) ? 128 : 256;
+  const int ntaps_total = a->kh * a->kw;
+  const cuuint64_t bdim[3] = {(cuuint64_t)a->cin, (cuuint64_t)a->cout, (cuuint64_t)ntaps_total};
+  const cuuint64_t bstr[2] = {(cuuint64_t)a->cin_pad * 2, (cuuint64_t)a->cout * a->cin_pad * 2};
+  const cuuint32_t bbox[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 1u};
+  const cuuint32_t ones3[3] = {1, 1, 1};
+  cr = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->wpk), bdim, bstr, bbox, ones3,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_igemm: weight tensor map encode failed (CUresult %d)", (int)cr);
+
+  const int64_t M = (int64_t)a->batch << log_ohw;
+  dim3 grid((unsigned)((M + kBM - 1) / kBM), (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
+  switch (BN) {
+    case 32: return launch_conv<32, 6>(tmA, tmB, p, grid, stream);
+    case 64: return launch_conv<64, 6>(tmA, tmB, p, grid, stream);
+    case 128: return launch_conv<128, 6>(tmA, tmB, p, grid, stream);
+    default: return launch_conv<256, 4>(tmA, tmB, p, grid, stream);
+  }
+}
+
+// ---------------------------------------------------------------- weight packing
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int taps, int rows,
+                                   int cols, int cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col) {
+  const int64_t total = (int64_t)taps * rows * cols_pad;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cols_pad);
+    const int64_t tr = idx / cols_pad;
+    const int r = (int)(tr % rows);
+    const int t = (int)(tr / rows);
+    float v = 0.f;
+    if (c < cols) v = w[t * s_tap + r * s_row + c * s_col];
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace sbm
+
+// ------------------------------------------------------------------------------------ C ABI
+static thread_local char g_err[512] = "";
+void sbm::set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+const char* sbm_last_error(void) { return g_err; }
+int sbm_version(void) { return 100; }
+unsigned long long sbm_launch_count(void) { return sbm::g_launches.load(); }
+
+int sbm_conv_igemm(const sbm_conv_args* a, void* stream) {
+  return sbm::conv_igemm_impl(a, static_cast<cudaStream_t>(stream));
+}
+
+int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
+                         int64_t s_tap, int64_t s_row, int64_t s_col, void* stream) {
+  SBM_CHECK_ARG(w && dst && taps > 0 && rows > 0 && cols > 0 && cols_pad >= cols, "sbm_pack_weight_bf16: bad args");
+  const int64_t total = (int64_t)taps * rows * cols_pad;
+  const int threads = 256;
+  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, (int64_t)sbm::sm_count() * 8);
+  sbm::pack_weight_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(dst), taps, rows, cols, cols_pad, s_tap, s_row, s_col);
+  SBM_CUDA_OK(cudaGetLastError());
+  sbm::g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+}  // extern "C"

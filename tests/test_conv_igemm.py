@@ -1,0 +1,151 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (sbm_conv_igemm) against float64
+torch convolutions on the SAME bf16-rounded operands, so the only difference is fp32
+accumulation order (tolerance 2e-5 of the output scale).  Geometry cases follow the layer
+shapes of the reference score nets (unet_model.py:30,33,107,110,208,272; unet_openai.py:185,207).
+"""
+import zlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from score_based_multimodal_autoencoder_b200 import _lib as L, ops
+    return L, ops
+
+
+def _nhwc_bf16(x_nchw: torch.Tensor, ld: int) -> torch.Tensor:
+    b, c, h, w = x_nchw.shape
+    out = torch.full((b, h, w, ld), 7.0, dtype=torch.bfloat16, device=x_nchw.device)  # poison the padding
+    out[..., :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def _gelu64(x):
+    return 0.5 * x * (1.0 + torch.erf(x / 2.0 ** 0.5))
+
+
+CASES = [
+    # name,        kind, k, B,  H,  W,  cin, cout
+    ("lin64",       "s1", 1, 128, 1, 1, 64, 64),
+    ("lin256x128",  "s1", 1, 200, 1, 1, 256, 128),
+    ("lin1024x512", "s1", 1, 64, 1, 1, 1024, 512),
+    ("c1x1_16",     "s1", 1, 3, 16, 16, 256, 384),
+    ("c3_16_64",    "s1", 3, 2, 16, 16, 64, 64),
+    ("c3_16_tail",  "s1", 3, 3, 16, 16, 170, 512),
+    ("c3_8_42",     "s1", 3, 5, 8, 8, 42, 128),
+    ("c3_8_big",    "s1", 3, 4, 8, 8, 512, 256),
+    ("c3_4",        "s1", 3, 9, 4, 4, 128, 256),
+    ("c3_2",        "s1", 3, 33, 2, 2, 256, 128),
+    ("c3_1",        "s1", 3, 70, 1, 1, 128, 256),
+    ("c3_32x16",    "s1", 3, 2, 32, 16, 64, 96),
+    ("c3_cout5",    "s1", 1, 4, 8, 8, 64, 5),
+    ("down4_16",    "s2", 4, 3, 16, 16, 64, 64),
+    ("down4_8",     "s2", 4, 5, 8, 8, 128, 128),
+    ("down4_2",     "s2", 4, 40, 2, 2, 128, 128),
+    ("down3_16",    "s2", 3, 3, 16, 16, 128, 128),
+    ("up4_4",       "t",  4, 5, 4, 4, 128, 128),
+    ("up4_1",       "t",  4, 50, 1, 1, 128, 128),
+    ("up4_8",       "t",  4, 3, 8, 8, 256, 256),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_geometry(case):
+    L, ops = _mods()
+    name, kind, k, B, H, W, cin, cout = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(name.encode()))
+    x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+    if kind == "t":
+        w = (torch.randn(cin, cout, k, k, generator=g) / (cin * 4) ** 0.5).to(dev).to(torch.bfloat16).float()
+    else:
+        w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    xb = _nhwc_bf16(x, ops.pad8(cin) + 8)  # ld > pad8(cin): exercises the pixel stride
+    if kind == "s1":
+        ref = F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2)
+        wpk = ops.pack_conv2d_weight(w)
+        out = ops.conv_igemm(xb, wpk, kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout, bias=bias)
+    elif kind == "s2":
+        ref = F.conv2d(x.double(), w.double(), bias.double(), stride=2, padding=1)
+        wpk = ops.pack_conv2d_weight(w)
+        out = ops.conv_igemm(xb, wpk, kind=L.CONV_S2, kh=k, kw=k, cin=cin, cout=cout, bias=bias)
+    else:
+        ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2, padding=1)
+        wpk = ops.pack_convT2d_weight(w)
+        out = ops.conv_igemm(xb, wpk, kind=L.CONVT_4X4_S2, kh=4, kw=4, cin=cin, cout=cout, bias=bias)
+    torch.cuda.synchronize()
+    got = out[..., :cout].permute(0, 3, 1, 2).double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * scale + 1e-6, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+def test_conv_epilogue_options():
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, H, W, cin, cout = 6, 8, 8, 128, 192
+    x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(B, H, W, cout, generator=g).to(dev)
+    xb = _nhwc_bf16(x, cin)
+    wpk = ops.pack_conv2d_weight(w)
+    pre = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+
+    # GELU + fp32 residual + statistics + bf16 side copy
+    stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+    out2 = torch.zeros(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+    out = ops.conv_igemm(xb, wpk, kind=L.CONV_S1, kh=3, kw=3, cin=cin, cout=cout, bias=bias, act=L.ACT_GELU,
+                         residual=res, stats=stats, out2=out2)
+    ref = _gelu64(pre) + res.double()
+    torch.cuda.synchronize()
+    assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+    assert (out2.double() - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()
+    ref_s = torch.stack([ref.sum(dim=(1, 2, 3)), (ref * ref).sum(dim=(1, 2, 3))], dim=1)
+    assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3)
+
+    # SiLU, bf16 output with statistics of the ROUNDED values
+    stats.zero_()
+    outb = ops.conv_igemm(xb, wpk, kind=L.CONV_S1, kh=3, kw=3, cin=cin, cout=cout, bias=bias, act=L.ACT_SILU,
+                          out_dtype=torch.bfloat16, stats=stats)
+    refs = pre * torch.sigmoid(pre)
+    torch.cuda.synchronize()
+    assert (outb.double() - refs).abs().max().item() <= 5e-3 * refs.abs().max().item()
+    ob = outb.double()
+    ref_s = torch.stack([ob.sum(dim=(1, 2, 3)), (ob * ob).sum(dim=(1, 2, 3))], dim=1)
+    assert torch.allclose(stats, ref_s, rtol=1e-6, atol=1e-4)
+
+    # NCHW fp32 output (final 1x1 projection to the latent channels)
+    w1 = (torch.randn(5, cin, 1, 1, generator=g) / cin ** 0.5).to(dev).to(torch.bfloat16).float()
+    b1 = torch.randn(5, generator=g).to(dev)
+    o = ops.conv_igemm(xb, ops.pack_conv2d_weight(w1), kind=L.CONV_S1, kh=1, kw=1, cin=cin, cout=5, bias=b1, nchw=True)
+    r = F.conv2d(x.double(), w1.double(), b1.double())
+    torch.cuda.synchronize()
+    assert o.shape == (B, 5, H, W)
+    assert (o.double() - r).abs().max().item() <= 2e-5 * r.abs().max().item()
+
+
+def test_conv_small_stats_segments():
+    """Per-sample statistics when several samples share one warp (OH*OW < 32)."""
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(9)
+    for hw in (1, 2, 4):
+        B, cin, cout = 37, 64, 64
+        x = torch.randn(B, cin, hw, hw, generator=g).to(dev).to(torch.bfloat16).float()
+        w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev).to(torch.bfloat16).float()
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        out = ops.conv_igemm(_nhwc_bf16(x, cin), ops.pack_conv2d_weight(w), kind=L.CONV_S1, kh=3, kw=3, cin=cin,
+                             cout=cout, stats=stats)
+        torch.cuda.synchronize()
+        o = out.double()
+        ref_s = torch.stack([o.sum(dim=(1, 2, 3)), (o * o).sum(dim=(1, 2, 3))], dim=1)
+        assert torch.allclose(stats, ref_s, rtol=1e-6, atol=1e-5), f"hw={hw}"
+        ref = F.conv2d(x.double(), w.double(), padding=1).permute(0, 2, 3, 1)
+        assert (o - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
