@@ -74,6 +74,76 @@ int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
                          int64_t s_tap, int64_t s_row, int64_t s_col, void* stream);
 
+/* ------------------------------------------------------------------ memory-bound score-net operators */
+/* fp32 NCHW latent -> bf16 im2col rows [B*H*W, ldk], column (c*kh + i)*kw + j; feeds the stem conv
+ * (unet_model.py:208,287; unet_openai.py:441) as a 1x1 sbm_conv_igemm. */
+int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                    int32_t ldk, void* stream);
+/* out = depthwise7x7(x) + bias[c] + cond[b][c]; stats[b] += (sum, sumsq).  unet_model.py:103,116-121.
+ * x/out fp32 channels-last, w is the nn.Conv2d(groups=C) weight [C,1,7,7]. */
+int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
+                    float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* stats[b][g] += (sum, sumsq) of group g of sample b.  nn.GroupNorm statistics (unet_model.py:106,109,160,183;
+ * unet_openai.py:10-12). */
+int sbm_group_stats(const void* x, int32_t in_dtype, int64_t ldx, int32_t B, int32_t HW, int32_t C, int32_t G,
+                    double* stats, void* stream);
+/* y = act(GroupNorm(x; stats) * gamma + beta) (+ residual); writes `out` (out_dtype) and/or `out_f32`. */
+int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const double* stats, const float* gamma,
+                        const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
+                        int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
+                        float eps, int32_t act, void* stream);
+/* sinusoidal embedding of t[B] -> bf16 [B, ld]; mode 0 = unet_model.py:40-47, mode 1 = unet_openai.py:66-83 */
+int sbm_time_embed(const float* t, void* out_bf16, float* out_f32, int32_t B, int32_t dim, int32_t ld, int32_t mode,
+                   void* stream);
+/* LinearAttention core (unet_model.py:162-177) on qkv fp32 [B,n,ldq] (channels q|k|v, heads x 32) -> bf16 [B,n,ldo] */
+int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
+                        float scale, void* stream);
+/* softmax attention core (unet_model.py:135-149; unet_openai.py:345-358): channel of (head,d) for q is
+ * q_off + head*head_stride + d (k_off, v_off likewise); logits scaled by `scale`. */
+int sbm_softmax_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
+                         int32_t dh, int32_t q_off, int32_t k_off, int32_t v_off, int32_t head_stride, float scale,
+                         void* stream);
+
+/* ------------------------------------------------------------------ sampler / DSM (latent [B, mods, D, D] fp32) */
+enum { SBM_SDE_VP = 0, SBM_SDE_SUBVP = 1, SBM_SDE_VE = 2 };
+typedef struct sbm_latent_shape { int32_t batch, mods, dd; /* dd = D*D */ } sbm_latent_shape;
+/* VPSDE/subVPSDE: (b0,b1) = (beta_min,beta_max); VESDE: (sigma_min,sigma_max).  sde_helper2.py:329-473 */
+typedef struct sbm_sde { int32_t kind; float b0, b1; int32_t N; float T; } sbm_sde;
+/* Philox4x32-10 stream: key = seed, counter = (global element index / 4, draw); sample_offset = index of this
+ * shard's first sample inside the global batch (multi-GPU sampling draws the same numbers as one GPU would). */
+typedef struct sbm_rng { uint64_t seed, draw, sample_offset; } sbm_rng;
+/* observed-modality imputation applied to the state a step WRITES (train_lat_celebhq_unet_cont2.py:293-303):
+ * channel m with bit m of obs_mask set := noise_obs ? exp(lmc(t_next))*z + std(t_next)*z : z */
+typedef struct sbm_impute { const float* z_obs; uint32_t obs_mask; int32_t noise_obs; float t_next; } sbm_impute;
+
+int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem_offset, float scale, void* stream);
+/* em_predictor, sde_helper2.py:45-52: x_mean = x + (f(x,t) - g^2 s [*0.5]) * (-1/N); x' = x_mean + g sqrt(1/N) z */
+int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
+                       const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
+                       const sbm_rng* rng, const sbm_impute* impute, void* stream);
+/* corrector, sde_helper2.py:96-98: acc2[0] += sum_b ||grad_b||, acc2[1] += sum_b ||noise_b|| (caller zeroes acc2;
+ * multi-GPU exact mode all-reduces the two doubles between the two calls) */
+int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
+                        double* acc2, void* stream);
+/* corrector, sde_helper2.py:56-60,99-101: step = (snr * mean||noise|| / mean||grad||)^2 * 2 * alpha[t];
+ * x_mean = x + step*grad; x' = x_mean + sqrt(2 step) * noise.  alphas = device copy of sde.alphas (NULL: alpha = 1) */
+int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* grad,
+                         const float* t, const float* noise, const double* acc2, const float* alphas, float* x_out,
+                         float* x_mean_out, float target_snr, int64_t global_batch, const sbm_rng* rng,
+                         const sbm_impute* impute, void* stream);
+int sbm_impute_observed(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, float* x_out,
+                        const sbm_impute* impute, void* stream);
+/* loss_fn, sde_helper2.py:167-170: t = u*(T-eps)+eps; xt = mean(x0,t) + std(t)*z.  u,z injected or drawn (rng) */
+int sbm_dsm_perturb(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x0, const float* u, const float* z,
+                    float* xt, float* z_out, float* t_out, float* std_out, float* g2_out, float eps,
+                    const sbm_rng* rng, void* stream);
+/* loss_fn, sde_helper2.py:173-185: *loss_acc += batch-mean loss (caller zeroes); dscore = d loss / d score */
+int sbm_dsm_loss(const sbm_latent_shape* ls, const float* score, const float* z, const float* std, const float* g2,
+                 float* dscore, double* loss_acc, int32_t likelihood_weighting, int32_t reduce_mean,
+                 int64_t global_batch, void* stream);
+int sbm_scale_by_scalar(const float* in, const float* scalar_dev, float* out, int64_t n, void* stream);
+int sbm_f64_to_f32(const double* in, float* out, int32_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,482 @@
+// Memory-bound score-net operators (channels-last, fp32 math, bf16 GEMM operands out):
+//   * stem im2col                      (unet_model.py:208,287 / unet_openai.py:441)
+//   * depthwise 7x7 + bias + time-embedding condition + GroupNorm statistics (unet_model.py:103,116-121)
+//   * GroupNorm apply (+affine, +SiLU, +residual)  (unet_model.py:106,109,160,183; unet_openai.py:10-12,63)
+//   * group statistics                 (same GroupNorm sites, when the producer cannot emit them)
+//   * sinusoidal time embeddings       (unet_model.py:40-47; unet_openai.py:66-83)
+//   * linear attention / softmax attention cores (unet_model.py:135-149,162-177; unet_openai.py:345-358)
+// All reductions are fp32 per thread, combined in fp64 (atomicAdd(double)) so the E[x^2]-E[x]^2 form is safe.
+#include <atomic>
+
+#include "../../include/sbmae_b200.h"
+#include "common.cuh"
+
+namespace sbm {
+extern std::atomic<unsigned long long> g_launches;
+static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------ stem im2col
+// x: fp32 NCHW [B,C,H,W]  ->  a: bf16 [B*H*W, ldk], column k = (c*KH + kh)*KW + kw (matches weight.view(O,-1))
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int C, int H,
+                                   int W, int KH, int KW, int ldk) {
+  const int K = C * KH * KW;
+  const int64_t total = (int64_t)B * H * W * ldk;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % ldk);
+    const int64_t pix = idx / ldk;
+    float v = 0.f;
+    if (k < K) {
+      const int kw = k % KW;
+      const int kh = (k / KW) % KH;
+      const int c = k / (KW * KH);
+      const int w = (int)(pix % W);
+      const int h = (int)((pix / W) % H);
+      const int b = (int)(pix / ((int64_t)W * H));
+      const int ih = h + kh - KH / 2, iw = w + kw - KW / 2;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((int64_t)b * C + c) * H + ih) * W + iw);
+    }
+    a[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------ depthwise 7x7
+// One block = one sample x one chunk of 32 channels x all pixels.  The input slab (H*W x 32 channels, fp32)
+// and the 49x32 filter taps are staged in shared memory, so global memory is read exactly once.
+// h = dwconv7(x) + bias[c] + cond[b][c];  stats[b] += (sum h, sum h^2)
+constexpr int kDwCh = 32;
+__global__ void __launch_bounds__(256)
+dwconv7_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
+               const float* __restrict__ cond, int64_t ldc, float* __restrict__ out, int64_t ldo,
+               double* __restrict__ stats, int C, int H, int W) {
+  extern __shared__ float sm[];
+  const int HW = H * W;
+  float* sx = sm;                      // [HW][33]
+  float* sw = sm + (size_t)HW * 33;    // [49][32]
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * kDwCh;
+  const int tid = threadIdx.x;
+  const int cl = tid & 31;
+  const int c = c0 + cl;
+  const bool c_ok = c < C;
+  for (int p = tid >> 5; p < HW; p += blockDim.x >> 5)
+    sx[p * 33 + cl] = c_ok ? __ldg(x + ((int64_t)b * HW + p) * ldx + c) : 0.f;
+  for (int i = tid; i < 49 * kDwCh; i += blockDim.x) {
+    const int ch = i / 49, tap = i - ch * 49;  // consecutive threads read consecutive taps of one channel
+    sw[tap * kDwCh + ch] = (c0 + ch < C) ? __ldg(w + (int64_t)(c0 + ch) * 49 + tap) : 0.f;
+  }
+  __syncthreads();
+  const float add = c_ok ? (bias ? __ldg(bias + c) : 0.f) + (cond ? __ldg(cond + (int64_t)b * ldc + c) : 0.f) : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int p = tid >> 5; p < HW; p += blockDim.x >> 5) {
+    const int ph = p / W, pw = p - ph * W;
+    float acc = 0.f;
+    const int kh0 = max(0, 3 - ph), kh1 = min(7, H + 3 - ph);
+    const int kw0 = max(0, 3 - pw), kw1 = min(7, W + 3 - pw);
+    for (int kh = kh0; kh < kh1; ++kh) {
+      const float* row = sx + ((ph + kh - 3) * W + (pw - 3)) * 33 + cl;
+      const float* wr = sw + (kh * 7) * kDwCh + cl;
+      for (int kw = kw0; kw < kw1; ++kw) acc = fmaf(row[kw * 33], wr[kw * kDwCh], acc);
+    }
+    acc += add;
+    if (c_ok) {
+      out[((int64_t)b * HW + p) * ldo + c] = acc;
+      s1 += acc;
+      s2 += acc * acc;
+    }
+  }
+  if (stats != nullptr) {
+    const float t1 = block_sum(s1, red);
+    const float t2 = block_sum(s2, red);
+    if (tid == 0) {
+      atomicAdd(stats + 2 * (int64_t)b, (double)t1);
+      atomicAdd(stats + 2 * (int64_t)b + 1, (double)t2);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ group statistics
+// stats[b][g] += (sum, sumsq) over the pixels x channels of group g.  grid = (chunks, groups, B)
+__global__ void __launch_bounds__(256)
+group_stats_kernel(const void* __restrict__ x, int in_dtype, int64_t ldx, int HW, int C, int G,
+                   double* __restrict__ stats) {
+  __shared__ float red[32];
+  const int g = blockIdx.y, b = blockIdx.z;
+  const int cpg = C / G;
+  const int64_t n = (int64_t)HW * cpg;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % cpg);
+    const int64_t p = i / cpg;
+    const int64_t off = ((int64_t)b * HW + p) * ldx + g * cpg + cc;
+    const float v = in_dtype == SBM_F32 ? reinterpret_cast<const float*>(x)[off]
+                                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[off]);
+    s1 += v;
+    s2 += v * v;
+  }
+  const float t1 = block_sum(s1, red);
+  const float t2 = block_sum(s2, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + 2 * ((int64_t)b * G + g), (double)t1);
+    atomicAdd(stats + 2 * ((int64_t)b * G + g) + 1, (double)t2);
+  }
+}
+
+// ------------------------------------------------------------------------------ GroupNorm apply
+// y = act((x - mean)*rstd*gamma + beta) (+ residual);  4 channels per thread.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __restrict__ stats,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       const float* __restrict__ residual, int64_t ldr, TOut* __restrict__ out, int64_t ldo,
+                       float* __restrict__ out_f32, int64_t ldo_f32, int64_t npix_total, int HW, int C, int G,
+                       float eps, int act) {
+  const int cq = (C + 3) >> 2;
+  const int cpg = C / G;
+  const double inv_n = 1.0 / ((double)HW * cpg);
+  const int64_t total = npix_total * cq;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % cq);
+    const int64_t pix = idx / cq;
+    const int b = (int)(pix / HW);
+    const int c = q * 4;
+    float v[4];
+    const TIn* xp = x + pix * ldx + c;
+    if (c + 4 <= C) {
+      if constexpr (sizeof(TIn) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(xp);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(xp);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(bb); v[3] = __high2float(bb);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
+    }
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ce = min(c + e, C - 1);
+      const int g = ce / cpg;
+      const double s1 = stats[2 * ((int64_t)b * G + g)], s2 = stats[2 * ((int64_t)b * G + g) + 1];
+      const double mean = s1 * inv_n;
+      const double var = fmax(s2 * inv_n - mean * mean, 0.0);
+      const float rstd = (float)rsqrt(var + (double)eps);
+      float y = (v[e] - (float)mean) * rstd * __ldg(gamma + ce) + __ldg(beta + ce);
+      if (act == SBM_ACT_SILU) y = silu(y);
+      else if (act == SBM_ACT_GELU) y = gelu_exact(y);
+      o[e] = y;
+    }
+    if (residual != nullptr) {
+      const float* rp = residual + pix * ldr + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < C) o[e] += rp[e];
+    }
+    if (out != nullptr) {
+      TOut* op = out + pix * ldo + c;
+      if (c + 4 <= C) {
+        if constexpr (sizeof(TOut) == 4) {
+          *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+          __nv_bfloat162 bb = __floats2bfloat162_rn(o[2], o[3]);
+          uint2 t;
+          t.x = *reinterpret_cast<uint32_t*>(&a);
+          t.y = *reinterpret_cast<uint32_t*>(&bb);
+          *reinterpret_cast<uint2*>(op) = t;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (c + e < C) op[e] = (TOut)o[e];
+      }
+    }
+    if (out_f32 != nullptr) {
+      float* op = out_f32 + pix * ldo_f32 + c;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < C) op[e] = o[e];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ time embedding
+// mode 0: unet_model.py:40-47   [sin | cos], freq_k = exp(-k*log(1e4)/(half-1))
+// mode 1: unet_openai.py:66-83  [cos | sin], freq_k = exp(-k*log(1e4)/half)
+__global__ void time_embed_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, float* out_f32,
+                                  int B, int dim, int ld, int mode) {
+  const int half = dim / 2;
+  const int64_t total = (int64_t)B * ld;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % ld);
+    const int b = (int)(idx / ld);
+    float v = 0.f;
+    if (j < 2 * half) {
+      const int k = j < half ? j : j - half;
+      const float denom = mode == 0 ? (float)(half - 1) : (float)half;
+      // same fp32 evaluation order as the reference: exp(k * -(log(1e4)/denom)) then t * freq
+      const float f = mode == 0 ? expf((float)k * -(9.210340371976184f / denom))
+                                : expf(-9.210340371976184f * (float)k / denom);
+      const float arg = t[b] * f;
+      const bool first = j < half;
+      v = (mode == 0) ? (first ? sinf(arg) : cosf(arg)) : (first ? cosf(arg) : sinf(arg));
+    }
+    out[idx] = __float2bfloat16_rn(v);
+    if (out_f32 != nullptr) out_f32[idx] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------ linear attention core
+// unet_model.py:162-177.  qkv: fp32 [B, n, ldq] with channels [q(h,d) | k(h,d) | v(h,d)], d = 32.
+// One block per (head, sample).  out: bf16 [B, n, ldo], channel h*32+e.
+constexpr int kHeadDim = 32;
+__global__ void __launch_bounds__(256)
+linear_attn_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo, int n,
+                   int heads, float scale) {
+  extern __shared__ float sm[];
+  float* sq = sm;                          // [n][33]
+  float* sk = sq + (size_t)n * 33;         // [n][33]
+  float* sv = sk + (size_t)n * 33;         // [n][33]
+  float* ctx = sv + (size_t)n * 33;        // [32][33]  ctx[d][e]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int hid = heads * kHeadDim;
+  for (int p = warp; p < n; p += nwarp) {
+    const float* row = qkv + ((int64_t)b * n + p) * ldq + h * kHeadDim + lane;
+    // q: softmax over d (the 32 lanes), then * scale
+    float qv = row[0];
+    float m = qv;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = expf(qv - m);
+    const float s = warp_sum(e);
+    sq[p * 33 + lane] = e / s * scale;
+    sk[p * 33 + lane] = row[hid];
+    sv[p * 33 + lane] = row[2 * hid];
+  }
+  __syncthreads();
+  // k: softmax over the n positions, per channel d
+  for (int d = warp; d < kHeadDim; d += nwarp) {
+    float m = -INFINITY;
+    for (int p = lane; p < n; p += 32) m = fmaxf(m, sk[p * 33 + d]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int p = lane; p < n; p += 32) {
+      const float e = expf(sk[p * 33 + d] - m);
+      sk[p * 33 + d] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int p = lane; p < n; p += 32) sk[p * 33 + d] *= inv;
+  }
+  __syncthreads();
+  // context[d][e] = sum_n k[d][n] v[e][n]
+  for (int i = tid; i < kHeadDim * kHeadDim; i += blockDim.x) {
+    const int d = i >> 5, e = i & 31;
+    float acc = 0.f;
+    for (int p = 0; p < n; ++p) acc = fmaf(sk[p * 33 + d], sv[p * 33 + e], acc);
+    ctx[d * 33 + e] = acc;
+  }
+  __syncthreads();
+  // out[e][n] = sum_d context[d][e] q[d][n]
+  for (int p = warp; p < n; p += nwarp) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < kHeadDim; ++d) acc = fmaf(ctx[d * 33 + lane], sq[p * 33 + d], acc);
+    out[((int64_t)b * n + p) * ldo + h * kHeadDim + lane] = __float2bfloat16_rn(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------ softmax attention core
+// qkv: fp32 [B, n, ldq]; layout selected by (q_off, k_off, v_off, head_stride): channel of (head, d) for q is
+// q_off + head*head_stride + d.   out[b, i, o_off + head*dh + d] = sum_j softmax_j(scale * q_i . k_j) v_j[d]
+//   unet_model.py:135-149  : q_off=0, k_off=hid, v_off=2*hid, head_stride=dh, scale=dh^-0.5
+//   unet_openai.py:333-358 : per head [q|k|v] blocks: q_off=0,k_off=ch,v_off=2ch, head_stride=3ch, scale=ch^-0.5
+// One block per (head, sample); K/V rows stream through shared memory in chunks of 32 channels.
+__global__ void __launch_bounds__(256)
+softmax_attn_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo, int n,
+                    int dh, int q_off, int k_off, int v_off, int head_stride, float scale) {
+  extern __shared__ float sm[];
+  float* sS = sm;                      // [n][n+1] scores / probabilities
+  float* sA = sS + (size_t)n * (n + 1);  // [n][33] chunk of q or v
+  float* sB = sA + (size_t)n * 33;       // [n][33] chunk of k
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const float* base = qkv + (int64_t)b * n * ldq + h * head_stride;
+  for (int i = tid; i < n * (n + 1); i += blockDim.x) sS[i] = 0.f;
+  for (int d0 = 0; d0 < dh; d0 += 32) {
+    __syncthreads();
+    for (int p = warp; p < n; p += nwarp) {
+      const bool ok = d0 + lane < dh;
+      sA[p * 33 + lane] = ok ? base[(int64_t)p * ldq + q_off + d0 + lane] : 0.f;
+      sB[p * 33 + lane] = ok ? base[(int64_t)p * ldq + k_off + d0 + lane] : 0.f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+      const int i = idx / n, j = idx - i * n;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < 32; ++d) acc = fmaf(sA[i * 33 + d], sB[j * 33 + d], acc);
+      sS[i * (n + 1) + j] += acc;
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < n; i += nwarp) {
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sS[i * (n + 1) + j] * scale);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float e = expf(sS[i * (n + 1) + j] * scale - m);
+      sS[i * (n + 1) + j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int j = lane; j < n; j += 32) sS[i * (n + 1) + j] *= inv;
+  }
+  for (int d0 = 0; d0 < dh; d0 += 32) {
+    __syncthreads();
+    for (int p = warp; p < n; p += nwarp)
+      sA[p * 33 + lane] = (d0 + lane < dh) ? base[(int64_t)p * ldq + v_off + d0 + lane] : 0.f;
+    __syncthreads();
+    for (int i = warp; i < n; i += nwarp) {
+      float acc = 0.f;
+      for (int j = 0; j < n; ++j) acc = fmaf(sS[i * (n + 1) + j], sA[j * 33 + lane], acc);
+      if (d0 + lane < dh) out[((int64_t)b * n + i) * ldo + h * dh + d0 + lane] = __float2bfloat16_rn(acc);
+    }
+  }
+}
+
+static int grid_for(int64_t total, int threads) {
+  const int64_t want = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+}  // namespace sbm
+
+using namespace sbm;
+
+extern "C" {
+
+int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
+                    int32_t ldk, void* stream) {
+  SBM_CHECK_ARG(x && a && B > 0 && C > 0 && ldk >= C * kh * kw, "sbm_stem_im2col: bad args");
+  const int64_t total = (int64_t)B * H * W * ldk;
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, B, C, H, W, kh, kw,
+                                                                             ldk);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
+                    float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C,
+                    void* stream) {
+  SBM_CHECK_ARG(x && w && out && B > 0 && C > 0 && H > 0 && W > 0, "sbm_dwconv7_fwd: bad args");
+  const size_t smem = ((size_t)H * W * 33 + 49 * kDwCh) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_dwconv7_fwd: %dx%d map does not fit the shared-memory slab", H, W);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((C + kDwCh - 1) / kDwCh, B);
+  dwconv7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, W);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_group_stats(const void* x, int32_t in_dtype, int64_t ldx, int32_t B, int32_t HW, int32_t C, int32_t G,
+                    double* stats, void* stream) {
+  SBM_CHECK_ARG(x && stats && B > 0 && G > 0 && C % G == 0, "sbm_group_stats: bad args");
+  const int64_t n = (int64_t)HW * (C / G);
+  int chunks = (int)std::min<int64_t>((n + 2047) / 2048, 64);
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, G, B);
+  group_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, in_dtype, ldx, HW, C, G, stats);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const double* stats, const float* gamma,
+                        const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
+                        int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
+                        float eps, int32_t act, void* stream) {
+  SBM_CHECK_ARG(x && stats && gamma && beta && (out || out_f32) && B > 0 && G > 0 && C % G == 0,
+                "sbm_groupnorm_apply: bad args");
+  SBM_CHECK_ARG(ldx % 4 == 0 && ldo % 4 == 0, "sbm_groupnorm_apply: row strides must be multiples of 4");
+  const int64_t npix = (int64_t)B * HW;
+  const int64_t total = npix * ((C + 3) / 4);
+  const int grid = grid_for(total, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+#define SBM_GN_LAUNCH(TI, TO)                                                                                   \
+  groupnorm_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x, ldx, stats, gamma, beta, residual, ldr,      \
+                                                      (TO*)out, ldo, out_f32, ldo_f32, npix, HW, C, G, eps, act)
+  if (in_dtype == SBM_F32 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(float, __nv_bfloat16);
+  else if (in_dtype == SBM_F32 && out_dtype == SBM_F32) SBM_GN_LAUNCH(float, float);
+  else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else SBM_GN_LAUNCH(__nv_bfloat16, float);
+#undef SBM_GN_LAUNCH
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_time_embed(const float* t, void* out_bf16, float* out_f32, int32_t B, int32_t dim, int32_t ld, int32_t mode,
+                   void* stream) {
+  SBM_CHECK_ARG(t && out_bf16 && B > 0 && dim >= 4 && ld >= dim, "sbm_time_embed: bad args");
+  time_embed_kernel<<<grid_for((int64_t)B * ld, 256), 256, 0, (cudaStream_t)stream>>>(
+      t, (__nv_bfloat16*)out_bf16, out_f32, B, dim, ld, mode);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
+                        float scale, void* stream) {
+  SBM_CHECK_ARG(qkv && out && B > 0 && n > 0 && heads > 0, "sbm_linear_attn_fwd: bad args");
+  const size_t smem = ((size_t)3 * n * 33 + 32 * 33) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_linear_attn_fwd: n=%d too large", n);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid(heads, B);
+  linear_attn_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, n, heads, scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_softmax_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
+                         int32_t dh, int32_t q_off, int32_t k_off, int32_t v_off, int32_t head_stride, float scale,
+                         void* stream) {
+  SBM_CHECK_ARG(qkv && out && B > 0 && n > 0 && heads > 0 && dh > 0, "sbm_softmax_attn_fwd: bad args");
+  const size_t smem = ((size_t)n * (n + 1) + 2 * (size_t)n * 33) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_softmax_attn_fwd: n=%d too large for the shared-memory score tile", n);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(softmax_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid(heads, B);
+  softmax_attn_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, n, dh, q_off,
+                                                                 k_off, v_off, head_stride, scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

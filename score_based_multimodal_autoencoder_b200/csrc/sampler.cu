@@ -1,0 +1,457 @@
+// Fused reverse-SDE predictor-corrector sampler steps and DSM-loss kernels (HBM-bound, fp32 state).
+//
+//   predictor step   : sde_helper2.py:45-52 + 277-317 + 352-356/402-407/445-450   (12 B / latent element)
+//   corrector step   : sde_helper2.py:54-101  -> norms kernel (4 B/elt) + update kernel (12 B/elt)
+//   observed-latent imputation : train_lat_celebhq_unet_cont2.py:293-303, 309-311 (fused as an epilogue)
+//   DSM perturb/loss : sde_helper2.py:167-185
+//
+// Noise: either an injected buffer (parity tests feed the oracle's noise) or Philox4x32-10 keyed by
+// (seed, draw id) with counter = GLOBAL element index / 4, so a batch shard on any GPU draws the same
+// numbers as the unsharded batch would.  Latent tensors are dense [B, M, D, D] fp32; E = M*D*D per sample.
+#include <atomic>
+
+#include "../../include/sbmae_b200.h"
+#include "common.cuh"
+
+namespace sbm {
+extern std::atomic<unsigned long long> g_launches;
+static inline void count_launch_s() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------ Philox4x32-10
+struct Philox {
+  static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+  __device__ __forceinline__ static uint4 round10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(kM0, c.x), lo0 = kM0 * c.x;
+      const uint32_t hi1 = __umulhi(kM1, c.z), lo1 = kM1 * c.z;
+      c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+      k.x += kW0;
+      k.y += kW1;
+    }
+    return c;
+  }
+};
+// Box-Muller exactly as curand_normal4 does it (curand_normal.h: _curand_box_muller)
+__device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
+  const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+  const float v = y * (2.3283064e-10f * 6.2831855f) + (2.3283064e-10f * 6.2831855f / 2.0f);
+  const float s = sqrtf(-2.0f * logf(u));
+  float sn, cs;
+  __sincosf(v, &sn, &cs);
+  return make_float2(s * sn, s * cs);
+}
+// 4 standard normals for global element quad `quad` of draw `draw` under `seed`
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t draw, uint64_t quad) {
+  const uint4 ctr = make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)draw, (uint32_t)(draw >> 32));
+  const uint4 r = Philox::round10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t draw, uint64_t idx) {
+  const uint64_t quad = idx >> 2;
+  const uint4 ctr = make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)draw, (uint32_t)(draw >> 32));
+  const uint4 r = Philox::round10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  // torch.rand convention: uniform in [0,1) from the top 24 bits
+  return (float)(w >> 8) * (1.0f / 16777216.0f);
+}
+
+// ------------------------------------------------------------------------------ SDE scalar functions
+struct SdeP {
+  int kind;     // SBM_SDE_VP / SUBVP / VE
+  float b0, b1; // beta_min,beta_max  or  sigma_min,sigma_max
+  int N;
+};
+__device__ __forceinline__ void sde_drift_diff(const SdeP& s, float t, float& drift_coef, float& g) {
+  if (s.kind == SBM_SDE_VE) {
+    const float sigma = s.b0 * powf(s.b1 / s.b0, t);
+    drift_coef = 0.f;
+    g = sigma * sqrtf(2.f * (logf(s.b1) - logf(s.b0)));
+  } else {
+    const float beta = s.b0 + t * (s.b1 - s.b0);
+    drift_coef = -0.5f * beta;
+    if (s.kind == SBM_SDE_VP) {
+      g = sqrtf(beta);
+    } else {
+      const float discount = 1.f - expf(-2.f * s.b0 * t - (s.b1 - s.b0) * t * t);
+      g = sqrtf(beta * discount);
+    }
+  }
+}
+__device__ __forceinline__ void sde_marginal(const SdeP& s, float t, float& mean_coef, float& std) {
+  if (s.kind == SBM_SDE_VE) {
+    mean_coef = 1.f;
+    std = s.b0 * powf(s.b1 / s.b0, t);
+  } else {
+    const float lmc = -0.25f * t * t * (s.b1 - s.b0) - 0.5f * t * s.b0;
+    mean_coef = expf(lmc);
+    const float v = 1.f - expf(2.f * lmc);
+    std = s.kind == SBM_SDE_VP ? sqrtf(v) : v;  // subVP: no sqrt (sde_helper2.py:412)
+  }
+}
+
+struct Impute {
+  const float* z_obs;   // clean latents [B,M,D,D] or NULL (no imputation)
+  uint32_t mask;        // bit m set = modality channel m observed
+  int noise_obs;
+  float t_next;         // time of the step the written state is the input of
+  int dd;               // D*D elements per modality channel
+};
+__device__ __forceinline__ float4 apply_impute(const Impute& im, const SdeP& s, float4 v, int64_t i4, int e_in_sample) {
+  if (im.z_obs == nullptr) return v;
+  const int m = e_in_sample / im.dd;  // the 4 elements of a quad share the channel (dd % 4 == 0)
+  if (!((im.mask >> m) & 1u)) return v;
+  const float4 z = *reinterpret_cast<const float4*>(im.z_obs + i4);
+  if (!im.noise_obs) return z;
+  float mc, sd;
+  sde_marginal(s, im.t_next, mc, sd);
+  return make_float4(mc * z.x + sd * z.x, mc * z.y + sd * z.y, mc * z.z + sd * z.z, mc * z.w + sd * z.w);
+}
+
+// ------------------------------------------------------------------------------ predictor
+__global__ void __launch_bounds__(256)
+predictor_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ t,
+                 const float* __restrict__ noise, float* __restrict__ x_out, float* __restrict__ x_mean_out,
+                 int64_t n_quads, int E, SdeP s, int ode, uint64_t seed, uint64_t draw, uint64_t quad_offset,
+                 Impute im) {
+  const float dt = -1.f / (float)s.N;
+  const float sq = sqrtf(-dt);
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i4 = q * 4;
+    const int b = (int)(i4 / E);
+    float dc, g;
+    sde_drift_diff(s, __ldg(t + b), dc, g);
+    const float4 xv = *reinterpret_cast<const float4*>(x + i4);
+    const float4 sv = *reinterpret_cast<const float4*>(score + i4);
+    const float g2 = g * g * (ode ? 0.5f : 1.f);
+    float4 mean;
+    mean.x = xv.x + (dc * xv.x - g2 * sv.x) * dt;
+    mean.y = xv.y + (dc * xv.y - g2 * sv.y) * dt;
+    mean.z = xv.z + (dc * xv.z - g2 * sv.z) * dt;
+    mean.w = xv.w + (dc * xv.w - g2 * sv.w) * dt;
+    float4 out = mean;
+    if (!ode) {
+      const float4 z = noise ? *reinterpret_cast<const float4*>(noise + i4)
+                             : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
+      const float gs = g * sq;
+      out.x += gs * z.x; out.y += gs * z.y; out.z += gs * z.z; out.w += gs * z.w;
+    }
+    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + i4) = mean;
+    out = apply_impute(im, s, out, i4, (int)(i4 - (int64_t)b * E));
+    *reinterpret_cast<float4*>(x_out + i4) = out;
+  }
+}
+
+// ------------------------------------------------------------------------------ corrector
+// norms: one warp per sample; acc[0] += ||grad_b||, acc[1] += ||noise_b||  (fp64 accumulators)
+__global__ void __launch_bounds__(256)
+corrector_norms_kernel(const float* __restrict__ grad, const float* __restrict__ noise, double* __restrict__ acc,
+                       int B, int E, uint64_t seed, uint64_t draw, uint64_t quad_offset) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int EQ = E >> 2;
+  double a0 = 0.0, a1 = 0.0;
+  for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
+    float sg = 0.f, sn = 0.f;
+    for (int q = lane; q < EQ; q += 32) {
+      const int64_t gq = (int64_t)b * EQ + q;
+      const float4 g = *reinterpret_cast<const float4*>(grad + gq * 4);
+      const float4 z = noise ? *reinterpret_cast<const float4*>(noise + gq * 4)
+                             : philox_normal4(seed, draw, quad_offset + (uint64_t)gq);
+      sg += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
+      sn += z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w;
+    }
+    sg = warp_sum(sg);
+    sn = warp_sum(sn);
+    a0 += (double)sqrtf(sg);
+    a1 += (double)sqrtf(sn);
+  }
+  if (lane == 0 && (a0 != 0.0 || a1 != 0.0)) {
+    atomicAdd(acc, a0);
+    atomicAdd(acc + 1, a1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+corrector_update_kernel(const float* __restrict__ x, const float* __restrict__ grad, const float* __restrict__ t,
+                        const float* __restrict__ noise, const double* __restrict__ acc,
+                        const float* __restrict__ alphas, float* __restrict__ x_out, float* __restrict__ x_mean_out,
+                        int64_t n_quads, int E, SdeP s, float T, float target_snr, double inv_global_batch,
+                        uint64_t seed, uint64_t draw, uint64_t quad_offset, Impute im) {
+  const float grad_norm = (float)(acc[0] * inv_global_batch);
+  const float noise_norm = (float)(acc[1] * inv_global_batch);
+  const float r = target_snr * noise_norm / grad_norm;
+  const float base = r * r * 2.f;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i4 = q * 4;
+    const int b = (int)(i4 / E);
+    float alpha = 1.f;
+    if (alphas != nullptr) {
+      // (t * (N - 1) / T).long(): fp32 product, fp32 divide, truncate (sde_helper2.py:57)
+      const long long idx = (long long)(__ldg(t + b) * (float)(s.N - 1) / T);
+      alpha = __ldg(alphas + min(max(idx, 0ll), (long long)s.N - 1));
+    }
+    const float step = base * alpha;
+    const float ns = sqrtf(step * 2.f);
+    const float4 xv = *reinterpret_cast<const float4*>(x + i4);
+    const float4 gv = *reinterpret_cast<const float4*>(grad + i4);
+    const float4 z = noise ? *reinterpret_cast<const float4*>(noise + i4)
+                           : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
+    float4 mean = make_float4(xv.x + step * gv.x, xv.y + step * gv.y, xv.z + step * gv.z, xv.w + step * gv.w);
+    float4 out = make_float4(mean.x + ns * z.x, mean.y + ns * z.y, mean.z + ns * z.z, mean.w + ns * z.w);
+    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + i4) = mean;
+    out = apply_impute(im, s, out, i4, (int)(i4 - (int64_t)b * E));
+    *reinterpret_cast<float4*>(x_out + i4) = out;
+  }
+}
+
+// standalone imputation (first step / finishing): x_out = imputed(x) ; final=1 writes the CLEAN latent
+__global__ void __launch_bounds__(256)
+impute_kernel(const float* __restrict__ x, float* __restrict__ x_out, int64_t n_quads, int E, SdeP s, Impute im) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i4 = q * 4;
+    const int b = (int)(i4 / E);
+    const float4 v = *reinterpret_cast<const float4*>(x + i4);
+    *reinterpret_cast<float4*>(x_out + i4) = apply_impute(im, s, v, i4, (int)(i4 - (int64_t)b * E));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+randn_kernel(float* __restrict__ out, int64_t n_quads, uint64_t seed, uint64_t draw, uint64_t quad_offset,
+             float scale) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    float4 z = philox_normal4(seed, draw, quad_offset + (uint64_t)q);
+    z.x *= scale; z.y *= scale; z.z *= scale; z.w *= scale;
+    *reinterpret_cast<float4*>(out + q * 4) = z;
+  }
+}
+
+// ------------------------------------------------------------------------------ DSM
+// t_b = u_b*(T-eps)+eps ; x~ = mean_coef(t_b)*x0 + std(t_b)*z.  Writes x~, z (kept for the loss), t, std, g2.
+__global__ void __launch_bounds__(256)
+dsm_perturb_kernel(const float* __restrict__ x0, const float* __restrict__ u_in, const float* __restrict__ z_in,
+                   float* __restrict__ xt, float* __restrict__ z_out, float* __restrict__ t_out,
+                   float* __restrict__ std_out, float* __restrict__ g2_out, int64_t n_quads, int E, SdeP s, float T,
+                   float eps, uint64_t seed, uint64_t draw_u, uint64_t draw_z, uint64_t sample_offset) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i4 = q * 4;
+    const int b = (int)(i4 / E);
+    const float u = u_in ? __ldg(u_in + b) : philox_uniform(seed, draw_u, sample_offset + (uint64_t)b);
+    const float t = u * (T - eps) + eps;
+    float mc, sd;
+    sde_marginal(s, t, mc, sd);
+    const float4 xv = *reinterpret_cast<const float4*>(x0 + i4);
+    const float4 z = z_in ? *reinterpret_cast<const float4*>(z_in + i4)
+                          : philox_normal4(seed, draw_z, sample_offset * (uint64_t)(E >> 2) + (uint64_t)q);
+    *reinterpret_cast<float4*>(xt + i4) =
+        make_float4(mc * xv.x + sd * z.x, mc * xv.y + sd * z.y, mc * xv.z + sd * z.z, mc * xv.w + sd * z.w);
+    if (z_out) *reinterpret_cast<float4*>(z_out + i4) = z;
+    if (i4 == (int64_t)b * E) {
+      t_out[b] = t;
+      std_out[b] = sd;
+      if (g2_out) {
+        float dc, g;
+        sde_drift_diff(s, t, dc, g);
+        g2_out[b] = g * g;
+      }
+    }
+  }
+}
+
+// loss_b = red_CHW(term^2) [* g2_b] ; loss = mean_b.  term = score*std+z  (mode 0)  or  score + z/std (mode 1).
+// Also writes dloss/dscore (unit upstream gradient).  One warp per sample; fp64 accumulation of the batch mean.
+__global__ void __launch_bounds__(256)
+dsm_loss_kernel(const float* __restrict__ score, const float* __restrict__ z, const float* __restrict__ std,
+                const float* __restrict__ g2, float* __restrict__ dscore, double* __restrict__ loss_acc, int B,
+                int E, int mode, int reduce_mean, double inv_global_batch) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int EQ = E >> 2;
+  const float red_scale = reduce_mean ? 1.f / (float)E : 0.5f;
+  double acc = 0.0;
+  for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
+    const float sd = __ldg(std + b);
+    const float w = mode == 1 ? __ldg(g2 + b) : 1.f;
+    // d loss / d score = (1/B) * w * red_scale * 2 * term * dterm/dscore
+    const float gscale = (float)inv_global_batch * w * red_scale * 2.f * (mode == 0 ? sd : 1.f);
+    float sum = 0.f;
+    for (int q = lane; q < EQ; q += 32) {
+      const int64_t i4 = ((int64_t)b * EQ + q) * 4;
+      const float4 sv = *reinterpret_cast<const float4*>(score + i4);
+      const float4 zv = *reinterpret_cast<const float4*>(z + i4);
+      float4 term;
+      if (mode == 0) term = make_float4(sv.x * sd + zv.x, sv.y * sd + zv.y, sv.z * sd + zv.z, sv.w * sd + zv.w);
+      else term = make_float4(sv.x + zv.x / sd, sv.y + zv.y / sd, sv.z + zv.z / sd, sv.w + zv.w / sd);
+      sum += term.x * term.x + term.y * term.y + term.z * term.z + term.w * term.w;
+      if (dscore)
+        *reinterpret_cast<float4*>(dscore + i4) =
+            make_float4(gscale * term.x, gscale * term.y, gscale * term.z, gscale * term.w);
+    }
+    sum = warp_sum(sum);
+    acc += (double)(sum * red_scale * w);
+  }
+  if (lane == 0 && acc != 0.0) atomicAdd(loss_acc, acc * inv_global_batch);
+}
+
+__global__ void scale_kernel(const float* __restrict__ in, const float* __restrict__ scalar, float* __restrict__ out,
+                             int64_t n) {
+  const float s = *scalar;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i] * s;
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+static int ew_grid(int64_t n_items) {
+  const int64_t want = (n_items + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
+}
+static int check_latent(const sbm_latent_shape* ls, const char* who) {
+  SBM_CHECK_ARG(ls && ls->batch > 0 && ls->mods > 0 && ls->mods <= 32 && ls->dd > 0, "%s: bad latent shape", who);
+  SBM_CHECK_ARG(ls->dd % 4 == 0, "%s: D*D = %d must be a multiple of 4 (vectorised latent access)", who, ls->dd);
+  return 0;
+}
+static SdeP to_sdep(const sbm_sde* s) { return SdeP{s->kind, s->b0, s->b1, s->N}; }
+static Impute to_impute(const sbm_impute* im, int dd) {
+  Impute r;
+  r.z_obs = im ? im->z_obs : nullptr;
+  r.mask = im ? im->obs_mask : 0u;
+  r.noise_obs = im ? im->noise_obs : 0;
+  r.t_next = im ? im->t_next : 0.f;
+  r.dd = dd;
+  if (r.mask == 0u) r.z_obs = nullptr;
+  return r;
+}
+
+}  // namespace sbm
+
+using namespace sbm;
+
+extern "C" {
+
+int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem_offset, float scale, void* stream) {
+  SBM_CHECK_ARG(out && n > 0 && n % 4 == 0 && elem_offset % 4 == 0, "sbm_randn: n and offset must be multiples of 4");
+  randn_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(out, n / 4, seed, draw, elem_offset / 4, scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
+                       const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
+                       const sbm_rng* rng, const sbm_impute* impute, void* stream) {
+  if (check_latent(ls, "sbm_predictor_step")) return 1;
+  SBM_CHECK_ARG(sde && x && score && t && x_out, "sbm_predictor_step: null pointer");
+  SBM_CHECK_ARG(noise || rng || probability_flow, "sbm_predictor_step: need injected noise or an rng");
+  const int E = ls->mods * ls->dd;
+  const int64_t nq = (int64_t)ls->batch * E / 4;
+  predictor_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
+      x, score, t, noise, x_out, x_mean_out, nq, E, to_sdep(sde), probability_flow, rng ? rng->seed : 0,
+      rng ? rng->draw : 0, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd));
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
+                        double* acc2, void* stream) {
+  if (check_latent(ls, "sbm_corrector_norms")) return 1;
+  SBM_CHECK_ARG(grad && acc2 && (noise || rng), "sbm_corrector_norms: null pointer");
+  const int E = ls->mods * ls->dd;
+  const int blocks = std::max(1, std::min((ls->batch + 7) / 8, sm_count() * 8));
+  corrector_norms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, noise, acc2, ls->batch, E,
+                                                                   rng ? rng->seed : 0, rng ? rng->draw : 0,
+                                                                   rng ? rng->sample_offset * (uint64_t)(E / 4) : 0);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* grad,
+                         const float* t, const float* noise, const double* acc2, const float* alphas, float* x_out,
+                         float* x_mean_out, float target_snr, int64_t global_batch, const sbm_rng* rng,
+                         const sbm_impute* impute, void* stream) {
+  if (check_latent(ls, "sbm_corrector_update")) return 1;
+  SBM_CHECK_ARG(sde && x && grad && t && acc2 && x_out && (noise || rng), "sbm_corrector_update: null pointer");
+  SBM_CHECK_ARG(global_batch >= ls->batch, "sbm_corrector_update: global_batch < local batch");
+  const int E = ls->mods * ls->dd;
+  const int64_t nq = (int64_t)ls->batch * E / 4;
+  corrector_update_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
+      x, grad, t, noise, acc2, alphas, x_out, x_mean_out, nq, E, to_sdep(sde), sde->T, target_snr,
+      1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0,
+      rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd));
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_impute_observed(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, float* x_out,
+                        const sbm_impute* impute, void* stream) {
+  if (check_latent(ls, "sbm_impute_observed")) return 1;
+  SBM_CHECK_ARG(sde && x && x_out && impute && impute->z_obs, "sbm_impute_observed: null pointer");
+  const int E = ls->mods * ls->dd;
+  const int64_t nq = (int64_t)ls->batch * E / 4;
+  impute_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(x, x_out, nq, E, to_sdep(sde),
+                                                               to_impute(impute, ls->dd));
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_dsm_perturb(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x0, const float* u, const float* z,
+                    float* xt, float* z_out, float* t_out, float* std_out, float* g2_out, float eps,
+                    const sbm_rng* rng, void* stream) {
+  if (check_latent(ls, "sbm_dsm_perturb")) return 1;
+  SBM_CHECK_ARG(sde && x0 && xt && t_out && std_out, "sbm_dsm_perturb: null pointer");
+  SBM_CHECK_ARG((u && z) || rng, "sbm_dsm_perturb: need injected (u, z) or an rng");
+  const int E = ls->mods * ls->dd;
+  const int64_t nq = (int64_t)ls->batch * E / 4;
+  dsm_perturb_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
+      x0, u, z, xt, z_out, t_out, std_out, g2_out, nq, E, to_sdep(sde), sde->T, eps, rng ? rng->seed : 0,
+      rng ? rng->draw : 0, rng ? rng->draw + 1 : 0, rng ? rng->sample_offset : 0);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_dsm_loss(const sbm_latent_shape* ls, const float* score, const float* z, const float* std, const float* g2,
+                 float* dscore, double* loss_acc, int32_t likelihood_weighting, int32_t reduce_mean,
+                 int64_t global_batch, void* stream) {
+  if (check_latent(ls, "sbm_dsm_loss")) return 1;
+  SBM_CHECK_ARG(score && z && std && loss_acc, "sbm_dsm_loss: null pointer");
+  SBM_CHECK_ARG(!likelihood_weighting || g2, "sbm_dsm_loss: likelihood weighting needs g2");
+  const int E = ls->mods * ls->dd;
+  const int blocks = std::max(1, std::min((ls->batch + 7) / 8, sm_count() * 8));
+  dsm_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(score, z, std, g2, dscore, loss_acc, ls->batch, E,
+                                                            likelihood_weighting ? 1 : 0, reduce_mean,
+                                                            1.0 / (double)global_batch);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_scale_by_scalar(const float* in, const float* scalar_dev, float* out, int64_t n, void* stream) {
+  SBM_CHECK_ARG(in && scalar_dev && out && n > 0, "sbm_scale_by_scalar: bad args");
+  scale_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(in, scalar_dev, out, n);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_f64_to_f32(const double* in, float* out, int32_t n, void* stream) {
+  SBM_CHECK_ARG(in && out && n > 0, "sbm_f64_to_f32: bad args");
+  f64_to_f32_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+}  // extern "C"
