@@ -111,10 +111,20 @@ typedef struct sbm_latent_shape { int32_t batch, mods, dd; /* dd = D*D */ } sbm_
 typedef struct sbm_sde { int32_t kind; float b0, b1; int32_t N; float T; } sbm_sde;
 /* Philox4x32-10 stream: key = seed, counter = (global element index / 4, draw); sample_offset = index of this
  * shard's first sample inside the global batch (multi-GPU sampling draws the same numbers as one GPU would). */
-typedef struct sbm_rng { uint64_t seed, draw, sample_offset; } sbm_rng;
+typedef struct sbm_rng {
+  uint64_t seed, draw, sample_offset;
+  const uint64_t* draw_dev; /* optional DEVICE counter added to `draw` (lets one captured CUDA graph serve every step) */
+} sbm_rng;
 /* observed-modality imputation applied to the state a step WRITES (train_lat_celebhq_unet_cont2.py:293-303):
  * channel m with bit m of obs_mask set := noise_obs ? exp(lmc(t_next))*z + std(t_next)*z : z */
-typedef struct sbm_impute { const float* z_obs; uint32_t obs_mask; int32_t noise_obs; float t_next; } sbm_impute;
+typedef struct sbm_impute {
+  const float* z_obs; uint32_t obs_mask; int32_t noise_obs; float t_next;
+  const float* t_next_dev; /* optional DEVICE scalar overriding t_next (CUDA-graph replay) */
+} sbm_impute;
+/* per-step device state of a graph-replayed sampler: t_vec[0..B) = ts[*step]; *t_next = ts[*step+1] (or ts[*step] when
+ * last); then, when `advance` != 0: *step += 1 and *draw += draws_per_step.  One tiny kernel. */
+int sbm_sampler_tick(const float* ts, int32_t n_ts, int32_t* step, uint64_t* draw, float* t_vec, int32_t B,
+                     float* t_next, int32_t advance, uint64_t draws_per_step, void* stream);
 
 int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem_offset, float scale, void* stream);
 /* em_predictor, sde_helper2.py:45-52: x_mean = x + (f(x,t) - g^2 s [*0.5]) * (-1/N); x' = x_mean + g sqrt(1/N) z */

@@ -76,3 +76,22 @@ class ConvArgs(C.Structure):
         ("stats", C.c_void_p),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
     ]
+
+SDE_VP, SDE_SUBVP, SDE_VE = 0, 1, 2
+
+
+class LatentShape(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("mods", C.c_int32), ("dd", C.c_int32)]
+
+
+class SdeC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("b0", C.c_float), ("b1", C.c_float), ("N", C.c_int32), ("T", C.c_float)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("draw", C.c_uint64), ("sample_offset", C.c_uint64), ("draw_dev", C.c_void_p)]
+
+
+class Impute(C.Structure):
+    _fields_ = [("z_obs", C.c_void_p), ("obs_mask", C.c_uint32), ("noise_obs", C.c_int32), ("t_next", C.c_float),
+                ("t_next_dev", C.c_void_p)]

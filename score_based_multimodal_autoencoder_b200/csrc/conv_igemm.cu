@@ -43,6 +43,7 @@ constexpr int kMaxTaps = 16;
 struct TapTable {
   int32_t ntaps;
   int32_t out_off;          // element offset of this phase inside the output tensor
+  int32_t out2_off;         // same for the optional bf16 copy
   int8_t dh[kMaxTaps];      // added to the tile's hv origin
   int8_t dw[kMaxTaps];      // wv coordinate of the box start
   int16_t q[kMaxTaps];      // coordinate in the parity dimension
@@ -176,7 +177,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool row_ok = b < p.batch;
     const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw + tt.out_off;
     const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
-    const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw;
+    const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw + tt.out2_off;
     float s1 = 0.f, s2 = 0.f;
 
     ptx::mbar_wait(tmem_full_bar, 0);
@@ -451,14 +452,15 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   p.o2_sw = sp * a->ldo2; p.o2_sh = sp * OWf * a->ldo2; p.o2_sb = OHf * OWf * a->ldo2;
   for (int ph = 0; ph < nphase; ++ph) {
     const int64_t phh = ph >> 1, pww = ph & 1;
-    int64_t off = 0;
+    int64_t off = 0, off2 = 0;
     if (a->kind == SBM_CONVT_4X4_S2) {
       off = a->out_nchw ? (phh * OWf + pww) : (phh * OWf + pww) * a->ldo;
-      SBM_CHECK_ARG(a->residual == nullptr && a->out2 == nullptr,
-                    "sbm_conv_igemm: transposed conv does not take residual/out2");
+      off2 = (phh * OWf + pww) * a->ldo2;
+      SBM_CHECK_ARG(a->residual == nullptr, "sbm_conv_igemm: transposed conv does not take a residual");
     }
-    SBM_CHECK_ARG(off < (int64_t(1) << 31), "sbm_conv_igemm: phase offset overflow");
+    SBM_CHECK_ARG(off < (int64_t(1) << 31) && off2 < (int64_t(1) << 31), "sbm_conv_igemm: phase offset overflow");
     p.taps[ph].out_off = (int32_t)off;
+    p.taps[ph].out2_off = (int32_t)off2;
     SBM_CHECK_ARG(p.taps[ph].ntaps > 0, "sbm_conv_igemm: empty tap table");
   }
   // 16-byte vector access is legal when every row start and channel chunk is 16-byte aligned

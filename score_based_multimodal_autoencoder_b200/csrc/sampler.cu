@@ -96,6 +96,7 @@ struct Impute {
   uint32_t mask;        // bit m set = modality channel m observed
   int noise_obs;
   float t_next;         // time of the step the written state is the input of
+  const float* t_next_dev;  // optional device scalar overriding t_next
   int dd;               // D*D elements per modality channel
 };
 __device__ __forceinline__ float4 apply_impute(const Impute& im, const SdeP& s, float4 v, int64_t i4, int e_in_sample) {
@@ -105,7 +106,7 @@ __device__ __forceinline__ float4 apply_impute(const Impute& im, const SdeP& s, 
   const float4 z = *reinterpret_cast<const float4*>(im.z_obs + i4);
   if (!im.noise_obs) return z;
   float mc, sd;
-  sde_marginal(s, im.t_next, mc, sd);
+  sde_marginal(s, im.t_next_dev ? __ldg(im.t_next_dev) : im.t_next, mc, sd);
   return make_float4(mc * z.x + sd * z.x, mc * z.y + sd * z.y, mc * z.z + sd * z.z, mc * z.w + sd * z.w);
 }
 
@@ -113,8 +114,9 @@ __device__ __forceinline__ float4 apply_impute(const Impute& im, const SdeP& s, 
 __global__ void __launch_bounds__(256)
 predictor_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ t,
                  const float* __restrict__ noise, float* __restrict__ x_out, float* __restrict__ x_mean_out,
-                 int64_t n_quads, int E, SdeP s, int ode, uint64_t seed, uint64_t draw, uint64_t quad_offset,
-                 Impute im) {
+                 int64_t n_quads, int E, SdeP s, int ode, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
+                 uint64_t quad_offset, Impute im) {
+  if (draw_dev) draw += *draw_dev;
   const float dt = -1.f / (float)s.N;
   const float sq = sqrtf(-dt);
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
@@ -148,7 +150,9 @@ predictor_kernel(const float* __restrict__ x, const float* __restrict__ score, c
 // norms: one warp per sample; acc[0] += ||grad_b||, acc[1] += ||noise_b||  (fp64 accumulators)
 __global__ void __launch_bounds__(256)
 corrector_norms_kernel(const float* __restrict__ grad, const float* __restrict__ noise, double* __restrict__ acc,
-                       int B, int E, uint64_t seed, uint64_t draw, uint64_t quad_offset) {
+                       int B, int E, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
+                       uint64_t quad_offset) {
+  if (draw_dev) draw += *draw_dev;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int EQ = E >> 2;
@@ -179,7 +183,8 @@ corrector_update_kernel(const float* __restrict__ x, const float* __restrict__ g
                         const float* __restrict__ noise, const double* __restrict__ acc,
                         const float* __restrict__ alphas, float* __restrict__ x_out, float* __restrict__ x_mean_out,
                         int64_t n_quads, int E, SdeP s, float T, float target_snr, double inv_global_batch,
-                        uint64_t seed, uint64_t draw, uint64_t quad_offset, Impute im) {
+                        uint64_t seed, uint64_t draw, const uint64_t* draw_dev, uint64_t quad_offset, Impute im) {
+  if (draw_dev) draw += *draw_dev;
   const float grad_norm = (float)(acc[0] * inv_global_batch);
   const float noise_norm = (float)(acc[1] * inv_global_batch);
   const float r = target_snr * noise_norm / grad_norm;
@@ -310,6 +315,23 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
   if (i < n) out[i] = (float)in[i];
 }
 
+__global__ void sampler_tick_kernel(const float* __restrict__ ts, int n_ts, int* step, unsigned long long* draw,
+                                    float* __restrict__ t_vec, int B, float* t_next, int advance,
+                                    unsigned long long draws_per_step) {
+  const int st = min(*step, n_ts - 1);
+  const float t = ts[st];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) t_vec[i] = t;
+  // every block has read *step before the single writer below may bump it: enforce with a grid of ONE block
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (t_next) *t_next = ts[min(st + 1, n_ts - 1)];
+    if (advance) {
+      *step = st + 1;
+      if (draw) *draw += draws_per_step;
+    }
+  }
+}
+
 static int ew_grid(int64_t n_items) {
   const int64_t want = (n_items + 255) / 256;
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
@@ -326,6 +348,7 @@ static Impute to_impute(const sbm_impute* im, int dd) {
   r.mask = im ? im->obs_mask : 0u;
   r.noise_obs = im ? im->noise_obs : 0;
   r.t_next = im ? im->t_next : 0.f;
+  r.t_next_dev = im ? im->t_next_dev : nullptr;
   r.dd = dd;
   if (r.mask == 0u) r.z_obs = nullptr;
   return r;
@@ -345,6 +368,16 @@ int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem
   return 0;
 }
 
+int sbm_sampler_tick(const float* ts, int32_t n_ts, int32_t* step, uint64_t* draw, float* t_vec, int32_t B,
+                     float* t_next, int32_t advance, uint64_t draws_per_step, void* stream) {
+  SBM_CHECK_ARG(ts && step && t_vec && n_ts > 0 && B > 0, "sbm_sampler_tick: bad args");
+  sampler_tick_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ts, n_ts, step, (unsigned long long*)draw, t_vec, B, t_next,
+                                                            advance, draws_per_step);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
 int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                        const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
                        const sbm_rng* rng, const sbm_impute* impute, void* stream) {
@@ -355,7 +388,8 @@ int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const flo
   const int64_t nq = (int64_t)ls->batch * E / 4;
   predictor_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
       x, score, t, noise, x_out, x_mean_out, nq, E, to_sdep(sde), probability_flow, rng ? rng->seed : 0,
-      rng ? rng->draw : 0, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd));
+      rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
+      to_impute(impute, ls->dd));
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;
@@ -369,6 +403,7 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
   const int blocks = std::max(1, std::min((ls->batch + 7) / 8, sm_count() * 8));
   corrector_norms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, noise, acc2, ls->batch, E,
                                                                    rng ? rng->seed : 0, rng ? rng->draw : 0,
+                                                                   rng ? rng->draw_dev : nullptr,
                                                                    rng ? rng->sample_offset * (uint64_t)(E / 4) : 0);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
@@ -386,7 +421,7 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
   const int64_t nq = (int64_t)ls->batch * E / 4;
   corrector_update_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
       x, grad, t, noise, acc2, alphas, x_out, x_mean_out, nq, E, to_sdep(sde), sde->T, target_snr,
-      1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0,
+      1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,
       rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd));
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();

@@ -91,3 +91,76 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
         a.out2, a.ldo2 = out2.data_ptr(), out2.stride(2)
     L.check(L.lib().sbm_conv_igemm(C.byref(a), L.stream_ptr()), "sbm_conv_igemm")
     return out
+
+
+# ---------------------------------------------------------------------------- score-net operators
+def _dt(t: torch.Tensor) -> int:
+    return L.BF16 if t.dtype == torch.bfloat16 else L.F32
+
+
+def stem_im2col(x: torch.Tensor, kh: int, kw: int) -> torch.Tensor:
+    """fp32 NCHW -> bf16 [B,H,W,pad8(C*kh*kw)] im2col rows."""
+    b, c, h, w = x.shape
+    ldk = pad8(c * kh * kw)
+    a = torch.empty((b, h, w, ldk), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().sbm_stem_im2col(L.ptr(x), L.ptr(a), C.c_int32(b), C.c_int32(c), C.c_int32(h), C.c_int32(w),
+                                    C.c_int32(kh), C.c_int32(kw), C.c_int32(ldk), L.stream_ptr()), "sbm_stem_im2col")
+    return a
+
+
+def dwconv7(x: torch.Tensor, c: int, w: torch.Tensor, bias, cond, ldc: int, stats) -> torch.Tensor:
+    b, h, wd, _ = x.shape
+    out = torch.empty((b, h, wd, pad8(c)), dtype=torch.float32, device=x.device)
+    L.check(L.lib().sbm_dwconv7_fwd(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(w), L.ptr(bias), L.ptr(cond),
+                                    C.c_int64(ldc), L.ptr(out), C.c_int64(out.stride(2)), L.ptr(stats), C.c_int32(b),
+                                    C.c_int32(h), C.c_int32(wd), C.c_int32(c), L.stream_ptr()), "sbm_dwconv7_fwd")
+    return out
+
+
+def group_stats(x: torch.Tensor, c: int, groups: int, stats: torch.Tensor) -> None:
+    b, h, w, _ = x.shape
+    L.check(L.lib().sbm_group_stats(L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), C.c_int32(b),
+                                    C.c_int32(h * w), C.c_int32(c), C.c_int32(groups), L.ptr(stats), L.stream_ptr()),
+            "sbm_group_stats")
+
+
+def groupnorm_apply(x: torch.Tensor, c: int, stats: torch.Tensor, gamma, beta, *, groups: int = 1, act: int = 0,
+                    residual=None, out=None, out_f32=None, eps: float = 1e-5) -> None:
+    b, h, w, _ = x.shape
+    L.check(L.lib().sbm_groupnorm_apply(
+        L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), L.ptr(stats), L.ptr(gamma), L.ptr(beta),
+        L.ptr(residual), C.c_int64(residual.stride(2) if residual is not None else 0),
+        L.ptr(out), C.c_int32(_dt(out) if out is not None else L.BF16),
+        C.c_int64(out.stride(2) if out is not None else 4),
+        L.ptr(out_f32), C.c_int64(out_f32.stride(2) if out_f32 is not None else 0),
+        C.c_int32(b), C.c_int32(h * w), C.c_int32(c), C.c_int32(groups), C.c_float(eps), C.c_int32(act),
+        L.stream_ptr()), "sbm_groupnorm_apply")
+
+
+def time_embed(t: torch.Tensor, dim: int, mode: int) -> torch.Tensor:
+    b = t.shape[0]
+    ld = pad8(dim)
+    out = torch.empty((b, 1, 1, ld), dtype=torch.bfloat16, device=t.device)
+    L.check(L.lib().sbm_time_embed(L.ptr(t), L.ptr(out), None, C.c_int32(b), C.c_int32(dim), C.c_int32(ld),
+                                   C.c_int32(mode), L.stream_ptr()), "sbm_time_embed")
+    return out
+
+
+def linear_attn(qkv: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
+    b, h, w, _ = qkv.shape
+    out = torch.empty((b, h, w, heads * 32), dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.lib().sbm_linear_attn_fwd(L.ptr(qkv), C.c_int64(qkv.stride(2)), L.ptr(out), C.c_int64(out.stride(2)),
+                                        C.c_int32(b), C.c_int32(h * w), C.c_int32(heads), C.c_float(scale),
+                                        L.stream_ptr()), "sbm_linear_attn_fwd")
+    return out
+
+
+def softmax_attn(qkv: torch.Tensor, heads: int, dh: int, q_off: int, k_off: int, v_off: int, head_stride: int,
+                 scale: float) -> torch.Tensor:
+    b, h, w, _ = qkv.shape
+    out = torch.empty((b, h, w, pad8(heads * dh)), dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.lib().sbm_softmax_attn_fwd(L.ptr(qkv), C.c_int64(qkv.stride(2)), L.ptr(out), C.c_int64(out.stride(2)),
+                                         C.c_int32(b), C.c_int32(h * w), C.c_int32(heads), C.c_int32(dh),
+                                         C.c_int32(q_off), C.c_int32(k_off), C.c_int32(v_off), C.c_int32(head_stride),
+                                         C.c_float(scale), L.stream_ptr()), "sbm_softmax_attn_fwd")
+    return out

@@ -1,0 +1,136 @@
+"""CPU tests (no GPU): the oracle restatement against the golden vectors produced by the real reference
+(oracle/gen_golden.py), the host-side SDE objects, state_dict compatibility and the C-ABI symbol table."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import sde_oracle as so
+from oracle import unet_oracle as uo
+from oracle.det_weights import fill_state_dict
+from tests.util import ROOT, golden, rel_l2
+
+
+@pytest.mark.parametrize("name", ["unet_poly", "unet_cel"])
+def test_oracle_unet_matches_reference_golden(name):
+    g = golden(name + ".pt")
+    sd = fill_state_dict(g["shapes"])
+    with torch.no_grad():
+        y = uo.unet_forward(sd, g["x"], g["t"], dim=g["kwargs"]["dim"], dim_mults=g["kwargs"]["dim_mults"])
+    assert rel_l2(y, g["y"]) < 1e-5
+
+
+def test_oracle_openai_unet_matches_reference_golden():
+    g = golden("unet_openai.pt")
+    sd = fill_state_dict(g["shapes"])
+    kw = dict(model_channels=32, num_res_blocks=1, attention_resolutions=(2,), channel_mult=(1, 2, 2), num_heads=2)
+    with torch.no_grad():
+        assert rel_l2(uo.unet_openai_forward(sd, g["x"], g["t"], z=g["z"], **kw), g["y"]) < 1e-5
+        assert rel_l2(uo.unet_openai_forward(sd, g["x"], g["t"], **kw), g["y_noz"]) < 1e-5
+
+
+def test_oracle_sde_objects_and_host_classes():
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    cls = {"vp": sh.VPSDE, "subvp": sh.subVPSDE, "ve": sh.VESDE}
+    for c in golden("sde_objects.pt"):
+        spec = so.SdeSpec(c["kind"], c["a"], c["b"], c["N"])
+        d, gdiff = so.sde_coeffs(spec, c["x"], c["t"])
+        m, s = so.marginal_prob(spec, c["x"], c["t"])
+        assert torch.equal(d, c["drift"]) and torch.allclose(gdiff, c["diffusion"], rtol=1e-6)
+        assert torch.equal(m, c["mean"]) and torch.equal(s, c["std"])
+        assert torch.allclose(so.prior_logp(spec, c["x"]), c["prior_logp"], rtol=1e-6)
+        # the drop-in SDE classes (host-side tensor expressions) reproduce the reference bit for bit on CPU
+        sde = cls[c["kind"]](c["a"], c["b"], c["N"])
+        d2, g2 = sde.sde(c["x"], c["t"])
+        m2, s2 = sde.marginal_prob(c["x"], c["t"])
+        assert torch.equal(d2, c["drift"]) and torch.allclose(g2, c["diffusion"], rtol=1e-6)
+        assert torch.equal(m2, c["mean"]) and torch.equal(s2, c["std"])
+        assert torch.allclose(sde.prior_logp(c["x"]), c["prior_logp"], rtol=1e-6)
+        if "disc_f" in c:
+            f, G = sde.discretize(c["x"], c["t"])
+            assert torch.allclose(f, c["disc_f"], rtol=1e-6, atol=1e-7) and torch.allclose(G, c["disc_G"], rtol=1e-6)
+        if "alphas" in c:
+            assert torch.equal(sde.alphas, c["alphas"])
+            assert torch.equal(sde.sqrt_1m_alphas_cumprod, c["sqrt_1m_alphas_cumprod"])
+            assert torch.equal(spec.alphas(), c["alphas"])
+        assert isinstance(sde, sh.SDE) and sde.T == 1 and sde.N == c["N"]
+
+
+def test_oracle_sampler_steps_and_loops():
+    g = golden("sampler_steps.pt")
+    kind, a, b, N = g["sde"]
+    spec = so.SdeSpec(kind, a, b, N)
+    x, t = g["x"], g["t"]
+    xp, xm = so.em_predictor_step(spec, x, t, g["score"], g["z_pred"])
+    assert rel_l2(xp, g["pred_x"]) < 1e-6 and rel_l2(xm, g["pred_mean"]) < 1e-6
+    xc, xcm = so.corrector_step(spec, x, t, g["score"], g["z_corr"], g["target_snr"])
+    assert rel_l2(xc, g["corr_x"]) < 1e-6 and rel_l2(xcm, g["corr_mean"]) < 1e-6
+    net = golden("unet_poly.pt")
+    sd = fill_state_dict(net["shapes"])
+    score_fn = lambda xx, tt: uo.unet_forward(sd, xx, tt, dim=net["kwargs"]["dim"], dim_mults=net["kwargs"]["dim_mults"])
+    with torch.no_grad():
+        for loop in g["loops"]:
+            mask = [m in loop["given"] for m in g["mods"]]
+            out = so.pc_sampler(spec, score_fn, g["loop_z0"], g["loop_npred"], g["loop_ncorr"], z_obs=g["loop_z0"],
+                                obs_mask=mask, noise_obs=loop["noise_obs"], predictor_first=loop["predictor_first"],
+                                num_steps=g["loop_steps"])
+            assert rel_l2(out, loop["out"]) < 1e-5, loop["given"]
+
+
+def test_oracle_dsm_loss():
+    g = golden("dsm_loss.pt")
+    net = golden("unet_poly.pt")
+    sd = fill_state_dict(net["shapes"])
+    score_fn = lambda xx, tt: uo.unet_forward(sd, xx, tt, dim=net["kwargs"]["dim"], dim_mults=net["kwargs"]["dim_mults"])
+    with torch.no_grad():
+        for c in g["cases"]:
+            spec = so.SdeSpec(c["kind"], c["a"], c["b"], c["N"])
+            loss = so.dsm_loss(spec, g["batch"], score_fn, g["u"], g["z"], reduce_mean=c["reduce_mean"],
+                               likelihood_weighting=c["likelihood_weighting"])
+            assert abs(loss.item() - c["loss"].item()) <= 1e-5 * abs(c["loss"].item())
+
+
+def test_state_dict_schema_matches_reference():
+    """Checkpoints of the reference must load: identical key order, names and shapes."""
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    for name in ("unet_poly", "unet_cel"):
+        g = golden(name + ".pt")
+        m = Unet(**g["kwargs"])
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(g["shapes"].keys())
+        assert {k: tuple(v.shape) for k, v in sd.items()} == g["shapes"]
+        m.load_state_dict(fill_state_dict(g["shapes"]))
+
+
+def test_cabi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "sbmae_b200.h")).read()
+    names = set(re.findall(r"\b(sbm_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 15
+    lib_path = os.path.join(ROOT, "score_based_multimodal_autoencoder_b200", "csrc", "libsbmae_b200.so")
+    if not os.path.exists(lib_path):
+        from score_based_multimodal_autoencoder_b200.build import build
+        build()
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+    lib.sbm_last_error.restype = ctypes.c_char_p
+    assert lib.sbm_version() >= 100
+
+
+def test_product_path_has_no_cpu_fallback():
+    from score_based_multimodal_autoencoder_b200 import _lib as L
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    m = Unet(dim=32, channels=5, dim_mults=(1, 2))
+    with pytest.raises(L.SbmError):
+        m(torch.zeros(1, 5, 8, 8), torch.ones(1))
+    with pytest.raises(L.SbmError):
+        sh.em_predictor(torch.zeros(1, 5, 8, 8), torch.ones(1), lambda x, t: x, sh.VPSDE())
+    # the product package never imports the oracle
+    import score_based_multimodal_autoencoder_b200 as pkg
+    for fn in os.listdir(os.path.dirname(pkg.__file__)):
+        if fn.endswith(".py"):
+            src = open(os.path.join(os.path.dirname(pkg.__file__), fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
