@@ -68,6 +68,8 @@ typedef struct sbm_conv_args {
 } sbm_conv_args;
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
+/* A/B switch for measurements: 1 = always use the single-CTA kernel instead of the CTA-pair (cta_group::2) one */
+int sbm_conv_force_single_cta(int32_t on);
 
 /* fp32 weights -> bf16 [taps][rows][cols_pad]; src element (tap,row,col) at
  * w[tap*s_tap + row*s_row + col*s_col]; optional per-column scale (GroupNorm gamma folding). */

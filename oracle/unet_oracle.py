@@ -206,3 +206,56 @@ def unet_openai_forward(sd: dict, x, timesteps, *, model_channels, num_res_block
             idx += 1
     h = F.silu(_gn32(h, sd, "out.0"))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
+
+
+def unet_param_shapes(dim: int, channels: int, dim_mults=(1, 2, 4, 8), init_dim=None, out_dim=None, mult=2,
+                      heads=4, dim_head=32) -> dict:
+    """Parameter names/shapes of unet_model.Unet (unet_model.py:203-273), so the oracle can be driven without
+    instantiating any module."""
+    init_dim = init_dim if init_dim is not None else dim // 3 * 2
+    out_dim = out_dim if out_dim is not None else channels
+    tdim = dim * 4
+    hid = heads * dim_head
+    s = {"init_conv.weight": (init_dim, channels, 7, 7), "init_conv.bias": (init_dim,),
+         "time_mlp.1.weight": (tdim, dim), "time_mlp.1.bias": (tdim,),
+         "time_mlp.3.weight": (tdim, tdim), "time_mlp.3.bias": (tdim,)}
+
+    def block(p, cin, cout, temb=True):
+        if temb:
+            s[p + ".mlp.1.weight"], s[p + ".mlp.1.bias"] = (cin, tdim), (cin,)
+        s[p + ".ds_conv.weight"], s[p + ".ds_conv.bias"] = (cin, 1, 7, 7), (cin,)
+        s[p + ".net.0.weight"], s[p + ".net.0.bias"] = (cin,), (cin,)
+        s[p + ".net.1.weight"], s[p + ".net.1.bias"] = (cout * mult, cin, 3, 3), (cout * mult,)
+        s[p + ".net.3.weight"], s[p + ".net.3.bias"] = (cout * mult,), (cout * mult,)
+        s[p + ".net.4.weight"], s[p + ".net.4.bias"] = (cout, cout * mult, 3, 3), (cout,)
+        if cin != cout:
+            s[p + ".res_conv.weight"], s[p + ".res_conv.bias"] = (cout, cin, 1, 1), (cout,)
+
+    def lin_attn(p, c):
+        s[p + ".fn.norm.weight"], s[p + ".fn.norm.bias"] = (c,), (c,)
+        s[p + ".fn.fn.to_qkv.weight"] = (3 * hid, c, 1, 1)
+        s[p + ".fn.fn.to_out.0.weight"], s[p + ".fn.fn.to_out.0.bias"] = (c, hid, 1, 1), (c,)
+        s[p + ".fn.fn.to_out.1.weight"], s[p + ".fn.fn.to_out.1.bias"] = (c,), (c,)
+
+    dims = [init_dim] + [dim * m for m in dim_mults]
+    in_out = list(zip(dims[:-1], dims[1:]))
+    for lv, (ci, co) in enumerate(in_out):
+        block(f"downs.{lv}.0", ci, co)
+        block(f"downs.{lv}.1", co, co)
+        lin_attn(f"downs.{lv}.2", co)
+        if lv < len(in_out) - 1:
+            s[f"downs.{lv}.3.weight"], s[f"downs.{lv}.3.bias"] = (co, co, 4, 4), (co,)
+    mid = dims[-1]
+    block("mid_block1", mid, mid)
+    s["mid_attn.fn.norm.weight"], s["mid_attn.fn.norm.bias"] = (mid,), (mid,)
+    s["mid_attn.fn.fn.to_qkv.weight"] = (3 * hid, mid, 1, 1)
+    s["mid_attn.fn.fn.to_out.weight"], s["mid_attn.fn.fn.to_out.bias"] = (mid, hid, 1, 1), (mid,)
+    block("mid_block2", mid, mid)
+    for u, (ci, co) in enumerate(reversed(in_out[1:])):
+        block(f"ups.{u}.0", co * 2, ci)
+        block(f"ups.{u}.1", ci, ci)
+        lin_attn(f"ups.{u}.2", ci)
+        s[f"ups.{u}.3.weight"], s[f"ups.{u}.3.bias"] = (ci, ci, 4, 4), (ci,)
+    block("final_conv.0", dim, dim, temb=False)
+    s["final_conv.1.weight"], s["final_conv.1.bias"] = (out_dim, dim, 1, 1), (out_dim,)
+    return s

@@ -35,6 +35,7 @@
 namespace sbm {
 
 std::atomic<unsigned long long> g_launches{0};
+static bool g_force_single = false;  // debugging / A-B timing switch (sbm_conv_force_single_cta)
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
@@ -67,6 +68,100 @@ struct ConvKernelParams {
   int32_t act, out_dtype, res_dtype, vec_ok;
   TapTable taps[4];
 };
+
+// bias + activation + residual + (bf16 rounding) + statistics + stores for 16 consecutive output channels of one
+// output pixel (row); `v` holds the fp32 accumulators read from TMEM.
+__device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint32_t* v, int n, bool row_ok,
+                                           int64_t o_base, int64_t r_base, int64_t o2_base, float& s1, float& s2) {
+  if (n >= p.cout) return;  // warp-uniform
+  float f[16];
+  const bool full = (n + 16 <= p.cout);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    float x = __uint_as_float(v[e]);
+    if (p.bias != nullptr && (full || n + e < p.cout)) x += __ldg(p.bias + n + e);
+    if (p.act == SBM_ACT_GELU) x = gelu_exact(x);
+    else if (p.act == SBM_ACT_SILU) x = silu(x);
+    f[e] = x;
+  }
+  if (row_ok) {
+    if (p.residual != nullptr) {
+      if (p.res_dtype == SBM_F32) {
+        const float* rp = reinterpret_cast<const float*>(p.residual) + r_base + n;
+        if (full && p.vec_ok) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(rp + e);
+            f[e] += t.x; f[e + 1] += t.y; f[e + 2] += t.z; f[e + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (n + e < p.cout) f[e] += rp[e];
+        }
+      } else {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_base + n;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (n + e < p.cout) f[e] += __bfloat162float(rp[e]);
+      }
+    }
+    if (p.out_dtype == SBM_BF16) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+    }
+    if (p.stats != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (full || n + e < p.cout) { s1 += f[e]; s2 += f[e] * f[e]; }
+    }
+    if (p.out_dtype == SBM_F32) {
+      float* op = reinterpret_cast<float*>(p.out) + o_base;
+      if (full && p.vec_ok && p.o_sc == 1) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<float4*>(op + n + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (n + e < p.cout) op[(int64_t)(n + e) * p.o_sc] = f[e];
+      }
+    } else {
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + o_base + n;
+      if (full && p.vec_ok) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
+      }
+    }
+    if (p.out2 != nullptr) {
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + o2_base + n;
+      if (full && p.vec_ok) {
+        uint32_t w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+          w[e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
+      }
+    }
+  }
+}
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -188,95 +283,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t v[16];
       ptx::tmem_ld16(tmem_base + (uint32_t(ew * 32) << 16) + c0, v);
       ptx::tmem_ld_wait();
-      const int n = n0 + c0;
-      if (n >= p.cout) continue;  // warp-uniform
-      float f[16];
-      const bool full = (n + 16 <= p.cout);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        float x = __uint_as_float(v[e]);
-        if (p.bias != nullptr && (full || n + e < p.cout)) x += __ldg(p.bias + n + e);
-        if (p.act == SBM_ACT_GELU) x = gelu_exact(x);
-        else if (p.act == SBM_ACT_SILU) x = silu(x);
-        f[e] = x;
-      }
-      if (row_ok) {
-        if (p.residual != nullptr) {
-          if (p.res_dtype == SBM_F32) {
-            const float* rp = reinterpret_cast<const float*>(p.residual) + r_base + n;
-            if (full && p.vec_ok) {
-#pragma unroll
-              for (int e = 0; e < 16; e += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(rp + e);
-                f[e] += t.x; f[e + 1] += t.y; f[e + 2] += t.z; f[e + 3] += t.w;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (n + e < p.cout) f[e] += rp[e];
-            }
-          } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + r_base + n;
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (n + e < p.cout) f[e] += __bfloat162float(rp[e]);
-          }
-        }
-        if (p.out_dtype == SBM_BF16) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
-        }
-        if (p.stats != nullptr) {
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (full || n + e < p.cout) { s1 += f[e]; s2 += f[e] * f[e]; }
-        }
-        if (p.out_dtype == SBM_F32) {
-          float* op = reinterpret_cast<float*>(p.out) + o_base;
-          if (full && p.vec_ok && p.o_sc == 1) {
-#pragma unroll
-            for (int e = 0; e < 16; e += 4)
-              *reinterpret_cast<float4*>(op + n + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (n + e < p.cout) op[(int64_t)(n + e) * p.o_sc] = f[e];
-          }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + o_base + n;
-          if (full && p.vec_ok) {
-            uint32_t w[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-              w[e] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
-          }
-        }
-        if (p.out2 != nullptr) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + o2_base + n;
-          if (full && p.vec_ok) {
-            uint32_t w[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-              w[e] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(op + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
-          }
-        }
-      }
+      epilogue16(p, v, n0 + c0, row_ok, o_base, r_base, o2_base, s1, s2);
     }
 
     if (p.stats != nullptr) {
@@ -298,6 +305,202 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+
+// =====================================================================================================
+// CTA-pair kernel (cta_group::2): two SMs of a TPC compute one 256 x BN output tile with ONE
+// tcgen05.mma per K step.  Each CTA stages its own 128 activation rows and HALF of the weight rows, so the
+// L2 -> shared-memory traffic per FLOP drops by 1.5x versus the single-CTA kernel (which measured L2-bound).
+// Persistent: one cluster per SM pair walks a static tile list; the accumulator is double-buffered in TMEM
+// (2 x BN columns) so the epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 0: TMA producer (both CTAs)      warp 1: MMA issuer (leader CTA only)
+//   warp 2: TMEM allocator                warps 4..11: epilogue (lane quarter = warp%4, column half = (warp-4)/4)
+// =====================================================================================================
+template <int BN, int STAGES>
+struct Smem2Layout {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+struct PairSchedule {
+  int32_t m_tiles, m_pairs, n_tiles, nphase, total;
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ ConvKernelParams p, const PairSchedule sch) {
+  using L = Smem2Layout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int log_ohw = p.log_oh + p.log_ow;
+  const int per_phase = sch.m_pairs * sch.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 16);  // 8 epilogue warps x 2 CTAs arrive on the leader's barrier
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc2<2 * BN>(tmem_slot);
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int t, int& ph, int& nt, int& b0, int& oh0) {
+    ph = t / per_phase;
+    const int rem = t - ph * per_phase;
+    const int mp = rem / sch.n_tiles;
+    nt = rem - mp * sch.n_tiles;
+    const int mt = 2 * mp + (int)rank;
+    if (log_ohw >= 7) {
+      const int tiles_per_img = 1 << (log_ohw - 7);
+      b0 = mt / tiles_per_img;
+      oh0 = (mt % tiles_per_img) << p.log_th;
+    } else {
+      b0 = mt << (7 - log_ohw);
+      oh0 = 0;
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (each CTA loads its own operand halves)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < sch.total; t += npairs) {
+        int ph, nt, b0, oh0;
+        tile_origin(t, ph, nt, b0, oh0);
+        const TapTable& tt = p.taps[ph];
+        const int n0 = nt * BN + (int)rank * (BN / 2);
+        const int num_kb = tt.ntaps * p.cblocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.cblocks;
+          const int cb = kb - tap * p.cblocks;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+          ptx::tma_load_5d_2sm(sa, &tmA, lead_bar, cb * kBK, tt.dw[tap], tt.q[tap], oh0 + tt.dh[tap], b0);
+          ptx::tma_load_3d_2sm(sb, &tmB, lead_bar, cb * kBK, n0, tt.wtap[tap]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(256, BN);
+      int stage = 0, astage = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int t = pair; t < sch.total; t += npairs) {
+        const int ph = t / per_phase;
+        const int num_kb = p.taps[ph].ntaps * p.cblocks;
+        ptx::mbar_wait(&tempty_bar[astage], aphase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t tacc = tmem_base + (uint32_t)(astage * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
+          const uint64_t adesc = ptx::make_desc_k_sw128(sa);
+          const uint64_t bdesc = ptx::make_desc_k_sw128(sa + L::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)
+            ptx::umma_bf16_2cta(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::umma_commit_2cta(&empty_bar[stage], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_2cta(&tfull_bar[astage], 3);
+        astage ^= 1;
+        if (astage == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue
+    const int e = warp - 4;
+    const int ew = e & 3;      // TMEM lane quarter
+    const int hc = e >> 2;     // column half
+    const int r = ew * 32 + lane;
+    const int j = r & ((1 << p.log_ow) - 1);
+    const int i = (r >> p.log_ow) & ((1 << p.log_th) - 1);
+    const int bl = r >> (p.log_ow + p.log_th);
+    const uint32_t lead_tempty0 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0);
+    int astage = 0;
+    uint32_t aphase = 0;
+    for (int t = pair; t < sch.total; t += npairs) {
+      int ph, nt, b0, oh0;
+      tile_origin(t, ph, nt, b0, oh0);
+      const TapTable& tt = p.taps[ph];
+      const int b = b0 + bl;
+      const int oh = oh0 + i;
+      const bool row_ok = b < p.batch;
+      const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw + tt.out_off;
+      const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
+      const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw + tt.out2_off;
+      float s1 = 0.f, s2 = 0.f;
+      ptx::mbar_wait(&tfull_bar[astage], aphase);
+      ptx::tc_fence_after_sync();
+      const uint32_t tacc = tmem_base + (uint32_t)(astage * BN) + (uint32_t(ew * 32) << 16);
+#pragma unroll 1
+      for (int c0 = hc * (BN / 2); c0 < (hc + 1) * (BN / 2); c0 += 32) {
+        uint32_t v0[16], v1[16];
+        ptx::tmem_ld16(tacc + c0, v0);
+        ptx::tmem_ld16(tacc + c0 + 16, v1);
+        ptx::tmem_ld_wait();
+        epilogue16(p, v0, nt * BN + c0, row_ok, o_base, r_base, o2_base, s1, s2);
+        epilogue16(p, v1, nt * BN + c0 + 16, row_ok, o_base, r_base, o2_base, s1, s2);
+      }
+      // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty0 + (uint32_t)astage * 8u);
+      if (p.stats != nullptr) {
+        if (!row_ok) { s1 = 0.f; s2 = 0.f; }
+        const int seg = log_ohw >= 5 ? 32 : (1 << log_ohw);
+        for (int o = seg >> 1; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if ((lane & (seg - 1)) == 0 && row_ok) {
+          atomicAdd(p.stats + 2 * (int64_t)b, (double)s1);
+          atomicAdd(p.stats + 2 * (int64_t)b + 1, (double)s2);
+        }
+      }
+      astage ^= 1;
+      if (astage == 0) aphase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  if (warp == 2) ptx::tmem_dealloc2<2 * BN>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -330,6 +533,29 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
     configured = true;
   }
   conv_igemm_kernel<BN, STAGES><<<grid, 256, L::kTotal, stream>>>(tmA, tmB, p);
+  SBM_CUDA_OK(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, int m_tiles,
+                            int n_tiles, int nphase, cudaStream_t stream) {
+  using L = Smem2Layout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(conv_igemm_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     L::kTotal));
+    configured = true;
+  }
+  PairSchedule sch;
+  sch.m_tiles = m_tiles;
+  sch.m_pairs = (m_tiles + 1) / 2;
+  sch.n_tiles = n_tiles;
+  sch.nphase = nphase;
+  sch.total = nphase * sch.m_pairs * n_tiles;
+  const int pairs = std::min(sch.total, sm_count() / 2);
+  conv_igemm_pair_kernel<BN, STAGES><<<dim3(2 * pairs), 384, L::kTotal, stream>>>(tmA, tmB, p, sch);
   SBM_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
@@ -488,18 +714,26 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   else if (a->cout <= 128) BN = 128;
   else if (a->cout % 256 == 0 || a->cout > 512) BN = 256;
   else BN = (a->cout % 128 == 0) ? 128 : 256;
+  const int64_t M = (int64_t)a->batch << log_ohw;
+  const int m_tiles = (int)((M + kBM - 1) / kBM);
+  // CTA-pair kernel: 256 x BN tiles; worth it once there is at least one full wave of pairs
+  const bool use_pair = !g_force_single && (BN == 256 || BN == 128) && a->cout % BN == 0 &&
+                        (int64_t)((m_tiles + 1) / 2) * (a->cout / BN) * nphase >= sm_count() / 2;
   const int ntaps_total = a->kh * a->kw;
   const cuuint64_t bdim[3] = {(cuuint64_t)a->cin, (cuuint64_t)a->cout, (cuuint64_t)ntaps_total};
   const cuuint64_t bstr[2] = {(cuuint64_t)a->cin_pad * 2, (cuuint64_t)a->cout * a->cin_pad * 2};
-  const cuuint32_t bbox[3] = {(cuuint32_t)kBK, (cuuint32_t)BN, 1u};
+  const cuuint32_t bbox[3] = {(cuuint32_t)kBK, (cuuint32_t)(use_pair ? BN / 2 : BN), 1u};
   const cuuint32_t ones3[3] = {1, 1, 1};
   cr = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->wpk), bdim, bstr, bbox, ones3,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_igemm: weight tensor map encode failed (CUresult %d)", (int)cr);
 
-  const int64_t M = (int64_t)a->batch << log_ohw;
-  dim3 grid((unsigned)((M + kBM - 1) / kBM), (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
+  if (use_pair) {
+    if (BN == 256) return launch_conv_pair<256, 6>(tmA, tmB, p, m_tiles, a->cout / BN, nphase, stream);
+    return launch_conv_pair<128, 8>(tmA, tmB, p, m_tiles, a->cout / BN, nphase, stream);
+  }
+  dim3 grid((unsigned)m_tiles, (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
   switch (BN) {
     case 32: return launch_conv<32, 6>(tmA, tmB, p, grid, stream);
     case 64: return launch_conv<64, 6>(tmA, tmB, p, grid, stream);
@@ -540,6 +774,11 @@ extern "C" {
 const char* sbm_last_error(void) { return g_err; }
 int sbm_version(void) { return 100; }
 unsigned long long sbm_launch_count(void) { return sbm::g_launches.load(); }
+
+int sbm_conv_force_single_cta(int32_t on) {
+  sbm::g_force_single = on != 0;
+  return 0;
+}
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream) {
   return sbm::conv_igemm_impl(a, static_cast<cudaStream_t>(stream));

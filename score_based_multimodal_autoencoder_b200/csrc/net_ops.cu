@@ -96,6 +96,90 @@ dwconv7_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
   }
 }
 
+
+// Register-tiled variant for W in {1,2,4,8,16}: one thread = one (channel, output row); the 49 taps live in
+// registers and every staged input value is read from shared memory once per kernel row (7 LDS per input
+// instead of 49), so the kernel is FMA-bound instead of LDS-bound.
+template <int W>
+__global__ void __launch_bounds__(256)
+dwconv7_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                    const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
+                    float* __restrict__ out, int64_t ldo, double* __restrict__ stats, int C, int H) {
+  extern __shared__ float sm[];
+  const int HW = H * W;
+  float* sx = sm;  // [HW][33]
+  __shared__ float red[32];
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * kDwCh;
+  const int tid = threadIdx.x;
+  const int cl = tid & 31;
+  const int c = c0 + cl;
+  const bool c_ok = c < C;
+  const int nrow = blockDim.x >> 5;
+  {
+    // coalesced slab load with 4 independent loads in flight per thread
+    const float* xb = x + (int64_t)b * HW * ldx + c;
+    int p = tid >> 5;
+    for (; p + 3 * nrow < HW; p += 4 * nrow) {
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+      if (c_ok) {
+        v0 = __ldg(xb + (int64_t)p * ldx);
+        v1 = __ldg(xb + (int64_t)(p + nrow) * ldx);
+        v2 = __ldg(xb + (int64_t)(p + 2 * nrow) * ldx);
+        v3 = __ldg(xb + (int64_t)(p + 3 * nrow) * ldx);
+      }
+      sx[p * 33 + cl] = v0;
+      sx[(p + nrow) * 33 + cl] = v1;
+      sx[(p + 2 * nrow) * 33 + cl] = v2;
+      sx[(p + 3 * nrow) * 33 + cl] = v3;
+    }
+    for (; p < HW; p += nrow) sx[p * 33 + cl] = c_ok ? __ldg(xb + (int64_t)p * ldx) : 0.f;
+  }
+  float wr[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) wr[i] = c_ok ? __ldg(w + (int64_t)c * 49 + i) : 0.f;
+  const float add = c_ok ? (bias ? __ldg(bias + c) : 0.f) + (cond ? __ldg(cond + (int64_t)b * ldc + c) : 0.f) : 0.f;
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+  for (int oh = tid >> 5; oh < H; oh += nrow) {
+    float acc[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) acc[i] = add;
+#pragma unroll
+    for (int kh = 0; kh < 7; ++kh) {
+      const int ih = oh + kh - 3;
+      if (ih < 0 || ih >= H) continue;
+      const float* row = sx + (ih * W) * 33 + cl;
+#pragma unroll
+      for (int iw = 0; iw < W; ++iw) {
+        const float v = row[iw * 33];
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) {
+          const int ow = iw - kw + 3;
+          if (ow >= 0 && ow < W) acc[ow] = fmaf(v, wr[kh * 7 + kw], acc[ow]);
+        }
+      }
+    }
+    if (c_ok) {
+      float* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        op[(int64_t)i * ldo] = acc[i];
+        s1 += acc[i];
+        s2 += acc[i] * acc[i];
+      }
+    }
+  }
+  if (stats != nullptr) {
+    const float t1 = block_sum(s1, red);
+    const float t2 = block_sum(s2, red);
+    if (tid == 0) {
+      atomicAdd(stats + 2 * (int64_t)b, (double)t1);
+      atomicAdd(stats + 2 * (int64_t)b + 1, (double)t2);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ group statistics
 // stats[b][g] += (sum, sumsq) over the pixels x channels of group g.  grid = (chunks, groups, B)
 __global__ void __launch_bounds__(256)
@@ -124,84 +208,121 @@ group_stats_kernel(const void* __restrict__ x, int in_dtype, int64_t ldx, int HW
 }
 
 // ------------------------------------------------------------------------------ GroupNorm apply
-// y = act((x - mean)*rstd*gamma + beta) (+ residual);  4 channels per thread.
+// y = act((x - mean)*rstd*gamma + beta) (+ residual).  grid = (chunks, B): a block streams a contiguous pixel range
+// of ONE sample, so mean / rstd of its groups are derived once (fp64 -> fp32) into shared memory; 8 channels per
+// thread (16-byte bf16 vectors / 2 x 16-byte fp32 vectors).
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    v[2 * i] = __low2float(h);
+    v[2 * i + 1] = __high2float(h);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float* v);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+  uint32_t u[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    u[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
+}
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        const float* __restrict__ residual, int64_t ldr, TOut* __restrict__ out, int64_t ldo,
-                       float* __restrict__ out_f32, int64_t ldo_f32, int64_t npix_total, int HW, int C, int G,
-                       float eps, int act) {
-  const int cq = (C + 3) >> 2;
+                       float* __restrict__ out_f32, int64_t ldo_f32, int HW, int C, int G, float eps, int act,
+                       int vec_ok) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.y;
   const int cpg = C / G;
-  const double inv_n = 1.0 / ((double)HW * cpg);
-  const int64_t total = npix_total * cq;
+  if (threadIdx.x < G) {
+    const double inv_n = 1.0 / ((double)HW * cpg);
+    const double s1 = stats[2 * ((int64_t)b * G + threadIdx.x)], s2 = stats[2 * ((int64_t)b * G + threadIdx.x) + 1];
+    const double mean = s1 * inv_n;
+    const double var = fmax(s2 * inv_n - mean * mean, 0.0);
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int co = (C + 7) >> 3;  // channel octets per pixel
+  const int64_t total = (int64_t)HW * co;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(idx % cq);
-    const int64_t pix = idx / cq;
-    const int b = (int)(pix / HW);
-    const int c = q * 4;
-    float v[4];
+    const int q = (int)(idx % co);
+    const int64_t pix = (int64_t)b * HW + idx / co;
+    const int c = q * 8;
+    const bool full = vec_ok && (c + 8 <= C);
+    float v[8];
     const TIn* xp = x + pix * ldx + c;
-    if (c + 4 <= C) {
-      if constexpr (sizeof(TIn) == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(xp);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-      } else {
-        const uint2 t = *reinterpret_cast<const uint2*>(xp);
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-        const __nv_bfloat162 bb = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(bb); v[3] = __high2float(bb);
-      }
+    if (full) {
+      load8<TIn>(xp, v);
     } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
+      for (int e = 0; e < 8; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
     }
-    float o[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 8; ++e) {
       const int ce = min(c + e, C - 1);
-      const int g = ce / cpg;
-      const double s1 = stats[2 * ((int64_t)b * G + g)], s2 = stats[2 * ((int64_t)b * G + g) + 1];
-      const double mean = s1 * inv_n;
-      const double var = fmax(s2 * inv_n - mean * mean, 0.0);
-      const float rstd = (float)rsqrt(var + (double)eps);
-      float y = (v[e] - (float)mean) * rstd * __ldg(gamma + ce) + __ldg(beta + ce);
+      const int g = (G == 1) ? 0 : ce / cpg;
+      float y = (v[e] - s_mean[g]) * s_rstd[g] * __ldg(gamma + ce) + __ldg(beta + ce);
       if (act == SBM_ACT_SILU) y = silu(y);
       else if (act == SBM_ACT_GELU) y = gelu_exact(y);
-      o[e] = y;
+      v[e] = y;
     }
     if (residual != nullptr) {
       const float* rp = residual + pix * ldr + c;
+      if (full) {
+        float r[8];
+        load8<float>(rp, r);
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (c + e < C) o[e] += rp[e];
+        for (int e = 0; e < 8; ++e) v[e] += r[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (c + e < C) v[e] += rp[e];
+      }
     }
     if (out != nullptr) {
       TOut* op = out + pix * ldo + c;
-      if (c + 4 <= C) {
-        if constexpr (sizeof(TOut) == 4) {
-          *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-          __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
-          __nv_bfloat162 bb = __floats2bfloat162_rn(o[2], o[3]);
-          uint2 t;
-          t.x = *reinterpret_cast<uint32_t*>(&a);
-          t.y = *reinterpret_cast<uint32_t*>(&bb);
-          *reinterpret_cast<uint2*>(op) = t;
-        }
+      if (full) {
+        store8<TOut>(op, v);
       } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (c + e < C) op[e] = (TOut)o[e];
+        for (int e = 0; e < 8; ++e)
+          if (c + e < C) op[e] = (TOut)v[e];
       }
     }
     if (out_f32 != nullptr) {
       float* op = out_f32 + pix * ldo_f32 + c;
+      if (full) {
+        store8<float>(op, v);
+      } else {
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (c + e < C) op[e] = o[e];
+        for (int e = 0; e < 8; ++e)
+          if (c + e < C) op[e] = v[e];
+      }
     }
   }
 }
@@ -248,17 +369,43 @@ linear_attn_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const int hid = heads * kHeadDim;
+  {
+    // stage q|k|v rows with 4 rows (12 independent 128-byte requests per warp) in flight
+    const float* base = qkv + (int64_t)b * n * ldq + h * kHeadDim + lane;
+    int p = warp;
+    for (; p + 3 * nwarp < n; p += 4 * nwarp) {
+      float r[12];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* row = base + (int64_t)(p + u * nwarp) * ldq;
+        r[3 * u] = __ldg(row);
+        r[3 * u + 1] = __ldg(row + hid);
+        r[3 * u + 2] = __ldg(row + 2 * hid);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + u * nwarp;
+        sq[pp * 33 + lane] = r[3 * u];
+        sk[pp * 33 + lane] = r[3 * u + 1];
+        sv[pp * 33 + lane] = r[3 * u + 2];
+      }
+    }
+    for (; p < n; p += nwarp) {
+      const float* row = base + (int64_t)p * ldq;
+      sq[p * 33 + lane] = __ldg(row);
+      sk[p * 33 + lane] = __ldg(row + hid);
+      sv[p * 33 + lane] = __ldg(row + 2 * hid);
+    }
+  }
+  __syncwarp();
   for (int p = warp; p < n; p += nwarp) {
-    const float* row = qkv + ((int64_t)b * n + p) * ldq + h * kHeadDim + lane;
     // q: softmax over d (the 32 lanes), then * scale
-    float qv = row[0];
+    const float qv = sq[p * 33 + lane];
     float m = qv;
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     const float e = expf(qv - m);
     const float s = warp_sum(e);
     sq[p * 33 + lane] = e / s * scale;
-    sk[p * 33 + lane] = row[hid];
-    sv[p * 33 + lane] = row[2 * hid];
   }
   __syncthreads();
   // k: softmax over the n positions, per channel d
@@ -390,7 +537,18 @@ int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bi
     configured = smem;
   }
   dim3 grid((C + kDwCh - 1) / kDwCh, B);
-  dwconv7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, W);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem_rows = (size_t)H * W * 33 * sizeof(float);
+  const int threads = 32 * std::max(1, std::min(8, H));
+#define SBM_DW_ROWS(WW)                                                                                            \
+  dwconv7_rows_kernel<WW><<<grid, threads, smem_rows, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H)
+  if (W == 16 && smem_rows <= 48 * 1024) SBM_DW_ROWS(16);
+  else if (W == 8) SBM_DW_ROWS(8);
+  else if (W == 4) SBM_DW_ROWS(4);
+  else if (W == 2) SBM_DW_ROWS(2);
+  else if (W == 1) SBM_DW_ROWS(1);
+  else dwconv7_kernel<<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, W);
+#undef SBM_DW_ROWS
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -415,14 +573,20 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
                         float eps, int32_t act, void* stream) {
   SBM_CHECK_ARG(x && stats && gamma && beta && (out || out_f32) && B > 0 && G > 0 && C % G == 0,
                 "sbm_groupnorm_apply: bad args");
-  SBM_CHECK_ARG(ldx % 4 == 0 && ldo % 4 == 0, "sbm_groupnorm_apply: row strides must be multiples of 4");
-  const int64_t npix = (int64_t)B * HW;
-  const int64_t total = npix * ((C + 3) / 4);
-  const int grid = grid_for(total, 256);
+  SBM_CHECK_ARG(G <= 64, "sbm_groupnorm_apply: at most 64 groups");
+  const int isz = in_dtype == SBM_F32 ? 4 : 2, osz = out_dtype == SBM_F32 ? 4 : 2;
+  auto al16 = [](const void* p, int64_t ld, int esz) {
+    return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld * esz) % 16 == 0));
+  };
+  const int vec_ok = al16(x, ldx, isz) && al16(out, ldo, osz) && al16(residual, ldr, 4) && al16(out_f32, ldo_f32, 4);
+  const int64_t per_sample = (int64_t)HW * ((C + 7) / 8);
+  int chunks = (int)std::min<int64_t>((per_sample + 255) / 256, std::max<int64_t>(1, (int64_t)sm_count() * 16 / B));
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, B);
   cudaStream_t s = (cudaStream_t)stream;
 #define SBM_GN_LAUNCH(TI, TO)                                                                                   \
   groupnorm_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x, ldx, stats, gamma, beta, residual, ldr,      \
-                                                      (TO*)out, ldo, out_f32, ldo_f32, npix, HW, C, G, eps, act)
+                                                      (TO*)out, ldo, out_f32, ldo_f32, HW, C, G, eps, act, vec_ok)
   if (in_dtype == SBM_F32 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(float, __nv_bfloat16);
   else if (in_dtype == SBM_F32 && out_dtype == SBM_F32) SBM_GN_LAUNCH(float, float);
   else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16);

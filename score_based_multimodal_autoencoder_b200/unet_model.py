@@ -209,7 +209,12 @@ class Unet(nn.Module):
 
     # ------------------------------------------------------------------ building blocks
     def _stats(self, b, dev):
-        return torch.zeros((b, 2), dtype=torch.float64, device=dev)
+        """One (sum, sumsq) slot per GroupNorm site, carved from an arena zeroed ONCE per forward."""
+        i = self._arena_next
+        self._arena_next += 1
+        if i >= self._arena.shape[0]:
+            return torch.zeros((b, 2), dtype=torch.float64, device=dev)
+        return self._arena[i]
 
     def _convnext(self, blk: ConvNextBlock, x: _Act, cond, cond_off, ldc, *, want_f32=True, want_bf16=False,
                   want_stats=False, out_f32=None, out_bf16=None) -> _Act:
@@ -309,6 +314,9 @@ class Unet(nn.Module):
         x = x.contiguous().float()
         time = time.contiguous().float()
         n_levels = len(self.downs)
+        self._arena = torch.zeros((3 * len(self._time_blocks) + 2 * n_levels + 12, b, 2), dtype=torch.float64,
+                                  device=dev)
+        self._arena_next = 0
 
         # --- time path: sinusoid -> Linear -> GELU -> Linear, then the per-block GELU -> Linear as ONE GEMM
         te = ops.time_embed(time, self.dim, 0)

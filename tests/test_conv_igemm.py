@@ -50,6 +50,15 @@ CASES = [
     ("up4_4",       "t",  4, 5, 4, 4, 128, 128),
     ("up4_1",       "t",  4, 50, 1, 1, 128, 128),
     ("up4_8",       "t",  4, 3, 8, 8, 256, 256),
+    # large enough for the persistent CTA-pair (cta_group::2) kernel: >= 74 pairs of 128-row tiles
+    ("pair_c3_16",   "s1", 3, 80, 16, 16, 64, 256),    # 160 m-tiles, BN=256
+    ("pair_odd",     "s1", 3, 149, 8, 8, 72, 256),     # 75 m-tiles (odd): last pair half empty, cin tail
+    ("pair_n512",    "s1", 1, 300, 8, 8, 128, 512),    # two n-tiles per pair row
+    ("pair_bn128",   "s1", 3, 160, 16, 16, 64, 128),   # BN=128 pair variant
+    ("pair_lin",     "s1", 1, 20000, 1, 1, 96, 256),   # linear layer, 157 m-tiles, ragged batch
+    ("pair_down",    "s2", 4, 330, 16, 16, 64, 256),   # stride-2 view through the pair kernel
+    ("pair_up",      "t",  4, 320, 4, 4, 64, 256),     # 4 output phases x 20 pairs... (80 pair tiles)
+    ("pair_small2",  "s1", 3, 9000, 2, 2, 64, 128),    # 2x2 maps: 32 images per tile
 ]
 
 
@@ -129,6 +138,38 @@ def test_conv_epilogue_options():
     torch.cuda.synchronize()
     assert o.shape == (B, 5, H, W)
     assert (o.double() - r).abs().max().item() <= 2e-5 * r.abs().max().item()
+
+
+def test_conv_pair_kernel_epilogue_and_ab():
+    """CTA-pair kernel with the full epilogue (GELU, residual, stats, bf16 copy) and A/B against the single-CTA kernel."""
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(21)
+    B, H, W, cin, cout = 100, 16, 16, 64, 256
+    x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(B, H, W, cout, generator=g).to(dev)
+    xb = _nhwc_bf16(x, cin)
+    wpk = ops.pack_conv2d_weight(w)
+    outs = []
+    for single in (1, 0):
+        L.lib().sbm_conv_force_single_cta(single)
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        out2 = torch.zeros(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+        out = ops.conv_igemm(xb, wpk, kind=L.CONV_S1, kh=3, kw=3, cin=cin, cout=cout, bias=bias, act=L.ACT_GELU,
+                             residual=res, stats=stats, out2=out2)
+        torch.cuda.synchronize()
+        outs.append((out, out2, stats))
+    L.lib().sbm_conv_force_single_cta(0)
+    pre = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    ref = _gelu64(pre) + res.double()
+    for out, out2, stats in outs:
+        assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+        assert (out2.double() - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()
+        ref_s = torch.stack([ref.sum(dim=(1, 2, 3)), (ref * ref).sum(dim=(1, 2, 3))], dim=1)
+        assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-6)
 
 
 def test_conv_small_stats_segments():
