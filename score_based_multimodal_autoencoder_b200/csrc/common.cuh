@@ -38,7 +38,20 @@ inline int sm_count() {
   return n;
 }
 
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-level): one MUFU.RCP + one MUFU.EX2 + 7 FMA,
+// branch-free -- about half the issue slots of erff(), which matters in the GEMM epilogue.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  return copysignf(1.0f - p * e, x);
+}
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 // d/dx of exact-erf GELU
 __device__ __forceinline__ float gelu_exact_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
