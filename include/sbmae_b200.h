@@ -71,6 +71,23 @@ int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 /* A/B switch for measurements: 1 = always use the single-CTA kernel instead of the CTA-pair (cta_group::2) one */
 int sbm_conv_force_single_cta(int32_t on);
 
+/* Weight gradient of sbm_conv_igemm: dwpk[tap][o][i] += sum_pixels dy[p][o] * x[p shifted by tap][i]  (fp32, split-K
+ * atomics: the caller zeroes dwpk).  x = the forward input operand (bf16), dy = gradient of the forward output (bf16,
+ * output geometry).  Backward of the nn.Conv2d / nn.ConvTranspose2d / nn.Linear weights under loss.backward()
+ * (train_lat_celebhq_unet_cont2.py:98-100). */
+typedef struct sbm_wgrad_args {
+  int32_t kind, kh, kw;
+  int32_t batch, h, w;      /* INPUT spatial extent of the forward convolution */
+  int32_t cin, cout;
+  const void* x;  int64_t ldx;
+  const void* dy; int64_t lddy;
+  float* dwpk;    int32_t cin_pad; int32_t reserved;
+} sbm_wgrad_args;
+int sbm_conv_wgrad(const sbm_wgrad_args* a, void* stream);
+/* packed fp32 gradient [taps][rows][cols_pad] -> parameter layout: dst[tap*s_tap + row*s_row + col*s_col] */
+int sbm_unpack_wgrad(const float* src, float* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
+                     int64_t s_tap, int64_t s_row, int64_t s_col, void* stream);
+
 /* fp32 weights -> bf16 [taps][rows][cols_pad]; src element (tap,row,col) at
  * w[tap*s_tap + row*s_row + col*s_col]; optional per-column scale (GroupNorm gamma folding). */
 int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,

@@ -95,3 +95,14 @@ class Rng(C.Structure):
 class Impute(C.Structure):
     _fields_ = [("z_obs", C.c_void_p), ("obs_mask", C.c_uint32), ("noise_obs", C.c_int32), ("t_next", C.c_float),
                 ("t_next_dev", C.c_void_p)]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
+        ("batch", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+        ("cin", C.c_int32), ("cout", C.c_int32),
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("dy", C.c_void_p), ("lddy", C.c_int64),
+        ("dwpk", C.c_void_p), ("cin_pad", C.c_int32), ("reserved", C.c_int32),
+    ]

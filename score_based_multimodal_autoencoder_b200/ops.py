@@ -164,3 +164,45 @@ def softmax_attn(qkv: torch.Tensor, heads: int, dh: int, q_off: int, k_off: int,
                                          C.c_int32(q_off), C.c_int32(k_off), C.c_int32(v_off), C.c_int32(head_stride),
                                          C.c_float(scale), L.stream_ptr()), "sbm_softmax_attn_fwd")
     return out
+
+
+# ---------------------------------------------------------------------------- backward operators
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, *, kind: int, kh: int, kw: int, cin: int, cout: int) -> torch.Tensor:
+    """Packed fp32 weight gradient [kh*kw, cout, pad8(cin)] of conv_igemm(x, ...) given dy (both bf16 channels-last)."""
+    assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
+    b, h, w, _ = x.shape
+    dwpk = torch.zeros((kh * kw, cout, pad8(cin)), dtype=torch.float32, device=x.device)
+    a = L.WgradArgs()
+    a.kind, a.kh, a.kw = kind, kh, kw
+    a.batch, a.h, a.w = b, h, w
+    a.cin, a.cout = cin, cout
+    a.x, a.ldx = x.data_ptr(), x.stride(2)
+    a.dy, a.lddy = dy.data_ptr(), dy.stride(2)
+    a.dwpk, a.cin_pad = dwpk.data_ptr(), dwpk.shape[2]
+    L.check(L.lib().sbm_conv_wgrad(C.byref(a), L.stream_ptr()), "sbm_conv_wgrad")
+    return dwpk
+
+
+def unpack_wgrad(dwpk: torch.Tensor, like: torch.Tensor, cols: int, s_tap: int, s_row: int, s_col: int) -> torch.Tensor:
+    """Packed gradient -> a tensor shaped like the parameter `like` (strides as in pack_weight)."""
+    taps, rows, cols_pad = dwpk.shape
+    out = torch.empty_like(like, dtype=torch.float32, memory_format=torch.contiguous_format)
+    L.check(L.lib().sbm_unpack_wgrad(L.ptr(dwpk), L.ptr(out), C.c_int32(taps), C.c_int32(rows), C.c_int32(cols),
+                                     C.c_int32(cols_pad), C.c_int64(s_tap), C.c_int64(s_row), C.c_int64(s_col),
+                                     L.stream_ptr()), "sbm_unpack_wgrad")
+    return out
+
+
+def unpack_conv2d_wgrad(dwpk, weight):
+    o, i, kh, kw = weight.shape
+    return unpack_wgrad(dwpk, weight, i, 1, i * kh * kw, kh * kw)
+
+
+def unpack_convT2d_wgrad(dwpk, weight):
+    i, o, kh, kw = weight.shape
+    return unpack_wgrad(dwpk, weight, i, 1, kh * kw, o * kh * kw)
+
+
+def unpack_linear_wgrad(dwpk, weight):
+    o, i = weight.shape
+    return unpack_wgrad(dwpk, weight, i, 0, i, 1)
