@@ -61,7 +61,7 @@ typedef struct sbm_conv_args {
   int32_t out_dtype;        /* SBM_F32 / SBM_BF16                                     */
   int32_t out_nchw;         /* 1: write fp32 [batch,cout,oh,ow] (final layer)         */
   int32_t res_dtype;        /* SBM_F32 / SBM_BF16                                     */
-  int32_t reserved;
+  int32_t out2_preact;      /* 1: out2 receives the PRE-activation value (bias added, before act/residual)   */
   double* stats;            /* [batch][2] += (sum, sum of squares) of the written values, or NULL */
   void* out2;               /* optional second copy of the output in bf16 (pixel stride ldo2), or NULL */
   int64_t ldo2;
@@ -102,6 +102,9 @@ int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, in
  * x/out fp32 channels-last, w is the nn.Conv2d(groups=C) weight [C,1,7,7]. */
 int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
                     float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* same kernel, backward w.r.t. the input: out = depthwise7x7(dy, taps flipped) (+ addend, same layout as out) */
+int sbm_dwconv7_bwd_input(const float* dy, int64_t lddy, const float* w, const float* addend, int64_t ldadd,
+                          float* out, int64_t ldo, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* stats[b][g] += (sum, sumsq) of group g of sample b.  nn.GroupNorm statistics (unet_model.py:106,109,160,183;
  * unet_openai.py:10-12). */
 int sbm_group_stats(const void* x, int32_t in_dtype, int64_t ldx, int32_t B, int32_t HW, int32_t C, int32_t G,
@@ -172,6 +175,40 @@ int sbm_dsm_loss(const sbm_latent_shape* ls, const float* score, const float* z,
                  int64_t global_batch, void* stream);
 int sbm_scale_by_scalar(const float* in, const float* scalar_dev, float* out, int64_t n, void* stream);
 int sbm_f64_to_f32(const double* in, float* out, int32_t n, void* stream);
+
+/* ------------------------------------------------------------------ backward operators (DSM training step) */
+/* out[c] += column sums of x[rows][C] (bias gradients); caller zeroes out */
+int sbm_colsum(const void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t C, float* out, void* stream);
+/* GroupNorm backward. x = the tensor that was normalised (x = act(pre) when in_act != 0 and the kernel is given pre);
+ * bst[B][G][2], dgamma[C], dbeta[C] are accumulated into (caller zeroes); dx (+ addend) -> out_f32 / out_bf16;
+ * with in_act the result is additionally multiplied by act'(pre), i.e. it is the gradient w.r.t. pre. */
+int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* dy, int32_t dy_dtype, int64_t lddy,
+                      const double* stats, const float* gamma, float* bst, float* dgamma, float* dbeta,
+                      const float* addend, int64_t ldadd, float* out_f32, int64_t ldo_f32, void* out_bf16,
+                      int64_t ldo_bf16, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t in_act,
+                      void* stream);
+/* depthwise 7x7: dw[C][49] += , db[C] += , dcond[b][c] = sum_p dy  (caller zeroes dw, db) */
+int sbm_dwconv7_wgrad(const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dw, float* db, float* dcond,
+                      int64_t ldc, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+int sbm_linear_attn_bwd(const float* qkv, int64_t ldq, const float* dout, int64_t ldd, void* dqkv_bf16, int64_t ldg,
+                        int32_t B, int32_t n, int32_t heads, float scale, void* stream);
+int sbm_softmax_attn_bwd(const float* qkv, int64_t ldq, const float* dout, int64_t ldd, void* dqkv_bf16, int64_t ldg,
+                         int32_t B, int32_t n, int32_t heads, int32_t dh, int32_t q_off, int32_t k_off, int32_t v_off,
+                         int32_t head_stride, float scale, void* stream);
+/* out = dy * act'(pre) */
+int sbm_act_bwd(const float* dy, int64_t lddy, const void* pre, int32_t pre_dtype, int64_t ldp, float* out_f32,
+                int64_t ldo, void* out_bf16, int64_t ldb, int64_t rows, int32_t C, int32_t act, void* stream);
+int sbm_nchw_to_nhwc(const float* x, void* out_bf16, int64_t ldb, float* out_f32, int64_t ldf, int32_t B, int32_t C,
+                     int32_t HW, void* stream);
+/* out = a + b (b may be NULL: plain copy / bf16 cast); rows x C elements with row strides */
+int sbm_add(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo, void* out_bf16,
+            int64_t ldh, int64_t rows, int32_t C, void* stream);
+/* torch.optim.Adam step over many tensors in ONE launch (train_lat_celebhq_unet_cont2.py:100, :477).
+ * tensors_dev: device array of descriptors; chunks_dev: device array of (tensor index, chunk index) pairs. */
+typedef struct sbm_adam_tensor { float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64_t n; } sbm_adam_tensor;
+int sbm_adam_step(const sbm_adam_tensor* tensors_dev, const int32_t* chunks_dev, int32_t n_chunks,
+                  int32_t chunk_elems, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                  void* stream);
 
 #ifdef __cplusplus
 }

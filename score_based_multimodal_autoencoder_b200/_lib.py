@@ -72,7 +72,7 @@ class ConvArgs(C.Structure):
         ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("out_dtype", C.c_int32), ("out_nchw", C.c_int32),
-        ("res_dtype", C.c_int32), ("reserved", C.c_int32),
+        ("res_dtype", C.c_int32), ("out2_preact", C.c_int32),
         ("stats", C.c_void_p),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
     ]
@@ -106,3 +106,8 @@ class WgradArgs(C.Structure):
         ("dy", C.c_void_p), ("lddy", C.c_int64),
         ("dwpk", C.c_void_p), ("cin_pad", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64)]

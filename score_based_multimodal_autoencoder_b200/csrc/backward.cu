@@ -1,0 +1,650 @@
+// Backward kernels of the memory-bound score-net operators + fused Adam, for the DSM training step
+// (loss.backward(); optimizer.step() -- train_lat_celebhq_unet_cont2.py:98-100, train_poly_unet_cont.py:272-276).
+//   * column sums (bias gradients)
+//   * GroupNorm backward (reduce + apply, optional GELU/SiLU chain on the normalised INPUT)
+//   * depthwise 7x7 backward w.r.t. weights / bias / time condition  (input gradient = forward kernel with flipped taps)
+//   * linear-attention and softmax-attention core backward
+//   * activation backward, NCHW->channels-last gradient staging, fp32 accumulate
+//   * multi-tensor Adam (torch.optim.Adam semantics: no amsgrad, no weight decay)
+#include <atomic>
+
+#include "../../include/sbmae_b200.h"
+#include "common.cuh"
+
+namespace sbm {
+extern std::atomic<unsigned long long> g_launches;
+static inline void count_launch_b() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  return act == SBM_ACT_GELU ? gelu_exact(x) : (act == SBM_ACT_SILU ? silu(x) : x);
+}
+__device__ __forceinline__ float act_grad(float x, int act) {
+  return act == SBM_ACT_GELU ? gelu_exact_grad(x) : (act == SBM_ACT_SILU ? silu_grad(x) : 1.f);
+}
+
+// ------------------------------------------------------------------------------ column sums
+// out[c] += sum over rows of x[row][c]   (caller zeroes out)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int C, float* __restrict__ out) {
+  // thread (cx, ry): column cx + k*32..., rows strided by 8*gridDim
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  __shared__ float red[8][33];
+  for (int c0 = blockIdx.y * 32; c0 < C; c0 += gridDim.y * 32) {
+    const int c = c0 + cx;
+    float acc = 0.f;
+    if (c < C)
+      for (int64_t r = blockIdx.x * 8 + ry; r < rows; r += (int64_t)gridDim.x * 8) acc += ldf<T>(x + r * ld + c);
+    red[ry][cx] = acc;
+    __syncthreads();
+    if (ry == 0 && c < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][cx];
+      atomicAdd(out + c, s);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------ GroupNorm backward
+// y = xh*gamma + beta, xh = (x - mean)*rstd, x = act(pre) when in_act != 0 (GroupNorm applied to an activation).
+// reduce: bst[b][g] += (sum dy*gamma, sum dy*gamma*xh);  dgamma[c] += sum dy*xh; dbeta[c] += sum dy
+template <typename TX, typename TDY>
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict__ dy, int64_t lddy,
+                     const double* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ bst,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C, int G, float eps,
+                     int in_act) {
+  extern __shared__ float sm[];
+  float* sdg = sm;          // [C]
+  float* sdb = sm + C;      // [C]
+  float* sst = sm + 2 * C;  // [2G]
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  for (int i = threadIdx.x; i < 2 * C + 2 * G; i += blockDim.x) sm[i] = 0.f;
+  if (threadIdx.x < G) {
+    const double inv_n = 1.0 / ((double)HW * cpg);
+    const double s1 = stats[2 * ((int64_t)b * G + threadIdx.x)], s2 = stats[2 * ((int64_t)b * G + threadIdx.x) + 1];
+    const double mean = s1 * inv_n;
+    const double var = fmax(s2 * inv_n - mean * mean, 0.0);
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)HW * C;
+  float a1 = 0.f, a2 = 0.f;  // group sums when G == 1
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t pix = (int64_t)b * HW + idx / C;
+    const int g = (G == 1) ? 0 : c / cpg;
+    float xv = ldf<TX>(x + pix * ldx + c);
+    if (in_act) xv = act_fwd(xv, in_act);
+    const float xh = (xv - s_mean[g]) * s_rstd[g];
+    const float d = ldf<TDY>(dy + pix * lddy + c);
+    const float t = d * __ldg(gamma + c);
+    if (G == 1) {
+      a1 += t;
+      a2 += t * xh;
+    } else {
+      atomicAdd(&sst[2 * g], t);
+      atomicAdd(&sst[2 * g + 1], t * xh);
+    }
+    atomicAdd(&sdg[c], d * xh);
+    atomicAdd(&sdb[c], d);
+  }
+  if (G == 1) {
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&sst[0], a1);
+      atomicAdd(&sst[1], a2);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, sdg[i]);
+    atomicAdd(dbeta + i, sdb[i]);
+  }
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(bst + ((int64_t)b * G) * 2 + i, sst[i]);
+}
+
+// apply: dx = rstd*(dy*gamma - S1/n - xh*S2/n) [* act'(pre)]  (+ addend)
+template <typename TX, typename TDY>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict__ dy, int64_t lddy,
+                    const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ bst,
+                    const float* __restrict__ addend, int64_t ldadd, float* __restrict__ out_f32, int64_t ldo_f32,
+                    __nv_bfloat16* __restrict__ out_bf16, int64_t ldo_bf16, int HW, int C, int G, float eps,
+                    int in_act) {
+  __shared__ float s_mean[64], s_rstd[64], s_c1[64], s_c2[64];
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    const double inv_n = 1.0 / ((double)HW * cpg);
+    const double s1 = stats[2 * ((int64_t)b * G + threadIdx.x)], s2 = stats[2 * ((int64_t)b * G + threadIdx.x) + 1];
+    const double mean = s1 * inv_n;
+    const double var = fmax(s2 * inv_n - mean * mean, 0.0);
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    s_c1[threadIdx.x] = bst[2 * ((int64_t)b * G + threadIdx.x)] * (float)inv_n;
+    s_c2[threadIdx.x] = bst[2 * ((int64_t)b * G + threadIdx.x) + 1] * (float)inv_n;
+  }
+  __syncthreads();
+  const int64_t total = (int64_t)HW * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t pix = (int64_t)b * HW + idx / C;
+    const int g = (G == 1) ? 0 : c / cpg;
+    const float pre = ldf<TX>(x + pix * ldx + c);
+    const float xv = in_act ? act_fwd(pre, in_act) : pre;
+    const float xh = (xv - s_mean[g]) * s_rstd[g];
+    const float d = ldf<TDY>(dy + pix * lddy + c);
+    float dx = s_rstd[g] * (d * __ldg(gamma + c) - s_c1[g] - xh * s_c2[g]);
+    if (in_act) dx *= act_grad(pre, in_act);
+    if (addend) dx += addend[pix * ldadd + c];
+    if (out_f32) out_f32[pix * ldo_f32 + c] = dx;
+    if (out_bf16) out_bf16[pix * ldo_bf16 + c] = __float2bfloat16_rn(dx);
+  }
+}
+
+// ------------------------------------------------------------------------------ depthwise 7x7 backward (weights)
+// block = one sample x 32 channels.  dw[c][tap] += sum_p dy[p] x[p+tap]; db[c] += sum_p dy[p]; dcond[b][c] = sum_p dy[p]
+template <int W>
+__global__ void __launch_bounds__(256)
+dwconv7_wgrad_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
+                     float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dcond, int64_t ldc, int C,
+                     int H) {
+  extern __shared__ float sm[];
+  const int HW = H * W;
+  float* sx = sm;                       // [HW][33]
+  float* sd = sm + (size_t)HW * 33;     // [HW][33]
+  float* sred = sd + (size_t)HW * 33;   // [50][32]  (49 taps + bias)
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * 32;
+  const int tid = threadIdx.x, cl = tid & 31;
+  const int c = c0 + cl;
+  const bool c_ok = c < C;
+  const int nrow = blockDim.x >> 5;
+  for (int p = tid >> 5; p < HW; p += nrow) {
+    sx[p * 33 + cl] = c_ok ? __ldg(x + ((int64_t)b * HW + p) * ldx + c) : 0.f;
+    sd[p * 33 + cl] = c_ok ? __ldg(dy + ((int64_t)b * HW + p) * lddy + c) : 0.f;
+  }
+  for (int i = tid; i < 50 * 32; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  float acc[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+  for (int oh = tid >> 5; oh < H; oh += nrow) {
+    float dr[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      dr[i] = sd[(oh * W + i) * 33 + cl];
+      bsum += dr[i];
+    }
+#pragma unroll
+    for (int kh = 0; kh < 7; ++kh) {
+      const int ih = oh + kh - 3;
+      if (ih < 0 || ih >= H) continue;
+      float xr[W];
+#pragma unroll
+      for (int i = 0; i < W; ++i) xr[i] = sx[(ih * W + i) * 33 + cl];
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw) {
+        float a = 0.f;
+#pragma unroll
+        for (int ow = 0; ow < W; ++ow) {
+          const int iw = ow + kw - 3;
+          if (iw >= 0 && iw < W) a = fmaf(dr[ow], xr[iw], a);
+        }
+        acc[kh * 7 + kw] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 49; ++i) atomicAdd(&sred[i * 32 + cl], acc[i]);
+  atomicAdd(&sred[49 * 32 + cl], bsum);
+  __syncthreads();
+  for (int i = tid; i < 49 * 32; i += blockDim.x) {
+    const int tap = i >> 5, ch = i & 31;
+    if (c0 + ch < C) atomicAdd(dw + (int64_t)(c0 + ch) * 49 + tap, sred[i]);
+  }
+  if (tid < 32 && c_ok) {
+    const float s = sred[49 * 32 + tid];
+    if (db) atomicAdd(db + c, s);
+    if (dcond) dcond[(int64_t)b * ldc + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------ linear attention backward
+// forward (unet_model.py:162-177): qs = softmax_d(q)*scale, ks = softmax_n(k), ctx[d][e] = sum_n ks v, out[n][e] = sum_d ctx qs
+__global__ void __launch_bounds__(256)
+linear_attn_bwd_kernel(const float* __restrict__ qkv, int64_t ldq, const float* __restrict__ dout, int64_t ldd,
+                       __nv_bfloat16* __restrict__ dqkv, int64_t ldg, int n, int heads, float scale) {
+  extern __shared__ float sm[];
+  float* sq = sm;                       // [n][33]  qs (softmax * scale)
+  float* sk = sq + (size_t)n * 33;      // ks
+  float* sv = sk + (size_t)n * 33;
+  float* sdo = sv + (size_t)n * 33;     // dout, later dks
+  float* ctx = sdo + (size_t)n * 33;    // [32][33]
+  float* dctx = ctx + 32 * 33;          // [32][33]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int hid = heads * 32;
+  for (int p = warp; p < n; p += nwarp) {
+    const float* row = qkv + ((int64_t)b * n + p) * ldq + h * 32 + lane;
+    const float qv = row[0];
+    float m = qv;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = expf(qv - m);
+    const float s = warp_sum(e);
+    sq[p * 33 + lane] = e / s * scale;
+    sk[p * 33 + lane] = row[hid];
+    sv[p * 33 + lane] = row[2 * hid];
+    sdo[p * 33 + lane] = dout[((int64_t)b * n + p) * ldd + h * 32 + lane];
+  }
+  __syncthreads();
+  for (int d = warp; d < 32; d += nwarp) {
+    float m = -INFINITY;
+    for (int p = lane; p < n; p += 32) m = fmaxf(m, sk[p * 33 + d]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int p = lane; p < n; p += 32) {
+      const float e = expf(sk[p * 33 + d] - m);
+      sk[p * 33 + d] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int p = lane; p < n; p += 32) sk[p * 33 + d] *= inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < 1024; i += blockDim.x) {
+    const int d = i >> 5, e = i & 31;
+    float a = 0.f, g = 0.f;
+    for (int p = 0; p < n; ++p) {
+      a = fmaf(sk[p * 33 + d], sv[p * 33 + e], a);
+      g = fmaf(sdo[p * 33 + e], sq[p * 33 + d], g);
+    }
+    ctx[d * 33 + e] = a;
+    dctx[d * 33 + e] = g;
+  }
+  __syncthreads();
+  for (int p = warp; p < n; p += nwarp) {
+    float dqs = 0.f, dv = 0.f, dks = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      const float dok = sdo[p * 33 + k];
+      dqs = fmaf(ctx[lane * 33 + k], dok, dqs);              // lane = d, k = e
+      dv = fmaf(sk[p * 33 + k], dctx[k * 33 + lane], dv);    // lane = e, k = d
+      dks = fmaf(dctx[lane * 33 + k], sv[p * 33 + k], dks);  // lane = d, k = e
+    }
+    // softmax over d (the lanes) backward: qsm = qs/scale, upstream g = dqs*scale
+    const float qsm = sq[p * 33 + lane] / scale;
+    const float g = dqs * scale;
+    const float dot = warp_sum(qsm * g);
+    const float dq = qsm * (g - dot);
+    __nv_bfloat16* orow = dqkv + ((int64_t)b * n + p) * ldg + h * 32 + lane;
+    orow[0] = __float2bfloat16_rn(dq);
+    orow[2 * hid] = __float2bfloat16_rn(dv);
+    __syncwarp();
+    sdo[p * 33 + lane] = dks;
+  }
+  __syncthreads();
+  for (int d = warp; d < 32; d += nwarp) {
+    float dot = 0.f;
+    for (int p = lane; p < n; p += 32) dot += sk[p * 33 + d] * sdo[p * 33 + d];
+    dot = warp_sum(dot);
+    for (int p = lane; p < n; p += 32) {
+      const float dk = sk[p * 33 + d] * (sdo[p * 33 + d] - dot);
+      dqkv[((int64_t)b * n + p) * ldg + hid + h * 32 + d] = __float2bfloat16_rn(dk);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ softmax attention backward
+// P = softmax_j(scale * q_i.k_j); out_i = sum_j P_ij v_j.   One block per (head, sample); d walked in chunks of 32.
+__global__ void __launch_bounds__(256)
+softmax_attn_bwd_kernel(const float* __restrict__ qkv, int64_t ldq, const float* __restrict__ dout, int64_t ldd,
+                        __nv_bfloat16* __restrict__ dqkv, int64_t ldg, int n, int dh, int q_off, int k_off,
+                        int v_off, int head_stride, float scale) {
+  extern __shared__ float sm[];
+  float* sP = sm;                           // [n][n+1]
+  float* sD = sP + (size_t)n * (n + 1);     // [n][n+1]  dP then dS
+  float* sA = sD + (size_t)n * (n + 1);     // [n][33]
+  float* sB = sA + (size_t)n * 33;          // [n][33]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const float* base = qkv + (int64_t)b * n * ldq + h * head_stride;
+  const float* dob = dout + (int64_t)b * n * ldd + h * dh;
+  __nv_bfloat16* gb = dqkv + (int64_t)b * n * ldg + h * head_stride;
+  for (int i = tid; i < n * (n + 1); i += blockDim.x) { sP[i] = 0.f; sD[i] = 0.f; }
+  // scores and dP = dout . v^T
+  for (int d0 = 0; d0 < dh; d0 += 32) {
+    const bool ok = d0 + lane < dh;
+    __syncthreads();
+    for (int p = warp; p < n; p += nwarp) {
+      sA[p * 33 + lane] = ok ? base[(int64_t)p * ldq + q_off + d0 + lane] : 0.f;
+      sB[p * 33 + lane] = ok ? base[(int64_t)p * ldq + k_off + d0 + lane] : 0.f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+      const int i = idx / n, j = idx - i * n;
+      float a = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < 32; ++d) a = fmaf(sA[i * 33 + d], sB[j * 33 + d], a);
+      sP[i * (n + 1) + j] += a;
+    }
+    __syncthreads();
+    for (int p = warp; p < n; p += nwarp) {
+      sA[p * 33 + lane] = ok ? dob[(int64_t)p * ldd + d0 + lane] : 0.f;
+      sB[p * 33 + lane] = ok ? base[(int64_t)p * ldq + v_off + d0 + lane] : 0.f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+      const int i = idx / n, j = idx - i * n;
+      float a = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < 32; ++d) a = fmaf(sA[i * 33 + d], sB[j * 33 + d], a);
+      sD[i * (n + 1) + j] += a;
+    }
+  }
+  __syncthreads();
+  // softmax rows, then dS = P o (dP - rowsum(P o dP))
+  for (int i = warp; i < n; i += nwarp) {
+    float m = -INFINITY;
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sP[i * (n + 1) + j] * scale);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float e = expf(sP[i * (n + 1) + j] * scale - m);
+      sP[i * (n + 1) + j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    float dot = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float pj = sP[i * (n + 1) + j] * inv;
+      sP[i * (n + 1) + j] = pj;
+      dot += pj * sD[i * (n + 1) + j];
+    }
+    dot = warp_sum(dot);
+    for (int j = lane; j < n; j += 32) sD[i * (n + 1) + j] = sP[i * (n + 1) + j] * (sD[i * (n + 1) + j] - dot) * scale;
+  }
+  // dv_j = sum_i P_ij dout_i ; dq_i = sum_j dS_ij k_j ; dk_j = sum_i dS_ij q_i
+  for (int d0 = 0; d0 < dh; d0 += 32) {
+    const bool ok = d0 + lane < dh;
+    __syncthreads();
+    for (int p = warp; p < n; p += nwarp) sA[p * 33 + lane] = ok ? dob[(int64_t)p * ldd + d0 + lane] : 0.f;
+    __syncthreads();
+    for (int j = warp; j < n; j += nwarp) {
+      float a = 0.f;
+      for (int i = 0; i < n; ++i) a = fmaf(sP[i * (n + 1) + j], sA[i * 33 + lane], a);
+      if (ok) gb[(int64_t)j * ldg + v_off + d0 + lane] = __float2bfloat16_rn(a);
+    }
+    __syncthreads();
+    for (int p = warp; p < n; p += nwarp) {
+      sA[p * 33 + lane] = ok ? base[(int64_t)p * ldq + k_off + d0 + lane] : 0.f;
+      sB[p * 33 + lane] = ok ? base[(int64_t)p * ldq + q_off + d0 + lane] : 0.f;
+    }
+    __syncthreads();
+    for (int r = warp; r < n; r += nwarp) {
+      float aq = 0.f, ak = 0.f;
+      for (int t = 0; t < n; ++t) {
+        aq = fmaf(sD[r * (n + 1) + t], sA[t * 33 + lane], aq);  // dq_r = sum_t dS[r][t] k_t
+        ak = fmaf(sD[t * (n + 1) + r], sB[t * 33 + lane], ak);  // dk_r = sum_t dS[t][r] q_t
+      }
+      if (ok) {
+        gb[(int64_t)r * ldg + q_off + d0 + lane] = __float2bfloat16_rn(aq);
+        gb[(int64_t)r * ldg + k_off + d0 + lane] = __float2bfloat16_rn(ak);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ small elementwise helpers
+// out = dy * act'(pre)
+template <typename TP>
+__global__ void act_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const TP* __restrict__ pre, int64_t ldp,
+                               float* __restrict__ out_f32, int64_t ldo, __nv_bfloat16* __restrict__ out_bf16,
+                               int64_t ldb, int64_t rows, int C, int act) {
+  const int64_t total = rows * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t r = idx / C;
+    const float v = dy[r * lddy + c] * act_grad(ldf<TP>(pre + r * ldp + c), act);
+    if (out_f32) out_f32[r * ldo + c] = v;
+    if (out_bf16) out_bf16[r * ldb + c] = __float2bfloat16_rn(v);
+  }
+}
+// fp32 NCHW -> bf16 (and fp32) channels-last
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out_bf16, int64_t ldb,
+                                    float* __restrict__ out_f32, int64_t ldf_, int B, int C, int HW) {
+  const int64_t total = (int64_t)B * HW * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t pix = idx / C;
+    const int p = (int)(pix % HW);
+    const int b = (int)(pix / HW);
+    const float v = x[((int64_t)b * C + c) * HW + p];
+    if (out_bf16) out_bf16[pix * ldb + c] = __float2bfloat16_rn(v);
+    if (out_f32) out_f32[pix * ldf_ + c] = v;
+  }
+}
+// strided fp32: out = a + b (out may alias a); optional bf16 copy of the sum
+__global__ void add_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb_,
+                           float* __restrict__ out, int64_t ldo, __nv_bfloat16* __restrict__ out_bf16, int64_t ldh,
+                           int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t r = idx / C;
+    const float v = a[r * lda + c] + (b ? b[r * ldb_ + c] : 0.f);
+    if (out) out[r * ldo + c] = v;
+    if (out_bf16) out_bf16[r * ldh + c] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------ multi-tensor Adam
+// torch.optim.Adam (no amsgrad / weight decay / maximize): exp_avg, exp_avg_sq updates, bias-corrected step.
+__global__ void __launch_bounds__(256)
+adam_kernel(const sbm_adam_tensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, float lr,
+            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  const int2 ck = chunks[blockIdx.x];
+  const sbm_adam_tensor t = tensors[ck.x];
+  const int64_t start = (int64_t)ck.y * chunk_elems;
+  const int64_t end = min(start + (int64_t)chunk_elems, t.n);
+  const float step = lr / bc1;
+  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) {
+    const float g = t.grad[i] * grad_scale;
+    const float m = beta1 * t.exp_avg[i] + (1.f - beta1) * g;
+    const float v = beta2 * t.exp_avg_sq[i] + (1.f - beta2) * g * g;
+    t.exp_avg[i] = m;
+    t.exp_avg_sq[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    t.param[i] -= step * (m / denom);
+  }
+}
+
+static int egrid(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
+}
+
+}  // namespace sbm
+
+using namespace sbm;
+
+extern "C" {
+
+int sbm_colsum(const void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t C, float* out, void* stream) {
+  SBM_CHECK_ARG(x && out && rows > 0 && C > 0, "sbm_colsum: bad args");
+  dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, 512)), (unsigned)std::min((C + 31) / 32, 64));
+  if (dtype == SBM_F32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, rows, C, out);
+  else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, rows, C, out);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* dy, int32_t dy_dtype, int64_t lddy,
+                      const double* stats, const float* gamma, float* bst, float* dgamma, float* dbeta,
+                      const float* addend, int64_t ldadd, float* out_f32, int64_t ldo_f32, void* out_bf16,
+                      int64_t ldo_bf16, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t in_act,
+                      void* stream) {
+  SBM_CHECK_ARG(x && dy && stats && gamma && bst && dgamma && dbeta && (out_f32 || out_bf16), "sbm_groupnorm_bwd: null");
+  SBM_CHECK_ARG(B > 0 && G > 0 && G <= 64 && C % G == 0, "sbm_groupnorm_bwd: bad sizes");
+  const int64_t per_sample = (int64_t)HW * C;
+  int chunks = (int)std::min<int64_t>((per_sample + 4095) / 4096, std::max<int64_t>(1, (int64_t)sm_count() * 8 / B));
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, B);
+  const size_t smem = (size_t)(2 * C + 2 * G) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 48 * 1024, "sbm_groupnorm_bwd: C=%d too large", C);
+  cudaStream_t s = (cudaStream_t)stream;
+#define SBM_GNB(TX, TDY)                                                                                            \
+  do {                                                                                                              \
+    gn_bwd_reduce_kernel<TX, TDY><<<grid, 256, smem, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats, gamma, bst, \
+                                                          dgamma, dbeta, HW, C, G, eps, in_act);                    \
+    gn_bwd_apply_kernel<TX, TDY><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats, gamma, bst,     \
+                                                      addend, ldadd, out_f32, ldo_f32, (__nv_bfloat16*)out_bf16,     \
+                                                      ldo_bf16, HW, C, G, eps, in_act);                             \
+  } while (0)
+  if (x_dtype == SBM_F32 && dy_dtype == SBM_F32) SBM_GNB(float, float);
+  else if (x_dtype == SBM_BF16 && dy_dtype == SBM_F32) SBM_GNB(__nv_bfloat16, float);
+  else if (x_dtype == SBM_F32 && dy_dtype == SBM_BF16) SBM_GNB(float, __nv_bfloat16);
+  else SBM_GNB(__nv_bfloat16, __nv_bfloat16);
+#undef SBM_GNB
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  count_launch_b();
+  return 0;
+}
+
+int sbm_dwconv7_wgrad(const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dw, float* db, float* dcond,
+                      int64_t ldc, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  SBM_CHECK_ARG(x && dy && dw && B > 0 && C > 0, "sbm_dwconv7_wgrad: bad args");
+  const size_t smem = ((size_t)2 * H * W * 33 + 50 * 32) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_dwconv7_wgrad: map too large");
+  dim3 grid((C + 31) / 32, B);
+  const int threads = 32 * std::max(1, std::min(8, H));
+  cudaStream_t s = (cudaStream_t)stream;
+#define SBM_DWW(WW)                                                                                                \
+  do {                                                                                                             \
+    static size_t conf = 0;                                                                                        \
+    if (smem > 48 * 1024 && smem > conf) {                                                                         \
+      SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_wgrad_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                       (int)smem));                                                                \
+      conf = smem;                                                                                                 \
+    }                                                                                                              \
+    dwconv7_wgrad_kernel<WW><<<grid, threads, smem, s>>>(x, ldx, dy, lddy, dw, db, dcond, ldc, C, H);               \
+  } while (0)
+  if (W == 16) SBM_DWW(16);
+  else if (W == 8) SBM_DWW(8);
+  else if (W == 4) SBM_DWW(4);
+  else if (W == 2) SBM_DWW(2);
+  else if (W == 1) SBM_DWW(1);
+  else SBM_CHECK_ARG(false, "sbm_dwconv7_wgrad: unsupported width %d", W);
+#undef SBM_DWW
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_linear_attn_bwd(const float* qkv, int64_t ldq, const float* dout, int64_t ldd, void* dqkv, int64_t ldg,
+                        int32_t B, int32_t n, int32_t heads, float scale, void* stream) {
+  SBM_CHECK_ARG(qkv && dout && dqkv && B > 0 && n > 0, "sbm_linear_attn_bwd: bad args");
+  const size_t smem = ((size_t)4 * n * 33 + 2 * 32 * 33) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_linear_attn_bwd: n=%d too large", n);
+  static size_t conf = 0;
+  if (smem > 48 * 1024 && smem > conf) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  linear_attn_bwd_kernel<<<dim3(heads, B), 256, smem, (cudaStream_t)stream>>>(qkv, ldq, dout, ldd, (__nv_bfloat16*)dqkv,
+                                                                              ldg, n, heads, scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_softmax_attn_bwd(const float* qkv, int64_t ldq, const float* dout, int64_t ldd, void* dqkv, int64_t ldg,
+                         int32_t B, int32_t n, int32_t heads, int32_t dh, int32_t q_off, int32_t k_off, int32_t v_off,
+                         int32_t head_stride, float scale, void* stream) {
+  SBM_CHECK_ARG(qkv && dout && dqkv && B > 0 && n > 0, "sbm_softmax_attn_bwd: bad args");
+  const size_t smem = ((size_t)2 * n * (n + 1) + 2 * (size_t)n * 33) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_softmax_attn_bwd: n=%d too large", n);
+  static size_t conf = 0;
+  if (smem > 48 * 1024 && smem > conf) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(softmax_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  softmax_attn_bwd_kernel<<<dim3(heads, B), 256, smem, (cudaStream_t)stream>>>(
+      qkv, ldq, dout, ldd, (__nv_bfloat16*)dqkv, ldg, n, dh, q_off, k_off, v_off, head_stride, scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_act_bwd(const float* dy, int64_t lddy, const void* pre, int32_t pre_dtype, int64_t ldp, float* out_f32,
+                int64_t ldo, void* out_bf16, int64_t ldb, int64_t rows, int32_t C, int32_t act, void* stream) {
+  SBM_CHECK_ARG(dy && pre && (out_f32 || out_bf16) && rows > 0 && C > 0, "sbm_act_bwd: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pre_dtype == SBM_F32)
+    act_bwd_kernel<float><<<egrid(rows * C), 256, 0, s>>>(dy, lddy, (const float*)pre, ldp, out_f32, ldo,
+                                                          (__nv_bfloat16*)out_bf16, ldb, rows, C, act);
+  else
+    act_bwd_kernel<__nv_bfloat16><<<egrid(rows * C), 256, 0, s>>>(dy, lddy, (const __nv_bfloat16*)pre, ldp, out_f32, ldo,
+                                                                  (__nv_bfloat16*)out_bf16, ldb, rows, C, act);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_nchw_to_nhwc(const float* x, void* out_bf16, int64_t ldb, float* out_f32, int64_t ldf, int32_t B, int32_t C,
+                     int32_t HW, void* stream) {
+  SBM_CHECK_ARG(x && (out_bf16 || out_f32) && B > 0 && C > 0 && HW > 0, "sbm_nchw_to_nhwc: bad args");
+  nchw_to_nhwc_kernel<<<egrid((int64_t)B * C * HW), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_bf16, ldb,
+                                                                                    out_f32, ldf, B, C, HW);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_add(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo, void* out_bf16,
+            int64_t ldh, int64_t rows, int32_t C, void* stream) {
+  SBM_CHECK_ARG(a && (out || out_bf16) && rows > 0 && C > 0, "sbm_add: bad args");
+  add_kernel<<<egrid(rows * C), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, ldo, (__nv_bfloat16*)out_bf16, ldh,
+                                                                rows, C);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_adam_step(const sbm_adam_tensor* tensors_dev, const int32_t* chunks_dev, int32_t n_chunks,
+                  int32_t chunk_elems, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                  void* stream) {
+  SBM_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && chunk_elems > 0 && step >= 1, "sbm_adam_step: bad args");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(tensors_dev, (const int2*)chunks_dev, chunk_elems, lr, beta1,
+                                                          beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+}  // extern "C"

@@ -66,6 +66,7 @@ struct ConvKernelParams {
   void* out2;
   double* stats;
   int32_t act, out_dtype, res_dtype, vec_ok;
+  int32_t out2_preact, pad0;
   TapTable taps[4];
 };
 
@@ -80,6 +81,8 @@ __device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint
   for (int e = 0; e < 16; ++e) {
     float x = __uint_as_float(v[e]);
     if (p.bias != nullptr && (full || n + e < p.cout)) x += __ldg(p.bias + n + e);
+    if (p.out2_preact && row_ok && (full || n + e < p.cout))
+      reinterpret_cast<__nv_bfloat16*>(p.out2)[o2_base + n + e] = __float2bfloat16_rn(x);
     if (p.act == SBM_ACT_GELU) x = gelu_exact(x);
     else if (p.act == SBM_ACT_SILU) x = silu(x);
     f[e] = x;
@@ -143,7 +146,7 @@ __device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint
           if (n + e < p.cout) op[e] = __float2bfloat16_rn(f[e]);
       }
     }
-    if (p.out2 != nullptr) {
+    if (p.out2 != nullptr && !p.out2_preact) {
       __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out2) + o2_base + n;
       if (full && p.vec_ok) {
         uint32_t w[8];
@@ -661,6 +664,7 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   p.cblocks = (a->cin + kBK - 1) / kBK;
   p.bias = a->bias; p.residual = a->residual; p.out = a->out; p.out2 = a->out2; p.stats = a->stats;
   p.act = a->act; p.out_dtype = a->out_dtype; p.res_dtype = a->res_dtype;
+  p.out2_preact = (a->out2 != nullptr && a->out2_preact) ? 1 : 0;
 
   // output addressing
   const int64_t OHf = (a->kind == SBM_CONVT_4X4_S2) ? 2 * oh : oh;

@@ -104,7 +104,8 @@ template <int W>
 __global__ void __launch_bounds__(256)
 dwconv7_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                     const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
-                    float* __restrict__ out, int64_t ldo, double* __restrict__ stats, int C, int H) {
+                    float* __restrict__ out, int64_t ldo, double* __restrict__ stats, int C, int H, int flip,
+                    const float* __restrict__ addend, int64_t ldadd) {
   extern __shared__ float sm[];
   const int HW = H * W;
   float* sx = sm;  // [HW][33]
@@ -137,7 +138,7 @@ dwconv7_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __res
   }
   float wr[49];
 #pragma unroll
-  for (int i = 0; i < 49; ++i) wr[i] = c_ok ? __ldg(w + (int64_t)c * 49 + i) : 0.f;
+  for (int i = 0; i < 49; ++i) wr[i] = c_ok ? __ldg(w + (int64_t)c * 49 + (flip ? 48 - i : i)) : 0.f;
   const float add = c_ok ? (bias ? __ldg(bias + c) : 0.f) + (cond ? __ldg(cond + (int64_t)b * ldc + c) : 0.f) : 0.f;
   __syncthreads();
   float s1 = 0.f, s2 = 0.f;
@@ -162,6 +163,11 @@ dwconv7_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __res
     }
     if (c_ok) {
       float* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
+      if (addend != nullptr) {
+        const float* ap = addend + ((int64_t)b * HW + oh * W) * ldadd + c;
+#pragma unroll
+        for (int i = 0; i < W; ++i) acc[i] += ap[(int64_t)i * ldadd];
+      }
 #pragma unroll
       for (int i = 0; i < W; ++i) {
         op[(int64_t)i * ldo] = acc[i];
@@ -525,33 +531,48 @@ int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, in
   return 0;
 }
 
-int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
-                    float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C,
-                    void* stream) {
-  SBM_CHECK_ARG(x && w && out && B > 0 && C > 0 && H > 0 && W > 0, "sbm_dwconv7_fwd: bad args");
+static int dwconv7_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
+                          int64_t ldc, float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W,
+                          int32_t C, int flip, const float* addend, int64_t ldadd, cudaStream_t st) {
+  SBM_CHECK_ARG(x && w && out && B > 0 && C > 0 && H > 0 && W > 0, "sbm_dwconv7: bad args");
   const size_t smem = ((size_t)H * W * 33 + 49 * kDwCh) * sizeof(float);
-  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_dwconv7_fwd: %dx%d map does not fit the shared-memory slab", H, W);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_dwconv7: %dx%d map does not fit the shared-memory slab", H, W);
   dim3 grid((C + kDwCh - 1) / kDwCh, B);
-  cudaStream_t st = (cudaStream_t)stream;
   const size_t smem_rows = (size_t)H * W * 33 * sizeof(float);
   const int threads = 32 * std::max(1, std::min(8, H));
 #define SBM_DW_ROWS(WW)                                                                                            \
-  dwconv7_rows_kernel<WW><<<grid, threads, smem_rows, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H)
+  dwconv7_rows_kernel<WW><<<grid, threads, smem_rows, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, flip, \
+                                                            addend, ldadd)
   if (W == 16 && smem_rows <= 48 * 1024) SBM_DW_ROWS(16);
   else if (W == 8) SBM_DW_ROWS(8);
   else if (W == 4) SBM_DW_ROWS(4);
   else if (W == 2) SBM_DW_ROWS(2);
   else if (W == 1) SBM_DW_ROWS(1);
-  else dwconv7_kernel<<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, W);
+  else {
+    SBM_CHECK_ARG(!flip && !addend, "sbm_dwconv7_bwd_input: unsupported width %d", W);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    dwconv7_kernel<<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, W);
+  }
 #undef SBM_DW_ROWS
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
+                    float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C,
+                    void* stream) {
+  return dwconv7_launch(x, ldx, w, bias, cond, ldc, out, ldo, stats, B, H, W, C, 0, nullptr, 0, (cudaStream_t)stream);
+}
+
+int sbm_dwconv7_bwd_input(const float* dy, int64_t lddy, const float* w, const float* addend, int64_t ldadd,
+                          float* out, int64_t ldo, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  return dwconv7_launch(dy, lddy, w, nullptr, nullptr, 0, out, ldo, nullptr, B, H, W, C, 1, addend, ldadd,
+                        (cudaStream_t)stream);
 }
 
 int sbm_group_stats(const void* x, int32_t in_dtype, int64_t ldx, int32_t B, int32_t HW, int32_t C, int32_t G,

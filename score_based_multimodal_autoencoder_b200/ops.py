@@ -54,7 +54,8 @@ def pack_linear_weight(w: torch.Tensor, out=None) -> torch.Tensor:
 def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: int, cin: int, cout: int,
                bias: torch.Tensor | None = None, act: int = L.ACT_NONE, residual: torch.Tensor | None = None,
                out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.float32, nchw: bool = False,
-               stats: torch.Tensor | None = None, out2: torch.Tensor | None = None) -> torch.Tensor:
+               stats: torch.Tensor | None = None, out2: torch.Tensor | None = None,
+               out2_preact: bool = False) -> torch.Tensor:
     """x: bf16 [B,H,W,ldx]; returns [B,OH,OW,pad8(cout)] (or fp32 NCHW [B,cout,OH,OW] when nchw)."""
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.stride(3) == 1
     b, h, w, _ = x.shape
@@ -89,6 +90,7 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
     a.stats = stats.data_ptr() if stats is not None else None
     if out2 is not None:
         a.out2, a.ldo2 = out2.data_ptr(), out2.stride(2)
+        a.out2_preact = 1 if out2_preact else 0
     L.check(L.lib().sbm_conv_igemm(C.byref(a), L.stream_ptr()), "sbm_conv_igemm")
     return out
 
@@ -206,3 +208,108 @@ def unpack_convT2d_wgrad(dwpk, weight):
 def unpack_linear_wgrad(dwpk, weight):
     o, i = weight.shape
     return unpack_wgrad(dwpk, weight, i, 0, i, 1)
+
+
+def _rows(t: torch.Tensor) -> int:
+    return t.shape[0] * t.shape[1] * t.shape[2]
+
+
+def colsum(x: torch.Tensor, c: int) -> torch.Tensor:
+    out = torch.zeros(c, dtype=torch.float32, device=x.device)
+    L.check(L.lib().sbm_colsum(L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), C.c_int64(_rows(x)), C.c_int32(c),
+                               L.ptr(out), L.stream_ptr()), "sbm_colsum")
+    return out
+
+
+def groupnorm_bwd(x, dy, c, stats, gamma, *, groups=1, in_act=0, addend=None, want_f32=True, want_bf16=False,
+                  eps=1e-5):
+    """-> (dx_f32 | None, dx_bf16 | None, dgamma, dbeta)"""
+    b, h, w, _ = x.shape
+    dev = x.device
+    bst = torch.zeros((b, groups, 2), dtype=torch.float32, device=dev)
+    dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
+    dbeta = torch.zeros(c, dtype=torch.float32, device=dev)
+    of = torch.empty((b, h, w, pad8(c)), dtype=torch.float32, device=dev) if want_f32 else None
+    ob = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    L.check(L.lib().sbm_groupnorm_bwd(
+        L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), L.ptr(dy), C.c_int32(_dt(dy)), C.c_int64(dy.stride(2)),
+        L.ptr(stats), L.ptr(gamma), L.ptr(bst), L.ptr(dgamma), L.ptr(dbeta),
+        L.ptr(addend), C.c_int64(addend.stride(2) if addend is not None else 0),
+        L.ptr(of), C.c_int64(of.stride(2) if of is not None else 0),
+        L.ptr(ob), C.c_int64(ob.stride(2) if ob is not None else 0),
+        C.c_int32(b), C.c_int32(h * w), C.c_int32(c), C.c_int32(groups), C.c_float(eps), C.c_int32(in_act),
+        L.stream_ptr()), "sbm_groupnorm_bwd")
+    return of, ob, dgamma, dbeta
+
+
+def dwconv7_bwd_input(dy, c, w, addend=None):
+    b, h, wd, _ = dy.shape
+    out = torch.empty((b, h, wd, pad8(c)), dtype=torch.float32, device=dy.device)
+    L.check(L.lib().sbm_dwconv7_bwd_input(L.ptr(dy), C.c_int64(dy.stride(2)), L.ptr(w), L.ptr(addend),
+                                          C.c_int64(addend.stride(2) if addend is not None else 0), L.ptr(out),
+                                          C.c_int64(out.stride(2)), C.c_int32(b), C.c_int32(h), C.c_int32(wd),
+                                          C.c_int32(c), L.stream_ptr()), "sbm_dwconv7_bwd_input")
+    return out
+
+
+def dwconv7_wgrad(x, dy, c, dcond=None, ldc=0, want_db=True):
+    """-> (dw [c,1,7,7], db [c] | None); dcond (a [B, >=c] slice view) is overwritten with sum_p dy."""
+    b, h, wd, _ = x.shape
+    dw = torch.zeros((c, 1, 7, 7), dtype=torch.float32, device=x.device)
+    db = torch.zeros(c, dtype=torch.float32, device=x.device) if want_db else None
+    L.check(L.lib().sbm_dwconv7_wgrad(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(dy), C.c_int64(dy.stride(2)), L.ptr(dw),
+                                      L.ptr(db), L.ptr(dcond), C.c_int64(ldc), C.c_int32(b), C.c_int32(h),
+                                      C.c_int32(wd), C.c_int32(c), L.stream_ptr()), "sbm_dwconv7_wgrad")
+    return dw, db
+
+
+def linear_attn_bwd(qkv, dout, heads, scale):
+    b, h, w, _ = qkv.shape
+    dqkv = torch.empty((b, h, w, 3 * heads * 32), dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.lib().sbm_linear_attn_bwd(L.ptr(qkv), C.c_int64(qkv.stride(2)), L.ptr(dout), C.c_int64(dout.stride(2)),
+                                        L.ptr(dqkv), C.c_int64(dqkv.stride(2)), C.c_int32(b), C.c_int32(h * w),
+                                        C.c_int32(heads), C.c_float(scale), L.stream_ptr()), "sbm_linear_attn_bwd")
+    return dqkv
+
+
+def softmax_attn_bwd(qkv, dout, heads, dh, q_off, k_off, v_off, head_stride, scale, width):
+    b, h, w, _ = qkv.shape
+    dqkv = torch.zeros((b, h, w, pad8(width)), dtype=torch.bfloat16, device=qkv.device)
+    L.check(L.lib().sbm_softmax_attn_bwd(L.ptr(qkv), C.c_int64(qkv.stride(2)), L.ptr(dout), C.c_int64(dout.stride(2)),
+                                         L.ptr(dqkv), C.c_int64(dqkv.stride(2)), C.c_int32(b), C.c_int32(h * w),
+                                         C.c_int32(heads), C.c_int32(dh), C.c_int32(q_off), C.c_int32(k_off),
+                                         C.c_int32(v_off), C.c_int32(head_stride), C.c_float(scale), L.stream_ptr()),
+            "sbm_softmax_attn_bwd")
+    return dqkv
+
+
+def act_bwd(dy, pre, c, act, want_f32=False, want_bf16=True):
+    b, h, w, _ = dy.shape
+    of = torch.empty((b, h, w, pad8(c)), dtype=torch.float32, device=dy.device) if want_f32 else None
+    ob = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=dy.device) if want_bf16 else None
+    L.check(L.lib().sbm_act_bwd(L.ptr(dy), C.c_int64(dy.stride(2)), L.ptr(pre), C.c_int32(_dt(pre)),
+                                C.c_int64(pre.stride(2)), L.ptr(of), C.c_int64(of.stride(2) if of is not None else 0),
+                                L.ptr(ob), C.c_int64(ob.stride(2) if ob is not None else 0), C.c_int64(_rows(dy)),
+                                C.c_int32(c), C.c_int32(act), L.stream_ptr()), "sbm_act_bwd")
+    return of, ob
+
+
+def nchw_to_nhwc(x, want_f32=False):
+    b, c, h, w = x.shape
+    ob = torch.zeros((b, h, w, pad8(c)), dtype=torch.bfloat16, device=x.device)
+    of = torch.zeros((b, h, w, pad8(c)), dtype=torch.float32, device=x.device) if want_f32 else None
+    L.check(L.lib().sbm_nchw_to_nhwc(L.ptr(x), L.ptr(ob), C.c_int64(ob.stride(2)), L.ptr(of),
+                                     C.c_int64(of.stride(2) if of is not None else 0), C.c_int32(b), C.c_int32(c),
+                                     C.c_int32(h * w), L.stream_ptr()), "sbm_nchw_to_nhwc")
+    return ob, of
+
+
+def add(a, b, c, out=None, want_bf16=False):
+    """fp32 channels-last a + b (b may be None) -> (out fp32 | None, bf16 copy | None)."""
+    bb, h, w, _ = a.shape
+    ob = torch.empty((bb, h, w, pad8(c)), dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    L.check(L.lib().sbm_add(L.ptr(a), C.c_int64(a.stride(2)), L.ptr(b), C.c_int64(b.stride(2) if b is not None else 0),
+                            L.ptr(out), C.c_int64(out.stride(2) if out is not None else 0), L.ptr(ob),
+                            C.c_int64(ob.stride(2) if ob is not None else 0), C.c_int64(_rows(a)), C.c_int32(c),
+                            L.stream_ptr()), "sbm_add")
+    return out, ob

@@ -67,3 +67,164 @@ def test_conv_wgrad(case):
     err = (got.double() - w.grad).abs().max().item()
     scale = w.grad.abs().max().item()
     assert err <= 3e-5 * scale + 1e-6, f"{name}: err {err:.3e} scale {scale:.3e}"
+
+
+def _nhwc(x_nchw, dtype=torch.float32):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+@pytest.mark.parametrize("groups,in_act,C,H", [(1, 0, 42, 8), (1, 1, 64, 4), (32, 2, 64, 8), (1, 0, 256, 1)])
+def test_groupnorm_backward(groups, in_act, C, H):
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(C + H)
+    B = 5
+    pre = torch.randn(B, C, H, H, generator=g).to(dev).double().requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev).double().requires_grad_(True)
+    beta = torch.randn(C, generator=g).to(dev).double().requires_grad_(True)
+    x = pre if in_act == 0 else (F.gelu(pre) if in_act == 1 else F.silu(pre))
+    y = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    dy = torch.randn(y.shape, generator=g).to(dev).double()
+    (y * dy).sum().backward()
+    ld = ops.pad8(C)
+    pre_n = torch.zeros(B, H, H, ld, device=dev)
+    pre_n[..., :C] = _nhwc(pre.detach().float())
+    dy_n = torch.zeros(B, H, H, ld, device=dev)
+    dy_n[..., :C] = _nhwc(dy.float())
+    xv = x.detach().float()
+    xg = xv.reshape(B, groups, -1).double()
+    stats = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], dim=-1).reshape(B, groups, 2).contiguous()
+    dx, dxb, dg, db = ops.groupnorm_bwd(pre_n, dy_n, C, stats, gamma.detach().float(), groups=groups, in_act=in_act,
+                                        want_f32=True, want_bf16=True)
+    torch.cuda.synchronize()
+    ref = _nhwc(pre.grad.float())
+    assert (dx[..., :C] - ref).abs().max().item() <= 2e-4 * ref.abs().max().item() + 1e-5
+    assert (dxb[..., :C].float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-5
+    assert torch.allclose(dg, gamma.grad.float(), rtol=2e-4, atol=2e-4)
+    assert torch.allclose(db, beta.grad.float(), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("H,C", [(16, 40), (8, 64), (4, 33), (2, 64), (1, 70)])
+def test_dwconv7_backward(H, C):
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 100 + C)
+    B = 6
+    x = torch.randn(B, C, H, H, generator=g).to(dev).double().requires_grad_(True)
+    w = (torch.randn(C, 1, 7, 7, generator=g) / 7).to(dev).double().requires_grad_(True)
+    bias = torch.randn(C, generator=g).to(dev).double().requires_grad_(True)
+    cond = torch.randn(B, C, generator=g).to(dev).double().requires_grad_(True)
+    y = F.conv2d(x, w, bias, padding=3, groups=C) + cond[:, :, None, None]
+    dy = torch.randn(y.shape, generator=g).to(dev).double()
+    (y * dy).sum().backward()
+    ld = ops.pad8(C)
+    xn = torch.zeros(B, H, H, ld, device=dev); xn[..., :C] = _nhwc(x.detach().float())
+    dyn = torch.zeros(B, H, H, ld, device=dev); dyn[..., :C] = _nhwc(dy.float())
+    addend = torch.randn(B, H, H, ld, generator=g).to(dev)
+    dx = ops.dwconv7_bwd_input(dyn, C, w.detach().float().contiguous(), addend=addend)
+    dcond = torch.zeros(B, 1, 1, ld + 8, device=dev)
+    dw, db = ops.dwconv7_wgrad(xn, dyn, C, dcond=dcond[:, :, :, 8:], ldc=dcond.stride(2))
+    torch.cuda.synchronize()
+    ref = _nhwc(x.grad.float()) + addend[..., :C]
+    assert (dx[..., :C] - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert torch.allclose(dw, w.grad.float(), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(db, bias.grad.float(), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(dcond[:, 0, 0, 8:8 + C], cond.grad.float(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("n_side", [1, 2, 4, 16])
+def test_linear_attention_backward(n_side):
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(n_side)
+    B, heads, d = 3, 4, 32
+    n = n_side * n_side
+    qkv = torch.randn(B, n, 3 * heads * d, generator=g).to(dev).double().requires_grad_(True)
+    q, k, v = (t.reshape(B, n, heads, d).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=-1))  # b h d n
+    qs = q.softmax(dim=-2) * d ** -0.5
+    ks = k.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", ks, v)
+    out = torch.einsum("bhde,bhdn->bhen", ctx, qs)  # b h e n
+    out_n = out.permute(0, 3, 1, 2).reshape(B, n, heads * d)
+    do = torch.randn(out_n.shape, generator=g).to(dev).double()
+    (out_n * do).sum().backward()
+    qkv_t = qkv.detach().float().reshape(B, n_side, n_side, -1).contiguous()
+    fwd = ops.linear_attn(qkv_t, heads, d ** -0.5)
+    dqkv = ops.linear_attn_bwd(qkv_t, do.float().reshape(B, n_side, n_side, -1).contiguous(), heads, d ** -0.5)
+    torch.cuda.synchronize()
+    assert (fwd.float().reshape(B, n, -1) - out_n.detach().float()).abs().max().item() <= 1e-2 * out_n.abs().max().item()
+    ref = qkv.grad.float()
+    got = dqkv.float().reshape(B, n, -1)
+    assert (got - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("n_side,heads,dh,layout", [(1, 4, 32, "unet"), (4, 4, 32, "unet"), (4, 2, 48, "openai"),
+                                                    (8, 1, 64, "openai")])
+def test_softmax_attention_backward(n_side, heads, dh, layout):
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(n_side * 7 + dh)
+    B = 3
+    n = n_side * n_side
+    hid = heads * dh
+    qkv = torch.randn(B, n, 3 * hid, generator=g).to(dev).double().requires_grad_(True)
+    if layout == "unet":
+        q, k, v = (t.reshape(B, n, heads, dh) for t in qkv.chunk(3, dim=-1))
+        offs = (0, hid, 2 * hid, dh)
+        scale = dh ** -0.5
+    else:
+        t = qkv.reshape(B, n, heads, 3, dh)
+        q, k, v = t[:, :, :, 0], t[:, :, :, 1], t[:, :, :, 2]
+        offs = (0, dh, 2 * dh, 3 * dh)
+        scale = dh ** -0.5
+    sim = torch.einsum("bihd,bjhd->bhij", q, k) * scale
+    attn = sim.softmax(dim=-1)
+    out = torch.einsum("bhij,bjhd->bihd", attn, v).reshape(B, n, hid)
+    do = torch.randn(out.shape, generator=g).to(dev).double()
+    (out * do).sum().backward()
+    qkv_t = qkv.detach().float().reshape(B, n_side, n_side, -1).contiguous()
+    fwd = ops.softmax_attn(qkv_t, heads, dh, offs[0], offs[1], offs[2], offs[3], scale)
+    dqkv = ops.softmax_attn_bwd(qkv_t, do.float().reshape(B, n_side, n_side, -1).contiguous(), heads, dh, offs[0],
+                                offs[1], offs[2], offs[3], scale, 3 * hid)
+    torch.cuda.synchronize()
+    assert (fwd.float().reshape(B, n, -1)[..., :hid] - out.detach().float()).abs().max().item() <= 1e-2 * out.abs().max().item()
+    ref = qkv.grad.float()
+    got = dqkv.float().reshape(B, n, -1)[..., :3 * hid]
+    assert (got - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-6
+
+
+def test_dsm_training_step_gradients_vs_reference_golden():
+    """loss_fn(...).backward() through the B200 Unet against gradients of the real reference (tests/golden/dsm_loss.pt)."""
+    from oracle.det_weights import fill_state_dict
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    from tests.util import golden
+    g = golden("dsm_loss.pt")
+    net = golden("unet_poly.pt")
+    m = Unet(**net["kwargs"])
+    m.load_state_dict(fill_state_dict(net["shapes"]))
+    m = m.cuda().train()
+    cls = {"vp": sh.VPSDE, "subvp": sh.subVPSDE, "ve": sh.VESDE}
+    for c in g["cases"][:3]:
+        sde = cls[c["kind"]](c["a"], c["b"], c["N"])
+        m.zero_grad()
+        loss = sh.loss_fn(g["batch"].cuda(), m, sde, reduce_mean=c["reduce_mean"],
+                          likelihood_weighting=c["likelihood_weighting"], u=g["u"].cuda(), z=g["z"].cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        assert abs(loss.item() - c["loss"].item()) <= 2e-2 * abs(c["loss"].item())
+        params = dict(m.named_parameters())
+        worst = 0.0
+        for k, ref in c["grads"].items():
+            got = params[k].grad
+            assert got is not None, k
+            head = got.flatten()[:512].float().cpu()
+            rel = ((head - ref["head"]).norm() / (ref["head"].norm() + 1e-12)).item()
+            nrel = abs(got.norm().item() - ref["norm"].item()) / (ref["norm"].item() + 1e-12)
+            print(f"{c['kind']} rm={c['reduce_mean']} lw={c['likelihood_weighting']} {k}: head rel {rel:.3e}, norm rel {nrel:.3e}")
+            worst = max(worst, rel)
+        gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters() if p.grad is not None)).item()
+        print(f"  total grad norm {gn:.5e} vs reference {c['grad_norm'].item():.5e}")
+        assert all(p.grad is not None for p in m.parameters())
+        assert abs(gn - c["grad_norm"].item()) <= 3e-2 * c["grad_norm"].item()
+        assert worst <= 6e-2, worst
