@@ -210,6 +210,8 @@ def run_ours(args):
             "roofline_sampler_kernels": samp and {**samp, "peak": pk["hbm_gbs"], "frac": samp["achieved"] / pk["hbm_gbs"],
                                                   "peak_source": pk_src},
         }
+        if world == 1 and not args.no_dsm:
+            line["dsm_train"] = dsm_train_bench(device, max(args.steps, 5), args.warmup, "poly")
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(workload, budget_s=20.0)
         print(json.dumps(line), flush=True)
@@ -269,6 +271,58 @@ class _GraphStepper:
 
     def step(self):
         self.graph.replay()
+
+
+def dsm_train_bench(device, steps, warmup, which="poly"):
+    """BASELINE configs[1]: PolyMNIST latent score UNet DSM training, batch 256, bf16 operands / fp32 master weights,
+    Adam lr 5e-4.  One step = loss_fn (fused perturb, net forward, fused loss) + backward (hand-written) + FusedAdam."""
+    from score_based_multimodal_autoencoder_b200 import _lib as L
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    from score_based_multimodal_autoencoder_b200.optim import FusedAdam
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    if which == "poly":
+        kw, shape, sde, lr, fwd_gf = dict(dim=64, channels=5, dim_mults=(1, 2, 2, 2)), (256, 5, 8, 8), sh.VPSDE(1.0, 5.0, 100), 5e-4, 0.1563
+    else:
+        kw, shape, sde, lr, fwd_gf = dict(dim=256, channels=3, dim_mults=(1, 2, 2, 2, 2)), (256, 3, 16, 16), sh.VPSDE(0.1, 20.0, 1000), 5e-5, 9.3496
+    torch.manual_seed(0)
+    model = Unet(**kw).to(device).train()
+    opt = FusedAdam(model.parameters(), lr=lr)
+    z_host = torch.randn(*shape, generator=torch.Generator().manual_seed(1234)).pin_memory()
+    z = z_host.to(device)
+
+    def step(batch):
+        loss = sh.loss_fn(batch, model, sde, reduce_mean=True, likelihood_weighting=False, eps=1e-5, rng="philox")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(warmup, 3)):
+        step(z)
+    torch.cuda.synchronize()
+    n0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step(z)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (L.launch_count() - n0) // steps
+    # end to end: H2D of the latent batch and D2H of the loss every step (the reference does loss.item() per step)
+    e0.record()
+    for _ in range(steps):
+        loss = step(z_host.to(device, non_blocking=True))
+        loss.item()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / steps
+    return {"metric": "dsm_train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms,
+            "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches_per_step": int(launches), "loss": float(loss.item()),
+            "model_tflops": 3 * fwd_gf * 1e9 * shape[0] / (ms * 1e-3) / 1e12,
+            "config": {"workload": f"{which}_dsm: Unet{tuple(kw.values())} DSM training, batch {shape[0]}, latent {list(shape[1:])}, "
+                                   f"Adam lr {lr}, bf16 GEMM operands / fp32 master weights, loss and statistics fp32/fp64"}}
 
 
 def conv_roofline(model, sde, x0, ops, L):
@@ -436,9 +490,14 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the global batch")
     ap.add_argument("--graph", type=int, default=1, help="replay one captured CUDA graph per PC step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dsm", action="store_true", help="skip the secondary DSM-training measurement")
+    ap.add_argument("--dsm-only", default="", help="poly|celeba: run only the DSM training measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.dsm_only:
+        torch.cuda.set_device(0)
+        print(json.dumps(dsm_train_bench(torch.device("cuda", 0), args.steps, args.warmup, args.dsm_only)), flush=True)
     else:
         run_ours(args)
 

@@ -65,6 +65,8 @@ typedef struct sbm_conv_args {
   double* stats;            /* [batch][2] += (sum, sum of squares) of the written values, or NULL */
   void* out2;               /* optional second copy of the output in bf16 (pixel stride ldo2), or NULL */
   int64_t ldo2;
+  const float* rowbias;     /* optional per-sample bias [batch][ld_rowbias] (unet_openai.py:303 `h + emb_out`), or NULL */
+  int64_t ld_rowbias;
 } sbm_conv_args;
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
@@ -114,6 +116,9 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
                         const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
                         int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
                         float eps, int32_t act, void* stream);
+/* nearest-neighbour 2x upsampling of a bf16 channels-last map (unet_openai.py:185) */
+int sbm_upsample_nearest2x(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t B, int32_t H, int32_t W,
+                           int32_t C, void* stream);
 /* sinusoidal embedding of t[B] -> bf16 [B, ld]; mode 0 = unet_model.py:40-47, mode 1 = unet_openai.py:66-83 */
 int sbm_time_embed(const float* t, void* out_bf16, float* out_f32, int32_t B, int32_t dim, int32_t ld, int32_t mode,
                    void* stream);

@@ -75,6 +75,7 @@ class ConvArgs(C.Structure):
         ("res_dtype", C.c_int32), ("out2_preact", C.c_int32),
         ("stats", C.c_void_p),
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
+        ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
     ]
 
 SDE_VP, SDE_SUBVP, SDE_VE = 0, 1, 2

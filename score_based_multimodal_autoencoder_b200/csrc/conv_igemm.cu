@@ -67,12 +67,14 @@ struct ConvKernelParams {
   double* stats;
   int32_t act, out_dtype, res_dtype, vec_ok;
   int32_t out2_preact, pad0;
+  const float* rowbias;     // optional per-sample bias [batch][ld_rowbias] added before the activation
+  int64_t ld_rowbias;
   TapTable taps[4];
 };
 
 // bias + activation + residual + (bf16 rounding) + statistics + stores for 16 consecutive output channels of one
 // output pixel (row); `v` holds the fp32 accumulators read from TMEM.
-__device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint32_t* v, int n, bool row_ok,
+__device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint32_t* v, int n, bool row_ok, int b,
                                            int64_t o_base, int64_t r_base, int64_t o2_base, float& s1, float& s2) {
   if (n >= p.cout) return;  // warp-uniform
   float f[16];
@@ -81,6 +83,7 @@ __device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint
   for (int e = 0; e < 16; ++e) {
     float x = __uint_as_float(v[e]);
     if (p.bias != nullptr && (full || n + e < p.cout)) x += __ldg(p.bias + n + e);
+    if (p.rowbias != nullptr && row_ok && (full || n + e < p.cout)) x += __ldg(p.rowbias + (int64_t)b * p.ld_rowbias + n + e);
     if (p.out2_preact && row_ok && (full || n + e < p.cout))
       reinterpret_cast<__nv_bfloat16*>(p.out2)[o2_base + n + e] = __float2bfloat16_rn(x);
     if (p.act == SBM_ACT_GELU) x = gelu_exact(x);
@@ -286,7 +289,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t v[16];
       ptx::tmem_ld16(tmem_base + (uint32_t(ew * 32) << 16) + c0, v);
       ptx::tmem_ld_wait();
-      epilogue16(p, v, n0 + c0, row_ok, o_base, r_base, o2_base, s1, s2);
+      epilogue16(p, v, n0 + c0, row_ok, b, o_base, r_base, o2_base, s1, s2);
     }
 
     if (p.stats != nullptr) {
@@ -477,8 +480,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         ptx::tmem_ld16(tacc + c0, v0);
         ptx::tmem_ld16(tacc + c0 + 16, v1);
         ptx::tmem_ld_wait();
-        epilogue16(p, v0, nt * BN + c0, row_ok, o_base, r_base, o2_base, s1, s2);
-        epilogue16(p, v1, nt * BN + c0 + 16, row_ok, o_base, r_base, o2_base, s1, s2);
+        epilogue16(p, v0, nt * BN + c0, row_ok, b, o_base, r_base, o2_base, s1, s2);
+        epilogue16(p, v1, nt * BN + c0 + 16, row_ok, b, o_base, r_base, o2_base, s1, s2);
       }
       // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
       ptx::tc_fence_before_sync();
@@ -665,6 +668,7 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   p.bias = a->bias; p.residual = a->residual; p.out = a->out; p.out2 = a->out2; p.stats = a->stats;
   p.act = a->act; p.out_dtype = a->out_dtype; p.res_dtype = a->res_dtype;
   p.out2_preact = (a->out2 != nullptr && a->out2_preact) ? 1 : 0;
+  p.rowbias = a->rowbias; p.ld_rowbias = a->ld_rowbias;
 
   // output addressing
   const int64_t OHf = (a->kind == SBM_CONVT_4X4_S2) ? 2 * oh : oh;

@@ -508,6 +508,22 @@ softmax_attn_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* _
   }
 }
 
+// nearest 2x upsampling, bf16 channels-last, 8 channels (16 bytes) per thread
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
+                                  int64_t ldo, int B, int H, int W, int C8) {
+  const int64_t total = (int64_t)B * (2 * H) * (2 * W) * C8;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % C8);
+    const int64_t pix = idx / C8;
+    const int ow = (int)(pix % (2 * W));
+    const int oh = (int)((pix / (2 * W)) % (2 * H));
+    const int b = (int)(pix / ((int64_t)4 * W * H));
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + (oh >> 1)) * W + (ow >> 1)) * ldx + q * 8);
+    *reinterpret_cast<uint4*>(out + pix * ldo + q * 8) = v;
+  }
+}
+
 static int grid_for(int64_t total, int threads) {
   const int64_t want = (total + threads - 1) / threads;
   const int64_t cap = (int64_t)sm_count() * 16;
@@ -613,6 +629,17 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
   else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else SBM_GN_LAUNCH(__nv_bfloat16, float);
 #undef SBM_GN_LAUNCH
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int sbm_upsample_nearest2x(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t B, int32_t H, int32_t W,
+                           int32_t C, void* stream) {
+  SBM_CHECK_ARG(x && out && B > 0 && C > 0 && ldx % 8 == 0 && ldo % 8 == 0, "sbm_upsample_nearest2x: bad args");
+  const int C8 = (C + 7) / 8;
+  upsample2x_kernel<<<grid_for((int64_t)B * 4 * H * W * C8, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)out, ldo, B, H, W, C8);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

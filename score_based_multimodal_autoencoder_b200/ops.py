@@ -55,7 +55,7 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
                bias: torch.Tensor | None = None, act: int = L.ACT_NONE, residual: torch.Tensor | None = None,
                out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.float32, nchw: bool = False,
                stats: torch.Tensor | None = None, out2: torch.Tensor | None = None,
-               out2_preact: bool = False) -> torch.Tensor:
+               out2_preact: bool = False, rowbias: torch.Tensor | None = None) -> torch.Tensor:
     """x: bf16 [B,H,W,ldx]; returns [B,OH,OW,pad8(cout)] (or fp32 NCHW [B,cout,OH,OW] when nchw)."""
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.stride(3) == 1
     b, h, w, _ = x.shape
@@ -91,6 +91,8 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
     if out2 is not None:
         a.out2, a.ldo2 = out2.data_ptr(), out2.stride(2)
         a.out2_preact = 1 if out2_preact else 0
+    if rowbias is not None:
+        a.rowbias, a.ld_rowbias = rowbias.data_ptr(), rowbias.stride(-2)
     L.check(L.lib().sbm_conv_igemm(C.byref(a), L.stream_ptr()), "sbm_conv_igemm")
     return out
 
@@ -313,3 +315,12 @@ def add(a, b, c, out=None, want_bf16=False):
                             C.c_int64(ob.stride(2) if ob is not None else 0), C.c_int64(_rows(a)), C.c_int32(c),
                             L.stream_ptr()), "sbm_add")
     return out, ob
+
+
+def upsample_nearest2x(x: torch.Tensor, c: int) -> torch.Tensor:
+    b, h, w, ld = x.shape
+    out = torch.empty((b, 2 * h, 2 * w, ld), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().sbm_upsample_nearest2x(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(out), C.c_int64(out.stride(2)),
+                                           C.c_int32(b), C.c_int32(h), C.c_int32(w), C.c_int32(c), L.stream_ptr()),
+            "sbm_upsample_nearest2x")
+    return out

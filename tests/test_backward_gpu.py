@@ -228,3 +228,22 @@ def test_dsm_training_step_gradients_vs_reference_golden():
         assert all(p.grad is not None for p in m.parameters())
         assert abs(gn - c["grad_norm"].item()) <= 3e-2 * c["grad_norm"].item()
         assert worst <= 6e-2, worst
+
+
+def test_fused_adam_matches_torch_adam():
+    from score_based_multimodal_autoencoder_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(300, 17), (5,), (70000,), (64, 3, 3, 3)]
+    p_ref = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    p_new = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    o_ref = torch.optim.Adam(p_ref, lr=5e-4)
+    o_new = FusedAdam(p_new, lr=5e-4)
+    for it in range(5):
+        for a, b in zip(p_ref, p_new):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        o_ref.step()
+        o_new.step()
+    for a, b in zip(p_ref, p_new):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
