@@ -72,6 +72,8 @@ typedef struct sbm_conv_args {
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 /* A/B switch for measurements: 1 = always use the single-CTA kernel instead of the CTA-pair (cta_group::2) one */
 int sbm_conv_force_single_cta(int32_t on);
+/* A/B switch: 1 = per-thread global stores in the CTA-pair kernel instead of the TMA-staged epilogue */
+int sbm_conv_force_direct_epilogue(int32_t on);
 
 /* Weight gradient of sbm_conv_igemm: dwpk[tap][o][i] += sum_pixels dy[p][o] * x[p shifted by tap][i]  (fp32, split-K
  * atomics: the caller zeroes dwpk).  x = the forward input operand (bf16), dy = gradient of the forward output (bf16,

@@ -36,6 +36,7 @@ namespace sbm {
 
 std::atomic<unsigned long long> g_launches{0};
 static bool g_force_single = false;  // debugging / A-B timing switch (sbm_conv_force_single_cta)
+static bool g_force_direct = false;  // A-B switch: per-thread global stores instead of the TMA-staged epilogue
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
@@ -45,6 +46,7 @@ struct TapTable {
   int32_t ntaps;
   int32_t out_off;          // element offset of this phase inside the output tensor
   int32_t out2_off;         // same for the optional bf16 copy
+  int32_t out_q;            // coordinate of this phase in the parity dimension of the output tensor maps
   int8_t dh[kMaxTaps];      // added to the tile's hv origin
   int8_t dw[kMaxTaps];      // wv coordinate of the box start
   int16_t q[kMaxTaps];      // coordinate in the parity dimension
@@ -167,6 +169,94 @@ __device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint
       }
     }
   }
+}
+
+// ---- staged epilogue (CTA-pair kernel): the thread's 16 output values go to a swizzled shared-memory row so that
+// global memory only ever sees TMA box transfers (full 32-byte sectors, no per-thread strided stores).
+//   fp32 rows: 64 B, CU_TENSOR_MAP_SWIZZLE_64B : 16-byte chunk k of row r lives at chunk k ^ ((r >> 1) & 3)
+//   bf16 rows: 32 B, CU_TENSOR_MAP_SWIZZLE_32B : 16-byte chunk k of row r lives at chunk k ^ ((r >> 2) & 1)
+// (buffers are 1024-byte aligned, so the swizzle's address bits are the row bits above).
+__device__ __forceinline__ float4* stg_f32(uint8_t* buf, int r, int k) {
+  return reinterpret_cast<float4*>(buf + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ uint4* stg_bf16(uint8_t* buf, int r, int k) {
+  return reinterpret_cast<uint4*>(buf + r * 32 + ((k ^ ((r >> 2) & 1)) << 4));
+}
+__device__ __forceinline__ void stg_store_bf16_row(uint8_t* buf, int r, const float* f) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    uint32_t w[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(f[8 * k + 2 * e], f[8 * k + 2 * e + 1]);
+      w[e] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *stg_bf16(buf, r, k) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// `stage` holds the residual chunk on entry (when has_res) and the output chunk on exit; `stage2` receives the bf16 copy.
+__device__ __forceinline__ void epilogue_chunk_staged(const ConvKernelParams& p, const uint32_t* v, int n, bool row_ok,
+                                                      int b, int lane, uint8_t* stage, uint8_t* stage2, bool has_res,
+                                                      float& s1, float& s2) {
+  float f[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+  const int cmax = p.cout - 1;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] += __ldg(p.bias + min(n + e, cmax));
+  }
+  if (p.rowbias != nullptr && row_ok) {
+    const float* rb = p.rowbias + (int64_t)b * p.ld_rowbias;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] += __ldg(rb + min(n + e, cmax));
+  }
+  if (p.out2_preact) stg_store_bf16_row(stage2, lane, f);
+  if (p.act == SBM_ACT_GELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = gelu_exact(f[e]);
+  } else if (p.act == SBM_ACT_SILU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = silu(f[e]);
+  }
+  if (has_res) {
+    if (p.res_dtype == SBM_F32) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = *stg_f32(stage, lane, k);
+        f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const uint4 t = *stg_bf16(stage, lane, k);
+        const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[e]);
+          f[8 * k + 2 * e] += __low2float(h);
+          f[8 * k + 2 * e + 1] += __high2float(h);
+        }
+      }
+    }
+    __syncwarp();  // every lane has read its residual row before any lane overwrites the buffer
+  }
+  if (p.out_dtype == SBM_BF16) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
+  }
+  if (p.stats != nullptr && row_ok) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (n + e <= cmax) { s1 += f[e]; s2 += f[e] * f[e]; }
+  }
+  if (p.out_dtype == SBM_F32) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *stg_f32(stage, lane, k) = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+  } else {
+    stg_store_bf16_row(stage, lane, f);
+  }
+  if (p.out2 != nullptr && !p.out2_preact) stg_store_bf16_row(stage2, lane, f);
 }
 
 template <int BN, int STAGES>
@@ -323,31 +413,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 //   warp 0: TMA producer (both CTAs)      warp 1: MMA issuer (leader CTA only)
 //   warp 2: TMEM allocator                warps 4..11: epilogue (lane quarter = warp%4, column half = (warp-4)/4)
 // =====================================================================================================
-template <int BN, int STAGES>
+// Epilogue staging (kStaged): every epilogue warp owns 3 x 2 KB buffers (residual chunk in / output chunk out,
+// 32 rows x 16 fp32 columns, 64-byte swizzle) and 2 x 1 KB buffers (bf16 copy, 32-byte swizzle).
+constexpr int kEC = 16;                 // output columns per epilogue chunk (= one tcgen05.ld.32x32b.x16)
+constexpr int kStgMain = 2048;
+constexpr int kStgOut2 = 1024;
+constexpr int kStgPerWarp = 3 * kStgMain + 2 * kStgOut2;  // 8 KB
+constexpr int kEpiWarps = 8;
+
+template <int BN, int STAGES, bool kStaged>
 struct Smem2Layout {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = (BN / 2) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static constexpr int kStagingOffset = STAGES * kStageBytes;
+  static constexpr int kBarOffset = kStagingOffset + (kStaged ? kEpiWarps * kStgPerWarp : 0);
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4 + 3 * kEpiWarps) * 8 + 16 + 1024;
 };
 
 struct PairSchedule {
   int32_t m_tiles, m_pairs, n_tiles, nphase, total;
 };
 
-template <int BN, int STAGES>
+struct EpiMaps {
+  CUtensorMap out, res, out2;  // 32-row x kEC-column boxes of the output / residual / bf16-copy tensors
+};
+
+template <int BN, int STAGES, bool kStaged>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                       const __grid_constant__ ConvKernelParams p, const PairSchedule sch) {
-  using L = Smem2Layout<BN, STAGES>;
+                       const __grid_constant__ EpiMaps em, const __grid_constant__ ConvKernelParams p,
+                       const PairSchedule sch) {
+  using L = Smem2Layout<BN, STAGES, kStaged>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;         // [kEpiWarps][3] residual-chunk arrival (staged epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 3 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -370,7 +475,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ptx::mbar_init(&tfull_bar[a], 1);
       ptx::mbar_init(&tempty_bar[a], 16);  // 8 epilogue warps x 2 CTAs arrive on the leader's barrier
     }
+    for (int a = 0; a < 3 * kEpiWarps; ++a) ptx::mbar_init(&res_bar[a], 1);
     ptx::fence_mbar_init();
+  }
+  if (kStaged && warp == 3 && lane == 0) {
+    ptx::prefetch_tmap(&em.out);
+    if (p.residual != nullptr) ptx::prefetch_tmap(&em.res);
+    if (p.out2 != nullptr) ptx::prefetch_tmap(&em.out2);
   }
   if (warp == 2) ptx::tmem_alloc2<2 * BN>(tmem_slot);
   ptx::tc_fence_before_sync();
@@ -458,6 +569,15 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int i = (r >> p.log_ow) & ((1 << p.log_th) - 1);
     const int bl = r >> (p.log_ow + p.log_th);
     const uint32_t lead_tempty0 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0);
+    // staged path: this warp's 32 rows are one TMA box (columns, ow-run, 1, rows, images) starting at
+    const int sub_j = (ew * 32) & ((1 << p.log_ow) - 1);
+    const int sub_i = ((ew * 32) >> p.log_ow) & ((1 << p.log_th) - 1);
+    const int sub_b = (ew * 32) >> (p.log_ow + p.log_th);
+    uint8_t* wst = smem + L::kStagingOffset + e * kStgPerWarp;
+    uint64_t* rbar = res_bar + 3 * e;
+    const bool has_res = p.residual != nullptr;
+    const uint32_t res_bytes = 32u * kEC * (p.res_dtype == SBM_F32 ? 4u : 2u);
+    uint32_t nchunk = 0;  // chunks this warp has staged so far (buffer rotation + barrier parity)
     int astage = 0;
     uint32_t aphase = 0;
     for (int t = pair; t < sch.total; t += npairs) {
@@ -467,21 +587,64 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int b = b0 + bl;
       const int oh = oh0 + i;
       const bool row_ok = b < p.batch;
-      const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw + tt.out_off;
-      const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
-      const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw + tt.out2_off;
       float s1 = 0.f, s2 = 0.f;
-      ptx::mbar_wait(&tfull_bar[astage], aphase);
-      ptx::tc_fence_after_sync();
-      const uint32_t tacc = tmem_base + (uint32_t)(astage * BN) + (uint32_t(ew * 32) << 16);
+      if constexpr (kStaged) {
+        const int cj = sub_j, ci = oh0 + sub_i, cb = b0 + sub_b, cq = tt.out_q;
+        const int ncol0 = nt * BN + hc * (BN / 2);
+        const int nch = min((BN / 2) / kEC, max(0, (p.cout - ncol0 + kEC - 1) / kEC));
+        if (has_res && nch > 0 && lane == 0) {
+          ptx::bulk_wait_group_read<1>();
+          uint64_t* rb = &rbar[nchunk % 3];
+          ptx::mbar_expect_tx(rb, res_bytes);
+          ptx::tma_load_5d(wst + (nchunk % 3) * kStgMain, &em.res, rb, ncol0, cj, 0, ci, cb);
+        }
+        ptx::mbar_wait(&tfull_bar[astage], aphase);
+        ptx::tc_fence_after_sync();
+        const uint32_t tacc = tmem_base + (uint32_t)(astage * BN) + (uint32_t(ew * 32) << 16) + (uint32_t)(hc * (BN / 2));
 #pragma unroll 1
-      for (int c0 = hc * (BN / 2); c0 < (hc + 1) * (BN / 2); c0 += 32) {
-        uint32_t v0[16], v1[16];
-        ptx::tmem_ld16(tacc + c0, v0);
-        ptx::tmem_ld16(tacc + c0 + 16, v1);
-        ptx::tmem_ld_wait();
-        epilogue16(p, v0, nt * BN + c0, row_ok, b, o_base, r_base, o2_base, s1, s2);
-        epilogue16(p, v1, nt * BN + c0 + 16, row_ok, b, o_base, r_base, o2_base, s1, s2);
+        for (int c = 0; c < nch; ++c) {
+          const int col0 = ncol0 + c * kEC;
+          uint32_t v[16];
+          __syncwarp();
+          ptx::tmem_ld16(tacc + c * kEC, v);
+          // buffers of chunk nchunk+1 (main) / nchunk (bf16 copy) were last used by the stores of chunk nchunk-2
+          if (lane == 0) {
+            ptx::bulk_wait_group_read<1>();
+            if (has_res && c + 1 < nch) {
+              uint64_t* rb = &rbar[(nchunk + 1) % 3];
+              ptx::mbar_expect_tx(rb, res_bytes);
+              ptx::tma_load_5d(wst + ((nchunk + 1) % 3) * kStgMain, &em.res, rb, col0 + kEC, cj, 0, ci, cb);
+            }
+          }
+          __syncwarp();
+          uint8_t* stage = wst + (nchunk % 3) * kStgMain;
+          uint8_t* stage2 = wst + 3 * kStgMain + (nchunk & 1) * kStgOut2;
+          if (has_res) ptx::mbar_wait(&rbar[nchunk % 3], (nchunk / 3) & 1);
+          ptx::tmem_ld_wait();
+          epilogue_chunk_staged(p, v, col0, row_ok, b, lane, stage, stage2, has_res, s1, s2);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_5d(&em.out, stage, col0, cj, cq, ci, cb);
+            if (p.out2 != nullptr) ptx::tma_store_5d(&em.out2, stage2, col0, cj, cq, ci, cb);
+            ptx::bulk_commit_group();
+          }
+          ++nchunk;
+        }
+      } else {
+        const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw + tt.out_off;
+        const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
+        const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw + tt.out2_off;
+        ptx::mbar_wait(&tfull_bar[astage], aphase);
+        ptx::tc_fence_after_sync();
+        const uint32_t tacc = tmem_base + (uint32_t)(astage * BN) + (uint32_t(ew * 32) << 16);
+#pragma unroll 1
+        for (int c0 = hc * (BN / 2); c0 < (hc + 1) * (BN / 2); c0 += 16) {
+          uint32_t v0[16];
+          ptx::tmem_ld16(tacc + c0, v0);
+          ptx::tmem_ld_wait();
+          epilogue16(p, v0, nt * BN + c0, row_ok, b, o_base, r_base, o2_base, s1, s2);
+        }
       }
       // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
       ptx::tc_fence_before_sync();
@@ -502,6 +665,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       astage ^= 1;
       if (astage == 0) aphase ^= 1;
     }
+    // shared memory must stay valid until every bulk store has read it
+    if (kStaged && lane == 0) ptx::bulk_wait_group<0>();
   }
 
   ptx::tc_fence_before_sync();
@@ -544,14 +709,15 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return 0;
 }
 
-template <int BN, int STAGES>
-static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p, int m_tiles,
-                            int n_tiles, int nphase, cudaStream_t stream) {
-  using L = Smem2Layout<BN, STAGES>;
+template <int BN, int STAGES, bool kStaged>
+static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em,
+                            const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream) {
+  using L = Smem2Layout<BN, STAGES, kStaged>;
+  static_assert(L::kTotal <= 232448, "shared-memory budget of one CTA exceeded");
   static bool configured = false;
   if (!configured) {
-    SBM_CUDA_OK(cudaFuncSetAttribute(conv_igemm_pair_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     L::kTotal));
+    SBM_CUDA_OK(cudaFuncSetAttribute(conv_igemm_pair_kernel<BN, STAGES, kStaged>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   PairSchedule sch;
@@ -561,10 +727,33 @@ static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   sch.nphase = nphase;
   sch.total = nphase * sch.m_pairs * n_tiles;
   const int pairs = std::min(sch.total, sm_count() / 2);
-  conv_igemm_pair_kernel<BN, STAGES><<<dim3(2 * pairs), 384, L::kTotal, stream>>>(tmA, tmB, p, sch);
+  conv_igemm_pair_kernel<BN, STAGES, kStaged><<<dim3(2 * pairs), 384, L::kTotal, stream>>>(tmA, tmB, em, p, sch);
   SBM_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
+}
+
+// Tensor map over an output-geometry tensor (output / residual / bf16 copy) whose box is the 32 rows x kEC columns one
+// epilogue warp produces per chunk: dims (c, j, q, i, b); q addresses the output-parity phase of a transposed conv.
+static bool encode_rowbox_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap* tm, const void* base, int dtype,
+                              int64_t ld, int cout, int ow, int oh, int batch, int sp, int log_ow, int log_th) {
+  const cuuint64_t esz = (dtype == SBM_F32) ? 4 : 2;
+  const cuuint64_t OWf = (cuuint64_t)sp * ow, OHf = (cuuint64_t)sp * oh;
+  const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)ow, sp == 2 ? OWf + 2 : 1, (cuuint64_t)oh,
+                              (cuuint64_t)batch};
+  const cuuint64_t strides[4] = {(cuuint64_t)sp * ld * esz, (cuuint64_t)ld * esz, (cuuint64_t)sp * OWf * ld * esz,
+                                 OHf * OWf * ld * esz};
+  const int th = 1 << log_th;
+  const int bw = std::min(ow, 32);
+  const int bh = std::min(th, 32 / bw);
+  const int bb = 32 / (bw * bh);
+  const cuuint32_t box[5] = {(cuuint32_t)kEC, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)bb};
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  const CUresult cr = encode(tm, dtype == SBM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                             5, const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             dtype == SBM_F32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return cr == CUDA_SUCCESS;
 }
 
 static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
@@ -738,8 +927,31 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_igemm: weight tensor map encode failed (CUresult %d)", (int)cr);
 
   if (use_pair) {
-    if (BN == 256) return launch_conv_pair<256, 6>(tmA, tmB, p, m_tiles, a->cout / BN, nphase, stream);
-    return launch_conv_pair<128, 8>(tmA, tmB, p, m_tiles, a->cout / BN, nphase, stream);
+    // staged epilogue: TMA box stores / residual loads; needs 16-byte aligned rows (vec) and at least one full warp box
+    EpiMaps em;
+    bool staged = !g_force_direct && vec && M >= 32;
+    if (staged) {
+      const int sp_i = (int)sp;
+      staged = encode_rowbox_map(encode, &em.out, a->out, a->out_dtype, a->ldo, a->cout, ow, oh, a->batch, sp_i, log_ow,
+                                 log_th);
+      if (staged && a->residual)
+        staged = encode_rowbox_map(encode, &em.res, a->residual, a->res_dtype, a->ldr, a->cout, ow, oh, a->batch, sp_i,
+                                   log_ow, log_th);
+      if (staged && a->out2)
+        staged = encode_rowbox_map(encode, &em.out2, a->out2, SBM_BF16, a->ldo2, a->cout, ow, oh, a->batch, sp_i,
+                                   log_ow, log_th);
+    }
+    if (staged) {
+      if (!a->residual) em.res = em.out;
+      if (!a->out2) em.out2 = em.out;
+      for (int ph = 0; ph < nphase; ++ph)
+        p.taps[ph].out_q = (a->kind == SBM_CONVT_4X4_S2) ? (int32_t)((ph >> 1) * OWf + (ph & 1)) : 0;
+      if (BN == 256) return launch_conv_pair<256, 5, true>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
+      return launch_conv_pair<128, 6, true>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
+    }
+    memset(&em, 0, sizeof(em));
+    if (BN == 256) return launch_conv_pair<256, 6, false>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
+    return launch_conv_pair<128, 8, false>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
   }
   dim3 grid((unsigned)m_tiles, (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
   switch (BN) {
@@ -785,6 +997,11 @@ unsigned long long sbm_launch_count(void) { return sbm::g_launches.load(); }
 
 int sbm_conv_force_single_cta(int32_t on) {
   sbm::g_force_single = on != 0;
+  return 0;
+}
+
+int sbm_conv_force_direct_epilogue(int32_t on) {
+  sbm::g_force_direct = on != 0;
   return 0;
 }
 

@@ -190,3 +190,105 @@ def test_conv_small_stats_segments():
         assert torch.allclose(stats, ref_s, rtol=1e-6, atol=1e-5), f"hw={hw}"
         ref = F.conv2d(x.double(), w.double(), padding=1).permute(0, 2, 3, 1)
         assert (o - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("variant", ["f32_res_out2", "bf16_gelu_preact", "bf16_out_f32_res", "bf16_res", "cat_views",
+                                     "rowbias_silu"])
+def test_conv_pair_staged_epilogue(variant):
+    """TMA-staged epilogue of the CTA-pair kernel (swizzled shared-memory rows -> box stores, residual box loads)
+    against float64 torch, and bit-for-bit against the per-thread-store epilogue (A/B switch)."""
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(variant.encode()))
+    B, H, W, cin, cout = 150, 8, 8, 64, 256
+    x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(cout, generator=g).to(dev)
+    xb = _nhwc_bf16(x, cin)
+    wpk = ops.pack_conv2d_weight(w)
+    pre = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    res32 = torch.randn(B, H, W, cout, generator=g).to(dev)
+    rb = torch.randn(B, cout, generator=g).to(dev)
+    results = []
+    for direct in (1, 0):
+        L.lib().sbm_conv_force_direct_epilogue(direct)
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        kw = dict(kind=L.CONV_S1, kh=3, kw=3, cin=cin, cout=cout, bias=bias, stats=stats)
+        if variant == "f32_res_out2":
+            out2 = torch.zeros(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+            out = ops.conv_igemm(xb, wpk, residual=res32, out2=out2, **kw)
+            ref, ref2, tol = pre + res32.double(), pre + res32.double(), 3e-5
+        elif variant == "bf16_gelu_preact":
+            out2 = torch.zeros(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+            out = ops.conv_igemm(xb, wpk, act=L.ACT_GELU, out_dtype=torch.bfloat16, out2=out2, out2_preact=True, **kw)
+            ref, ref2, tol = _gelu64(pre), pre, 5e-3
+        elif variant == "bf16_out_f32_res":
+            out2 = None
+            out = ops.conv_igemm(xb, wpk, residual=res32, out_dtype=torch.bfloat16, **kw)
+            ref, ref2, tol = pre + res32.double(), None, 5e-3
+        elif variant == "bf16_res":
+            out2 = None
+            resb = res32.to(torch.bfloat16)
+            out = ops.conv_igemm(xb, wpk, residual=resb, **kw)
+            ref, ref2, tol = pre + resb.double(), None, 3e-5
+        elif variant == "cat_views":
+            cat_f = torch.full((B, H, W, 2 * cout), 3.0, dtype=torch.float32, device=dev)
+            cat_b = torch.full((B, H, W, 2 * cout), 3.0, dtype=torch.bfloat16, device=dev)
+            out = ops.conv_igemm(xb, wpk, residual=res32, out=cat_f[..., cout:], out2=cat_b[..., cout:], **kw)
+            out2 = cat_b[..., cout:]
+            ref, ref2, tol = pre + res32.double(), pre + res32.double(), 3e-5
+            torch.cuda.synchronize()
+            assert (cat_f[..., :cout] == 3.0).all() and (cat_b[..., :cout] == 3.0).all()  # neighbours untouched
+        else:
+            out2 = None
+            out = ops.conv_igemm(xb, wpk, act=L.ACT_SILU, rowbias=rb, **kw)
+            pr = pre + rb.double()[:, None, None, :]
+            ref, ref2, tol = pr * torch.sigmoid(pr), None, 3e-5
+        torch.cuda.synchronize()
+        assert (out.double() - ref).abs().max().item() <= tol * ref.abs().max().item(), (variant, direct)
+        if ref2 is not None:
+            assert (out2.double() - ref2).abs().max().item() <= 5e-3 * ref2.abs().max().item(), (variant, direct)
+        o = out.double()
+        ref_s = torch.stack([o.sum(dim=(1, 2, 3)), (o * o).sum(dim=(1, 2, 3))], dim=1)
+        assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3), (variant, direct)
+        results.append((out.clone(), None if out2 is None else out2.clone()))
+    L.lib().sbm_conv_force_direct_epilogue(0)
+    assert torch.equal(results[0][0], results[1][0])
+    if results[0][1] is not None:
+        assert torch.equal(results[0][1], results[1][1])
+
+
+def test_conv_pair_staged_transposed_and_small_maps():
+    """Staged epilogue box geometry: 4 output-parity phases of the transposed conv (q coordinate), 2x2 maps
+    (8 images per warp box), 32-wide maps, ragged batch; out2 written into a channel-offset view."""
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(77)
+    # transposed conv, output into the first half of a concat buffer
+    B, H, W, c = 330, 4, 4, 256
+    x = torch.randn(B, 64, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(64, c, 4, 4, generator=g) / 16.0).to(dev).to(torch.bfloat16).float()
+    bias = torch.randn(c, generator=g).to(dev)
+    cat_f = torch.full((B, 2 * H, 2 * W, 2 * c), 3.0, dtype=torch.float32, device=dev)
+    cat_b = torch.full((B, 2 * H, 2 * W, 2 * c), 3.0, dtype=torch.bfloat16, device=dev)
+    ops.conv_igemm(_nhwc_bf16(x, 64), ops.pack_convT2d_weight(w), kind=L.CONVT_4X4_S2, kh=4, kw=4, cin=64, cout=c,
+                   bias=bias, out=cat_f[..., :c], out2=cat_b[..., :c])
+    ref = F.conv_transpose2d(x.double(), w.double(), bias.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert (cat_f[..., :c].double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    assert (cat_b[..., :c].double() - ref).abs().max().item() <= 5e-3 * ref.abs().max().item()
+    assert (cat_f[..., c:] == 3.0).all() and (cat_b[..., c:] == 3.0).all()
+    for (B, H, W, cin, cout) in [(9001, 2, 2, 64, 128), (41, 32, 32, 64, 256), (19999, 1, 1, 96, 256),
+                                 (300, 16, 16, 64, 128)]:
+        x = torch.randn(B, cin, H, W, generator=g).to(dev).to(torch.bfloat16).float()
+        k = 3 if H > 1 else 1
+        w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev).to(torch.bfloat16).float()
+        res = torch.randn(B, H, W, cout, generator=g).to(dev)
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        out = ops.conv_igemm(_nhwc_bf16(x, cin), ops.pack_conv2d_weight(w), kind=L.CONV_S1, kh=k, kw=k, cin=cin,
+                             cout=cout, residual=res, stats=stats)
+        ref = F.conv2d(x.double(), w.double(), padding=k // 2).permute(0, 2, 3, 1) + res.double()
+        torch.cuda.synchronize()
+        assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item(), (B, H, W)
+        ref_s = torch.stack([ref.sum(dim=(1, 2, 3)), (ref * ref).sum(dim=(1, 2, 3))], dim=1)
+        assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3), (B, H, W)

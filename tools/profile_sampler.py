@@ -1,0 +1,42 @@
+"""The fused sampler-step kernels (predictor, corrector norms, corrector update) and the DSM perturb / loss kernels
+on the large-batch sweep point, bracketed by cudaProfilerStart/Stop for `ncu --profile-from-start off`.
+Usage: python tools/profile_sampler.py [batch]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh  # noqa: E402
+
+batch = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+dev = torch.device("cuda")
+sde = sh.VPSDE(1.0, 5.0, 100)
+x = torch.randn(batch, 5, 8, 8, device=dev)
+s = torch.randn_like(x)
+t = torch.full((batch,), 0.5, device=dev)
+rng = sh._RngState()
+acc = torch.zeros(2, dtype=torch.float64, device=dev)
+out = torch.empty_like(x)
+
+
+def pc_kernels():
+    x1, _ = sh._predictor_kernel(sde, x, s, t, rng=rng.next(), want_mean=False, out=out)
+    sh._corrector_kernels(sde, x1, s, t, 0.16, rng=rng.next(), want_mean=False, acc=acc, out=out)
+
+
+def dsm():
+    return sh.loss_fn(x, lambda a, b: s, sde, likelihood_weighting=False)
+
+
+with torch.no_grad():
+    for _ in range(3):
+        pc_kernels()
+        dsm()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    pc_kernels()
+    dsm()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+print("done")
