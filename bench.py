@@ -236,7 +236,7 @@ class _GraphStepper:
         self.t_next = torch.zeros(1, dtype=torch.float32, device=dev)
         self.t_vec = torch.empty(B, dtype=torch.float32, device=dev)
         self.x = x.clone()
-        self.acc = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.acc = torch.zeros(3, dtype=torch.float64, device=dev)
         self.model, self.sde, self.z_obs, self.mask = model, sde, z_obs, mask
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -377,7 +377,7 @@ def sampler_kernel_roofline(sh, sde, device, batch=65536):
     s = torch.randn_like(x)
     t = torch.full((batch,), 0.5, device=device)
     rng = sh._RngState()
-    acc = torch.zeros(2, dtype=torch.float64, device=device)
+    acc = torch.zeros(3, dtype=torch.float64, device=device)
     out = torch.empty_like(x)
 
     def pc_kernels():
@@ -398,7 +398,7 @@ def sampler_kernel_roofline(sh, sde, device, batch=65536):
     nbytes = 28.0 * x.numel()
     return {"bound": "hbm", "kernel": "predictor + corrector_norms + corrector_update", "achieved": nbytes / (ms * 1e-3) / 1e9,
             "unit": "GB/s", "us_per_pc_step": ms * 1e3, "batch": batch, "algorithmic_bytes_per_step": nbytes,
-            "note": "includes one 16-byte accumulator zero-fill launch per step"}
+            "note": "3 launches per PC step; the update kernel re-zeroes the norm accumulator itself"}
 
 
 # --------------------------------------------------------------------------------------- CPU arms

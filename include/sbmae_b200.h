@@ -160,16 +160,18 @@ int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem
 int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                        const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
                        const sbm_rng* rng, const sbm_impute* impute, void* stream);
-/* corrector, sde_helper2.py:96-98: acc2[0] += sum_b ||grad_b||, acc2[1] += sum_b ||noise_b|| (caller zeroes acc2;
- * multi-GPU exact mode all-reduces the two doubles between the two calls) */
+/* corrector, sde_helper2.py:96-98: acc2[0] += sum_b ||grad_b||, acc2[1] += sum_b ||noise_b||.  acc2 is a buffer of
+ * THREE doubles, zero before the first call (the third is a completion ticket used by reset_acc below); multi-GPU
+ * exact mode all-reduces acc2[0..1] between the two calls */
 int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
                         double* acc2, void* stream);
 /* corrector, sde_helper2.py:56-60,99-101: step = (snr * mean||noise|| / mean||grad||)^2 * 2 * alpha[t];
  * x_mean = x + step*grad; x' = x_mean + sqrt(2 step) * noise.  alphas = device copy of sde.alphas (NULL: alpha = 1) */
 int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* grad,
-                         const float* t, const float* noise, const double* acc2, const float* alphas, float* x_out,
+                         const float* t, const float* noise, double* acc2, const float* alphas, float* x_out,
                          float* x_mean_out, float target_snr, int64_t global_batch, const sbm_rng* rng,
-                         const sbm_impute* impute, void* stream);
+                         const sbm_impute* impute, int32_t reset_acc /* 1: zero acc2 once every block has read it */,
+                         void* stream);
 int sbm_impute_observed(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, float* x_out,
                         const sbm_impute* impute, void* stream);
 /* loss_fn, sde_helper2.py:167-170: t = u*(T-eps)+eps; xt = mean(x0,t) + std(t)*z.  u,z injected or drawn (rng) */

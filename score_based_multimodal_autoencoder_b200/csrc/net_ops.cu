@@ -17,26 +17,45 @@ static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_re
 
 // ------------------------------------------------------------------------------ stem im2col
 // x: fp32 NCHW [B,C,H,W]  ->  a: bf16 [B*H*W, ldk], column k = (c*KH + kh)*KW + kw (matches weight.view(O,-1))
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int C, int H,
-                                   int W, int KH, int KW, int ldk) {
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int C, int H, int W, int KH, int KW,
+                   int ldk) {
+  // one thread = 8 consecutive im2col columns (one 16-byte store) of one pixel; the 49*C taps of a pixel come from a
+  // (KH x KW x C) window that stays L1/L2 resident across the threads of the pixel.
   const int K = C * KH * KW;
-  const int64_t total = (int64_t)B * H * W * ldk;
+  const int groups = ldk >> 3;
+  const int HWp = H * W;
+  const int64_t total = (int64_t)B * HWp * groups;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % ldk);
-    const int64_t pix = idx / ldk;
-    float v = 0.f;
-    if (k < K) {
-      const int kw = k % KW;
-      const int kh = (k / KW) % KH;
-      const int c = k / (KW * KH);
-      const int w = (int)(pix % W);
-      const int h = (int)((pix / W) % H);
-      const int b = (int)(pix / ((int64_t)W * H));
-      const int ih = h + kh - KH / 2, iw = w + kw - KW / 2;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + (((int64_t)b * C + c) * H + ih) * W + iw);
+    const int gq = (int)(idx % groups);
+    const int64_t pix = idx / groups;
+    const int pin = (int)(pix % HWp);
+    const int b = (int)(pix / HWp);
+    const int h = pin / W, w = pin - h * W;
+    const float* xb = x + (int64_t)b * C * HWp;
+    uint32_t packed[4];
+#pragma unroll
+    for (int e2 = 0; e2 < 4; ++e2) {
+      float v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = gq * 8 + e2 * 2 + u;
+        float val = 0.f;
+        if (k < K) {
+          const int kw = k % KW;
+          const int r = k / KW;
+          const int kh = r % KH;
+          const int c = r / KH;
+          const int ih = h + kh - KH / 2, iw = w + kw - KW / 2;
+          if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(xb + (c * H + ih) * W + iw);
+        }
+        v[u] = val;
+      }
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[0], v[1]);
+      packed[e2] = *reinterpret_cast<uint32_t*>(&t);
     }
-    a[idx] = __float2bfloat16_rn(v);
+    *reinterpret_cast<uint4*>(a + pix * ldk + gq * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 
@@ -253,6 +272,8 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
   *reinterpret_cast<uint4*>(p) = make_uint4(u[0], u[1], u[2], u[3]);
 }
 
+// A thread owns ONE channel octet (its gamma/beta/mean/rstd live in registers) and walks the pixels of the block's
+// pixel range with 4 independent 16-byte loads in flight; consecutive threads = consecutive octets of one pixel.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __restrict__ stats,
@@ -273,62 +294,88 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
   }
   __syncthreads();
   const int co = (C + 7) >> 3;  // channel octets per pixel
-  const int64_t total = (int64_t)HW * co;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(idx % co);
-    const int64_t pix = (int64_t)b * HW + idx / co;
+  const int tq = min(co, (int)blockDim.x);
+  const int lanes = blockDim.x / tq;      // pixels processed side by side by one block
+  const int pl = threadIdx.x / tq;
+  if (pl >= lanes) return;
+  const int pstride = lanes * gridDim.x;
+  const int p0 = blockIdx.x * lanes + pl;
+  for (int q = threadIdx.x - pl * tq; q < co; q += tq) {
     const int c = q * 8;
     const bool full = vec_ok && (c + 8 <= C);
-    float v[8];
-    const TIn* xp = x + pix * ldx + c;
-    if (full) {
-      load8<TIn>(xp, v);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
-    }
+    float sc[8], sh[8];  // y = x * sc + sh
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int ce = min(c + e, C - 1);
       const int g = (G == 1) ? 0 : ce / cpg;
-      float y = (v[e] - s_mean[g]) * s_rstd[g] * __ldg(gamma + ce) + __ldg(beta + ce);
-      if (act == SBM_ACT_SILU) y = silu(y);
-      else if (act == SBM_ACT_GELU) y = gelu_exact(y);
-      v[e] = y;
+      const float a = s_rstd[g] * __ldg(gamma + ce);
+      sc[e] = a;
+      sh[e] = __ldg(beta + ce) - s_mean[g] * a;
     }
-    if (residual != nullptr) {
-      const float* rp = residual + pix * ldr + c;
-      if (full) {
-        float r[8];
-        load8<float>(rp, r);
+    auto one = [&](int pix_in_sample, const float* v_in) {
+      const int64_t pix = (int64_t)b * HW + pix_in_sample;
+      float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] += r[e];
-      } else {
+      for (int e = 0; e < 8; ++e) {
+        float y = fmaf(v_in[e], sc[e], sh[e]);
+        if (act == SBM_ACT_SILU) y = silu(y);
+        else if (act == SBM_ACT_GELU) y = gelu_exact(y);
+        v[e] = y;
+      }
+      if (residual != nullptr) {
+        const float* rp = residual + pix * ldr + c;
+        if (full) {
+          float r[8];
+          load8<float>(rp, r);
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (c + e < C) v[e] += rp[e];
+          for (int e = 0; e < 8; ++e) v[e] += r[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c + e < C) v[e] += rp[e];
+        }
+      }
+      if (out != nullptr) {
+        TOut* op = out + pix * ldo + c;
+        if (full) {
+          store8<TOut>(op, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c + e < C) op[e] = (TOut)v[e];
+        }
+      }
+      if (out_f32 != nullptr) {
+        float* op = out_f32 + pix * ldo_f32 + c;
+        if (full) {
+          store8<float>(op, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c + e < C) op[e] = v[e];
+        }
+      }
+    };
+    int p = p0;
+    if (full) {
+      for (; p + 3 * pstride < HW; p += 4 * pstride) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8<TIn>(x + ((int64_t)b * HW + p + u * pstride) * ldx + c, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) one(p + u * pstride, v[u]);
       }
     }
-    if (out != nullptr) {
-      TOut* op = out + pix * ldo + c;
+    for (; p < HW; p += pstride) {
+      float v[8];
+      const TIn* xp = x + ((int64_t)b * HW + p) * ldx + c;
       if (full) {
-        store8<TOut>(op, v);
+        load8<TIn>(xp, v);
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (c + e < C) op[e] = (TOut)v[e];
+        for (int e = 0; e < 8; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
       }
-    }
-    if (out_f32 != nullptr) {
-      float* op = out_f32 + pix * ldo_f32 + c;
-      if (full) {
-        store8<float>(op, v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (c + e < C) op[e] = v[e];
-      }
+      one(p, v);
     }
   }
 }
@@ -539,7 +586,8 @@ extern "C" {
 int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kh, int32_t kw,
                     int32_t ldk, void* stream) {
   SBM_CHECK_ARG(x && a && B > 0 && C > 0 && ldk >= C * kh * kw, "sbm_stem_im2col: bad args");
-  const int64_t total = (int64_t)B * H * W * ldk;
+  SBM_CHECK_ARG(ldk % 8 == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0, "sbm_stem_im2col: ldk must be a multiple of 8");
+  const int64_t total = (int64_t)B * H * W * (ldk / 8);
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)a, B, C, H, W, kh, kw,
                                                                              ldk);
   SBM_CUDA_OK(cudaGetLastError());
@@ -616,8 +664,10 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
     return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld * esz) % 16 == 0));
   };
   const int vec_ok = al16(x, ldx, isz) && al16(out, ldo, osz) && al16(residual, ldr, 4) && al16(out_f32, ldo_f32, 4);
-  const int64_t per_sample = (int64_t)HW * ((C + 7) / 8);
-  int chunks = (int)std::min<int64_t>((per_sample + 255) / 256, std::max<int64_t>(1, (int64_t)sm_count() * 16 / B));
+  // block = (channel octets) x (pixel lanes); enough blocks to fill the machine ~8x, at most one pixel per lane trip
+  const int co = (C + 7) / 8;
+  const int lanes = std::max(1, 256 / std::min(co, 256));
+  int chunks = (int)std::min<int64_t>((HW + lanes - 1) / lanes, std::max<int64_t>(1, (int64_t)sm_count() * 8 / B));
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, B);
   cudaStream_t s = (cudaStream_t)stream;

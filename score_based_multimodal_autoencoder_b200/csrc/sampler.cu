@@ -32,11 +32,18 @@ struct Philox {
     return c;
   }
 };
-// Box-Muller exactly as curand_normal4 does it (curand_normal.h: _curand_box_muller)
+// Box-Muller on the hardware special-function unit: u in (0,1) from the top of the 32-bit word, r = sqrt(-2 ln u)
+// via MUFU.LG2 / MUFU.SQRT, angle via MUFU.SIN / MUFU.COS.  (The in-kernel stream is this library's own; the
+// reference's torch-CUDA stream is reproduced by rng="torch", which injects torch.randn_like draws.)
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
   const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
   const float v = y * (2.3283064e-10f * 6.2831855f) + (2.3283064e-10f * 6.2831855f / 2.0f);
-  const float s = sqrtf(-2.0f * logf(u));
+  const float s = fast_sqrt(-1.3862943611198906f * __log2f(u));  // -2 ln u = -2 ln2 log2 u
   float sn, cs;
   __sincosf(v, &sn, &cs);
   return make_float2(s * sn, s * cs);
@@ -55,6 +62,26 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t draw, ui
   const uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
   // torch.rand convention: uniform in [0,1) from the top 24 bits
   return (float)(w >> 8) * (1.0f / 16777216.0f);
+}
+
+// n / d for any 32-bit n by multiply-high (round-up method): the elementwise kernels recover (sample, offset in
+// sample) from the flat quad index without an integer division.
+struct FastDiv {
+  uint32_t d, m, s1, s2;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l < 1 ? 0 : l - 1;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
 }
 
 // ------------------------------------------------------------------------------ SDE scalar functions
@@ -97,131 +124,186 @@ struct Impute {
   int noise_obs;
   float t_next;         // time of the step the written state is the input of
   const float* t_next_dev;  // optional device scalar overriding t_next
-  int dd;               // D*D elements per modality channel
+  FastDiv ddq;          // D*D/4 quads per modality channel
 };
-__device__ __forceinline__ float4 apply_impute(const Impute& im, const SdeP& s, float4 v, int64_t i4, int e_in_sample) {
+// eq = quad index inside the sample; the 4 elements of a quad share the channel (dd % 4 == 0)
+__device__ __forceinline__ float4 apply_impute(const Impute& im, float2 cf, float4 v, uint32_t q, uint32_t eq) {
   if (im.z_obs == nullptr) return v;
-  const int m = e_in_sample / im.dd;  // the 4 elements of a quad share the channel (dd % 4 == 0)
+  const uint32_t m = fdiv(eq, im.ddq);
   if (!((im.mask >> m) & 1u)) return v;
-  const float4 z = *reinterpret_cast<const float4*>(im.z_obs + i4);
-  if (!im.noise_obs) return z;
+  const float4 z = __ldg(reinterpret_cast<const float4*>(im.z_obs) + q);
+  // noised observation = mean + std * z_obs with mean = exp(lmc) * z_obs (train_lat_celebhq_unet_cont2.py:296-297)
+  return make_float4(__fmaf_rn(cf.y, z.x, cf.x * z.x), __fmaf_rn(cf.y, z.y, cf.x * z.y), __fmaf_rn(cf.y, z.z, cf.x * z.z),
+                     __fmaf_rn(cf.y, z.w, cf.x * z.w));
+}
+// (mean coefficient, std) of the re-noised observation; (1, 0) = clean latent
+__device__ __forceinline__ float2 impute_coef(const Impute& im, const SdeP& s) {
+  if (im.z_obs == nullptr || !im.noise_obs) return make_float2(1.f, 0.f);
   float mc, sd;
   sde_marginal(s, im.t_next_dev ? __ldg(im.t_next_dev) : im.t_next, mc, sd);
-  return make_float4(mc * z.x + sd * z.x, mc * z.y + sd * z.y, mc * z.z + sd * z.z, mc * z.w + sd * z.w);
+  return make_float2(mc, sd);
 }
 
 // ------------------------------------------------------------------------------ predictor
+// One thread = one quad (4 consecutive latent elements), two quads in flight per loop trip.
 __global__ void __launch_bounds__(256)
-predictor_kernel(const float* __restrict__ x, const float* __restrict__ score, const float* __restrict__ t,
-                 const float* __restrict__ noise, float* __restrict__ x_out, float* __restrict__ x_mean_out,
-                 int64_t n_quads, int E, SdeP s, int ode, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
-                 uint64_t quad_offset, Impute im) {
+predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score, const float* __restrict__ t,
+                 const float4* __restrict__ noise, float4* __restrict__ x_out, float4* __restrict__ x_mean_out,
+                 uint32_t n_quads, FastDiv eqd, SdeP s, int ode, uint64_t seed, uint64_t draw,
+                 const uint64_t* draw_dev, uint64_t quad_offset, Impute im) {
   if (draw_dev) draw += *draw_dev;
   const float dt = -1.f / (float)s.N;
   const float sq = sqrtf(-dt);
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i4 = q * 4;
-    const int b = (int)(i4 / E);
-    float dc, g;
-    sde_drift_diff(s, __ldg(t + b), dc, g);
-    const float4 xv = *reinterpret_cast<const float4*>(x + i4);
-    const float4 sv = *reinterpret_cast<const float4*>(score + i4);
-    const float g2 = g * g * (ode ? 0.5f : 1.f);
-    float4 mean;
-    mean.x = xv.x + (dc * xv.x - g2 * sv.x) * dt;
-    mean.y = xv.y + (dc * xv.y - g2 * sv.y) * dt;
-    mean.z = xv.z + (dc * xv.z - g2 * sv.z) * dt;
-    mean.w = xv.w + (dc * xv.w - g2 * sv.w) * dt;
-    float4 out = mean;
-    if (!ode) {
-      const float4 z = noise ? *reinterpret_cast<const float4*>(noise + i4)
-                             : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
-      const float gs = g * sq;
-      out.x += gs * z.x; out.y += gs * z.y; out.z += gs * z.z; out.w += gs * z.w;
+  const float2 icoef = impute_coef(im, s);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_quads; q0 += 2 * stride) {
+    const uint32_t qs[2] = {q0, q0 + stride};
+    float4 xv[2], sv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (qs[u] < n_quads) {
+        xv[u] = x[qs[u]];
+        sv[u] = score[qs[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t q = qs[u];
+      if (q >= n_quads) break;
+      const uint32_t b = fdiv(q, eqd);
+      float dc, g;
+      sde_drift_diff(s, __ldg(t + b), dc, g);
+      const float g2 = g * g * (ode ? 0.5f : 1.f);
+      float4 mean;
+      mean.x = xv[u].x + (dc * xv[u].x - g2 * sv[u].x) * dt;
+      mean.y = xv[u].y + (dc * xv[u].y - g2 * sv[u].y) * dt;
+      mean.z = xv[u].z + (dc * xv[u].z - g2 * sv[u].z) * dt;
+      mean.w = xv[u].w + (dc * xv[u].w - g2 * sv[u].w) * dt;
+      float4 out = mean;
+      if (!ode) {
+        const float4 z = noise ? noise[q] : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
+        const float gs = g * sq;
+        out.x += gs * z.x; out.y += gs * z.y; out.z += gs * z.z; out.w += gs * z.w;
+      }
+      if (x_mean_out) x_mean_out[q] = mean;
+      x_out[q] = apply_impute(im, icoef, out, q, q - b * eqd.d);
     }
-    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + i4) = mean;
-    out = apply_impute(im, s, out, i4, (int)(i4 - (int64_t)b * E));
-    *reinterpret_cast<float4*>(x_out + i4) = out;
   }
 }
 
 // ------------------------------------------------------------------------------ corrector
 // norms: one warp per sample; acc[0] += ||grad_b||, acc[1] += ||noise_b||  (fp64 accumulators)
 __global__ void __launch_bounds__(256)
-corrector_norms_kernel(const float* __restrict__ grad, const float* __restrict__ noise, double* __restrict__ acc,
-                       int B, int E, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
+corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict__ noise, double* __restrict__ acc,
+                       int B, int EQ, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
                        uint64_t quad_offset) {
   if (draw_dev) draw += *draw_dev;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int EQ = E >> 2;
   double a0 = 0.0, a1 = 0.0;
   for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
     float sg = 0.f, sn = 0.f;
-    for (int q = lane; q < EQ; q += 32) {
-      const int64_t gq = (int64_t)b * EQ + q;
-      const float4 g = *reinterpret_cast<const float4*>(grad + gq * 4);
-      const float4 z = noise ? *reinterpret_cast<const float4*>(noise + gq * 4)
-                             : philox_normal4(seed, draw, quad_offset + (uint64_t)gq);
-      sg += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
-      sn += z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w;
+    const uint32_t base = (uint32_t)b * (uint32_t)EQ;
+    for (int q = lane; q < EQ; q += 64) {
+      const bool two = q + 32 < EQ;
+      const float4 g0 = grad[base + q];
+      const float4 g1 = two ? grad[base + q + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 z0 = noise ? noise[base + q] : philox_normal4(seed, draw, quad_offset + (uint64_t)(base + q));
+      sg += g0.x * g0.x + g0.y * g0.y + g0.z * g0.z + g0.w * g0.w;
+      sn += z0.x * z0.x + z0.y * z0.y + z0.z * z0.z + z0.w * z0.w;
+      if (two) {
+        const float4 z1 = noise ? noise[base + q + 32]
+                                : philox_normal4(seed, draw, quad_offset + (uint64_t)(base + q + 32));
+        sg += g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w;
+        sn += z1.x * z1.x + z1.y * z1.y + z1.z * z1.z + z1.w * z1.w;
+      }
     }
     sg = warp_sum(sg);
     sn = warp_sum(sn);
     a0 += (double)sqrtf(sg);
     a1 += (double)sqrtf(sn);
   }
-  if (lane == 0 && (a0 != 0.0 || a1 != 0.0)) {
-    atomicAdd(acc, a0);
-    atomicAdd(acc + 1, a1);
+  // one atomic pair per block
+  __shared__ double red[2][8];
+  if (lane == 0) {
+    red[0][threadIdx.x >> 5] = a0;
+    red[1][threadIdx.x >> 5] = a1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double v = 0.0;
+    for (int w = 0; w < warps_per_block; ++w) v += red[threadIdx.x][w];
+    if (v != 0.0) atomicAdd(acc + threadIdx.x, v);
   }
 }
 
+// acc = {sum ||grad_b||, sum ||noise_b||, ticket}: the last block to finish zeroes it for the next corrector step, so
+// a captured CUDA graph needs no separate memset launch.
 __global__ void __launch_bounds__(256)
-corrector_update_kernel(const float* __restrict__ x, const float* __restrict__ grad, const float* __restrict__ t,
-                        const float* __restrict__ noise, const double* __restrict__ acc,
-                        const float* __restrict__ alphas, float* __restrict__ x_out, float* __restrict__ x_mean_out,
-                        int64_t n_quads, int E, SdeP s, float T, float target_snr, double inv_global_batch,
-                        uint64_t seed, uint64_t draw, const uint64_t* draw_dev, uint64_t quad_offset, Impute im) {
+corrector_update_kernel(const float4* __restrict__ x, const float4* __restrict__ grad, const float* __restrict__ t,
+                        const float4* __restrict__ noise, double* __restrict__ acc,
+                        const float* __restrict__ alphas, float4* __restrict__ x_out, float4* __restrict__ x_mean_out,
+                        uint32_t n_quads, FastDiv eqd, SdeP s, float T, float target_snr, double inv_global_batch,
+                        uint64_t seed, uint64_t draw, const uint64_t* draw_dev, uint64_t quad_offset, Impute im,
+                        int reset_acc) {
   if (draw_dev) draw += *draw_dev;
   const float grad_norm = (float)(acc[0] * inv_global_batch);
   const float noise_norm = (float)(acc[1] * inv_global_batch);
   const float r = target_snr * noise_norm / grad_norm;
   const float base = r * r * 2.f;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i4 = q * 4;
-    const int b = (int)(i4 / E);
-    float alpha = 1.f;
-    if (alphas != nullptr) {
-      // (t * (N - 1) / T).long(): fp32 product, fp32 divide, truncate (sde_helper2.py:57)
-      const long long idx = (long long)(__ldg(t + b) * (float)(s.N - 1) / T);
-      alpha = __ldg(alphas + min(max(idx, 0ll), (long long)s.N - 1));
+  const float2 icoef = impute_coef(im, s);
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_quads; q0 += 2 * stride) {
+    const uint32_t qs[2] = {q0, q0 + stride};
+    float4 xv[2], gv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (qs[u] < n_quads) {
+        xv[u] = x[qs[u]];
+        gv[u] = grad[qs[u]];
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t q = qs[u];
+      if (q >= n_quads) break;
+      const uint32_t b = fdiv(q, eqd);
+      float alpha = 1.f;
+      if (alphas != nullptr) {
+        // (t * (N - 1) / T).long(): fp32 product, fp32 divide, truncate (sde_helper2.py:57)
+        const int idx = (int)(__ldg(t + b) * (float)(s.N - 1) / T);
+        alpha = __ldg(alphas + min(max(idx, 0), s.N - 1));
+      }
+      const float step = base * alpha;
+      const float ns = sqrtf(step * 2.f);
+      const float4 z = noise ? noise[q] : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
+      const float4 mean = make_float4(xv[u].x + step * gv[u].x, xv[u].y + step * gv[u].y, xv[u].z + step * gv[u].z,
+                                      xv[u].w + step * gv[u].w);
+      const float4 out = make_float4(mean.x + ns * z.x, mean.y + ns * z.y, mean.z + ns * z.z, mean.w + ns * z.w);
+      if (x_mean_out) x_mean_out[q] = mean;
+      x_out[q] = apply_impute(im, icoef, out, q, q - b * eqd.d);
     }
-    const float step = base * alpha;
-    const float ns = sqrtf(step * 2.f);
-    const float4 xv = *reinterpret_cast<const float4*>(x + i4);
-    const float4 gv = *reinterpret_cast<const float4*>(grad + i4);
-    const float4 z = noise ? *reinterpret_cast<const float4*>(noise + i4)
-                           : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
-    float4 mean = make_float4(xv.x + step * gv.x, xv.y + step * gv.y, xv.z + step * gv.z, xv.w + step * gv.w);
-    float4 out = make_float4(mean.x + ns * z.x, mean.y + ns * z.y, mean.z + ns * z.z, mean.w + ns * z.w);
-    if (x_mean_out) *reinterpret_cast<float4*>(x_mean_out + i4) = mean;
-    out = apply_impute(im, s, out, i4, (int)(i4 - (int64_t)b * E));
-    *reinterpret_cast<float4*>(x_out + i4) = out;
+  }
+  if (reset_acc) {
+    __syncthreads();  // every thread of this block has read acc
+    if (threadIdx.x == 0) {
+      unsigned int* ticket = reinterpret_cast<unsigned int*>(acc + 2);
+      __threadfence();
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        acc[0] = 0.0;
+        acc[1] = 0.0;
+        *ticket = 0u;
+      }
+    }
   }
 }
 
 // standalone imputation (first step / finishing): x_out = imputed(x) ; final=1 writes the CLEAN latent
 __global__ void __launch_bounds__(256)
-impute_kernel(const float* __restrict__ x, float* __restrict__ x_out, int64_t n_quads, int E, SdeP s, Impute im) {
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i4 = q * 4;
-    const int b = (int)(i4 / E);
-    const float4 v = *reinterpret_cast<const float4*>(x + i4);
-    *reinterpret_cast<float4*>(x_out + i4) = apply_impute(im, s, v, i4, (int)(i4 - (int64_t)b * E));
+impute_kernel(const float4* __restrict__ x, float4* __restrict__ x_out, uint32_t n_quads, FastDiv eqd, SdeP s,
+              Impute im) {
+  const float2 icoef = impute_coef(im, s);
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
+    const uint32_t b = fdiv(q, eqd);
+    x_out[q] = apply_impute(im, icoef, x[q], q, q - b * eqd.d);
   }
 }
 
@@ -339,6 +421,8 @@ static int ew_grid(int64_t n_items) {
 static int check_latent(const sbm_latent_shape* ls, const char* who) {
   SBM_CHECK_ARG(ls && ls->batch > 0 && ls->mods > 0 && ls->mods <= 32 && ls->dd > 0, "%s: bad latent shape", who);
   SBM_CHECK_ARG(ls->dd % 4 == 0, "%s: D*D = %d must be a multiple of 4 (vectorised latent access)", who, ls->dd);
+  SBM_CHECK_ARG((int64_t)ls->batch * ls->mods * ls->dd / 4 < (int64_t(1) << 31),
+                "%s: more than 2^31 latent quads in one call (shard the batch)", who);
   return 0;
 }
 static SdeP to_sdep(const sbm_sde* s) { return SdeP{s->kind, s->b0, s->b1, s->N}; }
@@ -349,7 +433,7 @@ static Impute to_impute(const sbm_impute* im, int dd) {
   r.noise_obs = im ? im->noise_obs : 0;
   r.t_next = im ? im->t_next : 0.f;
   r.t_next_dev = im ? im->t_next_dev : nullptr;
-  r.dd = dd;
+  r.ddq = make_fastdiv((uint32_t)(dd / 4));
   if (r.mask == 0u) r.z_obs = nullptr;
   return r;
 }
@@ -386,8 +470,9 @@ int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const flo
   SBM_CHECK_ARG(noise || rng || probability_flow, "sbm_predictor_step: need injected noise or an rng");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  predictor_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
-      x, score, t, noise, x_out, x_mean_out, nq, E, to_sdep(sde), probability_flow, rng ? rng->seed : 0,
+  predictor_kernel<<<ew_grid((nq + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,
+      (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,
       rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
       to_impute(impute, ls->dd));
   SBM_CUDA_OK(cudaGetLastError());
@@ -401,7 +486,8 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
   SBM_CHECK_ARG(grad && acc2 && (noise || rng), "sbm_corrector_norms: null pointer");
   const int E = ls->mods * ls->dd;
   const int blocks = std::max(1, std::min((ls->batch + 7) / 8, sm_count() * 8));
-  corrector_norms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, noise, acc2, ls->batch, E,
+  corrector_norms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)grad, (const float4*)noise, acc2,
+                                                                   ls->batch, E / 4,
                                                                    rng ? rng->seed : 0, rng ? rng->draw : 0,
                                                                    rng ? rng->draw_dev : nullptr,
                                                                    rng ? rng->sample_offset * (uint64_t)(E / 4) : 0);
@@ -411,18 +497,19 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
 }
 
 int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* grad,
-                         const float* t, const float* noise, const double* acc2, const float* alphas, float* x_out,
+                         const float* t, const float* noise, double* acc2, const float* alphas, float* x_out,
                          float* x_mean_out, float target_snr, int64_t global_batch, const sbm_rng* rng,
-                         const sbm_impute* impute, void* stream) {
+                         const sbm_impute* impute, int32_t reset_acc, void* stream) {
   if (check_latent(ls, "sbm_corrector_update")) return 1;
   SBM_CHECK_ARG(sde && x && grad && t && acc2 && x_out && (noise || rng), "sbm_corrector_update: null pointer");
   SBM_CHECK_ARG(global_batch >= ls->batch, "sbm_corrector_update: global_batch < local batch");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  corrector_update_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
-      x, grad, t, noise, acc2, alphas, x_out, x_mean_out, nq, E, to_sdep(sde), sde->T, target_snr,
+  corrector_update_kernel<<<ew_grid((nq + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)grad, t, (const float4*)noise, acc2, alphas, (float4*)x_out,
+      (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,
       1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,
-      rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd));
+      rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd), reset_acc);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;
@@ -434,7 +521,8 @@ int sbm_impute_observed(const sbm_latent_shape* ls, const sbm_sde* sde, const fl
   SBM_CHECK_ARG(sde && x && x_out && impute && impute->z_obs, "sbm_impute_observed: null pointer");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  impute_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(x, x_out, nq, E, to_sdep(sde),
+  impute_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (float4*)x_out, (uint32_t)nq,
+                                                               make_fastdiv((uint32_t)(E / 4)), to_sdep(sde),
                                                                to_impute(impute, ls->dd));
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();

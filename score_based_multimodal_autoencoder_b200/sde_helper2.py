@@ -311,16 +311,18 @@ def _predictor_kernel(sde, x, score, t, *, noise=None, rng=None, probability_flo
 
 def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, impute=None, want_mean=True,
                        global_batch=None, reduce_fn=None, acc=None, out=None):
+    """norms kernel -> (optional cross-rank sum of the two batch norms) -> update kernel.  `acc` is a zeroed buffer of
+    3 doubles (2 sums + a completion ticket); the update kernel re-zeroes it, so a reused `acc` never needs a memset."""
     ls = _latent_shape(x)
     if acc is None:
-        acc = torch.zeros(2, dtype=torch.float64, device=x.device)
-    else:
-        acc.zero_()
+        acc = torch.zeros(3, dtype=torch.float64, device=x.device)
+    elif acc.numel() < 3:
+        raise L.SbmError("corrector accumulator needs 3 doubles (2 sums + ticket)")
     rp = C.byref(rng) if rng is not None else None
     L.check(L.lib().sbm_corrector_norms(C.byref(ls), L.ptr(grad), L.ptr(noise), rp, L.ptr(acc), L.stream_ptr()),
             "sbm_corrector_norms")
     if reduce_fn is not None:  # multi-GPU exact mode: sum the two batch norms over ranks
-        reduce_fn(acc)
+        reduce_fn(acc[:2])
     x_new = out if out is not None else torch.empty_like(x)
     x_mean = torch.empty_like(x) if want_mean else None
     sc = sde._c()
@@ -328,7 +330,8 @@ def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, imp
     L.check(L.lib().sbm_corrector_update(C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(grad), L.ptr(t), L.ptr(noise),
                                          L.ptr(acc), L.ptr(alphas), L.ptr(x_new), L.ptr(x_mean),
                                          C.c_float(target_snr), C.c_int64(global_batch or x.shape[0]), rp,
-                                         C.byref(impute) if impute is not None else None, L.stream_ptr()),
+                                         C.byref(impute) if impute is not None else None, C.c_int32(1),
+                                         L.stream_ptr()),
             "sbm_corrector_update")
     return x_new, x_mean
 
@@ -416,7 +419,7 @@ def pc_sampler(x0, model, sde, *, z_obs=None, obs_mask=0, eps=1e-3, noise_obs=Tr
     inject = noise_pred is not None
     torch_rng = (rng == "torch") and not inject
     t_vec = torch.empty(B, device=dev, dtype=torch.float32)
-    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    acc = torch.zeros(3, dtype=torch.float64, device=dev)
     x_mean = x
 
     def one_step(i, x, *, last, graph_state=None):

@@ -16,7 +16,7 @@ x = torch.randn(batch, 5, 8, 8, device=dev)
 s = torch.randn_like(x)
 t = torch.full((batch,), 0.5, device=dev)
 rng = sh._RngState()
-acc = torch.zeros(2, dtype=torch.float64, device=dev)
+acc = torch.zeros(3, dtype=torch.float64, device=dev)
 out = torch.empty_like(x)
 
 
