@@ -134,3 +134,14 @@ def test_product_path_has_no_cpu_fallback():
         if fn.endswith(".py"):
             src = open(os.path.join(os.path.dirname(pkg.__file__), fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_unet_openai_state_dict_schema_matches_reference_golden():
+    """`UNetModel` keeps the reference's parameter names and shapes (checkpoints load unchanged)."""
+    from score_based_multimodal_autoencoder_b200.unet_openai import UNetModel
+    g = golden("unet_openai.pt")
+    m = UNetModel(**g["kwargs"])
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in g["shapes"].items()}
+    with pytest.raises(Exception):
+        m(g["x"], g["t"])  # CPU tensors: no fallback
