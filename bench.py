@@ -186,6 +186,11 @@ def run_ours(args):
     # ---------------- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions), timed live
     roof = conv_roofline(model, sde, x0, ops, L) if rank == 0 else None
     samp = sampler_kernel_roofline(sh, sde, device) if rank == 0 else None
+    dsm = None
+    if not args.no_dsm:
+        del stepper
+        torch.cuda.empty_cache()
+        dsm = dsm_train_bench(device, max(args.steps, 5), args.warmup, "poly" if world == 1 else "celeba", world, rank)
 
     line = None
     if rank == 0:
@@ -210,8 +215,8 @@ def run_ours(args):
             "roofline_sampler_kernels": samp and {**samp, "peak": pk["hbm_gbs"], "frac": samp["achieved"] / pk["hbm_gbs"],
                                                   "peak_source": pk_src},
         }
-        if world == 1 and not args.no_dsm:
-            line["dsm_train"] = dsm_train_bench(device, max(args.steps, 5), args.warmup, "poly")
+        if dsm is not None:
+            line["dsm_train"] = dsm
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(workload, budget_s=20.0)
         print(json.dumps(line), flush=True)
@@ -273,11 +278,15 @@ class _GraphStepper:
         self.graph.replay()
 
 
-def dsm_train_bench(device, steps, warmup, which="poly"):
-    """BASELINE configs[1]: PolyMNIST latent score UNet DSM training, batch 256, bf16 operands / fp32 master weights,
-    Adam lr 5e-4.  One step = loss_fn (fused perturb, net forward, fused loss) + backward (hand-written) + FusedAdam."""
+def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0):
+    """DSM training step.  which="poly": BASELINE configs[1] (PolyMNIST latent score UNet, batch 256, 1 GPU);
+    which="celeba": configs[3] (CelebAMask-HQ latent UNet, data parallel, 256 latents per GPU = weak scaling, bucketed
+    NCCL gradient all-reduce overlapped with the hand-written backward).  bf16 GEMM operands / fp32 master weights.
+    One step = loss_fn (fused perturb, net forward, fused loss) + backward + FusedAdam.  Collective: call on all ranks."""
+    import torch.distributed as dist
     from score_based_multimodal_autoencoder_b200 import _lib as L
     from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    from score_based_multimodal_autoencoder_b200.distributed import DataParallelScoreNet
     from score_based_multimodal_autoencoder_b200.optim import FusedAdam
     from score_based_multimodal_autoencoder_b200.unet_model import Unet
     if which == "poly":
@@ -286,43 +295,59 @@ def dsm_train_bench(device, steps, warmup, which="poly"):
         kw, shape, sde, lr, fwd_gf = dict(dim=256, channels=3, dim_mults=(1, 2, 2, 2, 2)), (256, 3, 16, 16), sh.VPSDE(0.1, 20.0, 1000), 5e-5, 9.3496
     torch.manual_seed(0)
     model = Unet(**kw).to(device).train()
+    net = DataParallelScoreNet(model, bucket_mb=64.0) if world > 1 else model
     opt = FusedAdam(model.parameters(), lr=lr)
-    z_host = torch.randn(*shape, generator=torch.Generator().manual_seed(1234)).pin_memory()
+    sh.manual_seed(777, sample_offset=rank * shape[0])
+    z_host = torch.randn(*shape, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory()
     z = z_host.to(device)
 
     def step(batch):
-        loss = sh.loss_fn(batch, model, sde, reduce_mean=True, likelihood_weighting=False, eps=1e-5, rng="philox")
+        loss = sh.loss_fn(batch, net, sde, reduce_mean=True, likelihood_weighting=False, eps=1e-5, rng="philox")
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return loss
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+
     for _ in range(max(warmup, 3)):
-        step(z)
-    torch.cuda.synchronize()
-    n0 = L.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
         loss = step(z)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    barrier()
+    n0 = L.launch_count()
+    ms = timed(lambda: step(z))
     launches = (L.launch_count() - n0) // steps
     # end to end: H2D of the latent batch and D2H of the loss every step (the reference does loss.item() per step)
-    e0.record()
-    for _ in range(steps):
-        loss = step(z_host.to(device, non_blocking=True))
-        loss.item()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_e2e = e0.elapsed_time(e1) / steps
+    ms_e2e = timed(lambda: step(z_host.to(device, non_blocking=True)).item())
+    loss_val = float(step(z).item())
+    gb = shape[0] * world
     return {"metric": "dsm_train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms,
-            "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches_per_step": int(launches), "loss": float(loss.item()),
-            "model_tflops": 3 * fwd_gf * 1e9 * shape[0] / (ms * 1e-3) / 1e12,
-            "config": {"workload": f"{which}_dsm: Unet{tuple(kw.values())} DSM training, batch {shape[0]}, latent {list(shape[1:])}, "
-                                   f"Adam lr {lr}, bf16 GEMM operands / fp32 master weights, loss and statistics fp32/fp64"}}
+            "n_gpus": world, "scaling": "weak", "global_batch": gb, "latents_per_sec": gb * 1e3 / ms,
+            "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": z_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches_per_step": int(launches), "loss": loss_val,
+            "model_tflops_per_gpu": 3 * fwd_gf * 1e9 * shape[0] / (ms * 1e-3) / 1e12,
+            "grad_allreduce": None if world == 1 else {"backend": "nccl", "bucket_mb": 64,
+                                                       "bytes_per_step": sum(p.numel() for p in model.parameters()) * 4,
+                                                       "overlap": "buckets launched from inside the backward pass"},
+            "config": {"workload": f"{which}_dsm: Unet{tuple(kw.values())} DSM training, batch {shape[0]} per GPU x {world}, "
+                                   f"latent {list(shape[1:])}, Adam lr {lr}, bf16 GEMM operands / fp32 master weights, "
+                                   f"loss and statistics fp32/fp64"}}
 
 
 def conv_roofline(model, sde, x0, ops, L):
@@ -496,8 +521,18 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     elif args.dsm_only:
-        torch.cuda.set_device(0)
-        print(json.dumps(dsm_train_bench(torch.device("cuda", 0), args.steps, args.warmup, args.dsm_only)), flush=True)
+        import torch.distributed as dist
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=device)
+        res = dsm_train_bench(device, args.steps, args.warmup, args.dsm_only, world, rank)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
     else:
         run_ours(args)
 

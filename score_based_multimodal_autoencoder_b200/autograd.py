@@ -65,6 +65,9 @@ class _Plan:
         return self.m._cached((id(lin), "dg"), (w,), lambda: ops.pack_weight(w.detach().contiguous(), 1, i, o, 0, 1, i))
 
     def _grad(self, p, g):
+        sink = getattr(self.m, "_grad_sink", None)
+        if sink is not None:  # data-parallel training: copy into the flat bucket buffer, all-reduce when a bucket fills
+            g = sink.grad_ready(p, g)
         self.pg[p] = g if p not in self.pg else self.pg[p] + g
 
     # ------------------------------------------------------------------ generic conv backward pieces
@@ -388,10 +391,15 @@ class _Plan:
         return out
 
     def backward(self, dout):
+        sink = getattr(self.m, "_grad_sink", None)
+        if sink is not None:
+            sink.begin()
         self.bwd_last(dout.contiguous().float())
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        if sink is not None:
+            sink.finish()
 
 
 class UnetFn(torch.autograd.Function):
