@@ -6,7 +6,8 @@
 Default workload (BASELINE.json configs[2], the config the headline metric "PC-sampler latent samples/sec" is
 quoted on): CelebAMask-HQ 3-modality latent score net `Unet(dim=256, channels=3, dim_mults=(1,2,2,2,2))`,
 VPSDE(0.1, 20, N=1000), conditional predictor-corrector sampling (1 of 3 modalities observed, noise_obs,
-predictor -> corrector, n_steps=1, snr 0.16), global batch 1024 sharded over the ranks (strong scaling).
+predictor -> corrector, n_steps=1, snr 0.16), 1024 latents PER GPU (batch-sharded, weak scaling: every rank samples
+its own 1024 latents, no data-path collective; a reference run at N GPUs would be N such batches).
 One "step" = one predictor-corrector step over the batch = 2 score-net forwards + the fused sampler kernels.
 value = latent samples/s for a full N-step sample = global_batch / (N * seconds_per_step).
 Synthetic latents, random-init weights (no datasets/checkpoints exist offline).
@@ -98,6 +99,8 @@ def build_problem(workload, local_batch, rank, device):
 
 
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     import torch.distributed as dist
     from score_based_multimodal_autoencoder_b200 import _lib as L
     from score_based_multimodal_autoencoder_b200 import ops
@@ -111,10 +114,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     workload = args.workload
-    kw, (M, D), (b0, b1, N), given, mods, global_batch = WORKLOADS[workload]
+    kw, (M, D), (b0, b1, N), given, mods, local_batch = WORKLOADS[workload]
     if args.batch:
-        global_batch = args.batch
-    local_batch = global_batch // world
+        local_batch = args.batch
+    # weak scaling: every rank samples its own `local_batch` latents (independent shards, no data-path collective)
+    global_batch = local_batch * world
     model, sde, z_host, x_host, given, mods = build_problem(workload, local_batch, rank, device)
     sh.manual_seed(20240607, sample_offset=rank * local_batch)
     mask = sh._obs_mask_from(given, mods)
@@ -199,7 +203,7 @@ def run_ours(args):
         line = {
             "metric": "pc_sampler_latent_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic latents N(0,1), random-init weights (torch.manual_seed(0))",
             "config": {"workload": f"{workload}: Unet{tuple(kw.values())} cond. PC sampling given={given!r} of {mods!r}, "
                                    f"VPSDE({b0},{b1},N={N}), n_steps=1, snr=0.16, predictor->corrector",
@@ -477,6 +481,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     workload = args.workload
     kw, (M, D), (b0, b1, N), given, mods, global_batch = WORKLOADS[workload]
+    global_batch *= int(os.environ.get("WORLD_SIZE", "1"))
     batch = 4 if workload == "celeba_pc" else 64
     so, spec, score_fn, z, mask, N = _oracle_problem(workload, batch)
     g = torch.Generator().manual_seed(1)
@@ -496,7 +501,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "pc_sampler_latent_samples_per_sec", "value": value, "unit": "samples/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic latents N(0,1), random-init weights (torch.manual_seed(0))",
         "config": {"workload": f"{workload}: same net / SDE / sampler settings as the B200 arm", "global_batch": global_batch,
                    "sample_batch": batch, "sde_steps_per_sample": N},
@@ -512,7 +517,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="celeba_pc", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="override the global batch")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--graph", type=int, default=1, help="replay one captured CUDA graph per PC step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dsm", action="store_true", help="skip the secondary DSM-training measurement")

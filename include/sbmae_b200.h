@@ -67,6 +67,14 @@ typedef struct sbm_conv_args {
   int64_t ldo2;
   const float* rowbias;     /* optional per-sample bias [batch][ld_rowbias] (unet_openai.py:303 `h + emb_out`), or NULL */
   int64_t ld_rowbias;
+  /* GroupNorm(1, cin) of the input folded into this convolution (unet_model.py:106-110: GN -> conv): x is the RAW
+   * (un-normalised) tensor, wpk / gn_tab come from sbm_conv_fold_groupnorm, gn_stats = (sum, sumsq) per sample of x
+   * (e.g. the `stats` output of the producing convolution), gn_count = H*W*cin.  bias must be NULL (it is in gn_tab).
+   * The epilogue computes rstd*(acc - mean*Sg[cls]) + Tb[cls]; cls tells which 3x3 taps see real pixels. */
+  const double* gn_stats;
+  const float* gn_tab;      /* [2][16][cout] */
+  float gn_count;
+  float gn_eps;
 } sbm_conv_args;
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
@@ -92,6 +100,12 @@ int sbm_conv_wgrad(const sbm_wgrad_args* a, void* stream);
 int sbm_unpack_wgrad(const float* src, float* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
                      int64_t s_tap, int64_t s_row, int64_t s_col, void* stream);
 
+/* GroupNorm(1,C) -> conv folding: dst = bf16 [kh*kw][rows][cols_pad] of w*gamma[col]; tab[0][cls][row] = sum over the
+ * taps valid in border class cls of sum_col bf16(w*gamma), tab[1][cls][row] = same sum of w*beta, + bias[row].
+ * cls bit0: tap row 0 valid (pixel row >= 1), bit1: tap row 2 valid, bit2 / bit3: same for columns. */
+int sbm_conv_fold_groupnorm(const float* w, void* dst, float* tab, int32_t kh, int32_t kw, int32_t rows, int32_t cols,
+                            int32_t cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col, const float* gamma,
+                            const float* beta, const float* bias, void* stream);
 /* fp32 weights -> bf16 [taps][rows][cols_pad]; src element (tap,row,col) at
  * w[tap*s_tap + row*s_row + col*s_col]; optional per-column scale (GroupNorm gamma folding). */
 int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
@@ -106,6 +120,11 @@ int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, in
  * x/out fp32 channels-last, w is the nn.Conv2d(groups=C) weight [C,1,7,7]. */
 int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
                     float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* same, output stored as bf16 (the statistics are those of the unrounded values): feeds a convolution that has the
+ * following GroupNorm folded in (sbm_conv_fold_groupnorm).  Square power-of-two maps up to 16x16. */
+int sbm_dwconv7_fwd_bf16(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
+                         int64_t ldc, void* out_bf16, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W,
+                         int32_t C, void* stream);
 /* same kernel, backward w.r.t. the input: out = depthwise7x7(dy, taps flipped) (+ addend, same layout as out) */
 int sbm_dwconv7_bwd_input(const float* dy, int64_t lddy, const float* w, const float* addend, int64_t ldadd,
                           float* out, int64_t ldo, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);

@@ -71,19 +71,75 @@ struct ConvKernelParams {
   int32_t out2_preact, pad0;
   const float* rowbias;     // optional per-sample bias [batch][ld_rowbias] added before the activation
   int64_t ld_rowbias;
+  // GroupNorm(1, cin) of the INPUT folded into the convolution (weights carry gamma; see sbm_conv_fold_groupnorm):
+  //   y = rstd_b * (acc - mean_b * Sg[cls][n]) + Tb[cls][n],  cls = which 3x3 taps see real pixels at this position
+  const double* gn_stats;   // [batch][2] (sum, sum of squares) of the input tensor, or NULL
+  const float* gn_tab;      // [2][16][cout]: Sg then Tb
+  double gn_inv_count;
+  float gn_eps, pad1;
   TapTable taps[4];
 };
+
+// per-thread (= per output row) constants of the folded GroupNorm
+struct GnRow {
+  float mu, rstd;
+  const float* sg;
+  const float* tb;
+};
+__device__ __forceinline__ GnRow gn_row(const ConvKernelParams& p, int b, int i, int j, bool row_ok) {
+  GnRow g;
+  g.mu = 0.f; g.rstd = 1.f; g.sg = p.gn_tab; g.tb = p.gn_tab;
+  if (p.gn_tab == nullptr) return g;
+  const int H = 1 << p.log_oh, W = 1 << p.log_ow;
+  int cls = 0;
+  if (row_ok) {
+    const double s1 = p.gn_stats[2 * (int64_t)b], s2 = p.gn_stats[2 * (int64_t)b + 1];
+    const double mean = s1 * p.gn_inv_count;
+    const double var = fmax(s2 * p.gn_inv_count - mean * mean, 0.0);
+    g.mu = (float)mean;
+    g.rstd = (float)(1.0 / sqrt(var + (double)p.gn_eps));
+    cls = (i >= 1 ? 1 : 0) | (i <= H - 2 ? 2 : 0) | (j >= 1 ? 4 : 0) | (j <= W - 2 ? 8 : 0);
+  }
+  g.sg = p.gn_tab + (int64_t)cls * p.cout;
+  g.tb = p.gn_tab + (int64_t)(16 + cls) * p.cout;
+  return g;
+}
+__device__ __forceinline__ void gn_apply16(const ConvKernelParams& p, const GnRow& g, float* f, int n) {
+  if (p.gn_tab == nullptr) return;
+  const int cmax = p.cout - 1;
+  if (n + 16 <= p.cout && (p.cout & 3) == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(g.sg + n) + k);
+      const float4 t = __ldg(reinterpret_cast<const float4*>(g.tb + n) + k);
+      f[4 * k] = fmaf(g.rstd, f[4 * k] - g.mu * a.x, t.x);
+      f[4 * k + 1] = fmaf(g.rstd, f[4 * k + 1] - g.mu * a.y, t.y);
+      f[4 * k + 2] = fmaf(g.rstd, f[4 * k + 2] - g.mu * a.z, t.z);
+      f[4 * k + 3] = fmaf(g.rstd, f[4 * k + 3] - g.mu * a.w, t.w);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int c = min(n + e, cmax);
+      f[e] = fmaf(g.rstd, f[e] - g.mu * __ldg(g.sg + c), __ldg(g.tb + c));
+    }
+  }
+}
 
 // bias + activation + residual + (bf16 rounding) + statistics + stores for 16 consecutive output channels of one
 // output pixel (row); `v` holds the fp32 accumulators read from TMEM.
 __device__ __forceinline__ void epilogue16(const ConvKernelParams& p, const uint32_t* v, int n, bool row_ok, int b,
-                                           int64_t o_base, int64_t r_base, int64_t o2_base, float& s1, float& s2) {
+                                           int64_t o_base, int64_t r_base, int64_t o2_base, float& s1, float& s2,
+                                           const GnRow& gr) {
   if (n >= p.cout) return;  // warp-uniform
   float f[16];
   const bool full = (n + 16 <= p.cout);
 #pragma unroll
+  for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+  gn_apply16(p, gr, f, n);
+#pragma unroll
   for (int e = 0; e < 16; ++e) {
-    float x = __uint_as_float(v[e]);
+    float x = f[e];
     if (p.bias != nullptr && (full || n + e < p.cout)) x += __ldg(p.bias + n + e);
     if (p.rowbias != nullptr && row_ok && (full || n + e < p.cout)) x += __ldg(p.rowbias + (int64_t)b * p.ld_rowbias + n + e);
     if (p.out2_preact && row_ok && (full || n + e < p.cout))
@@ -197,10 +253,11 @@ __device__ __forceinline__ void stg_store_bf16_row(uint8_t* buf, int r, const fl
 // `stage` holds the residual chunk on entry (when has_res) and the output chunk on exit; `stage2` receives the bf16 copy.
 __device__ __forceinline__ void epilogue_chunk_staged(const ConvKernelParams& p, const uint32_t* v, int n, bool row_ok,
                                                       int b, int lane, uint8_t* stage, uint8_t* stage2, bool has_res,
-                                                      float& s1, float& s2) {
+                                                      float& s1, float& s2, const GnRow& gr) {
   float f[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+  gn_apply16(p, gr, f, n);
   const int cmax = p.cout - 1;
   if (p.bias != nullptr) {
 #pragma unroll
@@ -370,6 +427,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
     const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw + tt.out2_off;
     float s1 = 0.f, s2 = 0.f;
+    const GnRow gr = gn_row(p, b, oh, j, row_ok);
 
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
@@ -379,7 +437,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t v[16];
       ptx::tmem_ld16(tmem_base + (uint32_t(ew * 32) << 16) + c0, v);
       ptx::tmem_ld_wait();
-      epilogue16(p, v, n0 + c0, row_ok, b, o_base, r_base, o2_base, s1, s2);
+      epilogue16(p, v, n0 + c0, row_ok, b, o_base, r_base, o2_base, s1, s2, gr);
     }
 
     if (p.stats != nullptr) {
@@ -588,6 +646,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int oh = oh0 + i;
       const bool row_ok = b < p.batch;
       float s1 = 0.f, s2 = 0.f;
+      const GnRow gr = gn_row(p, b, oh, j, row_ok);
       if constexpr (kStaged) {
         const int cj = sub_j, ci = oh0 + sub_i, cb = b0 + sub_b, cq = tt.out_q;
         const int ncol0 = nt * BN + hc * (BN / 2);
@@ -621,7 +680,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           uint8_t* stage2 = wst + 3 * kStgMain + (nchunk & 1) * kStgOut2;
           if (has_res) ptx::mbar_wait(&rbar[nchunk % 3], (nchunk / 3) & 1);
           ptx::tmem_ld_wait();
-          epilogue_chunk_staged(p, v, col0, row_ok, b, lane, stage, stage2, has_res, s1, s2);
+          epilogue_chunk_staged(p, v, col0, row_ok, b, lane, stage, stage2, has_res, s1, s2, gr);
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -643,7 +702,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           uint32_t v0[16];
           ptx::tmem_ld16(tacc + c0, v0);
           ptx::tmem_ld_wait();
-          epilogue16(p, v0, nt * BN + c0, row_ok, b, o_base, r_base, o2_base, s1, s2);
+          epilogue16(p, v0, nt * BN + c0, row_ok, b, o_base, r_base, o2_base, s1, s2, gr);
         }
       }
       // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
@@ -858,6 +917,14 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   p.act = a->act; p.out_dtype = a->out_dtype; p.res_dtype = a->res_dtype;
   p.out2_preact = (a->out2 != nullptr && a->out2_preact) ? 1 : 0;
   p.rowbias = a->rowbias; p.ld_rowbias = a->ld_rowbias;
+  if (a->gn_tab != nullptr) {
+    SBM_CHECK_ARG(a->kind == SBM_CONV_S1 && (a->kh == 1 || a->kh == 3) && a->kh == a->kw,
+                  "sbm_conv_igemm: GroupNorm folding supports 1x1 and 3x3 stride-1 convolutions");
+    SBM_CHECK_ARG(a->gn_stats != nullptr && a->gn_count > 0 && a->bias == nullptr,
+                  "sbm_conv_igemm: folded GroupNorm needs input statistics and carries the bias in its table");
+    p.gn_stats = a->gn_stats; p.gn_tab = a->gn_tab;
+    p.gn_inv_count = 1.0 / (double)a->gn_count; p.gn_eps = a->gn_eps;
+  }
 
   // output addressing
   const int64_t OHf = (a->kind == SBM_CONVT_4X4_S2) ? 2 * oh : oh;
@@ -914,8 +981,10 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   const int64_t M = (int64_t)a->batch << log_ohw;
   const int m_tiles = (int)((M + kBM - 1) / kBM);
   // CTA-pair kernel: 256 x BN tiles; worth it once there is at least one full wave of pairs
-  const bool use_pair = !g_force_single && (BN == 256 || BN == 128) && a->cout % BN == 0 &&
-                        (int64_t)((m_tiles + 1) / 2) * (a->cout / BN) * nphase >= sm_count() / 2;
+  // (a cout tail is fine: weight rows beyond cout are TMA zero fill, the epilogue clips the columns)
+  const int n_tiles_pair = (a->cout + BN - 1) / BN;
+  const bool use_pair = !g_force_single && (BN == 256 || BN == 128) && !a->out_nchw &&
+                        (int64_t)((m_tiles + 1) / 2) * n_tiles_pair * nphase >= sm_count() / 2;
   const int ntaps_total = a->kh * a->kw;
   const cuuint64_t bdim[3] = {(cuuint64_t)a->cin, (cuuint64_t)a->cout, (cuuint64_t)ntaps_total};
   const cuuint64_t bstr[2] = {(cuuint64_t)a->cin_pad * 2, (cuuint64_t)a->cout * a->cin_pad * 2};
@@ -946,12 +1015,12 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       if (!a->out2) em.out2 = em.out;
       for (int ph = 0; ph < nphase; ++ph)
         p.taps[ph].out_q = (a->kind == SBM_CONVT_4X4_S2) ? (int32_t)((ph >> 1) * OWf + (ph & 1)) : 0;
-      if (BN == 256) return launch_conv_pair<256, 5, true>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
-      return launch_conv_pair<128, 6, true>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
+      if (BN == 256) return launch_conv_pair<256, 5, true>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
+      return launch_conv_pair<128, 6, true>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
     }
     memset(&em, 0, sizeof(em));
-    if (BN == 256) return launch_conv_pair<256, 6, false>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
-    return launch_conv_pair<128, 8, false>(tmA, tmB, em, p, m_tiles, a->cout / BN, nphase, stream);
+    if (BN == 256) return launch_conv_pair<256, 6, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
+    return launch_conv_pair<128, 8, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
   }
   dim3 grid((unsigned)m_tiles, (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
   switch (BN) {
@@ -975,6 +1044,58 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     float v = 0.f;
     if (c < cols) v = w[t * s_tap + r * s_row + c * s_col];
     dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// One block per output channel n: writes the gamma-folded bf16 weight rows [tap][n][:] and the per-tap partial sums
+//   Pg[tap] = sum_c bf16(w*gamma)   Pb[tap] = sum_c w*beta
+// then combines them into the 16 border classes (which of the 3x3 taps see real pixels).
+__global__ void __launch_bounds__(256)
+fold_groupnorm_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int kh, int kw, int rows, int cols,
+                      int cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ tab) {
+  __shared__ double red[2][9][8];
+  __shared__ double tot[2][9];
+  const int n = blockIdx.x;
+  const int taps = kh * kw;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int t = 0; t < taps; ++t) {
+    float pg = 0.f, pb = 0.f;
+    for (int c = threadIdx.x; c < cols_pad; c += blockDim.x) {
+      float wg = 0.f;
+      if (c < cols) {
+        const float wv = w[t * s_tap + n * s_row + c * s_col];
+        const __nv_bfloat16 h = __float2bfloat16_rn(wv * __ldg(gamma + c));
+        wg = __bfloat162float(h);
+        pb += wv * __ldg(beta + c);
+        dst[((int64_t)t * rows + n) * cols_pad + c] = h;
+      } else {
+        dst[((int64_t)t * rows + n) * cols_pad + c] = __float2bfloat16_rn(0.f);
+      }
+      pg += wg;
+    }
+    const double dg = warp_sum((double)pg), db = warp_sum((double)pb);
+    if (lane == 0) { red[0][t][wid] = dg; red[1][t][wid] = db; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * taps) {
+    const int which = threadIdx.x / taps, t = threadIdx.x % taps;
+    double v = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[which][t][i];
+    tot[which][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int which = threadIdx.x >> 4, cls = threadIdx.x & 15;
+    double v = 0.0;
+    for (int a = 0; a < kh; ++a)
+      for (int b = 0; b < kw; ++b) {
+        const bool okh = (kh == 1) || a == 1 || (a == 0 && (cls & 1)) || (a == 2 && (cls & 2));
+        const bool okw = (kw == 1) || b == 1 || (b == 0 && (cls & 4)) || (b == 2 && (cls & 8));
+        if (okh && okw) v += tot[which][a * kw + b];
+      }
+    if (which == 1 && bias != nullptr) v += (double)bias[n];
+    tab[((int64_t)which * 16 + cls) * rows + n] = (float)v;
   }
 }
 
@@ -1007,6 +1128,19 @@ int sbm_conv_force_direct_epilogue(int32_t on) {
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream) {
   return sbm::conv_igemm_impl(a, static_cast<cudaStream_t>(stream));
+}
+
+int sbm_conv_fold_groupnorm(const float* w, void* dst, float* tab, int32_t kh, int32_t kw, int32_t rows, int32_t cols,
+                            int32_t cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col, const float* gamma,
+                            const float* beta, const float* bias, void* stream) {
+  SBM_CHECK_ARG(w && dst && tab && gamma && beta && rows > 0 && cols > 0 && cols_pad >= cols,
+                "sbm_conv_fold_groupnorm: bad args");
+  SBM_CHECK_ARG(kh == kw && (kh == 1 || kh == 3), "sbm_conv_fold_groupnorm: 1x1 or 3x3 kernels only");
+  sbm::fold_groupnorm_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(dst), kh, kw, rows, cols, cols_pad, s_tap, s_row, s_col, gamma, beta, bias, tab);
+  SBM_CUDA_OK(cudaGetLastError());
+  sbm::g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
 }
 
 int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,

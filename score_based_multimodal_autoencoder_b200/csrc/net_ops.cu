@@ -205,6 +205,121 @@ dwconv7_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __res
   }
 }
 
+// Pipelined variant (the one the forward pass uses): a block owns ONE 32-channel chunk (its 49 taps stay in registers)
+// and walks the samples; the input slab of the next step is fetched with cp.async (all 16-byte requests of the slab in
+// flight at once) while the current one is convolved, so the kernel is FMA-bound instead of load-latency-bound.
+// Maps smaller than 8 rows pack 8/H samples per step so that all 8 warps stay busy.  Output fp32 or bf16.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int W, typename TOut>
+__global__ void __launch_bounds__(256, 2)
+dwconv7_pipe_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                    const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
+                    TOut* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C, int H, int flip,
+                    const float* __restrict__ addend, int64_t ldadd) {
+  extern __shared__ __align__(16) float sm[];
+  const int HW = H * W;
+  const int spb = H >= 8 ? 1 : 8 / H;          // samples per step
+  const int slab = spb * HW * kDwCh;           // floats per buffer
+  const int c0 = blockIdx.x * kDwCh;
+  const int tid = threadIdx.x;
+  const int cl = tid & 31, warp = tid >> 5;
+  const int c = c0 + cl;
+  const bool c_ok = c < C;
+  const int ls = H >= 8 ? 0 : warp / H;        // local sample of this warp
+  const int row0 = H >= 8 ? warp : warp % H;   // first output row of this warp
+  const int rstep = H >= 8 ? 8 : H;
+  const int nsteps = (B + spb - 1) / spb;
+
+  auto prefetch = [&](int step, float* buf) {
+    // slab = spb samples x HW pixels x 32 channels: 8 sixteen-byte chunks per pixel
+    const int chunks = spb * HW * 8;
+    for (int i = tid; i < chunks; i += 256) {
+      const int q = i & 7, pix = i >> 3;
+      const int s_ = pix / HW, p_ = pix - s_ * HW;
+      const int b = step * spb + s_;
+      if (b < B && c0 + q * 4 < C)
+        cp_async16(buf + pix * kDwCh + q * 4, x + ((int64_t)b * HW + p_) * ldx + c0 + q * 4);
+    }
+    cp_async_commit();
+  };
+
+  float wr[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) wr[i] = c_ok ? __ldg(w + (int64_t)c * 49 + (flip ? 48 - i : i)) : 0.f;
+  const float bias_c = (c_ok && bias) ? __ldg(bias + c) : 0.f;
+
+  int step = blockIdx.y;
+  if (step < nsteps) prefetch(step, sm);
+  int cur = 0;
+  for (; step < nsteps; step += gridDim.y) {
+    const int nxt = step + gridDim.y;
+    if (nxt < nsteps) {
+      prefetch(nxt, sm + (cur ^ 1) * slab);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* sx = sm + cur * slab + ls * HW * kDwCh;
+    const int b = step * spb + ls;
+    if (b < B) {
+      const float add = bias_c + ((c_ok && cond) ? __ldg(cond + (int64_t)b * ldc + c) : 0.f);
+      float s1 = 0.f, s2 = 0.f;
+      for (int oh = row0; oh < H; oh += rstep) {
+        float acc[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) acc[i] = add;
+#pragma unroll
+        for (int kh = 0; kh < 7; ++kh) {
+          const int ih = oh + kh - 3;
+          if (ih < 0 || ih >= H) continue;
+          const float* row = sx + (ih * W) * kDwCh + cl;
+#pragma unroll
+          for (int iw = 0; iw < W; ++iw) {
+            const float v = row[iw * kDwCh];
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              const int ow = iw - kw + 3;
+              if (ow >= 0 && ow < W) acc[ow] = fmaf(v, wr[kh * 7 + kw], acc[ow]);
+            }
+          }
+        }
+        if (c_ok) {
+          TOut* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
+          if (addend != nullptr) {
+            const float* ap = addend + ((int64_t)b * HW + oh * W) * ldadd + c;
+#pragma unroll
+            for (int i = 0; i < W; ++i) acc[i] += ap[(int64_t)i * ldadd];
+          }
+#pragma unroll
+          for (int i = 0; i < W; ++i) {
+            op[(int64_t)i * ldo] = (TOut)acc[i];
+            s1 += acc[i];
+            s2 += acc[i] * acc[i];
+          }
+        }
+      }
+      if (stats != nullptr) {
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (cl == 0) {
+          atomicAdd(stats + 2 * (int64_t)b, (double)s1);
+          atomicAdd(stats + 2 * (int64_t)b + 1, (double)s2);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with this buffer before the next prefetch overwrites it
+    cur ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------ group statistics
 // stats[b][g] += (sum, sumsq) over the pixels x channels of group g.  grid = (chunks, groups, B)
 __global__ void __launch_bounds__(256)
@@ -494,6 +609,138 @@ linear_attn_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __
   }
 }
 
+// Register-tiled variant (the one the forward pass uses).  Same math, organised so that every shared-memory
+// access is a conflict-free 16-byte load feeding 16 FMAs:
+//   load : lane = channel; q is soft-maxed over d with warp shuffles on the fly and stored TRANSPOSED (qT[d][p]);
+//          k, v stored [p][32]
+//   k    : soft-max over the n positions with lane = channel (column max / sum combined across the 8 warps);
+//          the 1/sum factor is applied to the 32x32 context instead of the n x 32 matrix
+//   ctx  : thread = 4(d) x 4(e) tile, the n positions split over 4 thread groups, partial sums reduced in smem
+//   out  : thread = 4(p) x 4(e) tile, out[p][e] = sum_d ctx[d][e] qT[d][p]
+__global__ void __launch_bounds__(256, 2)
+linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo, int n,
+                         int heads, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int n4 = (n + 3) & ~3;
+  const int qs = n4 + 4;                    // qT row stride (multiple of 4 floats)
+  float* qT = sm;                           // [32][qs]
+  float* sk = qT + 32 * qs;                 // [n4][32]   (re-used for the 4 partial contexts [4][32][32])
+  float* sv = sk + max(n4 * 32, 4 * 1024);  // [n4][32]
+  float* ctx = sv + n4 * 32;                // [32][32]
+  float* red = ctx + 1024;                  // [2][8][32]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hid = heads * kHeadDim;
+  const float* base = qkv + (int64_t)b * n * ldq + h * kHeadDim + lane;
+
+  // ---- load (4 rows = 12 independent 128-byte requests per warp in flight), q soft-max over d, k column max
+  float kmax = -INFINITY;
+  for (int p0 = warp * 4; p0 < n4; p0 += 32) {
+    float r[12];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u;
+      const bool ok = p < n;
+      const float* row = base + (int64_t)p * ldq;
+      r[3 * u] = ok ? __ldg(row) : 0.f;
+      r[3 * u + 1] = ok ? __ldg(row + hid) : -INFINITY;
+      r[3 * u + 2] = ok ? __ldg(row + 2 * hid) : 0.f;
+    }
+    float qv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float m = r[3 * u];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float e = __expf(r[3 * u] - m);
+      const float ssum = warp_sum(e);
+      qv[u] = (p0 + u < n) ? e / ssum * scale : 0.f;
+      sk[(p0 + u) * 32 + lane] = r[3 * u + 1];
+      sv[(p0 + u) * 32 + lane] = r[3 * u + 2];
+      kmax = fmaxf(kmax, r[3 * u + 1]);
+    }
+    *reinterpret_cast<float4*>(qT + lane * qs + p0) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+  }
+  red[warp * 32 + lane] = kmax;
+  __syncthreads();
+  float cmax = red[lane];
+#pragma unroll
+  for (int w2 = 1; w2 < 8; ++w2) cmax = fmaxf(cmax, red[w2 * 32 + lane]);
+  // ---- k: exp(k - max) in place, column sums
+  float ksum = 0.f;
+  for (int p = warp; p < n4; p += 8) {
+    const float e = __expf(sk[p * 32 + lane] - cmax);  // padded rows hold -inf -> 0
+    sk[p * 32 + lane] = e;
+    ksum += e;
+  }
+  red[256 + warp * 32 + lane] = ksum;
+  __syncthreads();
+  // ---- context partials: thread = (group g, 4x4 tile (d0, e0))
+  {
+    const int g = tid >> 6, t = tid & 63;
+    const int d0 = (t >> 3) * 4, e0 = (t & 7) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = 0.f;
+    const int per = (n4 + 3) >> 2;
+    const int pe = min(n4, (g + 1) * per);
+    for (int p = g * per; p < pe; ++p) {
+      const float4 kd = *reinterpret_cast<const float4*>(sk + p * 32 + d0);
+      const float4 ve = *reinterpret_cast<const float4*>(sv + p * 32 + e0);
+      const float kk[4] = {kd.x, kd.y, kd.z, kd.w}, vv[4] = {ve.x, ve.y, ve.z, ve.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = fmaf(kk[i], vv[j2], acc[i][j2]);
+    }
+    __syncthreads();  // everyone is done reading sk before it is overwritten with the partial contexts
+    float* part = sk + g * 1024;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(part + (d0 + i) * 32 + e0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 1024; i += 256) {
+    const int d = i >> 5;
+    float ssum = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) ssum += red[256 + w2 * 32 + d];
+    ctx[i] = (sk[i] + sk[1024 + i] + sk[2048 + i] + sk[3072 + i]) / ssum;
+  }
+  __syncthreads();
+  // ---- out: thread = 4(p) x 4(e) tile
+  const int ptiles = n4 >> 2;
+  for (int t = tid; t < ptiles * 8; t += 256) {
+    const int p0 = (t >> 3) * 4, e0 = (t & 7) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) {
+      const float4 qd = *reinterpret_cast<const float4*>(qT + d * qs + p0);
+      const float4 ce = *reinterpret_cast<const float4*>(ctx + d * 32 + e0);
+      const float qq[4] = {qd.x, qd.y, qd.z, qd.w}, cc[4] = {ce.x, ce.y, ce.z, ce.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = fmaf(qq[i], cc[j2], acc[i][j2]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (p0 + i >= n) break;
+      __nv_bfloat162 lo = __floats2bfloat162_rn(acc[i][0], acc[i][1]), hi = __floats2bfloat162_rn(acc[i][2], acc[i][3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out + ((int64_t)b * n + p0 + i) * ldo + h * kHeadDim + e0) = pk;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ softmax attention core
 // qkv: fp32 [B, n, ldq]; layout selected by (q_off, k_off, v_off, head_stride): channel of (head, d) for q is
 // q_off + head*head_stride + d.   out[b, i, o_off + head*dh + d] = sum_j softmax_j(scale * q_i . k_j) v_j[d]
@@ -577,6 +824,81 @@ static int grid_for(int64_t total, int threads) {
   return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 
+template <int W, typename TOut>
+static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
+                               int64_t ldc, void* out, int64_t ldo, double* stats, int B, int H, int C, int flip,
+                               const float* addend, int64_t ldadd, cudaStream_t st) {
+  const int spb = H >= 8 ? 1 : 8 / H;
+  const size_t smem = (size_t)2 * spb * H * W * kDwCh * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_pipe_kernel<W, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    configured = smem;
+  }
+  const int chunks = (C + kDwCh - 1) / kDwCh;
+  const int nsteps = (B + spb - 1) / spb;
+  // ~2 resident blocks per SM, every block walks >= 2 steps when there is enough work (so the prefetch overlaps)
+  int gy = std::max(1, std::min(nsteps, (2 * sm_count() + chunks - 1) / chunks));
+  dim3 grid(chunks, gy);
+  dwconv7_pipe_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H,
+                                                        flip, addend, ldadd);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static int dwconv7_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
+                          int64_t ldc, void* out, int out_dtype, int64_t ldo, double* stats, int32_t B, int32_t H,
+                          int32_t W, int32_t C, int flip, const float* addend, int64_t ldadd, cudaStream_t st) {
+  SBM_CHECK_ARG(x && w && out && B > 0 && C > 0 && H > 0 && W > 0, "sbm_dwconv7: bad args");
+  const bool aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (aligned && H == W && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16)) {
+#define SBM_DW_PIPE(WW)                                                                                              \
+  return out_dtype == SBM_BF16                                                                                       \
+             ? dwconv7_pipe_launch<WW, __nv_bfloat16>(x, ldx, w, bias, cond, ldc, out, ldo, stats, B, H, C, flip,   \
+                                                      addend, ldadd, st)                                             \
+             : dwconv7_pipe_launch<WW, float>(x, ldx, w, bias, cond, ldc, out, ldo, stats, B, H, C, flip, addend,   \
+                                              ldadd, st)
+    switch (W) {
+      case 1: SBM_DW_PIPE(1);
+      case 2: SBM_DW_PIPE(2);
+      case 4: SBM_DW_PIPE(4);
+      case 8: SBM_DW_PIPE(8);
+      default: SBM_DW_PIPE(16);
+    }
+#undef SBM_DW_PIPE
+  }
+  SBM_CHECK_ARG(out_dtype == SBM_F32, "sbm_dwconv7: bf16 output needs a square power-of-two map <= 16");
+  float* outf = (float*)out;
+  const size_t smem = ((size_t)H * W * 33 + 49 * kDwCh) * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_dwconv7: %dx%d map does not fit the shared-memory slab", H, W);
+  dim3 grid((C + kDwCh - 1) / kDwCh, B);
+  const size_t smem_rows = (size_t)H * W * 33 * sizeof(float);
+  const int threads = 32 * std::max(1, std::min(8, H));
+#define SBM_DW_ROWS(WW)                                                                                             \
+  dwconv7_rows_kernel<WW><<<grid, threads, smem_rows, st>>>(x, ldx, w, bias, cond, ldc, outf, ldo, stats, C, H, flip, \
+                                                            addend, ldadd)
+  if (W == 16 && smem_rows <= 48 * 1024) SBM_DW_ROWS(16);
+  else if (W == 8) SBM_DW_ROWS(8);
+  else if (W == 4) SBM_DW_ROWS(4);
+  else if (W == 2) SBM_DW_ROWS(2);
+  else if (W == 1) SBM_DW_ROWS(1);
+  else {
+    SBM_CHECK_ARG(!flip && !addend, "sbm_dwconv7_bwd_input: unsupported width %d", W);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    dwconv7_kernel<<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, outf, ldo, stats, C, H, W);
+  }
+#undef SBM_DW_ROWS
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 }  // namespace sbm
 
 using namespace sbm;
@@ -595,47 +917,23 @@ int sbm_stem_im2col(const float* x, void* a, int32_t B, int32_t C, int32_t H, in
   return 0;
 }
 
-static int dwconv7_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
-                          int64_t ldc, float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W,
-                          int32_t C, int flip, const float* addend, int64_t ldadd, cudaStream_t st) {
-  SBM_CHECK_ARG(x && w && out && B > 0 && C > 0 && H > 0 && W > 0, "sbm_dwconv7: bad args");
-  const size_t smem = ((size_t)H * W * 33 + 49 * kDwCh) * sizeof(float);
-  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_dwconv7: %dx%d map does not fit the shared-memory slab", H, W);
-  dim3 grid((C + kDwCh - 1) / kDwCh, B);
-  const size_t smem_rows = (size_t)H * W * 33 * sizeof(float);
-  const int threads = 32 * std::max(1, std::min(8, H));
-#define SBM_DW_ROWS(WW)                                                                                            \
-  dwconv7_rows_kernel<WW><<<grid, threads, smem_rows, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, flip, \
-                                                            addend, ldadd)
-  if (W == 16 && smem_rows <= 48 * 1024) SBM_DW_ROWS(16);
-  else if (W == 8) SBM_DW_ROWS(8);
-  else if (W == 4) SBM_DW_ROWS(4);
-  else if (W == 2) SBM_DW_ROWS(2);
-  else if (W == 1) SBM_DW_ROWS(1);
-  else {
-    SBM_CHECK_ARG(!flip && !addend, "sbm_dwconv7_bwd_input: unsupported width %d", W);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-    dwconv7_kernel<<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, out, ldo, stats, C, H, W);
-  }
-#undef SBM_DW_ROWS
-  SBM_CUDA_OK(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
 int sbm_dwconv7_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
                     float* out, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W, int32_t C,
                     void* stream) {
-  return dwconv7_launch(x, ldx, w, bias, cond, ldc, out, ldo, stats, B, H, W, C, 0, nullptr, 0, (cudaStream_t)stream);
+  return dwconv7_launch(x, ldx, w, bias, cond, ldc, out, SBM_F32, ldo, stats, B, H, W, C, 0, nullptr, 0,
+                        (cudaStream_t)stream);
+}
+
+int sbm_dwconv7_fwd_bf16(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
+                         int64_t ldc, void* out_bf16, int64_t ldo, double* stats, int32_t B, int32_t H, int32_t W,
+                         int32_t C, void* stream) {
+  return dwconv7_launch(x, ldx, w, bias, cond, ldc, out_bf16, SBM_BF16, ldo, stats, B, H, W, C, 0, nullptr, 0,
+                        (cudaStream_t)stream);
 }
 
 int sbm_dwconv7_bwd_input(const float* dy, int64_t lddy, const float* w, const float* addend, int64_t ldadd,
                           float* out, int64_t ldo, int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
-  return dwconv7_launch(dy, lddy, w, nullptr, nullptr, 0, out, ldo, nullptr, B, H, W, C, 1, addend, ldadd,
+  return dwconv7_launch(dy, lddy, w, nullptr, nullptr, 0, out, SBM_F32, ldo, nullptr, B, H, W, C, 1, addend, ldadd,
                         (cudaStream_t)stream);
 }
 
@@ -708,6 +1006,22 @@ int sbm_time_embed(const float* t, void* out_bf16, float* out_f32, int32_t B, in
 int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
                         float scale, void* stream) {
   SBM_CHECK_ARG(qkv && out && B > 0 && n > 0 && heads > 0, "sbm_linear_attn_fwd: bad args");
+  dim3 grid(heads, B);
+  const int n4 = (n + 3) & ~3;
+  const size_t smem_t = ((size_t)32 * (n4 + 4) + std::max(n4 * 32, 4096) + (size_t)n4 * 32 + 1024 + 512) * sizeof(float);
+  if (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 && smem_t <= 110 * 1024) {
+    static size_t configured = 0;
+    if (smem_t > 48 * 1024 && smem_t > configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem_t));
+      configured = smem_t;
+    }
+    linear_attn_tiled_kernel<<<grid, 256, smem_t, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, n, heads,
+                                                                          scale);
+    SBM_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const size_t smem = ((size_t)3 * n * 33 + 32 * 33) * sizeof(float);
   SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_linear_attn_fwd: n=%d too large", n);
   static size_t configured = 0;
@@ -715,7 +1029,6 @@ int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, i
     SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid(heads, B);
   linear_attn_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, n, heads, scale);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();

@@ -44,6 +44,22 @@ def pack_convT2d_weight(w: torch.Tensor, out=None) -> torch.Tensor:
     return pack_weight(w, kh * kw, o, i, 1, kh * kw, o * kh * kw, out)
 
 
+def fold_groupnorm_conv(w: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor):
+    """nn.GroupNorm(1, I) followed by nn.Conv2d(I, O, k) -> (bf16 [k*k, O, pad8(I)] weights carrying gamma,
+    fp32 [2, 16, O] border-class tables carrying mean-correction sums, beta and the conv bias)."""
+    w = w.detach().contiguous()
+    o, i, kh, kw = w.shape
+    cols_pad = pad8(i)
+    wpk = torch.empty((kh * kw, o, cols_pad), dtype=torch.bfloat16, device=w.device)
+    tab = torch.empty((2, 16, o), dtype=torch.float32, device=w.device)
+    L.check(L.lib().sbm_conv_fold_groupnorm(L.ptr(w), L.ptr(wpk), L.ptr(tab), C.c_int32(kh), C.c_int32(kw), C.c_int32(o),
+                                            C.c_int32(i), C.c_int32(cols_pad), C.c_int64(1), C.c_int64(i * kh * kw),
+                                            C.c_int64(kh * kw), L.ptr(gamma.detach()), L.ptr(beta.detach()),
+                                            L.ptr(bias.detach() if bias is not None else None), L.stream_ptr()),
+            "sbm_conv_fold_groupnorm")
+    return wpk, tab
+
+
 def pack_linear_weight(w: torch.Tensor, out=None) -> torch.Tensor:
     """nn.Linear weight [O, I] -> [1, O, pad8(I)] bf16."""
     w = w.detach().contiguous()
@@ -55,7 +71,8 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
                bias: torch.Tensor | None = None, act: int = L.ACT_NONE, residual: torch.Tensor | None = None,
                out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.float32, nchw: bool = False,
                stats: torch.Tensor | None = None, out2: torch.Tensor | None = None,
-               out2_preact: bool = False, rowbias: torch.Tensor | None = None) -> torch.Tensor:
+               out2_preact: bool = False, rowbias: torch.Tensor | None = None, gn_stats: torch.Tensor | None = None,
+               gn_tab: torch.Tensor | None = None, gn_eps: float = 1e-5) -> torch.Tensor:
     """x: bf16 [B,H,W,ldx]; returns [B,OH,OW,pad8(cout)] (or fp32 NCHW [B,cout,OH,OW] when nchw)."""
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.stride(3) == 1
     b, h, w, _ = x.shape
@@ -93,6 +110,9 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
         a.out2_preact = 1 if out2_preact else 0
     if rowbias is not None:
         a.rowbias, a.ld_rowbias = rowbias.data_ptr(), rowbias.stride(-2)
+    if gn_tab is not None:  # GroupNorm(1, cin) of x folded into the weights (fold_groupnorm_conv)
+        a.gn_stats, a.gn_tab = gn_stats.data_ptr(), gn_tab.data_ptr()
+        a.gn_count, a.gn_eps = float(h * w * cin), gn_eps
     L.check(L.lib().sbm_conv_igemm(C.byref(a), L.stream_ptr()), "sbm_conv_igemm")
     return out
 
@@ -112,12 +132,14 @@ def stem_im2col(x: torch.Tensor, kh: int, kw: int) -> torch.Tensor:
     return a
 
 
-def dwconv7(x: torch.Tensor, c: int, w: torch.Tensor, bias, cond, ldc: int, stats) -> torch.Tensor:
+def dwconv7(x: torch.Tensor, c: int, w: torch.Tensor, bias, cond, ldc: int, stats,
+            out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     b, h, wd, _ = x.shape
-    out = torch.empty((b, h, wd, pad8(c)), dtype=torch.float32, device=x.device)
-    L.check(L.lib().sbm_dwconv7_fwd(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(w), L.ptr(bias), L.ptr(cond),
-                                    C.c_int64(ldc), L.ptr(out), C.c_int64(out.stride(2)), L.ptr(stats), C.c_int32(b),
-                                    C.c_int32(h), C.c_int32(wd), C.c_int32(c), L.stream_ptr()), "sbm_dwconv7_fwd")
+    out = torch.empty((b, h, wd, pad8(c)), dtype=out_dtype, device=x.device)
+    fn = L.lib().sbm_dwconv7_fwd_bf16 if out_dtype == torch.bfloat16 else L.lib().sbm_dwconv7_fwd
+    L.check(fn(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(w), L.ptr(bias), L.ptr(cond), C.c_int64(ldc), L.ptr(out),
+               C.c_int64(out.stride(2)), L.ptr(stats), C.c_int32(b), C.c_int32(h), C.c_int32(wd), C.c_int32(c),
+               L.stream_ptr()), "sbm_dwconv7_fwd")
     return out
 
 

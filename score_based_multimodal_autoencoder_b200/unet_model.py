@@ -163,6 +163,8 @@ class Unet(nn.Module):
         self._time_blocks = [m for m in self.modules() if isinstance(m, ConvNextBlock) and m.mlp is not None]
         # bf16 storage for the GELU'd hidden activation between the two 3x3 convolutions of a block
         self.hidden_dtype = torch.bfloat16
+        # inference: fold the block's first GroupNorm into its 3x3 convolution (depthwise output kept in bf16)
+        self.fold_input_norm = True
 
     # ------------------------------------------------------------------ packed-weight cache
     def _cached(self, key, params, build):
@@ -177,6 +179,11 @@ class Unet(nn.Module):
 
     def _w_conv(self, conv: nn.Conv2d):
         return self._cached(id(conv), (conv.weight,), lambda: ops.pack_conv2d_weight(conv.weight))
+
+    def _w_conv_gn(self, conv: nn.Conv2d, gn: nn.GroupNorm):
+        """GroupNorm(1,C) -> conv folded: (bf16 weights carrying gamma, border-class tables with beta / bias)."""
+        return self._cached((id(conv), "gn"), (conv.weight, conv.bias, gn.weight, gn.bias),
+                            lambda: ops.fold_groupnorm_conv(conv.weight, conv.bias, gn.weight, gn.bias))
 
     def _w_convT(self, conv: nn.ConvTranspose2d):
         return self._cached(id(conv), (conv.weight,), lambda: ops.pack_convT2d_weight(conv.weight))
@@ -224,14 +231,25 @@ class Unet(nn.Module):
         c_in, c_hid, c_out = blk.dim, blk.hidden, blk.dim_out
         st1 = self._stats(b, dev)
         cptr = cond[:, :, :, cond_off:] if (cond is not None and blk.mlp is not None) else None
-        hdw = ops.dwconv7(xf, c_in, blk.ds_conv.weight, blk.ds_conv.bias, cptr, ldc, st1)
-        a1 = torch.empty((b, h, w, pad8(c_in)), dtype=torch.bfloat16, device=dev)
-        ops.groupnorm_apply(hdw, c_in, st1, blk.net[0].weight, blk.net[0].bias, out=a1)
         st2 = self._stats(b, dev)
-        h2 = ops.conv_igemm(a1, self._w_conv(blk.net[1]), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_hid,
-                            bias=blk.net[1].bias, act=L.ACT_GELU, out_dtype=self.hidden_dtype, stats=st2)
-        a2 = torch.empty((b, h, w, pad8(c_hid)), dtype=torch.bfloat16, device=dev)
-        ops.groupnorm_apply(h2, c_hid, st2, blk.net[3].weight, blk.net[3].bias, out=a2)
+        if self.fold_input_norm and isinstance(blk.net[0], nn.GroupNorm):
+            # depthwise output stored once as bf16 (statistics from the unrounded values); the first GroupNorm is
+            # folded into the 3x3 convolution like the second one
+            hdw = ops.dwconv7(xf, c_in, blk.ds_conv.weight, blk.ds_conv.bias, cptr, ldc, st1, out_dtype=torch.bfloat16)
+            w1, tab1 = self._w_conv_gn(blk.net[1], blk.net[0])
+            h2 = ops.conv_igemm(hdw, w1, kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_hid, act=L.ACT_GELU,
+                                out_dtype=self.hidden_dtype, stats=st2, gn_stats=st1, gn_tab=tab1,
+                                gn_eps=blk.net[0].eps)
+        else:
+            hdw = ops.dwconv7(xf, c_in, blk.ds_conv.weight, blk.ds_conv.bias, cptr, ldc, st1)
+            a1 = torch.empty((b, h, w, pad8(c_in)), dtype=torch.bfloat16, device=dev)
+            ops.groupnorm_apply(hdw, c_in, st1, blk.net[0].weight, blk.net[0].bias, out=a1)
+            h2 = ops.conv_igemm(a1, self._w_conv(blk.net[1]), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_hid,
+                                bias=blk.net[1].bias, act=L.ACT_GELU, out_dtype=self.hidden_dtype, stats=st2)
+        # the second GroupNorm is folded into the last convolution: it consumes the raw GELU output (bf16) with
+        # gamma-carrying weights and applies mean / rstd / beta in its epilogue (no GroupNorm-apply pass)
+        w4, tab4 = self._w_conv_gn(blk.net[4], blk.net[3])
+        gn_kw = dict(gn_stats=st2, gn_tab=tab4, gn_eps=blk.net[3].eps)
         if isinstance(blk.res_conv, nn.Conv2d):
             res = ops.conv_igemm(x.bf16, self._w_conv(blk.res_conv), kind=L.CONV_S1, kh=1, kw=1, cin=c_in, cout=c_out,
                                  bias=blk.res_conv.bias)
@@ -245,13 +263,13 @@ class Unet(nn.Module):
             if want_bf16:
                 ob = out_bf16 if out_bf16 is not None else torch.empty((b, h, w, pad8(c_out)), dtype=torch.bfloat16,
                                                                         device=dev)
-            ops.conv_igemm(a2, self._w_conv(blk.net[4]), kind=L.CONV_S1, kh=3, kw=3, cin=c_hid, cout=c_out,
-                           bias=blk.net[4].bias, residual=res, out=of, stats=st_out, out2=ob)
+            ops.conv_igemm(h2, w4, kind=L.CONV_S1, kh=3, kw=3, cin=c_hid, cout=c_out, residual=res, out=of,
+                           stats=st_out, out2=ob, **gn_kw)
             return _Act(c_out, f32=of, bf16=ob, stats=st_out)
         ob = out_bf16 if out_bf16 is not None else torch.empty((b, h, w, pad8(c_out)), dtype=torch.bfloat16,
                                                                 device=dev)
-        ops.conv_igemm(a2, self._w_conv(blk.net[4]), kind=L.CONV_S1, kh=3, kw=3, cin=c_hid, cout=c_out,
-                       bias=blk.net[4].bias, residual=res, out=ob, stats=st_out)
+        ops.conv_igemm(h2, w4, kind=L.CONV_S1, kh=3, kw=3, cin=c_hid, cout=c_out, residual=res, out=ob, stats=st_out,
+                       **gn_kw)
         return _Act(c_out, bf16=ob, stats=st_out)
 
     def _linear_attention(self, mod: Residual, x: _Act, *, out_f32=None, out_bf16=None, want_bf16=True) -> _Act:

@@ -292,3 +292,43 @@ def test_conv_pair_staged_transposed_and_small_maps():
         assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item(), (B, H, W)
         ref_s = torch.stack([ref.sum(dim=(1, 2, 3)), (ref * ref).sum(dim=(1, 2, 3))], dim=1)
         assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3), (B, H, W)
+
+
+@pytest.mark.parametrize("case", [
+    # B,   H,  W, cin, cout, k
+    (6,    8,  8, 96, 128, 3),     # single-CTA kernel, all 9 border classes
+    (300,  8,  8, 64, 256, 3),     # CTA-pair kernel (staged epilogue)
+    (700,  2,  2, 64, 128, 3),     # 2x2 maps: every pixel is a corner
+    (200,  1,  1, 128, 64, 3),     # 1x1 maps: centre tap only
+    (40,  16, 16, 72, 40, 1),      # 1x1 kernel, cout not a multiple of 16
+    (90,  16, 16, 64, 256, 3),     # pair kernel on 16x16
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_folded_groupnorm(case):
+    """GroupNorm(1,C) -> conv with the normalisation folded into the GEMM: gamma in the weights, mean / rstd / beta
+    applied in the epilogue through per-border-class tables (unet_model.py:106-110 without the GroupNorm-apply pass)."""
+    L, ops = _mods()
+    B, H, W, cin, cout, k = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(B * 7 + H)
+    x = (torch.randn(B, cin, H, W, generator=g) * 1.7 + 0.6).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    gamma = (1.0 + 0.3 * torch.randn(cin, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(cin, generator=g)).to(dev)
+    res = torch.randn(B, H, W, cout, generator=g).to(dev)
+    xd = x.double()
+    ref = F.conv2d(F.group_norm(xd, 1, gamma.double(), beta.double(), eps=1e-5), w.double(), bias.double(),
+                   padding=k // 2).permute(0, 2, 3, 1) + res.double()
+    stats = torch.stack([xd.sum(dim=(1, 2, 3)), (xd * xd).sum(dim=(1, 2, 3))], dim=1).contiguous()
+    wpk, tab = ops.fold_groupnorm_conv(w, bias, gamma, beta)
+    st_out = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+    out = ops.conv_igemm(_nhwc_bf16(x, ops.pad8(cin)), wpk, kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout,
+                         residual=res, gn_stats=stats, gn_tab=tab, stats=st_out)
+    torch.cuda.synchronize()
+    got = out[..., :cout].double()
+    err = (got - ref).abs().max().item()
+    assert err <= 6e-3 * ref.abs().max().item(), f"{case}: {err:.3e} vs {ref.abs().max().item():.3e}"
+    rel = ((got - ref).norm() / ref.norm()).item()
+    assert rel < 2.5e-3, rel
+    ref_s = torch.stack([got.sum(dim=(1, 2, 3)), (got * got).sum(dim=(1, 2, 3))], dim=1)
+    assert torch.allclose(st_out, ref_s, rtol=1e-5, atol=1e-3)
