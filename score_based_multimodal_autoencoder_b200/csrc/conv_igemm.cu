@@ -412,9 +412,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       ptx::umma_commit(tmem_full_bar);
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue: one output pixel (row) per thread
-    const int ew = warp & 3;  // TMEM lane quarter this warp may read
+  }
+  // ===================== epilogue: ALL 8 warps (the producer / issuer warps join once their loops are done; a small
+  // problem runs one tile per CTA, so the epilogue is pure latency).  One output pixel (row) per thread; warp w reads
+  // TMEM lane quarter w % 4 and the column half w / 4.
+  __syncwarp();
+  {
+    const int ew = warp & 3;
+    const int hc = warp >> 2;
     const int r = ew * 32 + lane;
     const int ow_mask = (1 << p.log_ow) - 1;
     const int j = r & ow_mask;
@@ -431,9 +436,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after_sync();
+    __syncwarp();
 
+    constexpr int kHalf = BN >= 32 ? BN / 2 : BN;  // BN = 32 -> 16 columns per half
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = hc * kHalf; c0 < (hc + 1) * kHalf && c0 < BN; c0 += 16) {
       uint32_t v[16];
       ptx::tmem_ld16(tmem_base + (uint32_t(ew * 32) << 16) + c0, v);
       ptx::tmem_ld_wait();
@@ -980,6 +987,8 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   else BN = (a->cout % 128 == 0) ? 128 : 256;
   const int64_t M = (int64_t)a->batch << log_ohw;
   const int m_tiles = (int)((M + kBM - 1) / kBM);
+  // small problems (one tile per CTA, less than a wave): narrower tiles spread the K loop and the epilogue over more SMs
+  while (BN > 64 && (int64_t)m_tiles * ((a->cout + BN - 1) / BN) * nphase < sm_count()) BN >>= 1;
   // CTA-pair kernel: 256 x BN tiles; worth it once there is at least one full wave of pairs
   // (a cout tail is fine: weight rows beyond cout are TMA zero fill, the epilogue clips the columns)
   const int n_tiles_pair = (a->cout + BN - 1) / BN;

@@ -221,31 +221,27 @@ template <int W, typename TOut>
 __global__ void __launch_bounds__(256, 2)
 dwconv7_pipe_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                     const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
-                    TOut* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C, int H, int flip,
-                    const float* __restrict__ addend, int64_t ldadd) {
+                    TOut* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C, int H, int spb,
+                    int flip, const float* __restrict__ addend, int64_t ldadd) {
   extern __shared__ __align__(16) float sm[];
   const int HW = H * W;
-  const int spb = H >= 8 ? 1 : 8 / H;          // samples per step
-  const int slab = spb * HW * kDwCh;           // floats per buffer
+  const int slab = spb * HW * kDwCh;           // floats per buffer (spb samples per step)
   const int c0 = blockIdx.x * kDwCh;
   const int tid = threadIdx.x;
   const int cl = tid & 31, warp = tid >> 5;
   const int c = c0 + cl;
   const bool c_ok = c < C;
-  const int ls = H >= 8 ? 0 : warp / H;        // local sample of this warp
-  const int row0 = H >= 8 ? warp : warp % H;   // first output row of this warp
-  const int rstep = H >= 8 ? 8 : H;
   const int nsteps = (B + spb - 1) / spb;
+  const int log_hw = 31 - __clz(HW);           // maps are powers of two
 
   auto prefetch = [&](int step, float* buf) {
-    // slab = spb samples x HW pixels x 32 channels: 8 sixteen-byte chunks per pixel
+    // slab = spb samples x HW pixels x 32 channels: 8 sixteen-byte chunks per pixel, all requests in flight at once
     const int chunks = spb * HW * 8;
     for (int i = tid; i < chunks; i += 256) {
       const int q = i & 7, pix = i >> 3;
-      const int s_ = pix / HW, p_ = pix - s_ * HW;
-      const int b = step * spb + s_;
+      const int b = step * spb + (pix >> log_hw);
       if (b < B && c0 + q * 4 < C)
-        cp_async16(buf + pix * kDwCh + q * 4, x + ((int64_t)b * HW + p_) * ldx + c0 + q * 4);
+        cp_async16(buf + pix * kDwCh + q * 4, x + ((int64_t)step * spb * HW + pix) * ldx + c0 + q * 4);
     }
     cp_async_commit();
   };
@@ -267,43 +263,47 @@ dwconv7_pipe_kernel(const float* __restrict__ x, int64_t ldx, const float* __res
       cp_async_wait<0>();
     }
     __syncthreads();
-    const float* sx = sm + cur * slab + ls * HW * kDwCh;
-    const int b = step * spb + ls;
-    if (b < B) {
+    // work item = one output row of one sample; a warp takes every 8th item
+    for (int item = warp; item < spb * H; item += 8) {
+      const int ls = item / H, oh = item - ls * H;
+      const int b = step * spb + ls;
+      if (b >= B) break;
+      // issued now, consumed after the FMA block: the global-load latency hides behind the convolution
       const float add = bias_c + ((c_ok && cond) ? __ldg(cond + (int64_t)b * ldc + c) : 0.f);
-      float s1 = 0.f, s2 = 0.f;
-      for (int oh = row0; oh < H; oh += rstep) {
-        float acc[W];
+      const float* sx = sm + cur * slab + ls * HW * kDwCh;
+      float acc[W];
 #pragma unroll
-        for (int i = 0; i < W; ++i) acc[i] = add;
+      for (int i = 0; i < W; ++i) acc[i] = 0.f;
 #pragma unroll
-        for (int kh = 0; kh < 7; ++kh) {
-          const int ih = oh + kh - 3;
-          if (ih < 0 || ih >= H) continue;
-          const float* row = sx + (ih * W) * kDwCh + cl;
+      for (int kh = 0; kh < 7; ++kh) {
+        const int ih = oh + kh - 3;
+        if (ih < 0 || ih >= H) continue;
+        const float* row = sx + (ih * W) * kDwCh + cl;
 #pragma unroll
-          for (int iw = 0; iw < W; ++iw) {
-            const float v = row[iw * kDwCh];
+        for (int iw = 0; iw < W; ++iw) {
+          const float v = row[iw * kDwCh];
 #pragma unroll
-            for (int kw = 0; kw < 7; ++kw) {
-              const int ow = iw - kw + 3;
-              if (ow >= 0 && ow < W) acc[ow] = fmaf(v, wr[kh * 7 + kw], acc[ow]);
-            }
+          for (int kw = 0; kw < 7; ++kw) {
+            const int ow = iw - kw + 3;
+            if (ow >= 0 && ow < W) acc[ow] = fmaf(v, wr[kh * 7 + kw], acc[ow]);
           }
         }
-        if (c_ok) {
-          TOut* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
-          if (addend != nullptr) {
-            const float* ap = addend + ((int64_t)b * HW + oh * W) * ldadd + c;
+      }
+      float s1 = 0.f, s2 = 0.f;
+      if (c_ok) {
+        TOut* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
 #pragma unroll
-            for (int i = 0; i < W; ++i) acc[i] += ap[(int64_t)i * ldadd];
-          }
+        for (int i = 0; i < W; ++i) acc[i] += add;
+        if (addend != nullptr) {
+          const float* ap = addend + ((int64_t)b * HW + oh * W) * ldadd + c;
 #pragma unroll
-          for (int i = 0; i < W; ++i) {
-            op[(int64_t)i * ldo] = (TOut)acc[i];
-            s1 += acc[i];
-            s2 += acc[i] * acc[i];
-          }
+          for (int i = 0; i < W; ++i) acc[i] += ap[(int64_t)i * ldadd];
+        }
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+          op[(int64_t)i * ldo] = (TOut)acc[i];
+          s1 += acc[i];
+          s2 += acc[i] * acc[i];
         }
       }
       if (stats != nullptr) {
@@ -609,57 +609,55 @@ linear_attn_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __
   }
 }
 
-// Register-tiled variant (the one the forward pass uses).  Same math, organised so that every shared-memory
-// access is a conflict-free 16-byte load feeding 16 FMAs:
-//   load : lane = channel; q is soft-maxed over d with warp shuffles on the fly and stored TRANSPOSED (qT[d][p]);
-//          k, v stored [p][32]
-//   k    : soft-max over the n positions with lane = channel (column max / sum combined across the 8 warps);
-//          the 1/sum factor is applied to the 32x32 context instead of the n x 32 matrix
+// Register-tiled variant (the one the forward pass uses).  Same math, organised so that global memory is read with
+// ONE wave of cp.async requests per block and every shared-memory access of the two small matmuls is a conflict-free
+// 16-byte load feeding 16 FMAs:
+//   load : raw q | k | v rows -> sq, sk, sv [p][32] with cp.async (all requests in flight at once)
+//   q    : soft-max over d in place (lane = channel, warp shuffles); k: column max with lane = channel
+//   k    : exp(k - max) in place + column sums; the 1/sum factor is applied to the 32x32 context, not to n x 32
 //   ctx  : thread = 4(d) x 4(e) tile, the n positions split over 4 thread groups, partial sums reduced in smem
-//   out  : thread = 4(p) x 4(e) tile, out[p][e] = sum_d ctx[d][e] qT[d][p]
+//   out  : thread = 4(p) x 4(e) tile, out[p][e] = sum_d ctx[d][e] q[p][d]
 __global__ void __launch_bounds__(256, 2)
 linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo, int n,
                          int heads, float scale) {
   extern __shared__ __align__(16) float sm[];
   const int n4 = (n + 3) & ~3;
-  const int qs = n4 + 4;                    // qT row stride (multiple of 4 floats)
-  float* qT = sm;                           // [32][qs]
-  float* sk = qT + 32 * qs;                 // [n4][32]   (re-used for the 4 partial contexts [4][32][32])
+  float* sq = sm;                           // [n4][32]
+  float* sk = sq + n4 * 32;                 // [n4][32]   (re-used for the 4 partial contexts [4][32][32])
   float* sv = sk + max(n4 * 32, 4 * 1024);  // [n4][32]
   float* ctx = sv + n4 * 32;                // [32][32]
   float* red = ctx + 1024;                  // [2][8][32]
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hid = heads * kHeadDim;
-  const float* base = qkv + (int64_t)b * n * ldq + h * kHeadDim + lane;
+  const float* base = qkv + (int64_t)b * n * ldq + h * kHeadDim;
 
-  // ---- load (4 rows = 12 independent 128-byte requests per warp in flight), q soft-max over d, k column max
+  // ---- load: 3 matrices x n rows x 8 sixteen-byte chunks
+  for (int i = tid; i < 3 * n * 8; i += 256) {
+    const int q8 = i & 7, rw = i >> 3;
+    const int which = rw / n, p = rw - which * n;
+    float* dst = (which == 0 ? sq : which == 1 ? sk : sv) + p * 32 + q8 * 4;
+    cp_async16(dst, base + (int64_t)p * ldq + which * hid + q8 * 4);
+  }
+  cp_async_commit();
+  for (int i = n * 32 + tid; i < n4 * 32; i += 256) {  // padded rows: q = v = 0, k = -inf
+    sq[i] = 0.f;
+    sk[i] = -INFINITY;
+    sv[i] = 0.f;
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- q soft-max over d (lane = channel), k column max
   float kmax = -INFINITY;
-  for (int p0 = warp * 4; p0 < n4; p0 += 32) {
-    float r[12];
+  for (int p = warp; p < n; p += 8) {
+    const float qv = sq[p * 32 + lane];
+    float m = qv;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u;
-      const bool ok = p < n;
-      const float* row = base + (int64_t)p * ldq;
-      r[3 * u] = ok ? __ldg(row) : 0.f;
-      r[3 * u + 1] = ok ? __ldg(row + hid) : -INFINITY;
-      r[3 * u + 2] = ok ? __ldg(row + 2 * hid) : 0.f;
-    }
-    float qv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float m = r[3 * u];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float e = __expf(r[3 * u] - m);
-      const float ssum = warp_sum(e);
-      qv[u] = (p0 + u < n) ? e / ssum * scale : 0.f;
-      sk[(p0 + u) * 32 + lane] = r[3 * u + 1];
-      sv[(p0 + u) * 32 + lane] = r[3 * u + 2];
-      kmax = fmaxf(kmax, r[3 * u + 1]);
-    }
-    *reinterpret_cast<float4*>(qT + lane * qs + p0) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = __expf(qv - m);
+    const float ssum = warp_sum(e);
+    sq[p * 32 + lane] = e / ssum * scale;
+    kmax = fmaxf(kmax, sk[p * 32 + lane]);
   }
   red[warp * 32 + lane] = kmax;
   __syncthreads();
@@ -710,7 +708,7 @@ linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
     ctx[i] = (sk[i] + sk[1024 + i] + sk[2048 + i] + sk[3072 + i]) / ssum;
   }
   __syncthreads();
-  // ---- out: thread = 4(p) x 4(e) tile
+  // ---- out: thread = 4(p) x 4(e) tile; the 8 lanes of a quarter warp share p0, so the q loads broadcast
   const int ptiles = n4 >> 2;
   for (int t = tid; t < ptiles * 8; t += 256) {
     const int p0 = (t >> 3) * 4, e0 = (t & 7) * 4;
@@ -719,15 +717,22 @@ linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 32; ++d) {
-      const float4 qd = *reinterpret_cast<const float4*>(qT + d * qs + p0);
-      const float4 ce = *reinterpret_cast<const float4*>(ctx + d * 32 + e0);
-      const float qq[4] = {qd.x, qd.y, qd.z, qd.w}, cc[4] = {ce.x, ce.y, ce.z, ce.w};
+#pragma unroll 2
+    for (int d4 = 0; d4 < 8; ++d4) {
+      float qq[4][4], cc[4][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {
+        const float4 t4 = *reinterpret_cast<const float4*>(sq + (p0 + i) * 32 + d4 * 4);
+        qq[i][0] = t4.x; qq[i][1] = t4.y; qq[i][2] = t4.z; qq[i][3] = t4.w;
+        const float4 c4 = *reinterpret_cast<const float4*>(ctx + (d4 * 4 + i) * 32 + e0);
+        cc[i][0] = c4.x; cc[i][1] = c4.y; cc[i][2] = c4.z; cc[i][3] = c4.w;
+      }
 #pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = fmaf(qq[i], cc[j2], acc[i][j2]);
+      for (int dd = 0; dd < 4; ++dd)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) acc[i][j2] = fmaf(qq[i][dd], cc[dd][j2], acc[i][j2]);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -828,7 +833,8 @@ template <int W, typename TOut>
 static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
                                int64_t ldc, void* out, int64_t ldo, double* stats, int B, int H, int C, int flip,
                                const float* addend, int64_t ldadd, cudaStream_t st) {
-  const int spb = H >= 8 ? 1 : 8 / H;
+  // 256 pixels (32 KB) per step: 1 sample of 16x16, 4 of 8x8, 16 of 4x4, ...
+  const int spb = std::max(1, std::min(B, 256 / (H * W)));
   const size_t smem = (size_t)2 * spb * H * W * kDwCh * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -838,11 +844,11 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
   }
   const int chunks = (C + kDwCh - 1) / kDwCh;
   const int nsteps = (B + spb - 1) / spb;
-  // ~2 resident blocks per SM, every block walks >= 2 steps when there is enough work (so the prefetch overlaps)
+  // ~2 resident blocks per SM; a block walks several steps when there is enough work (so the prefetch overlaps)
   int gy = std::max(1, std::min(nsteps, (2 * sm_count() + chunks - 1) / chunks));
   dim3 grid(chunks, gy);
   dwconv7_pipe_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H,
-                                                        flip, addend, ldadd);
+                                                        spb, flip, addend, ldadd);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -1008,8 +1014,9 @@ int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, i
   SBM_CHECK_ARG(qkv && out && B > 0 && n > 0 && heads > 0, "sbm_linear_attn_fwd: bad args");
   dim3 grid(heads, B);
   const int n4 = (n + 3) & ~3;
-  const size_t smem_t = ((size_t)32 * (n4 + 4) + std::max(n4 * 32, 4096) + (size_t)n4 * 32 + 1024 + 512) * sizeof(float);
-  if (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 && smem_t <= 110 * 1024) {
+  const size_t smem_t = ((size_t)n4 * 32 + std::max(n4 * 32, 4096) + (size_t)n4 * 32 + 1024 + 512) * sizeof(float);
+  if (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 && ldq % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && smem_t <= 110 * 1024) {
     static size_t configured = 0;
     if (smem_t > 48 * 1024 && smem_t > configured) {
       SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
