@@ -55,6 +55,16 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t draw, u
   const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+// z0^2 + z1^2 + z2^2 + z3^2 of philox_normal4(seed, draw, quad) without forming the normals: a Box-Muller pair is
+// (s sin v, s cos v) with s^2 = -2 ln u, so its sum of squares is s^2 (sin^2 + cos^2 = 1; equal to the sum over the
+// materialised values up to fp32 rounding).  Used by the corrector's noise-norm reduction.
+__device__ __forceinline__ float philox_sumsq4(uint64_t seed, uint64_t draw, uint64_t quad) {
+  const uint4 ctr = make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)draw, (uint32_t)(draw >> 32));
+  const uint4 r = Philox::round10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float ua = r.x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+  const float ub = r.z * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+  return -1.3862943611198906f * (__log2f(ua) + __log2f(ub));
+}
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t draw, uint64_t idx) {
   const uint64_t quad = idx >> 2;
   const uint4 ctr = make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)draw, (uint32_t)(draw >> 32));
@@ -207,14 +217,18 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
       const bool two = q + 32 < EQ;
       const float4 g0 = grad[base + q];
       const float4 g1 = two ? grad[base + q + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 z0 = noise ? noise[base + q] : philox_normal4(seed, draw, quad_offset + (uint64_t)(base + q));
       sg += g0.x * g0.x + g0.y * g0.y + g0.z * g0.z + g0.w * g0.w;
-      sn += z0.x * z0.x + z0.y * z0.y + z0.z * z0.z + z0.w * z0.w;
-      if (two) {
-        const float4 z1 = noise ? noise[base + q + 32]
-                                : philox_normal4(seed, draw, quad_offset + (uint64_t)(base + q + 32));
-        sg += g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w;
-        sn += z1.x * z1.x + z1.y * z1.y + z1.z * z1.z + z1.w * z1.w;
+      sg += g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w;
+      if (noise) {
+        const float4 z0 = noise[base + q];
+        sn += z0.x * z0.x + z0.y * z0.y + z0.z * z0.z + z0.w * z0.w;
+        if (two) {
+          const float4 z1 = noise[base + q + 32];
+          sn += z1.x * z1.x + z1.y * z1.y + z1.z * z1.z + z1.w * z1.w;
+        }
+      } else {
+        sn += philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q));
+        if (two) sn += philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q + 32));
       }
     }
     sg = warp_sum(sg);

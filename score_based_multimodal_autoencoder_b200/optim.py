@@ -66,4 +66,7 @@ class FusedAdam(torch.optim.Optimizer):
             L.check(L.lib().sbm_adam_step(L.ptr(t_dev), L.ptr(c_dev), C.c_int32(n_chunks), C.c_int32(_CHUNK),
                                           C.c_float(group["lr"]), C.c_float(b1), C.c_float(b2), C.c_float(group["eps"]),
                                           C.c_int32(step), C.c_float(grad_scale), L.stream_ptr()), "sbm_adam_step")
+            # the kernel wrote the parameters through raw pointers: tell autograd (and the score net's packed-weight
+            # cache, keyed by `_version`) that they changed
+            torch.autograd.graph.increment_version(ps)
         return loss
