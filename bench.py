@@ -194,7 +194,8 @@ def run_ours(args):
     if not args.no_dsm:
         del stepper
         torch.cuda.empty_cache()
-        dsm = dsm_train_bench(device, max(args.steps, 5), args.warmup, "poly" if world == 1 else "celeba", world, rank)
+        dsm = dsm_train_bench(device, max(args.steps, 5), args.warmup, "poly" if world == 1 else "celeba", world, rank,
+                              bool(args.graph))
 
     line = None
     if rank == 0:
@@ -282,7 +283,7 @@ class _GraphStepper:
         self.graph.replay()
 
 
-def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0):
+def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_graph=True):
     """DSM training step.  which="poly": BASELINE configs[1] (PolyMNIST latent score UNet, batch 256, 1 GPU);
     which="celeba": configs[3] (CelebAMask-HQ latent UNet, data parallel, 256 latents per GPU = weak scaling, bucketed
     NCCL gradient all-reduce overlapped with the hand-written backward).  bf16 GEMM operands / fp32 master weights.
@@ -305,12 +306,19 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0):
     z_host = torch.randn(*shape, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory()
     z = z_host.to(device)
 
-    def step(batch):
-        loss = sh.loss_fn(batch, net, sde, reduce_mean=True, likelihood_weighting=False, eps=1e-5, rng="philox")
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        opt.step()
-        return loss
+    graphed = None
+    if world == 1 and use_graph:
+        # the whole step (loss_fn + backward + FusedAdam) replayed as ONE CUDA graph; per-step state lives on the device
+        from score_based_multimodal_autoencoder_b200.optim import GraphedTrainStep
+        graphed = GraphedTrainStep(model, sde, z, lr=lr, warmup=3)
+        step = graphed
+    else:
+        def step(batch):
+            loss = sh.loss_fn(batch, net, sde, reduce_mean=True, likelihood_weighting=False, eps=1e-5, rng="philox")
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
 
     def barrier():
         if world > 1:
@@ -335,7 +343,7 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0):
     barrier()
     n0 = L.launch_count()
     ms = timed(lambda: step(z))
-    launches = (L.launch_count() - n0) // steps
+    launches = graphed.launches_per_step if graphed is not None else (L.launch_count() - n0) // steps
     # end to end: H2D of the latent batch and D2H of the loss every step (the reference does loss.item() per step)
     ms_e2e = timed(lambda: step(z_host.to(device, non_blocking=True)).item())
     loss_val = float(step(z).item())
@@ -344,7 +352,7 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0):
             "n_gpus": world, "scaling": "weak", "global_batch": gb, "latents_per_sec": gb * 1e3 / ms,
             "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": z_host.numel() * 4 * world,
                     "d2h_bytes_per_step": 4 * world},
-            "gpu_launches_per_step": int(launches), "loss": loss_val,
+            "gpu_launches_per_step": int(launches), "loss": loss_val, "cuda_graph": graphed is not None,
             "model_tflops_per_gpu": 3 * fwd_gf * 1e9 * shape[0] / (ms * 1e-3) / 1e12,
             "grad_allreduce": None if world == 1 else {"backend": "nccl", "bucket_mb": 64,
                                                        "bytes_per_step": sum(p.numel() for p in model.parameters()) * 4,
@@ -533,7 +541,7 @@ def main():
         device = torch.device("cuda", local_rank)
         if world > 1:
             dist.init_process_group("nccl", device_id=device)
-        res = dsm_train_bench(device, args.steps, args.warmup, args.dsm_only, world, rank)
+        res = dsm_train_bench(device, args.steps, args.warmup, args.dsm_only, world, rank, bool(args.graph))
         if rank == 0:
             print(json.dumps(res), flush=True)
         if world > 1:

@@ -464,7 +464,13 @@ __global__ void add_kernel(const float* __restrict__ a, int64_t lda, const float
 // torch.optim.Adam (no amsgrad / weight decay / maximize): exp_avg, exp_avg_sq updates, bias-corrected step.
 __global__ void __launch_bounds__(256)
 adam_kernel(const sbm_adam_tensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, float lr,
-            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale,
+            const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {  // CUDA-graph replay: the step count lives in device memory (sbm_train_tick advances it)
+    const double st = (double)(*step_dev + 1);
+    bc1 = (float)(1.0 - pow((double)beta1, st));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, st));
+  }
   const int2 ck = chunks[blockIdx.x];
   const sbm_adam_tensor t = tensors[ck.x];
   const int64_t start = (int64_t)ck.y * chunk_elems;
@@ -636,12 +642,15 @@ int sbm_add(const float* a, int64_t lda, const float* b, int64_t ldb, float* out
 
 int sbm_adam_step(const sbm_adam_tensor* tensors_dev, const int32_t* chunks_dev, int32_t n_chunks,
                   int32_t chunk_elems, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
-                  void* stream) {
-  SBM_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && chunk_elems > 0 && step >= 1, "sbm_adam_step: bad args");
+                  const int32_t* step_dev, void* stream) {
+  SBM_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && chunk_elems > 0 && (step >= 1 || step_dev),
+                "sbm_adam_step: bad args");
+  if (step < 1) step = 1;
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(tensors_dev, (const int2*)chunks_dev, chunk_elems, lr, beta1,
-                                                          beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                          beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale,
+                                                          (const int*)step_dev);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_b();
   return 0;

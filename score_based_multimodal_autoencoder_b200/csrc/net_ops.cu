@@ -632,11 +632,12 @@ linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
   const int hid = heads * kHeadDim;
   const float* base = qkv + (int64_t)b * n * ldq + h * kHeadDim;
 
-  // ---- load: 3 matrices x n rows x 8 sixteen-byte chunks
+  // ---- load: 3 matrices x n rows x 8 sixteen-byte chunks.  q rows are stored with their 16-byte chunks XOR-swizzled
+  // by (row & 7) so that a thread can later read "its" whole row with conflict-free 16-byte loads.
   for (int i = tid; i < 3 * n * 8; i += 256) {
     const int q8 = i & 7, rw = i >> 3;
     const int which = rw / n, p = rw - which * n;
-    float* dst = (which == 0 ? sq : which == 1 ? sk : sv) + p * 32 + q8 * 4;
+    float* dst = which == 0 ? sq + p * 32 + ((q8 ^ (p & 7)) << 2) : (which == 1 ? sk : sv) + p * 32 + q8 * 4;
     cp_async16(dst, base + (int64_t)p * ldq + which * hid + q8 * 4);
   }
   cp_async_commit();
@@ -647,18 +648,28 @@ linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
   }
   cp_async_wait<0>();
   __syncthreads();
-  // ---- q soft-max over d (lane = channel), k column max
-  float kmax = -INFINITY;
-  for (int p = warp; p < n; p += 8) {
-    const float qv = sq[p * 32 + lane];
-    float m = qv;
+  // ---- q soft-max over d: one thread = one row, all 32 channels in registers (no shuffle chains)
+  for (int p = tid; p < n; p += 256) {
+    float4* rowp = reinterpret_cast<float4*>(sq + p * 32);
+    float4 v[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    const float e = __expf(qv - m);
-    const float ssum = warp_sum(e);
-    sq[p * 32 + lane] = e / ssum * scale;
-    kmax = fmaxf(kmax, sk[p * 32 + lane]);
+    for (int k = 0; k < 8; ++k) v[k] = rowp[k ^ (p & 7)];
+    float m = v[0].x;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m = fmaxf(fmaxf(fmaxf(m, v[k].x), fmaxf(v[k].y, v[k].z)), v[k].w);
+    float ssum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k].x = __expf(v[k].x - m); v[k].y = __expf(v[k].y - m); v[k].z = __expf(v[k].z - m); v[k].w = __expf(v[k].w - m);
+      ssum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    const float inv = scale / ssum;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rowp[k ^ (p & 7)] = make_float4(v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv);
   }
+  // ---- k column max with lane = channel
+  float kmax = -INFINITY;
+  for (int p = warp; p < n; p += 8) kmax = fmaxf(kmax, sk[p * 32 + lane]);
   red[warp * 32 + lane] = kmax;
   __syncthreads();
   float cmax = red[lane];
@@ -722,7 +733,7 @@ linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
       float qq[4][4], cc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 t4 = *reinterpret_cast<const float4*>(sq + (p0 + i) * 32 + d4 * 4);
+        const float4 t4 = *reinterpret_cast<const float4*>(sq + (p0 + i) * 32 + ((d4 ^ ((p0 + i) & 7)) << 2));
         qq[i][0] = t4.x; qq[i][1] = t4.y; qq[i][2] = t4.z; qq[i][3] = t4.w;
         const float4 c4 = *reinterpret_cast<const float4*>(ctx + (d4 * 4 + i) * 32 + e0);
         cc[i][0] = c4.x; cc[i][1] = c4.y; cc[i][2] = c4.z; cc[i][3] = c4.w;

@@ -338,7 +338,12 @@ __global__ void __launch_bounds__(256)
 dsm_perturb_kernel(const float* __restrict__ x0, const float* __restrict__ u_in, const float* __restrict__ z_in,
                    float* __restrict__ xt, float* __restrict__ z_out, float* __restrict__ t_out,
                    float* __restrict__ std_out, float* __restrict__ g2_out, int64_t n_quads, int E, SdeP s, float T,
-                   float eps, uint64_t seed, uint64_t draw_u, uint64_t draw_z, uint64_t sample_offset) {
+                   float eps, uint64_t seed, uint64_t draw_u, uint64_t draw_z, const uint64_t* draw_dev,
+                   uint64_t sample_offset) {
+  if (draw_dev) {  // CUDA-graph replay: the per-step draw id lives in device memory (sbm_train_tick advances it)
+    draw_u += *draw_dev;
+    draw_z += *draw_dev;
+  }
   for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n_quads;
        q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i4 = q * 4;
@@ -476,6 +481,18 @@ int sbm_sampler_tick(const float* ts, int32_t n_ts, int32_t* step, uint64_t* dra
   return 0;
 }
 
+__global__ void train_tick_kernel(int* step, unsigned long long* draw, unsigned long long draw_inc) {
+  if (step) *step += 1;
+  if (draw) *draw += draw_inc;
+}
+int sbm_train_tick(int32_t* step_dev, uint64_t* draw_dev, uint64_t draw_inc, void* stream) {
+  SBM_CHECK_ARG(step_dev || draw_dev, "sbm_train_tick: nothing to advance");
+  train_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev, (unsigned long long*)draw_dev, draw_inc);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
 int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                        const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
                        const sbm_rng* rng, const sbm_impute* impute, void* stream) {
@@ -553,7 +570,7 @@ int sbm_dsm_perturb(const sbm_latent_shape* ls, const sbm_sde* sde, const float*
   const int64_t nq = (int64_t)ls->batch * E / 4;
   dsm_perturb_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
       x0, u, z, xt, z_out, t_out, std_out, g2_out, nq, E, to_sdep(sde), sde->T, eps, rng ? rng->seed : 0,
-      rng ? rng->draw : 0, rng ? rng->draw + 1 : 0, rng ? rng->sample_offset : 0);
+      rng ? rng->draw : 0, rng ? rng->draw + 1 : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset : 0);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;

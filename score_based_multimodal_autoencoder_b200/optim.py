@@ -1,6 +1,11 @@
 """`FusedAdam`: torch.optim.Adam semantics (train_lat_celebhq_unet_cont2.py:477, lr 5e-5; train_poly_unet_cont.py:782,
 lr 5e-4; betas (0.9, 0.999), eps 1e-8, no weight decay / amsgrad) as ONE kernel launch over all parameter tensors
 (`sbm_adam_step`), instead of the reference's per-tensor loop over 286-354 tensors.
+
+`GraphedTrainStep`: the reference's whole DSM training step (train_lat_celebhq_unet_cont2.py:95-100: loss_fn ->
+zero_grad -> backward -> Adam.step) captured ONCE as a CUDA graph and replayed per batch.  A Poly-sized step is ~700
+kernels of a few microseconds each, i.e. launch-bound from Python; everything that changes between steps (Philox draw
+id, Adam step count) lives in device memory and is advanced by a 1-thread tick kernel inside the graph.
 """
 from __future__ import annotations
 
@@ -14,9 +19,12 @@ _CHUNK = 65536
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self._tables = {}
+        self._stage = {}  # per group: pinned staging + device tables (allocated once, refreshed in place)
+        self.capturable = capturable
+        self.step_dev = None  # device counter of completed steps (capturable mode)
 
     def _table(self, gi, group):
         """Device-side descriptor + chunk tables; rebuilt whenever a grad / state pointer changes."""
@@ -42,12 +50,23 @@ class FusedAdam(torch.optim.Optimizer):
             arr[i] = L.AdamTensor(p.data_ptr(), p.grad.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                   p.numel())
             chunks += [(i, k) for k in range((p.numel() + _CHUNK - 1) // _CHUNK)]
-        raw = bytes(arr)
         dev = ps[0].device
-        t_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-        c_dev = torch.tensor(chunks, dtype=torch.int32).to(dev)
-        self._tables[gi] = (sig, t_dev, c_dev, len(chunks), ps)
-        return t_dev, c_dev, len(chunks), ps
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        cht = torch.tensor(chunks, dtype=torch.int32)
+        stage = self._stage.get(gi)
+        if stage is None or stage[0].numel() != raw.numel() or stage[1].shape != cht.shape:
+            # pinned staging + device tables are allocated once (outside any CUDA-graph capture) and refreshed in place:
+            # a captured copy node re-reads the pinned buffer at every replay
+            stage = (raw.pin_memory(), cht.pin_memory(), torch.empty(raw.numel(), dtype=torch.uint8, device=dev),
+                     torch.empty(cht.shape, dtype=torch.int32, device=dev))
+            self._stage[gi] = stage
+        else:
+            stage[0].copy_(raw)
+            stage[1].copy_(cht)
+        stage[2].copy_(stage[0], non_blocking=True)
+        stage[3].copy_(stage[1], non_blocking=True)
+        self._tables[gi] = (sig, stage[2], stage[3], len(chunks), ps)
+        return stage[2], stage[3], len(chunks), ps
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
@@ -62,11 +81,73 @@ class FusedAdam(torch.optim.Optimizer):
             step = self.state[ps[0]]["step"] + 1
             for p in ps:
                 self.state[p]["step"] = step
+            if self.capturable and self.step_dev is None:
+                self.step_dev = torch.full((1,), step - 1, dtype=torch.int32, device=ps[0].device)
             b1, b2 = group["betas"]
             L.check(L.lib().sbm_adam_step(L.ptr(t_dev), L.ptr(c_dev), C.c_int32(n_chunks), C.c_int32(_CHUNK),
                                           C.c_float(group["lr"]), C.c_float(b1), C.c_float(b2), C.c_float(group["eps"]),
-                                          C.c_int32(step), C.c_float(grad_scale), L.stream_ptr()), "sbm_adam_step")
+                                          C.c_int32(step), C.c_float(grad_scale),
+                                          L.ptr(self.step_dev) if self.capturable else None, L.stream_ptr()),
+                    "sbm_adam_step")
             # the kernel wrote the parameters through raw pointers: tell autograd (and the score net's packed-weight
             # cache, keyed by `_version`) that they changed
             torch.autograd.graph.increment_version(ps)
         return loss
+
+
+class GraphedTrainStep:
+    """One DSM training step as a replayable CUDA graph.
+
+        step = GraphedTrainStep(model, sde, example_batch, lr=5e-4)     # warm-up (3 eager steps) + capture
+        for batch in loader: loss = step(batch)                          # copy-in + one graph launch; loss: 0-d tensor
+
+    Semantics = the eager sequence `loss = loss_fn(batch, model, sde, ...); opt.zero_grad(); loss.backward();
+    opt.step()` with in-kernel Philox (t, z) draws; verified step-for-step against it (tests/test_backward_gpu.py)."""
+
+    def __init__(self, model, sde, example_batch, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss_kwargs=None, warmup=3,
+                 optimizer=None):
+        from . import sde_helper2 as sh
+        self.model, self.sde = model, sde
+        self.loss_kwargs = dict(reduce_mean=True, likelihood_weighting=False, eps=1e-5)
+        self.loss_kwargs.update(loss_kwargs or {})
+        self.opt = optimizer or FusedAdam(model.parameters(), lr=lr, betas=betas, eps=eps, capturable=True)
+        if not self.opt.capturable:
+            raise L.SbmError("GraphedTrainStep needs FusedAdam(capturable=True)")
+        dev = example_batch.device
+        self.batch = example_batch.detach().clone().float().contiguous()
+        self.draw_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._sh = sh
+        self._params = [p for p in model.parameters() if p.requires_grad]
+        self._base_draw = sh._rng.draw  # host draw id baked into the graph; the device offset advances it
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(max(warmup, 1)):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        n0 = L.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.launches_per_step = L.launch_count() - n0
+        # capture does not execute: the counters still hold the post-warm-up state the first replay must start from
+
+    def _body(self):
+        sh = self._sh
+        sh._rng.draw = self._base_draw  # same baked id every time; the device-side offset makes the draws differ
+        loss = sh.loss_fn(self.batch, self.model, self.sde, rng="philox", draw_dev=self.draw_dev, **self.loss_kwargs)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self.opt.step()
+        L.check(L.lib().sbm_train_tick(L.ptr(self.opt.step_dev), L.ptr(self.draw_dev), C.c_uint64(2), L.stream_ptr()),
+                "sbm_train_tick")
+        return loss
+
+    def __call__(self, batch):
+        self.batch.copy_(batch, non_blocking=True)
+        self.graph.replay()
+        # replays update the parameters behind autograd's back: invalidate version-keyed caches for later eager use
+        torch.autograd.graph.increment_version(self._params)
+        return self.loss

@@ -619,7 +619,7 @@ class _DsmLossFn(torch.autograd.Function):
 
 
 def loss_fn(batch, score_fn, sde, reduce_mean=True, likelihood_weighting=True, eps=1e-5, im_sample=False, *,
-            u=None, z=None, rng="torch", global_batch=None):
+            u=None, z=None, rng="torch", global_batch=None, draw_dev=None):
     """Denoising-score-matching loss (sde_helper2.py:152-186) -> 0-d tensor, differentiable w.r.t. the score net.
     Two fused kernels around the net call: perturb (t, x~ = mean + std z) and loss (+ its gradient)."""
     _need_cuda(batch)
@@ -637,7 +637,7 @@ def loss_fn(batch, score_fn, sde, reduce_mean=True, likelihood_weighting=True, e
             u = torch.rand(B, device=dev) if u is None else u      # t first (:167) ...
             z = torch.randn_like(batch) if z is None else z        # ... then z (:168)
         else:
-            r = _rng.next()
+            r = _rng.next(draw_dev)  # draw_dev: device-side draw-id offset (CUDA-graph replay of a training step)
             _rng.draw += 1  # perturb consumes two draw ids (u, z)
     ls = _latent_shape(batch)
     sc = sde._c()

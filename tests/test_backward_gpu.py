@@ -282,3 +282,43 @@ def test_dsm_training_tracks_reference_loss_curve():
         assert losses[-1] < 0.85 * losses[0]
         for got, ref in zip(losses, REF_TRAIN_CURVE):
             assert abs(got - ref) <= 2e-2 * ref, (opt_cls.__name__, losses)
+
+
+def test_graphed_train_step_equals_eager_steps():
+    """The CUDA-graph replay of the training step (loss_fn + backward + FusedAdam, device-side Philox draw id and Adam
+    step count) produces the same losses and parameters as the eager loop with the same seeds."""
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    from score_based_multimodal_autoencoder_b200.optim import FusedAdam, GraphedTrainStep
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    g = torch.Generator().manual_seed(4)
+    batches = [torch.randn(16, 5, 8, 8, generator=g).cuda() for _ in range(8)]
+    sde = sh.VPSDE(1.0, 5.0, 100)
+    kw = dict(dim=32, channels=5, dim_mults=(1, 2))
+
+    torch.manual_seed(0)
+    m_e = Unet(**kw).cuda().train()
+    opt = FusedAdam(m_e.parameters(), lr=5e-4)
+    sh.manual_seed(99)
+    eager = []
+    for b in batches[:3] + batches:  # the graphed run spends its 3 warm-up steps on batches[0..2] too
+        loss = sh.loss_fn(b, m_e, sde, likelihood_weighting=False, rng="philox")
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        eager.append(loss.item())
+
+    torch.manual_seed(0)
+    m_g = Unet(**kw).cuda().train()
+    sh.manual_seed(99)
+    # warm-up consumes batches[0] three times in GraphedTrainStep; feed the same sequence as the eager run instead
+    step = GraphedTrainStep(m_g, sde, batches[0], lr=5e-4, warmup=1)
+    got = [step(b).item() for b in batches[1:3] + batches]
+    # eager[0] used batches[0] (= the graphed warm-up step); compare from the second step on
+    for a, b in zip(got, eager[1:]):
+        assert abs(a - b) <= 2e-3 * abs(b), (got, eager)
+    # Adam's normalised update turns split-K summation-order noise on near-zero gradients into O(lr) differences on
+    # single elements, so compare the tensors in norm
+    num = sum(((pe.double() - pg.double()) ** 2).sum() for pe, pg in zip(m_e.parameters(), m_g.parameters()))
+    den = sum((pe.double() ** 2).sum() for pe in m_e.parameters())
+    assert (num / den).sqrt().item() < 5e-3
+    assert step.launches_per_step > 100
