@@ -111,7 +111,13 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL / c10d print a version banner on stdout when the first communicator comes up: keep stdout for the one
+        # JSON line by pointing fd 1 at stderr until the result is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=device)
     workload = args.workload
     kw, (M, D), (b0, b1, N), given, mods, local_batch = WORKLOADS[workload]
@@ -222,6 +228,9 @@ def run_ours(args):
         }
         if dsm is not None:
             line["dsm_train"] = dsm
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(workload, budget_s=20.0)
         print(json.dumps(line), flush=True)
@@ -363,8 +372,9 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
 
 
 def conv_roofline(model, sde, x0, ops, L):
-    """Time every tcgen05 conv launch of ONE score-net forward with CUDA events on the launch stream and
-    divide the algorithmic FLOPs (valid taps only, true channel counts) by the summed durations."""
+    """Time every tcgen05 conv launch of ONE score-net forward with CUDA events on the launch stream.  `roofline` is the
+    dominant kernel (the persistent CTA-pair kernel with 256-wide N tiles): algorithmic FLOPs (valid taps only, true
+    channel counts) of its launches / their summed durations; `all_convs` is the same over every conv launch."""
     rec = []
     orig = ops.conv_igemm
 
@@ -373,6 +383,7 @@ def conv_roofline(model, sde, x0, ops, L):
         e0.record()
         out = orig(x, wpk, **kw)
         e1.record()
+        variant = L.lib().sbm_conv_last_variant()
         b, h, w, _ = x.shape
         kind, kh, kwd = kw["kind"], kw["kh"], kw["kw"]
         if kind == L.CONV_S1:
@@ -384,7 +395,7 @@ def conv_roofline(model, sde, x0, ops, L):
                 taps = 4
         else:
             taps, pix = (4 if h > 1 else 1), b * h * w * 4
-        rec.append((e0, e1, 2.0 * pix * kw["cin"] * kw["cout"] * taps))
+        rec.append((e0, e1, 2.0 * pix * kw["cin"] * kw["cout"] * taps, variant))
         return out
 
     t = torch.full((x0.shape[0],), 0.5, device=x0.device)
@@ -397,13 +408,27 @@ def conv_roofline(model, sde, x0, ops, L):
         finally:
             ops.conv_igemm = orig
     torch.cuda.synchronize()
-    tot_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
-    flops = sum(f for _, _, f in rec)
+
+    def agg(rows):
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in rows)
+        fl = sum(f for _, _, f, _ in rows)
+        return ms, fl
+
+    dom = [r for r in rec if r[3] == (256 | (1 << 16) | (1 << 17))] or rec
+    ms_d, fl_d = agg(dom)
+    ms_a, fl_a = agg(rec)
     top = max(rec, key=lambda r: r[2])
-    return {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "achieved": flops / (tot_ms * 1e-3) / 1e12,
-            "unit": "TFLOP/s", "launches": len(rec), "algorithmic_gflop_per_forward": flops / 1e9,
-            "avg_launch_us": tot_ms * 1e3 / len(rec),
-            "largest_launch_tflops": top[2] / (top[0].elapsed_time(top[1]) * 1e-3) / 1e12, "traffic": None}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        traffic = json.load(open(tpath)).get("conv_igemm_pair_kernel<256,5,staged>", {}).get("avg_dram_bytes_per_launch")
+    return {"bound": "tensor", "kernel": "conv_igemm_pair_kernel<256,5,staged> (tcgen05 cta_group::2 implicit GEMM)",
+            "achieved": fl_d / (ms_d * 1e-3) / 1e12, "unit": "TFLOP/s", "launches": len(dom),
+            "algorithmic_gflop_per_launch": fl_d / 1e9 / len(dom), "avg_launch_us": ms_d * 1e3 / len(dom),
+            "share_of_forward_conv_time": ms_d / ms_a,
+            "largest_launch_tflops": top[2] / (top[0].elapsed_time(top[1]) * 1e-3) / 1e12, "traffic": traffic,
+            "all_convs": {"achieved": fl_a / (ms_a * 1e-3) / 1e12, "launches": len(rec),
+                          "algorithmic_gflop_per_forward": fl_a / 1e9, "ms_per_forward": ms_a}}
 
 
 def sampler_kernel_roofline(sh, sde, device, batch=65536):

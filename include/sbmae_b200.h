@@ -82,6 +82,8 @@ int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 int sbm_conv_force_single_cta(int32_t on);
 /* A/B switch: 1 = per-thread global stores in the CTA-pair kernel instead of the TMA-staged epilogue */
 int sbm_conv_force_direct_epilogue(int32_t on);
+/* which kernel the calling thread's last sbm_conv_igemm used: N tile | CTA-pair << 16 | staged epilogue << 17 */
+int sbm_conv_last_variant(void);
 
 /* Weight gradient of sbm_conv_igemm: dwpk[tap][o][i] += sum_pixels dy[p][o] * x[p shifted by tap][i]  (fp32, split-K
  * atomics: the caller zeroes dwpk).  x = the forward input operand (bf16), dy = gradient of the forward output (bf16,

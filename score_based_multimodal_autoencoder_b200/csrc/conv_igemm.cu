@@ -36,6 +36,7 @@ namespace sbm {
 
 std::atomic<unsigned long long> g_launches{0};
 static bool g_force_single = false;  // debugging / A-B timing switch (sbm_conv_force_single_cta)
+static thread_local int g_last_variant = 0;  // BN | pair << 16 | staged << 17 of the last launch (bench bookkeeping)
 static bool g_force_direct = false;  // A-B switch: per-thread global stores instead of the TMA-staged epilogue
 
 constexpr int kBM = 128;
@@ -1019,6 +1020,7 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
         staged = encode_rowbox_map(encode, &em.out2, a->out2, SBM_BF16, a->ldo2, a->cout, ow, oh, a->batch, sp_i,
                                    log_ow, log_th);
     }
+    g_last_variant = BN | (1 << 16) | (staged ? (1 << 17) : 0);
     if (staged) {
       if (!a->residual) em.res = em.out;
       if (!a->out2) em.out2 = em.out;
@@ -1032,6 +1034,7 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
     return launch_conv_pair<128, 8, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
   }
   dim3 grid((unsigned)m_tiles, (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
+  g_last_variant = BN;
   switch (BN) {
     case 32: return launch_conv<32, 6>(tmA, tmB, p, grid, stream);
     case 64: return launch_conv<64, 6>(tmA, tmB, p, grid, stream);
@@ -1129,6 +1132,8 @@ int sbm_conv_force_single_cta(int32_t on) {
   sbm::g_force_single = on != 0;
   return 0;
 }
+
+int sbm_conv_last_variant(void) { return sbm::g_last_variant; }
 
 int sbm_conv_force_direct_epilogue(int32_t on) {
   sbm::g_force_direct = on != 0;

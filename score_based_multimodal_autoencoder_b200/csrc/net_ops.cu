@@ -218,7 +218,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int W, typename TOut>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (W <= 8 ? 3 : 2))
 dwconv7_pipe_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                     const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
                     TOut* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C, int H, int spb,
@@ -263,57 +263,73 @@ dwconv7_pipe_kernel(const float* __restrict__ x, int64_t ldx, const float* __res
       cp_async_wait<0>();
     }
     __syncthreads();
-    // work item = one output row of one sample; a warp takes every 8th item
-    for (int item = warp; item < spb * H; item += 8) {
-      const int ls = item / H, oh = item - ls * H;
-      const int b = step * spb + ls;
-      if (b >= B) break;
-      // issued now, consumed after the FMA block: the global-load latency hides behind the convolution
-      const float add = bias_c + ((c_ok && cond) ? __ldg(cond + (int64_t)b * ldc + c) : 0.f);
-      const float* sx = sm + cur * slab + ls * HW * kDwCh;
-      float acc[W];
+    // a warp owns a contiguous run of output rows, i.e. rows of ONE sample when H >= 8 / whole samples otherwise, so
+    // the GroupNorm statistics need one warp reduction per sample instead of one per row
+    {
+      const int rows_total = spb * H;
+      const int per_warp = (rows_total + 7) >> 3;
+      const int r_begin = warp * per_warp, r_end = min(rows_total, r_begin + per_warp);
+      int cur_ls = -1;
+      float s1 = 0.f, s2 = 0.f, add = 0.f;
+      auto flush = [&](int ls_) {
+        if (stats != nullptr && ls_ >= 0) {
+          const float t1 = warp_sum(s1), t2 = warp_sum(s2);
+          if (cl == 0) {
+            const int bb = step * spb + ls_;
+            atomicAdd(stats + 2 * (int64_t)bb, (double)t1);
+            atomicAdd(stats + 2 * (int64_t)bb + 1, (double)t2);
+          }
+        }
+        s1 = 0.f;
+        s2 = 0.f;
+      };
+      for (int item = r_begin; item < r_end; ++item) {
+        const int ls = item / H, oh = item - ls * H;
+        const int b = step * spb + ls;
+        if (b >= B) break;
+        if (ls != cur_ls) {
+          flush(cur_ls);
+          cur_ls = ls;
+          // issued now, consumed after the FMA block: the global-load latency hides behind the convolution
+          add = bias_c + ((c_ok && cond) ? __ldg(cond + (int64_t)b * ldc + c) : 0.f);
+        }
+        const float* sx = sm + cur * slab + ls * HW * kDwCh;
+        float acc[W];
 #pragma unroll
-      for (int i = 0; i < W; ++i) acc[i] = 0.f;
+        for (int i = 0; i < W; ++i) acc[i] = 0.f;
 #pragma unroll
-      for (int kh = 0; kh < 7; ++kh) {
-        const int ih = oh + kh - 3;
-        if (ih < 0 || ih >= H) continue;
-        const float* row = sx + (ih * W) * kDwCh + cl;
+        for (int kh = 0; kh < 7; ++kh) {
+          const int ih = oh + kh - 3;
+          if (ih < 0 || ih >= H) continue;
+          const float* row = sx + (ih * W) * kDwCh + cl;
 #pragma unroll
-        for (int iw = 0; iw < W; ++iw) {
-          const float v = row[iw * kDwCh];
+          for (int iw = 0; iw < W; ++iw) {
+            const float v = row[iw * kDwCh];
 #pragma unroll
-          for (int kw = 0; kw < 7; ++kw) {
-            const int ow = iw - kw + 3;
-            if (ow >= 0 && ow < W) acc[ow] = fmaf(v, wr[kh * 7 + kw], acc[ow]);
+            for (int kw = 0; kw < 7; ++kw) {
+              const int ow = iw - kw + 3;
+              if (ow >= 0 && ow < W) acc[ow] = fmaf(v, wr[kh * 7 + kw], acc[ow]);
+            }
+          }
+        }
+        if (c_ok) {
+          TOut* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
+#pragma unroll
+          for (int i = 0; i < W; ++i) acc[i] += add;
+          if (addend != nullptr) {
+            const float* ap = addend + ((int64_t)b * HW + oh * W) * ldadd + c;
+#pragma unroll
+            for (int i = 0; i < W; ++i) acc[i] += ap[(int64_t)i * ldadd];
+          }
+#pragma unroll
+          for (int i = 0; i < W; ++i) {
+            op[(int64_t)i * ldo] = (TOut)acc[i];
+            s1 += acc[i];
+            s2 += acc[i] * acc[i];
           }
         }
       }
-      float s1 = 0.f, s2 = 0.f;
-      if (c_ok) {
-        TOut* op = out + ((int64_t)b * HW + oh * W) * ldo + c;
-#pragma unroll
-        for (int i = 0; i < W; ++i) acc[i] += add;
-        if (addend != nullptr) {
-          const float* ap = addend + ((int64_t)b * HW + oh * W) * ldadd + c;
-#pragma unroll
-          for (int i = 0; i < W; ++i) acc[i] += ap[(int64_t)i * ldadd];
-        }
-#pragma unroll
-        for (int i = 0; i < W; ++i) {
-          op[(int64_t)i * ldo] = (TOut)acc[i];
-          s1 += acc[i];
-          s2 += acc[i] * acc[i];
-        }
-      }
-      if (stats != nullptr) {
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (cl == 0) {
-          atomicAdd(stats + 2 * (int64_t)b, (double)s1);
-          atomicAdd(stats + 2 * (int64_t)b + 1, (double)s2);
-        }
-      }
+      flush(cur_ls);
     }
     __syncthreads();  // every warp is done with this buffer before the next prefetch overwrites it
     cur ^= 1;
@@ -855,8 +871,8 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
   }
   const int chunks = (C + kDwCh - 1) / kDwCh;
   const int nsteps = (B + spb - 1) / spb;
-  // ~2 resident blocks per SM; a block walks several steps when there is enough work (so the prefetch overlaps)
-  int gy = std::max(1, std::min(nsteps, (2 * sm_count() + chunks - 1) / chunks));
+  // 2-3 resident blocks per SM; a block walks several steps when there is enough work (so the prefetch overlaps)
+  int gy = std::max(1, std::min(nsteps, ((W <= 8 ? 3 : 2) * sm_count() + chunks - 1) / chunks));
   dim3 grid(chunks, gy);
   dwconv7_pipe_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H,
                                                         spb, flip, addend, ldadd);

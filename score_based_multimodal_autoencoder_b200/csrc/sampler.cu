@@ -201,7 +201,10 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
 }
 
 // ------------------------------------------------------------------------------ corrector
-// norms: one warp per sample; acc[0] += ||grad_b||, acc[1] += ||noise_b||  (fp64 accumulators)
+// norms: acc[0] += sum_b ||grad_b||, acc[1] += sum_b ||noise_b||  (fp64 accumulators).  One warp reduces S consecutive
+// samples at a time, S chosen so that S * (E/4) quads are a multiple of 32: every lane is busy on every trip (a
+// PolyMNIST latent has 80 quads, i.e. 2.5 warp trips per sample).
+template <int S>
 __global__ void __launch_bounds__(256)
 corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict__ noise, double* __restrict__ acc,
                        int B, int EQ, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
@@ -209,32 +212,54 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
   if (draw_dev) draw += *draw_dev;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int groups = (B + S - 1) / S;
   double a0 = 0.0, a1 = 0.0;
-  for (int b = blockIdx.x * warps_per_block + (threadIdx.x >> 5); b < B; b += gridDim.x * warps_per_block) {
-    float sg = 0.f, sn = 0.f;
-    const uint32_t base = (uint32_t)b * (uint32_t)EQ;
-    for (int q = lane; q < EQ; q += 64) {
-      const bool two = q + 32 < EQ;
+  for (int gidx = blockIdx.x * warps_per_block + (threadIdx.x >> 5); gidx < groups; gidx += gridDim.x * warps_per_block) {
+    const int b0 = gidx * S;
+    const int ns = min(S, B - b0);
+    const uint32_t base = (uint32_t)b0 * (uint32_t)EQ;
+    const int total = ns * EQ;
+    float sg[S], sn[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) { sg[k] = 0.f; sn[k] = 0.f; }
+    for (int q = lane; q < total; q += 64) {
+      const bool two = q + 32 < total;
       const float4 g0 = grad[base + q];
       const float4 g1 = two ? grad[base + q + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
-      sg += g0.x * g0.x + g0.y * g0.y + g0.z * g0.z + g0.w * g0.w;
-      sg += g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w;
+      float n0, n1 = 0.f;
       if (noise) {
         const float4 z0 = noise[base + q];
-        sn += z0.x * z0.x + z0.y * z0.y + z0.z * z0.z + z0.w * z0.w;
+        n0 = z0.x * z0.x + z0.y * z0.y + z0.z * z0.z + z0.w * z0.w;
         if (two) {
           const float4 z1 = noise[base + q + 32];
-          sn += z1.x * z1.x + z1.y * z1.y + z1.z * z1.z + z1.w * z1.w;
+          n1 = z1.x * z1.x + z1.y * z1.y + z1.z * z1.z + z1.w * z1.w;
         }
       } else {
-        sn += philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q));
-        if (two) sn += philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q + 32));
+        n0 = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q));
+        if (two) n1 = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q + 32));
+      }
+      const float q0 = g0.x * g0.x + g0.y * g0.y + g0.z * g0.z + g0.w * g0.w;
+      const float q1 = g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w;
+      if (S == 1) {
+        sg[0] += q0 + q1;
+        sn[0] += n0 + n1;
+      } else {
+        const int s0 = q / EQ, s1i = (q + 32) / EQ;
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          if (s0 == k) { sg[k] += q0; sn[k] += n0; }
+          if (two && s1i == k) { sg[k] += q1; sn[k] += n1; }
+        }
       }
     }
-    sg = warp_sum(sg);
-    sn = warp_sum(sn);
-    a0 += (double)sqrtf(sg);
-    a1 += (double)sqrtf(sn);
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+      const float tg = warp_sum(sg[k]), tn = warp_sum(sn[k]);
+      if (k < ns) {
+        a0 += (double)sqrtf(tg);
+        a1 += (double)sqrtf(tn);
+      }
+    }
   }
   // one atomic pair per block
   __shared__ double red[2][8];
@@ -516,12 +541,23 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
   if (check_latent(ls, "sbm_corrector_norms")) return 1;
   SBM_CHECK_ARG(grad && acc2 && (noise || rng), "sbm_corrector_norms: null pointer");
   const int E = ls->mods * ls->dd;
-  const int blocks = std::max(1, std::min((ls->batch + 7) / 8, sm_count() * 8));
-  corrector_norms_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)grad, (const float4*)noise, acc2,
-                                                                   ls->batch, E / 4,
-                                                                   rng ? rng->seed : 0, rng ? rng->draw : 0,
-                                                                   rng ? rng->draw_dev : nullptr,
-                                                                   rng ? rng->sample_offset * (uint64_t)(E / 4) : 0);
+  const int EQ = E / 4;
+  const int S = (EQ % 32 == 0) ? 1 : ((2 * EQ) % 32 == 0 ? 2 : ((4 * EQ) % 32 == 0 ? 4 : 1));
+  const int groups = (ls->batch + S - 1) / S;
+  const int blocks = std::max(1, std::min((groups + 7) / 8, sm_count() * 8));
+  const uint64_t seed = rng ? rng->seed : 0, draw = rng ? rng->draw : 0;
+  const uint64_t* ddev = rng ? rng->draw_dev : nullptr;
+  const uint64_t qoff = rng ? rng->sample_offset * (uint64_t)EQ : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 1)
+    corrector_norms_kernel<1><<<blocks, 256, 0, st>>>((const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, seed,
+                                                      draw, ddev, qoff);
+  else if (S == 2)
+    corrector_norms_kernel<2><<<blocks, 256, 0, st>>>((const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, seed,
+                                                      draw, ddev, qoff);
+  else
+    corrector_norms_kernel<4><<<blocks, 256, 0, st>>>((const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, seed,
+                                                      draw, ddev, qoff);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;
