@@ -337,8 +337,14 @@ def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, imp
 
 
 # ======================================================================================= step functions
+def _call_score(score_fn, x, t, z_cond):
+    """score_fn(x, t) of the reference; with a conditioning code the z-conditioned call of
+    train_lat_celebhq_unet_cont2_cond.py:123,225-226,307-309 (`score_fn(x, t, z=z_cond)`, UNetModel(use_z=True))."""
+    return score_fn(x, t) if z_cond is None else score_fn(x, t, z=z_cond)
+
+
 def em_predictor(x, t, score_fn, sde, probability_flow=False, cl_g=None, cl_s=None, target=None, given=None,
-                 all_mods=None, *, noise=None, rng="torch"):
+                 all_mods=None, z_cond=None, *, noise=None, rng="torch"):
     """Euler-Maruyama reverse-SDE predictor step (sde_helper2.py:45-52) -> (x, x_mean).
     One fused kernel after the score-net call; the noise is drawn BEFORE the net call like the reference."""
     _reject_guidance(cl_g, given)
@@ -350,12 +356,12 @@ def em_predictor(x, t, score_fn, sde, probability_flow=False, cl_g=None, cl_s=No
             noise = torch.randn_like(x)
         else:
             r = _rng.next()
-    score = _f32c(score_fn(x, t))
+    score = _f32c(_call_score(score_fn, x, t, z_cond))
     return _predictor_kernel(sde, x, score, t, noise=noise, rng=r, probability_flow=probability_flow)
 
 
 def corrector(x, t, score_fn, sde, n_steps, target_snr, cl_g=None, cl_s=None, target=None, given=None, all_mods=None,
-              *, noise=None, rng="torch", global_batch=None, reduce_fn=None):
+              z_cond=None, *, noise=None, rng="torch", global_batch=None, reduce_fn=None):
     """Langevin corrector (sde_helper2.py:54-106) -> (x, x_mean).  Two fused kernels per Langevin step
     (batch-coupled norms, then the update); the noise is drawn AFTER the net call like the reference.
     `noise`: optional [n_steps, B, M, D, D] injected noise."""
@@ -364,7 +370,7 @@ def corrector(x, t, score_fn, sde, n_steps, target_snr, cl_g=None, cl_s=None, ta
     x, t = _f32c(x), _f32c(t)
     x_mean = x
     for i in range(n_steps):
-        grad = _f32c(score_fn(x, t))
+        grad = _f32c(_call_score(score_fn, x, t, z_cond))
         nz, r = None, None
         if noise is not None:
             nz = noise[i] if noise.dim() == 5 else noise
@@ -391,7 +397,7 @@ def _obs_mask_from(given, all_mods) -> int:
 def pc_sampler(x0, model, sde, *, z_obs=None, obs_mask=0, eps=1e-3, noise_obs=True, pc=True, n_steps=1,
                target_snr=0.16, predictor_first=True, probability_flow=False, noise_pred=None, noise_corr=None,
                num_steps=None, global_batch=None, reduce_fn=None, use_graph=False, return_state=False,
-               rng="philox"):
+               rng="philox", z_cond=None):
     """N-step predictor-corrector sampler over a stacked latent [B,M,D,D] with observed-modality imputation.
 
     Semantics = the reference's inline loop (train_lat_celebhq_unet_cont2.py:287-316 for predictor_first=True,
@@ -436,14 +442,14 @@ def pc_sampler(x0, model, sde, *, z_obs=None, obs_mask=0, eps=1e-3, noise_obs=Tr
             if torch_rng and not probability_flow:
                 nz = torch.randn_like(x)  # reference order: drawn BEFORE the net call (sde_helper2.py:47)
             r = None if (nz is not None or probability_flow) else _rng.next(draw_dev)
-            score = model(x, t_vec)
+            score = _call_score(model, x, t_vec, z_cond)
             return _predictor_kernel(sde, x, score, t_vec, noise=nz, rng=r, probability_flow=probability_flow,
                                      impute=impute, want_mean=want_mean)
 
         def langevin(x, impute, want_mean):
             xm = x
             for k in range(n_steps):
-                grad = model(x, t_vec)
+                grad = _call_score(model, x, t_vec, z_cond)
                 nz = noise_corr[i, k] if inject else None
                 if torch_rng:
                     nz = torch.randn_like(x)  # reference order: drawn AFTER the net call (sde_helper2.py:96)
@@ -559,7 +565,8 @@ def randn(shape, device, scale=1.0):
 
 def cond_sampler(z_obs, given, all_mods, model, sde, eps=1e-3, noise_obs=True, pc=True, n_steps=1, target_snr=0.16,
                  pc_order="predictor_first", probability_flow=False, *, x_init=None, dim=None, use_graph=False,
-                 global_batch=None, reduce_fn=None, noise_pred=None, noise_corr=None, num_steps=None, rng="philox"):
+                 global_batch=None, reduce_fn=None, noise_pred=None, noise_corr=None, num_steps=None, rng="philox",
+                 z_cond=None):
     """Conditional generation: sample the missing modalities given the observed ones.
 
     z_obs   : dict {mod: [B, size_z]} of clean encoder latents for the observed modalities (the reference's
@@ -587,7 +594,8 @@ def cond_sampler(z_obs, given, all_mods, model, sde, eps=1e-3, noise_obs=True, p
     return pc_sampler(x_init, model, sde, z_obs=stacked, obs_mask=mask, eps=eps, noise_obs=noise_obs, pc=pc,
                       n_steps=n_steps, target_snr=target_snr, predictor_first=(pc_order == "predictor_first"),
                       probability_flow=probability_flow, use_graph=use_graph, global_batch=global_batch,
-                      reduce_fn=reduce_fn, noise_pred=noise_pred, noise_corr=noise_corr, num_steps=num_steps, rng=rng)
+                      reduce_fn=reduce_fn, noise_pred=noise_pred, noise_corr=noise_corr, num_steps=num_steps, rng=rng,
+                      z_cond=z_cond)
 
 
 # ======================================================================================= DSM loss
@@ -619,7 +627,7 @@ class _DsmLossFn(torch.autograd.Function):
 
 
 def loss_fn(batch, score_fn, sde, reduce_mean=True, likelihood_weighting=True, eps=1e-5, im_sample=False, *,
-            u=None, z=None, rng="torch", global_batch=None, draw_dev=None):
+            u=None, z=None, rng="torch", global_batch=None, draw_dev=None, z_cond=None):
     """Denoising-score-matching loss (sde_helper2.py:152-186) -> 0-d tensor, differentiable w.r.t. the score net.
     Two fused kernels around the net call: perturb (t, x~ = mean + std z) and loss (+ its gradient)."""
     _need_cuda(batch)
@@ -650,7 +658,7 @@ def loss_fn(batch, score_fn, sde, reduce_mean=True, likelihood_weighting=True, e
     L.check(L.lib().sbm_dsm_perturb(C.byref(ls), C.byref(sc), L.ptr(batch), L.ptr(u), L.ptr(z), L.ptr(xt),
                                     L.ptr(z_out), L.ptr(t), L.ptr(std), L.ptr(g2), C.c_float(eps),
                                     C.byref(r) if r is not None else None, L.stream_ptr()), "sbm_dsm_perturb")
-    score = score_fn(xt, t)
+    score = _call_score(score_fn, xt, t, z_cond)
     return _DsmLossFn.apply(score.float(), z_out, std, g2, lw_branch, bool(reduce_mean), global_batch or B)
 
 

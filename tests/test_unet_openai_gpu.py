@@ -84,3 +84,34 @@ def test_unet_openai_as_score_fn_in_sampler():
                                                        attention_resolutions=(), channel_mult=(1, 2), num_heads=1)
         rn, rm = so.em_predictor_step(so.SdeSpec("vp", 0.1, 20.0, 10), x, t, score_fn(x, t), n)
     assert rel_l2(xn, rn) < 5e-3 and rel_l2(xm, rm) < 5e-3
+
+
+def test_z_conditioned_sampling_matches_oracle():
+    """the `z_cond` extension of em_predictor / corrector / cond_sampler (train_lat_celebhq_unet_cont2_cond.py
+    :123, 225-226, 307-309 call `score_fn(x, t, z=z_cond)`; the shipped sde_helper2.py lacks the kwarg) with the
+    z-conditioned UNetModel, against the oracle PC loop driven by the oracle net."""
+    from oracle import sde_oracle as so
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    kw = dict(in_channels=3, model_channels=32, out_channels=3, num_res_blocks=1, attention_resolutions=(),
+              channel_mult=(1, 2), num_heads=1, use_z=True, z_dim=16)
+    m, sd = _build(kw)
+    g = torch.Generator().manual_seed(21)
+    B, N, steps = 4, 100, 3
+    z_obs = torch.randn(B, 3, 8, 8, generator=g)
+    zc = torch.randn(B, 16, generator=g)
+    npred = torch.randn(steps, B, 3, 8, 8, generator=g)
+    ncorr = torch.randn(steps, 1, B, 3, 8, 8, generator=g)
+    sde = sh.VPSDE(1.0, 5.0, N)
+    score_fn = lambda a, b: uo.unet_openai_forward(sd, a, b, z=zc, model_channels=32, num_res_blocks=1,
+                                                   attention_resolutions=(), channel_mult=(1, 2), num_heads=1)
+    with torch.no_grad():
+        out = sh.cond_sampler(z_obs.cuda(), "0", "012", m, sde, x_init=z_obs.cuda(), noise_pred=npred.cuda(),
+                              noise_corr=ncorr.cuda(), num_steps=steps, z_cond=zc.cuda())
+        ref = so.pc_sampler(so.SdeSpec("vp", 1.0, 5.0, N), score_fn, z_obs, npred, ncorr, z_obs=z_obs,
+                            obs_mask=[True, False, False], num_steps=steps)
+        x1, _ = sh.em_predictor(z_obs.cuda(), torch.full((B,), 0.5).cuda(), m, sde, z_cond=zc.cuda(), noise=npred[0].cuda())
+        r1, _ = so.em_predictor_step(so.SdeSpec("vp", 1.0, 5.0, N), z_obs, torch.full((B,), 0.5),
+                                     score_fn(z_obs, torch.full((B,), 0.5)), npred[0])
+    assert torch.isfinite(ref).all()
+    assert rel_l2(out, ref) < 2e-2
+    assert rel_l2(x1, r1) < 5e-3
