@@ -40,7 +40,7 @@ unsigned long long sbm_launch_count(void);
  */
 enum { SBM_CONV_S1 = 0,     /* KHxKW, stride 1, padding (K-1)/2 ("same")            */
        SBM_CONV_S2 = 1,     /* KHxKW (4x4 or 3x3), stride 2, padding 1              */
-       SBM_CONVT_4X4_S2 = 2 /* ConvTranspose2d 4x4, stride 2, padding 1             */ };
+       SBM_CONVT_4X4_S2 = 2 /* ConvTranspose2d 4x4 (or 3x3 + output_padding 1), stride 2, padding 1 */ };
 enum { SBM_ACT_NONE = 0, SBM_ACT_GELU = 1, SBM_ACT_SILU = 2 };
 enum { SBM_F32 = 0, SBM_BF16 = 1 };
 
@@ -216,7 +216,15 @@ int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* d
                       const double* stats, const float* gamma, float* bst, float* dgamma, float* dbeta,
                       const float* addend, int64_t ldadd, float* out_f32, int64_t ldo_f32, void* out_bf16,
                       int64_t ldo_bf16, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t in_act,
+                      const float* beta /* needed when out_act != 0 */,
+                      int32_t out_act /* activation applied AFTER the norm (GroupNorm32 -> SiLU, unet_openai.py:252) */,
                       void* stream);
+/* out[b][c] = sum over the pixels of sample b of x[b][p][c]: gradient of a per-sample row bias (unet_openai.py:303) */
+int sbm_colsum_per_sample(const void* x, int32_t dtype, int64_t ld, int32_t B, int32_t HW, int32_t C, float* out,
+                          int64_t ldo, void* stream);
+/* backward of sbm_upsample_nearest2x: out[b,i,j,c] = sum of the 2x2 block of dy (fp32 [B,2H,2W,lddy]) */
+int sbm_upsample_nearest2x_bwd(const float* dy, int64_t lddy, float* out, int64_t ldo, void* out_bf16, int64_t ldb,
+                               int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* depthwise 7x7: dw[C][49] += , db[C] += , dcond[b][c] = sum_p dy  (caller zeroes dw, db) */
 int sbm_dwconv7_wgrad(const float* x, int64_t ldx, const float* dy, int64_t lddy, float* dw, float* db, float* dcond,
                       int64_t ldc, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict__ dy, int64_t lddy,
                      const double* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ bst,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C, int G, float eps,
-                     int in_act) {
+                     int in_act, const float* __restrict__ beta, int out_act) {
   extern __shared__ float sm[];
   float* sdg = sm;          // [C]
   float* sdb = sm + C;      // [C]
@@ -90,7 +90,9 @@ gn_bwd_reduce_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restric
     float xv = ldf<TX>(x + pix * ldx + c);
     if (in_act) xv = act_fwd(xv, in_act);
     const float xh = (xv - s_mean[g]) * s_rstd[g];
-    const float d = ldf<TDY>(dy + pix * lddy + c);
+    float d = ldf<TDY>(dy + pix * lddy + c);
+    // out = act(y), y = xh*gamma + beta (unet_openai.py:252-253 GroupNorm32 -> SiLU): chain through the activation
+    if (out_act) d *= act_grad(fmaf(xh, __ldg(gamma + c), __ldg(beta + c)), out_act);
     const float t = d * __ldg(gamma + c);
     if (G == 1) {
       a1 += t;
@@ -125,7 +127,7 @@ gn_bwd_apply_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict
                     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ bst,
                     const float* __restrict__ addend, int64_t ldadd, float* __restrict__ out_f32, int64_t ldo_f32,
                     __nv_bfloat16* __restrict__ out_bf16, int64_t ldo_bf16, int HW, int C, int G, float eps,
-                    int in_act) {
+                    int in_act, const float* __restrict__ beta, int out_act) {
   __shared__ float s_mean[64], s_rstd[64], s_c1[64], s_c2[64];
   const int b = blockIdx.y;
   const int cpg = C / G;
@@ -149,7 +151,8 @@ gn_bwd_apply_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict
     const float pre = ldf<TX>(x + pix * ldx + c);
     const float xv = in_act ? act_fwd(pre, in_act) : pre;
     const float xh = (xv - s_mean[g]) * s_rstd[g];
-    const float d = ldf<TDY>(dy + pix * lddy + c);
+    float d = ldf<TDY>(dy + pix * lddy + c);
+    if (out_act) d *= act_grad(fmaf(xh, __ldg(gamma + c), __ldg(beta + c)), out_act);
     float dx = s_rstd[g] * (d * __ldg(gamma + c) - s_c1[g] - xh * s_c2[g]);
     if (in_act) dx *= act_grad(pre, in_act);
     if (addend) dx += addend[pix * ldadd + c];
@@ -487,6 +490,46 @@ adam_kernel(const sbm_adam_tensor* __restrict__ tensors, const int2* __restrict_
   }
 }
 
+// out[b][c] = sum over the HW pixels of sample b of x[b][p][c]  (gradient of a per-sample row bias, unet_openai.py:303)
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_per_sample_kernel(const T* __restrict__ x, int64_t ld, int HW, int C, float* __restrict__ out, int64_t ldo) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  __shared__ float red[8][33];
+  float acc = 0.f;
+  if (c < C)
+    for (int p = threadIdx.x >> 5; p < HW; p += 8) acc += ldf<T>(x + ((int64_t)b * HW + p) * ld + c);
+  red[threadIdx.x >> 5][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    out[(int64_t)b * ldo + c] = t;
+  }
+}
+
+// backward of nearest-neighbour 2x upsampling (unet_openai.py:185): out[b,i,j,c] = sum of the 2x2 block of dy
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const float* __restrict__ dy, int64_t lddy, float* __restrict__ out, int64_t ldo,
+                      __nv_bfloat16* __restrict__ out_bf16, int64_t ldb, int B, int H, int W, int C) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    const int64_t pix = idx / C;
+    const int j = (int)(pix % W);
+    const int i = (int)((pix / W) % H);
+    const int64_t b = pix / ((int64_t)W * H);
+    const float* r0 = dy + ((b * 2 * H + 2 * i) * 2 * W + 2 * j) * lddy + c;
+    const float* r1 = r0 + (int64_t)2 * W * lddy;
+    const float v = r0[0] + r0[lddy] + r1[0] + r1[lddy];
+    if (out) out[pix * ldo + c] = v;
+    if (out_bf16) out_bf16[pix * ldb + c] = __float2bfloat16_rn(v);
+  }
+}
+
 static int egrid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
 }
@@ -507,12 +550,37 @@ int sbm_colsum(const void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t C
   return 0;
 }
 
+int sbm_colsum_per_sample(const void* x, int32_t dtype, int64_t ld, int32_t B, int32_t HW, int32_t C, float* out,
+                          int64_t ldo, void* stream) {
+  SBM_CHECK_ARG(x && out && B > 0 && HW > 0 && C > 0, "sbm_colsum_per_sample: bad args");
+  dim3 grid((C + 31) / 32, B);
+  if (dtype == SBM_F32)
+    colsum_per_sample_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ld, HW, C, out, ldo);
+  else
+    colsum_per_sample_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, HW, C,
+                                                                                    out, ldo);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_upsample_nearest2x_bwd(const float* dy, int64_t lddy, float* out, int64_t ldo, void* out_bf16, int64_t ldb,
+                               int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  SBM_CHECK_ARG(dy && (out || out_bf16) && B > 0 && H > 0 && W > 0 && C > 0, "sbm_upsample_nearest2x_bwd: bad args");
+  upsample2x_bwd_kernel<<<egrid((int64_t)B * H * W * C), 256, 0, (cudaStream_t)stream>>>(
+      dy, lddy, out, ldo, (__nv_bfloat16*)out_bf16, ldb, B, H, W, C);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
 int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* dy, int32_t dy_dtype, int64_t lddy,
                       const double* stats, const float* gamma, float* bst, float* dgamma, float* dbeta,
                       const float* addend, int64_t ldadd, float* out_f32, int64_t ldo_f32, void* out_bf16,
                       int64_t ldo_bf16, int32_t B, int32_t HW, int32_t C, int32_t G, float eps, int32_t in_act,
-                      void* stream) {
+                      const float* beta, int32_t out_act, void* stream) {
   SBM_CHECK_ARG(x && dy && stats && gamma && bst && dgamma && dbeta && (out_f32 || out_bf16), "sbm_groupnorm_bwd: null");
+  SBM_CHECK_ARG(out_act == 0 || beta != nullptr, "sbm_groupnorm_bwd: an output activation needs beta");
   SBM_CHECK_ARG(B > 0 && G > 0 && G <= 64 && C % G == 0, "sbm_groupnorm_bwd: bad sizes");
   const int64_t per_sample = (int64_t)HW * C;
   int chunks = (int)std::min<int64_t>((per_sample + 4095) / 4096, std::max<int64_t>(1, (int64_t)sm_count() * 8 / B));
@@ -524,10 +592,10 @@ int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* d
 #define SBM_GNB(TX, TDY)                                                                                            \
   do {                                                                                                              \
     gn_bwd_reduce_kernel<TX, TDY><<<grid, 256, smem, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats, gamma, bst, \
-                                                          dgamma, dbeta, HW, C, G, eps, in_act);                    \
+                                                          dgamma, dbeta, HW, C, G, eps, in_act, beta, out_act);     \
     gn_bwd_apply_kernel<TX, TDY><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats, gamma, bst,     \
                                                       addend, ldadd, out_f32, ldo_f32, (__nv_bfloat16*)out_bf16,     \
-                                                      ldo_bf16, HW, C, G, eps, in_act);                             \
+                                                      ldo_bf16, HW, C, G, eps, in_act, beta, out_act);              \
   } while (0)
   if (x_dtype == SBM_F32 && dy_dtype == SBM_F32) SBM_GNB(float, float);
   else if (x_dtype == SBM_BF16 && dy_dtype == SBM_F32) SBM_GNB(__nv_bfloat16, float);

@@ -885,7 +885,10 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
         ++t.ntaps;
       }
   } else if (a->kind == SBM_CONVT_4X4_S2) {
-    SBM_CHECK_ARG(a->kh == 4 && a->kw == 4, "sbm_conv_igemm: transposed conv must be 4x4");
+    // ConvTranspose2d(k, stride 2, padding 1) with output 2h x 2w: k = 4 (unet_model.py:30) or k = 3 with
+    // output_padding 1 (= the data gradient of the 3x3 stride-2 convolution of unet_openai.py:207)
+    SBM_CHECK_ARG((a->kh == 4 && a->kw == 4) || (a->kh == 3 && a->kw == 3),
+                  "sbm_conv_igemm: transposed conv must be 4x4 or 3x3");
     SBM_CHECK_ARG(a->h <= 64 && a->w <= 64, "sbm_conv_igemm: transposed conv input must be <= 64x64");
     oh = a->h; ow = a->w;  // per-phase output grid; full output is 2h x 2w
     nphase = 4;
@@ -896,15 +899,15 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       for (int pw = 0; pw < 2; ++pw) {
         TapTable& t = p.taps[ph * 2 + pw];
         // out[2i+ph, 2j+pw] += in[i+dh, j+dw] * W[kh][kw] with 2(i+dh) = 2i + ph + 1 - kh
-        for (int kh = 0; kh < 4; ++kh) {
+        for (int kh = 0; kh < a->kh; ++kh) {
           if (((ph + 1 - kh) & 1) != 0) continue;
           const int dh = (ph + 1 - kh) / 2;
-          for (int kw = 0; kw < 4; ++kw) {
+          for (int kw = 0; kw < a->kw; ++kw) {
             if (((pw + 1 - kw) & 1) != 0) continue;
             const int dw = (pw + 1 - kw) / 2;
             if (abs(dh) >= a->h || abs(dw) >= a->w) continue;
             t.dh[t.ntaps] = (int8_t)dh; t.dw[t.ntaps] = (int8_t)dw; t.q[t.ntaps] = 0;
-            t.wtap[t.ntaps] = (int16_t)(kh * 4 + kw);
+            t.wtap[t.ntaps] = (int16_t)(kh * a->kw + kw);
             ++t.ntaps;
           }
         }

@@ -246,8 +246,8 @@ def colsum(x: torch.Tensor, c: int) -> torch.Tensor:
 
 
 def groupnorm_bwd(x, dy, c, stats, gamma, *, groups=1, in_act=0, addend=None, want_f32=True, want_bf16=False,
-                  eps=1e-5):
-    """-> (dx_f32 | None, dx_bf16 | None, dgamma, dbeta)"""
+                  eps=1e-5, beta=None, out_act=0):
+    """-> (dx_f32 | None, dx_bf16 | None, dgamma, dbeta).  out_act: activation applied after the norm (needs beta)."""
     b, h, w, _ = x.shape
     dev = x.device
     bst = torch.zeros((b, groups, 2), dtype=torch.float32, device=dev)
@@ -262,7 +262,7 @@ def groupnorm_bwd(x, dy, c, stats, gamma, *, groups=1, in_act=0, addend=None, wa
         L.ptr(of), C.c_int64(of.stride(2) if of is not None else 0),
         L.ptr(ob), C.c_int64(ob.stride(2) if ob is not None else 0),
         C.c_int32(b), C.c_int32(h * w), C.c_int32(c), C.c_int32(groups), C.c_float(eps), C.c_int32(in_act),
-        L.stream_ptr()), "sbm_groupnorm_bwd")
+        L.ptr(beta), C.c_int32(out_act), L.stream_ptr()), "sbm_groupnorm_bwd")
     return of, ob, dgamma, dbeta
 
 
@@ -345,4 +345,21 @@ def upsample_nearest2x(x: torch.Tensor, c: int) -> torch.Tensor:
     L.check(L.lib().sbm_upsample_nearest2x(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(out), C.c_int64(out.stride(2)),
                                            C.c_int32(b), C.c_int32(h), C.c_int32(w), C.c_int32(c), L.stream_ptr()),
             "sbm_upsample_nearest2x")
+    return out
+
+
+def colsum_per_sample(x: torch.Tensor, c: int, out: torch.Tensor) -> None:
+    """out[b, :c] = sum over the pixels of sample b of x[b, :, :, :c] (out: a [B, >=c] fp32 view with row stride)."""
+    b, h, w, _ = x.shape
+    L.check(L.lib().sbm_colsum_per_sample(L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), C.c_int32(b),
+                                          C.c_int32(h * w), C.c_int32(c), L.ptr(out), C.c_int64(out.stride(0)),
+                                          L.stream_ptr()), "sbm_colsum_per_sample")
+
+
+def upsample_nearest2x_bwd(dy: torch.Tensor, c: int) -> torch.Tensor:
+    b, h2, w2, _ = dy.shape
+    out = torch.empty((b, h2 // 2, w2 // 2, pad8(c)), dtype=torch.float32, device=dy.device)
+    L.check(L.lib().sbm_upsample_nearest2x_bwd(L.ptr(dy), C.c_int64(dy.stride(2)), L.ptr(out), C.c_int64(out.stride(2)),
+                                               None, C.c_int64(0), C.c_int32(b), C.c_int32(h2 // 2), C.c_int32(w2 // 2),
+                                               C.c_int32(c), L.stream_ptr()), "sbm_upsample_nearest2x_bwd")
     return out

@@ -15,8 +15,8 @@ sm_100a kernels through the C ABI (ops.py -> libsbmae_b200.so):
   * `torch.cat([h, hs.pop()])` (unet_openai.py:571) never materialises: producers write into the two channel ranges
     of a pre-planned concat buffer.
 
-Inference path (samplers run under no_grad, sde_helper2.py:116).  Training through this net (the z-conditioned
-`train_lat_celebhq_unet_cont2_cond.py`) is a "next" row: calling it with autograd enabled raises.
+With autograd enabled the forward runs through `autograd_openai.py` (one autograd node, hand-written backward): the
+z-conditioned DSM training of `train_lat_celebhq_unet_cont2_cond.py`; dropout must be 0 there.
 There is no CPU / eager fallback.
 """
 from __future__ import annotations
@@ -331,11 +331,12 @@ class UNetModel(nn.Module):
             raise NotImplementedError("class-conditional embedding is not used by any reference score-net command")
         if not x.is_cuda:
             raise L.SbmError("UNetModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("UNetModel on the B200 path is inference-only so far (samplers run under "
-                                      "torch.no_grad()); use Unet for DSM training")
         if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in train() mode: call eval() (samplers) or build with dropout=0")
+            raise NotImplementedError("dropout > 0 in train() mode is not built (mask kernel): call eval() for sampling "
+                                      "or construct the net with dropout=0 for training")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd_openai import unet_openai_forward_train
+            return unet_openai_forward_train(self, x, timesteps, z)
         with torch.no_grad():
             return self._forward_infer(x, timesteps, z)
 
