@@ -248,6 +248,11 @@ int sbm_adam_step(const sbm_adam_tensor* tensors_dev, const int32_t* chunks_dev,
                   int32_t chunk_elems, float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
                   const int32_t* step_dev /* optional DEVICE counter of completed steps: overrides `step` (CUDA graphs) */,
                   void* stream);
+/* utils.py:79-90 update_ema over many tensors in ONE launch: ema = ema*decay + src*(1-decay)
+ * (train_lat_celebhq_unet_cont2_cond.py:129, 672-674). */
+typedef struct sbm_ema_tensor { float* ema; const float* src; int64_t n; } sbm_ema_tensor;
+int sbm_ema_step(const sbm_ema_tensor* tensors_dev, const int32_t* chunks_dev, int32_t n_chunks, int32_t chunk_elems,
+                 float decay, void* stream);
 /* per-step device state of a graph-replayed TRAINING step: *step_dev += 1 (Adam bias correction), *draw_dev += draw_inc
  * (Philox draw id of sbm_dsm_perturb, which consumes 2 per step).  One 1-thread kernel. */
 int sbm_train_tick(int32_t* step_dev, uint64_t* draw_dev, uint64_t draw_inc, void* stream);

@@ -113,3 +113,7 @@ class WgradArgs(C.Structure):
 class AdamTensor(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("n", C.c_int64)]
+
+
+class EmaTensor(C.Structure):
+    _fields_ = [("ema", C.c_void_p), ("src", C.c_void_p), ("n", C.c_int64)]

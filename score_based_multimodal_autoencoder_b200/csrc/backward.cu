@@ -530,6 +530,17 @@ upsample2x_bwd_kernel(const float* __restrict__ dy, int64_t lddy, float* __restr
   }
 }
 
+// utils.py:79-90 update_ema: ema = ema*decay + param*(1 - decay), all tensors in one launch
+__global__ void __launch_bounds__(256)
+ema_kernel(const sbm_ema_tensor* __restrict__ tensors, const int2* __restrict__ chunks, int chunk_elems, float decay) {
+  const int2 ck = chunks[blockIdx.x];
+  const sbm_ema_tensor t = tensors[ck.x];
+  const int64_t start = (int64_t)ck.y * chunk_elems;
+  const int64_t end = min(start + (int64_t)chunk_elems, t.n);
+  const float a = 1.f - decay;
+  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) t.ema[i] = t.ema[i] * decay + a * t.src[i];
+}
+
 static int egrid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
 }
@@ -703,6 +714,15 @@ int sbm_add(const float* a, int64_t lda, const float* b, int64_t ldb, float* out
   SBM_CHECK_ARG(a && (out || out_bf16) && rows > 0 && C > 0, "sbm_add: bad args");
   add_kernel<<<egrid(rows * C), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, ldo, (__nv_bfloat16*)out_bf16, ldh,
                                                                 rows, C);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_ema_step(const sbm_ema_tensor* tensors_dev, const int32_t* chunks_dev, int32_t n_chunks, int32_t chunk_elems,
+                 float decay, void* stream) {
+  SBM_CHECK_ARG(tensors_dev && chunks_dev && n_chunks > 0 && chunk_elems > 0, "sbm_ema_step: bad args");
+  ema_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(tensors_dev, (const int2*)chunks_dev, chunk_elems, decay);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_b();
   return 0;

@@ -69,7 +69,7 @@ struct ConvKernelParams {
   void* out2;
   double* stats;
   int32_t act, out_dtype, res_dtype, vec_ok;
-  int32_t out2_preact, pad0;
+  int32_t out2_preact, bias_vec;
   const float* rowbias;     // optional per-sample bias [batch][ld_rowbias] added before the activation
   int64_t ld_rowbias;
   // GroupNorm(1, cin) of the INPUT folded into the convolution (weights carry gamma; see sbm_conv_fold_groupnorm):
@@ -261,8 +261,16 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvKernelParams& p,
   gn_apply16(p, gr, f, n);
   const int cmax = p.cout - 1;
   if (p.bias != nullptr) {
+    if (p.bias_vec && n + 16 <= p.cout) {  // 4 broadcast 16-byte loads instead of 16 clamped scalar ones
 #pragma unroll
-    for (int e = 0; e < 16; ++e) f[e] += __ldg(p.bias + min(n + e, cmax));
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n) + k);
+        f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] += __ldg(p.bias + min(n + e, cmax));
+    }
   }
   if (p.rowbias != nullptr && row_ok) {
     const float* rb = p.rowbias + (int64_t)b * p.ld_rowbias;
@@ -304,9 +312,14 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvKernelParams& p,
     for (int e = 0; e < 16; ++e) f[e] = __bfloat162float(__float2bfloat16_rn(f[e]));
   }
   if (p.stats != nullptr && row_ok) {
+    if (n + 16 <= p.cout) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
-      if (n + e <= cmax) { s1 += f[e]; s2 += f[e] * f[e]; }
+      for (int e = 0; e < 16; ++e) { s1 += f[e]; s2 = fmaf(f[e], f[e], s2); }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (n + e <= cmax) { s1 += f[e]; s2 += f[e] * f[e]; }
+    }
   }
   if (p.out_dtype == SBM_F32) {
 #pragma unroll
@@ -928,6 +941,7 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   p.act = a->act; p.out_dtype = a->out_dtype; p.res_dtype = a->res_dtype;
   p.out2_preact = (a->out2 != nullptr && a->out2_preact) ? 1 : 0;
   p.rowbias = a->rowbias; p.ld_rowbias = a->ld_rowbias;
+  p.bias_vec = (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) ? 1 : 0;
   if (a->gn_tab != nullptr) {
     SBM_CHECK_ARG(a->kind == SBM_CONV_S1 && (a->kh == 1 || a->kh == 3) && a->kh == a->kw,
                   "sbm_conv_igemm: GroupNorm folding supports 1x1 and 3x3 stride-1 convolutions");

@@ -151,3 +151,33 @@ class GraphedTrainStep:
         # replays update the parameters behind autograd's back: invalidate version-keyed caches for later eager use
         torch.autograd.graph.increment_version(self._params)
         return self.loss
+
+
+_ema_tables: dict = {}
+
+
+@torch.no_grad()
+def update_ema(ema_model, model, decay=0.999):
+    """utils.py:79-90 (`ema_params[name].mul_(decay).add_(param, alpha=1-decay)` over every parameter;
+    train_lat_celebhq_unet_cont2_cond.py:129, 672-674) as ONE multi-tensor kernel launch."""
+    ema_params = dict(ema_model.named_parameters())
+    pairs = [(ema_params[name.replace("module.", "")], p) for name, p in model.named_parameters()]
+    sig = tuple((e.data_ptr(), p.data_ptr()) for e, p in pairs)
+    key = (id(ema_model), id(model))
+    hit = _ema_tables.get(key)
+    if hit is None or hit[0] != sig:
+        arr = (L.EmaTensor * len(pairs))()
+        chunks = []
+        for i, (e, p) in enumerate(pairs):
+            if not (e.is_cuda and p.is_cuda and e.dtype == p.dtype == torch.float32 and e.is_contiguous()
+                    and p.is_contiguous() and e.numel() == p.numel()):
+                raise L.SbmError("update_ema needs matching contiguous fp32 CUDA parameters")
+            arr[i] = L.EmaTensor(e.data_ptr(), p.data_ptr(), p.numel())
+            chunks += [(i, k) for k in range((p.numel() + _CHUNK - 1) // _CHUNK)]
+        dev = pairs[0][0].device
+        hit = (sig, torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev),
+               torch.tensor(chunks, dtype=torch.int32).to(dev), len(chunks))
+        _ema_tables[key] = hit
+    L.check(L.lib().sbm_ema_step(L.ptr(hit[1]), L.ptr(hit[2]), C.c_int32(hit[3]), C.c_int32(_CHUNK), C.c_float(decay),
+                                 L.stream_ptr()), "sbm_ema_step")
+    torch.autograd.graph.increment_version([e for e, _ in pairs])

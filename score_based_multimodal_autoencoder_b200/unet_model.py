@@ -168,7 +168,7 @@ class Unet(nn.Module):
 
     # ------------------------------------------------------------------ packed-weight cache
     def _cached(self, key, params, build):
-        sig = tuple((p.data_ptr(), p._version) for p in params)
+        sig = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
         hit = self._packed.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
@@ -272,6 +272,21 @@ class Unet(nn.Module):
                        **gn_kw)
         return _Act(c_out, bf16=ob, stats=st_out)
 
+    def _qkv(self, pre: PreNorm, att, x: _Act):
+        """PreNorm GroupNorm -> to_qkv (1x1, no bias).  With the bf16 copy of the residual stream at hand the norm is folded
+        into the GEMM (gamma in the weights, mean / rstd / beta in the epilogue); otherwise GroupNorm-apply + GEMM."""
+        xf = x.f32
+        b, h, w, _ = xf.shape
+        c = x.c
+        hid = att.heads * att.dim_head
+        if self.fold_input_norm and x.bf16 is not None:
+            wq, tabq = self._w_conv_gn(att.to_qkv, pre.norm)
+            return ops.conv_igemm(x.bf16, wq, kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid, gn_stats=x.stats,
+                                  gn_tab=tabq, gn_eps=pre.norm.eps)
+        a = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=xf.device)
+        ops.groupnorm_apply(xf, c, x.stats, pre.norm.weight, pre.norm.bias, out=a)
+        return ops.conv_igemm(a, self._w_conv(att.to_qkv), kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid)
+
     def _linear_attention(self, mod: Residual, x: _Act, *, out_f32=None, out_bf16=None, want_bf16=True) -> _Act:
         pre: PreNorm = mod.fn
         att: LinearAttention = pre.fn
@@ -279,10 +294,8 @@ class Unet(nn.Module):
         b, h, w, _ = xf.shape
         dev = xf.device
         c = x.c
-        a = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=dev)
-        ops.groupnorm_apply(xf, c, x.stats, pre.norm.weight, pre.norm.bias, out=a)
         hid = att.heads * att.dim_head
-        qkv = ops.conv_igemm(a, self._w_conv(att.to_qkv), kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid)
+        qkv = self._qkv(pre, att, x)
         o = ops.linear_attn(qkv, att.heads, att.scale)
         st = self._stats(b, dev)
         y = ops.conv_igemm(o, self._w_conv(att.to_out[0]), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=c,
@@ -299,12 +312,9 @@ class Unet(nn.Module):
         pre: PreNorm = mod.fn
         att: Attention = pre.fn
         xf = x.f32
-        b, h, w, _ = xf.shape
         c = x.c
-        a = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=xf.device)
-        ops.groupnorm_apply(xf, c, x.stats, pre.norm.weight, pre.norm.bias, out=a)
         hid = att.heads * att.dim_head
-        qkv = ops.conv_igemm(a, self._w_conv(att.to_qkv), kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid)
+        qkv = self._qkv(pre, att, x)
         o = ops.softmax_attn(qkv, att.heads, att.dim_head, 0, hid, 2 * hid, att.dim_head, att.scale)
         y = ops.conv_igemm(o, self._w_conv(att.to_out), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=c,
                            bias=att.to_out.bias, residual=xf)
@@ -360,7 +370,8 @@ class Unet(nn.Module):
         skips = []
         for lv, (block1, block2, attn, down) in enumerate(self.downs):
             cur = self._convnext(block1, cur, cond, offs[id(block1)], ldc)
-            cur = self._convnext(block2, cur, cond, offs[id(block2)], ldc, want_stats=True)
+            cur = self._convnext(block2, cur, cond, offs[id(block2)], ldc, want_stats=True,
+                                 want_bf16=self.fold_input_norm)
             c = cur.c
             h, w = cur.f32.shape[1:3]
             # the level's output is the skip: write it straight into the 2nd half of the up path's concat buffer
@@ -379,7 +390,8 @@ class Unet(nn.Module):
                                    bias=down.bias, out2=ob)
                 cur = _Act(c, f32=y, bf16=ob)
 
-        cur = self._convnext(self.mid_block1, cur, cond, offs[id(self.mid_block1)], ldc, want_stats=True)
+        cur = self._convnext(self.mid_block1, cur, cond, offs[id(self.mid_block1)], ldc, want_stats=True,
+                             want_bf16=self.fold_input_norm)
         cur = self._mid_attention(self.mid_attn, cur)
         # mid_block2's output is the first half of the first concat buffer
         cat_f, cat_b, c = skips.pop()
@@ -388,7 +400,8 @@ class Unet(nn.Module):
         for u, (block1, block2, attn, up) in enumerate(self.ups):
             cur = _Act(2 * c, f32=cat_f, bf16=cat_b)
             cur = self._convnext(block1, cur, cond, offs[id(block1)], ldc)
-            cur = self._convnext(block2, cur, cond, offs[id(block2)], ldc, want_stats=True)
+            cur = self._convnext(block2, cur, cond, offs[id(block2)], ldc, want_stats=True,
+                                 want_bf16=self.fold_input_norm)
             cur = self._linear_attention(attn, cur)
             cu = cur.c
             h, w = cur.f32.shape[1:3]

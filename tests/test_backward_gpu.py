@@ -322,3 +322,26 @@ def test_graphed_train_step_equals_eager_steps():
     den = sum((pe.double() ** 2).sum() for pe in m_e.parameters())
     assert (num / den).sqrt().item() < 5e-3
     assert step.launches_per_step > 100
+
+
+def test_update_ema_matches_reference_semantics():
+    """utils.py:79-90: decay=0 copies the model (…_cond.py:674), then ema = ema*decay + p*(1-decay)."""
+    from score_based_multimodal_autoencoder_b200.optim import update_ema
+    torch.manual_seed(0)
+    a = torch.nn.Sequential(torch.nn.Linear(70, 300), torch.nn.Linear(300, 5)).cuda()
+    e = torch.nn.Sequential(torch.nn.Linear(70, 300), torch.nn.Linear(300, 5)).cuda()
+    update_ema(e, a, decay=0)
+    for pe, pa in zip(e.parameters(), a.parameters()):
+        assert torch.equal(pe, pa)
+    ref = [p.detach().clone() for p in e.parameters()]
+    for it in range(3):
+        with torch.no_grad():
+            for p in a.parameters():
+                p.add_(torch.randn_like(p) * 0.1)
+            for r, p in zip(ref, a.parameters()):
+                r.mul_(0.99).add_(p, alpha=0.01)
+        v0 = next(e.parameters())._version
+        update_ema(e, a, decay=0.99)
+        assert next(e.parameters())._version > v0
+    for pe, r in zip(e.parameters(), ref):
+        assert torch.allclose(pe, r, rtol=1e-6, atol=1e-7)

@@ -16,6 +16,10 @@ SHAPES = [  # H, cin, cout, k
     (1, 1024, 384, 1), (1, 128, 1024, 1), (16, 147, 170, 1), (16, 170, 256, 1),
 ]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+MODES = [("staged", 0)] + ([("direct", 1)] if os.environ.get("SBM_AB_EPILOGUE") else [])
+if os.environ.get("SBM_SMALLK"):
+    SHAPES = [(16, 147, 170, 1), (16, 170, 256, 1), (16, 256, 384, 1), (16, 128, 256, 1), (8, 512, 384, 1), (8, 128, 512, 1),
+              (16, 512, 256, 1), (16, 256, 512, 3)]
 for (H, cin, cout, k) in SHAPES:
     x = torch.randn(B, H, H, ops.pad8(cin), device=dev).to(torch.bfloat16)
     w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
@@ -25,16 +29,20 @@ for (H, cin, cout, k) in SHAPES:
     st = torch.zeros(B, 2, dtype=torch.float64, device=dev)
     taps = sum(1 for i in range(k) for j in range(k) if abs(i - k // 2) < H and abs(j - k // 2) < H)
     flops = 2.0 * B * H * H * cin * cout * taps
-    ts = []
-    for it in range(6):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.conv_igemm(x, wpk, kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout, bias=bias, act=L.ACT_GELU, out=out,
-                       stats=st)
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    t = sorted(ts[1:])[len(ts[1:]) // 2]
-    print(f"H={H:2d} {cin:4d}->{cout:4d} k={k} M={B * H * H:6d} taps={taps}: {t:8.1f} us  {flops / t / 1e6:7.1f} TFLOP/s "
-          f"(weights {taps * cin * cout * 2 / 1e6:.1f} MB)", flush=True)
+    outf = torch.empty(B, H, H, ops.pad8(cout), dtype=torch.float32, device=dev)
+    for mode, flag in MODES:
+        L.lib().sbm_conv_force_direct_epilogue(flag)
+        for label, kw in [("bf16+gelu+stats", dict(act=L.ACT_GELU, out=out, stats=st)), ("fp32+bf16copy", dict(out=outf, out2=out))]:
+            ts = []
+            for it in range(6):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.conv_igemm(x, wpk, kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout, bias=bias, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            t = sorted(ts[1:])[len(ts[1:]) // 2]
+            print(f"H={H:2d} {cin:4d}->{cout:4d} k={k} M={B * H * H:6d} taps={taps} {mode:6s} {label:16s}: {t:8.1f} us  "
+                  f"{flops / t / 1e6:7.1f} TFLOP/s", flush=True)
+    L.lib().sbm_conv_force_direct_epilogue(0)
