@@ -108,6 +108,19 @@ int sbm_unpack_wgrad(const float* src, float* dst, int32_t taps, int32_t rows, i
 int sbm_conv_fold_groupnorm(const float* w, void* dst, float* tab, int32_t kh, int32_t kw, int32_t rows, int32_t cols,
                             int32_t cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col, const float* gamma,
                             const float* beta, const float* bias, void* stream);
+/* Multi-tensor form of sbm_pack_weight_bf16: re-packs every listed weight in ONE launch (a training step re-packs all
+ * ~180 GEMM operands after the optimizer step).  descs_dev: DEVICE array sorted by first_block; tensor k owns blocks
+ * [first_block, first_block + ceil(rows/32)*tiles_c), tiles_c = ceil(cols_pad/32);
+ * taps_magic = taps > 1 ? ceil(2^32 / taps) : 0. */
+typedef struct sbm_pack_desc {
+  const float* src; void* dst;
+  int32_t taps, rows, cols, cols_pad;
+  int64_t s_tap, s_row, s_col;
+  int32_t tiles_c, first_block;
+  uint32_t taps_magic; int32_t reserved;
+} sbm_pack_desc;
+int sbm_pack_weights_multi(const sbm_pack_desc* descs_dev, int32_t n_descs, int32_t n_blocks, int32_t max_taps,
+                           void* stream);
 /* fp32 weights -> bf16 [taps][rows][cols_pad]; src element (tap,row,col) at
  * w[tap*s_tap + row*s_row + col*s_col]; optional per-column scale (GroupNorm gamma folding). */
 int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,

@@ -117,3 +117,9 @@ class AdamTensor(C.Structure):
 
 class EmaTensor(C.Structure):
     _fields_ = [("ema", C.c_void_p), ("src", C.c_void_p), ("n", C.c_int64)]
+
+
+class PackDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("taps", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("cols_pad", C.c_int32), ("s_tap", C.c_int64), ("s_row", C.c_int64), ("s_col", C.c_int64),
+                ("tiles_c", C.c_int32), ("first_block", C.c_int32), ("taps_magic", C.c_uint32), ("reserved", C.c_int32)]

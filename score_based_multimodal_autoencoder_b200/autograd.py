@@ -394,9 +394,14 @@ class _Plan:
         sink = getattr(self.m, "_grad_sink", None)
         if sink is not None:
             sink.begin()
-        self.bwd_last(dout.contiguous().float())
-        for fn in reversed(self.tape):
-            fn()
+        # every zero-initialised accumulator of this pass comes out of ONE zeroed buffer (one fill launch)
+        ops.arena_begin(getattr(self.m, "_zero_arena_words", 0), dout.device)
+        try:
+            self.bwd_last(dout.contiguous().float())
+            for fn in reversed(self.tape):
+                fn()
+        finally:
+            self.m._zero_arena_words = ops.arena_end()
         self.tape = []
         if sink is not None:
             sink.finish()
@@ -423,5 +428,6 @@ class UnetFn(torch.autograd.Function):
 
 
 def unet_forward_train(model, x, time):
+    model._refresh_packed()  # one launch re-packs every GEMM operand the last optimizer step invalidated
     params = tuple(p for p in model.parameters() if p.requires_grad)
     return UnetFn.apply(model, x, time, *params)

@@ -55,14 +55,45 @@ colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t rows, int C, float* _
 }
 
 // ------------------------------------------------------------------------------ GroupNorm backward
-// y = xh*gamma + beta, xh = (x - mean)*rstd, x = act(pre) when in_act != 0 (GroupNorm applied to an activation).
+// y = xh*gamma + beta, xh = (x - mean)*rstd, x = act(pre) when in_act != 0 (GroupNorm applied to an activation),
+// out = out_act(y) when out_act != 0 (activation applied after the norm).
 // reduce: bst[b][g] += (sum dy*gamma, sum dy*gamma*xh);  dgamma[c] += sum dy*xh; dbeta[c] += sum dy
-template <typename TX, typename TDY>
+// Thread = one channel octet (16-byte vector loads) x a strided set of pixels of ONE sample: the per-channel sums stay in
+// registers over the pixel loop; shared-memory atomics happen once per thread, global atomics once per block.
+template <typename T>
+__device__ __forceinline__ void gld8(const T* p, float* v);
+template <>
+__device__ __forceinline__ void gld8<float>(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void gld8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+    v[2 * i] = __low2float(h);
+    v[2 * i + 1] = __high2float(h);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void gld8_any(const T* p, float* v, int c, int C, bool vec) {
+  if (vec && c + 8 <= C) {
+    gld8<T>(p, v);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = (c + e < C) ? ldf<T>(p + e) : 0.f;
+  }
+}
+
+template <typename TX, typename TDY, bool G1>
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict__ dy, int64_t lddy,
                      const double* __restrict__ stats, const float* __restrict__ gamma, float* __restrict__ bst,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int HW, int C, int G, float eps,
-                     int in_act, const float* __restrict__ beta, int out_act) {
+                     int in_act, const float* __restrict__ beta, int out_act, int vec) {
   extern __shared__ float sm[];
   float* sdg = sm;          // [C]
   float* sdb = sm + C;      // [C]
@@ -80,31 +111,69 @@ gn_bwd_reduce_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restric
     s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  const int64_t total = (int64_t)HW * C;
-  float a1 = 0.f, a2 = 0.f;  // group sums when G == 1
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    const int64_t pix = (int64_t)b * HW + idx / C;
-    const int g = (G == 1) ? 0 : c / cpg;
-    float xv = ldf<TX>(x + pix * ldx + c);
-    if (in_act) xv = act_fwd(xv, in_act);
-    const float xh = (xv - s_mean[g]) * s_rstd[g];
-    float d = ldf<TDY>(dy + pix * lddy + c);
-    // out = act(y), y = xh*gamma + beta (unet_openai.py:252-253 GroupNorm32 -> SiLU): chain through the activation
-    if (out_act) d *= act_grad(fmaf(xh, __ldg(gamma + c), __ldg(beta + c)), out_act);
-    const float t = d * __ldg(gamma + c);
-    if (G == 1) {
-      a1 += t;
-      a2 += t * xh;
-    } else {
-      atomicAdd(&sst[2 * g], t);
-      atomicAdd(&sst[2 * g + 1], t * xh);
+  const int co = (C + 7) >> 3;
+  const int tq = min(co, (int)blockDim.x);
+  const int lanes = blockDim.x / tq;
+  const int pl = threadIdx.x / tq;
+  float a1 = 0.f, a2 = 0.f;  // group sums when there is one group (G1)
+  if (pl < lanes) {
+    const int pstride = lanes * gridDim.x;
+    for (int q = threadIdx.x - pl * tq; q < co; q += tq) {
+      const int c = q * 8;
+      float gm[8], dg[8], db[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gm[e] = __ldg(gamma + min(c + e, C - 1));
+        dg[e] = db[e] = 0.f;
+      }
+      auto body = [&](const float* xv, const float* d) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int g = G1 ? 0 : min(c + e, C - 1) / cpg;
+          float v = xv[e];
+          if (in_act) v = act_fwd(v, in_act);
+          const float xh = (v - s_mean[g]) * s_rstd[g];
+          float de = d[e];
+          if (out_act) de *= act_grad(fmaf(xh, gm[e], __ldg(beta + min(c + e, C - 1))), out_act);
+          const float t = de * gm[e];
+          if (G1) {
+            a1 += t;
+            a2 = fmaf(t, xh, a2);
+          } else if (c + e < C) {
+            atomicAdd(&sst[2 * g], t);
+            atomicAdd(&sst[2 * g + 1], t * xh);
+          }
+          dg[e] = fmaf(de, xh, dg[e]);
+          db[e] += de;
+        }
+      };
+      int p = blockIdx.x * lanes + pl;
+      for (; p + pstride < HW; p += 2 * pstride) {  // two pixels (4 independent 16-byte loads) in flight
+        const int64_t pix0 = (int64_t)b * HW + p, pix1 = pix0 + pstride;
+        float x0[8], d0[8], x1[8], d1[8];
+        gld8_any<TX>(x + pix0 * ldx + c, x0, c, C, vec);
+        gld8_any<TDY>(dy + pix0 * lddy + c, d0, c, C, vec);
+        gld8_any<TX>(x + pix1 * ldx + c, x1, c, C, vec);
+        gld8_any<TDY>(dy + pix1 * lddy + c, d1, c, C, vec);
+        body(x0, d0);
+        body(x1, d1);
+      }
+      for (; p < HW; p += pstride) {
+        const int64_t pix = (int64_t)b * HW + p;
+        float x0[8], d0[8];
+        gld8_any<TX>(x + pix * ldx + c, x0, c, C, vec);
+        gld8_any<TDY>(dy + pix * lddy + c, d0, c, C, vec);
+        body(x0, d0);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c + e < C) {
+          atomicAdd(&sdg[c + e], dg[e]);
+          atomicAdd(&sdb[c + e], db[e]);
+        }
     }
-    atomicAdd(&sdg[c], d * xh);
-    atomicAdd(&sdb[c], d);
   }
-  if (G == 1) {
+  if (G1) {  // padded channels contribute 0 (their dy / x loads are zero-filled)
     a1 = warp_sum(a1);
     a2 = warp_sum(a2);
     if ((threadIdx.x & 31) == 0) {
@@ -127,7 +196,7 @@ gn_bwd_apply_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict
                     const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ bst,
                     const float* __restrict__ addend, int64_t ldadd, float* __restrict__ out_f32, int64_t ldo_f32,
                     __nv_bfloat16* __restrict__ out_bf16, int64_t ldo_bf16, int HW, int C, int G, float eps,
-                    int in_act, const float* __restrict__ beta, int out_act) {
+                    int in_act, const float* __restrict__ beta, int out_act, int vec) {
   __shared__ float s_mean[64], s_rstd[64], s_c1[64], s_c2[64];
   const int b = blockIdx.y;
   const int cpg = C / G;
@@ -142,22 +211,76 @@ gn_bwd_apply_kernel(const TX* __restrict__ x, int64_t ldx, const TDY* __restrict
     s_c2[threadIdx.x] = bst[2 * ((int64_t)b * G + threadIdx.x) + 1] * (float)inv_n;
   }
   __syncthreads();
-  const int64_t total = (int64_t)HW * C;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    const int64_t pix = (int64_t)b * HW + idx / C;
-    const int g = (G == 1) ? 0 : c / cpg;
-    const float pre = ldf<TX>(x + pix * ldx + c);
-    const float xv = in_act ? act_fwd(pre, in_act) : pre;
-    const float xh = (xv - s_mean[g]) * s_rstd[g];
-    float d = ldf<TDY>(dy + pix * lddy + c);
-    if (out_act) d *= act_grad(fmaf(xh, __ldg(gamma + c), __ldg(beta + c)), out_act);
-    float dx = s_rstd[g] * (d * __ldg(gamma + c) - s_c1[g] - xh * s_c2[g]);
-    if (in_act) dx *= act_grad(pre, in_act);
-    if (addend) dx += addend[pix * ldadd + c];
-    if (out_f32) out_f32[pix * ldo_f32 + c] = dx;
-    if (out_bf16) out_bf16[pix * ldo_bf16 + c] = __float2bfloat16_rn(dx);
+  const int co = (C + 7) >> 3;
+  const int tq = min(co, (int)blockDim.x);
+  const int lanes = blockDim.x / tq;
+  const int pl = threadIdx.x / tq;
+  if (pl >= lanes) return;
+  const int pstride = lanes * gridDim.x;
+  for (int q = threadIdx.x - pl * tq; q < co; q += tq) {
+    const int c = q * 8;
+    const bool full = vec && (c + 8 <= C);
+    float gm[8], bt[8], mu[8], rs[8], c1[8], c2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ce = min(c + e, C - 1);
+      const int g = (G == 1) ? 0 : ce / cpg;
+      gm[e] = __ldg(gamma + ce);
+      bt[e] = out_act ? __ldg(beta + ce) : 0.f;
+      mu[e] = s_mean[g];
+      rs[e] = s_rstd[g];
+      c1[e] = s_c1[g];
+      c2[e] = s_c2[g];
+    }
+    for (int p = blockIdx.x * lanes + pl; p < HW; p += pstride) {
+      const int64_t pix = (int64_t)b * HW + p;
+      float pre[8], d[8], dx[8];
+      gld8_any<TX>(x + pix * ldx + c, pre, c, C, vec);
+      gld8_any<TDY>(dy + pix * lddy + c, d, c, C, vec);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = in_act ? act_fwd(pre[e], in_act) : pre[e];
+        const float xh = (xv - mu[e]) * rs[e];
+        float de = d[e];
+        if (out_act) de *= act_grad(fmaf(xh, gm[e], bt[e]), out_act);
+        float r = rs[e] * (de * gm[e] - c1[e] - xh * c2[e]);
+        if (in_act) r *= act_grad(pre[e], in_act);
+        dx[e] = r;
+      }
+      if (addend) {
+        float ad[8];
+        gld8_any<float>(addend + pix * ldadd + c, ad, c, C, vec);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dx[e] += ad[e];
+      }
+      if (out_f32) {
+        float* op = out_f32 + pix * ldo_f32 + c;
+        if (full) {
+          *reinterpret_cast<float4*>(op) = make_float4(dx[0], dx[1], dx[2], dx[3]);
+          *reinterpret_cast<float4*>(op + 4) = make_float4(dx[4], dx[5], dx[6], dx[7]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c + e < C) op[e] = dx[e];
+        }
+      }
+      if (out_bf16) {
+        __nv_bfloat16* op = out_bf16 + pix * ldo_bf16 + c;
+        if (full) {
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(dx[2 * e], dx[2 * e + 1]);
+            w[e] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          *reinterpret_cast<uint4*>(op) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (c + e < C) op[e] = __float2bfloat16_rn(dx[e]);
+        }
+      }
+    }
   }
 }
 
@@ -593,20 +716,34 @@ int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* d
   SBM_CHECK_ARG(x && dy && stats && gamma && bst && dgamma && dbeta && (out_f32 || out_bf16), "sbm_groupnorm_bwd: null");
   SBM_CHECK_ARG(out_act == 0 || beta != nullptr, "sbm_groupnorm_bwd: an output activation needs beta");
   SBM_CHECK_ARG(B > 0 && G > 0 && G <= 64 && C % G == 0, "sbm_groupnorm_bwd: bad sizes");
-  const int64_t per_sample = (int64_t)HW * C;
-  int chunks = (int)std::min<int64_t>((per_sample + 4095) / 4096, std::max<int64_t>(1, (int64_t)sm_count() * 8 / B));
+  // block = (channel octets) x (pixel lanes), like the forward apply kernel
+  const int co = (C + 7) / 8;
+  const int lanes = std::max(1, 256 / std::min(co, 256));
+  int chunks = (int)std::min<int64_t>((HW + lanes - 1) / lanes, std::max<int64_t>(1, (int64_t)sm_count() * 8 / B));
   if (chunks < 1) chunks = 1;
   dim3 grid(chunks, B);
   const size_t smem = (size_t)(2 * C + 2 * G) * sizeof(float);
   SBM_CHECK_ARG(smem <= 48 * 1024, "sbm_groupnorm_bwd: C=%d too large", C);
+  const int xs = x_dtype == SBM_F32 ? 4 : 2, ds = dy_dtype == SBM_F32 ? 4 : 2;
+  auto al16 = [](const void* p, int64_t ld, int esz) {
+    return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((ld * esz) % 16 == 0));
+  };
+  const int vec = al16(x, ldx, xs) && al16(dy, lddy, ds) && al16(addend, ldadd, 4) && al16(out_f32, ldo_f32, 4) &&
+                  al16(out_bf16, ldo_bf16, 2);
   cudaStream_t s = (cudaStream_t)stream;
 #define SBM_GNB(TX, TDY)                                                                                            \
   do {                                                                                                              \
-    gn_bwd_reduce_kernel<TX, TDY><<<grid, 256, smem, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats, gamma, bst, \
-                                                          dgamma, dbeta, HW, C, G, eps, in_act, beta, out_act);     \
+    if (G == 1)                                                                                                     \
+      gn_bwd_reduce_kernel<TX, TDY, true><<<grid, 256, smem, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats,     \
+                                                                  gamma, bst, dgamma, dbeta, HW, C, G, eps, in_act,  \
+                                                                  beta, out_act, vec);                              \
+    else                                                                                                            \
+      gn_bwd_reduce_kernel<TX, TDY, false><<<grid, 256, smem, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats,    \
+                                                                   gamma, bst, dgamma, dbeta, HW, C, G, eps, in_act, \
+                                                                   beta, out_act, vec);                             \
     gn_bwd_apply_kernel<TX, TDY><<<grid, 256, 0, s>>>((const TX*)x, ldx, (const TDY*)dy, lddy, stats, gamma, bst,     \
                                                       addend, ldadd, out_f32, ldo_f32, (__nv_bfloat16*)out_bf16,     \
-                                                      ldo_bf16, HW, C, G, eps, in_act, beta, out_act);              \
+                                                      ldo_bf16, HW, C, G, eps, in_act, beta, out_act, vec);         \
   } while (0)
   if (x_dtype == SBM_F32 && dy_dtype == SBM_F32) SBM_GNB(float, float);
   else if (x_dtype == SBM_BF16 && dy_dtype == SBM_F32) SBM_GNB(__nv_bfloat16, float);

@@ -1076,6 +1076,71 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// Tiled variant: a block re-lays one 32 x 32 (rows x cols) tile for all taps through shared memory, reading in
+// SOURCE-contiguous order (taps, then whichever of row / col has the smaller stride) and writing runs of 32 bf16 along
+// the destination's column axis -- both sides coalesced (the element-wise kernel above reads conv weights with a
+// stride of kh*kw floats; re-packing 223 M parameters every training step made that 7 % of the step).
+struct PackDesc {          // one weight tensor of a multi-tensor re-pack
+  const float* src;
+  __nv_bfloat16* dst;
+  int32_t taps, rows, cols, cols_pad;
+  int64_t s_tap, s_row, s_col;
+  int32_t tiles_c, first_block;   // 32-column tiles per tile row; index of this tensor's first block
+  uint32_t taps_magic;
+  int32_t pad;
+};
+static_assert(sizeof(PackDesc) == sizeof(sbm_pack_desc), "PackDesc must mirror sbm_pack_desc");
+
+__device__ __forceinline__ void pack_tile(const PackDesc& d, int tile, float* tile_smem) {
+  const int taps = d.taps, rows = d.rows, cols = d.cols, cols_pad = d.cols_pad;
+  const int TP = taps | 1;  // [32 rows][33][TP]: conflict-free for both access orders
+  const int r0 = (tile / d.tiles_c) * 32, c0 = (tile % d.tiles_c) * 32;
+  const bool col_inner = llabs(d.s_col) <= llabs(d.s_row);
+  const int n = taps * 1024;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < n; e += 256) {
+    const int rc = taps == 1 ? e : (int)__umulhi((uint32_t)e, d.taps_magic);  // e / taps (exact for e < 2^16)
+    const int t = e - rc * taps;
+    const int inner = rc & 31, outer = rc >> 5;
+    const int rr = col_inner ? outer : inner, cc = col_inner ? inner : outer;
+    const int r = r0 + rr, c = c0 + cc;
+    float v = 0.f;
+    if (r < rows && c < cols) v = __ldg(d.src + t * d.s_tap + (int64_t)r * d.s_row + (int64_t)c * d.s_col);
+    tile_smem[(rr * 33 + cc) * TP + t] = v;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int e = threadIdx.x; e < n; e += 256) {
+    const int cc = e & 31, rr = (e >> 5) & 31, t = e >> 10;
+    const int r = r0 + rr, c = c0 + cc;
+    if (r < rows && c < cols_pad)
+      d.dst[((int64_t)t * rows + r) * cols_pad + c] = __float2bfloat16_rn(tile_smem[(rr * 33 + cc) * TP + t]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_weight_tiled_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int taps, int rows, int cols,
+                         int cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col, uint32_t taps_magic) {
+  extern __shared__ float tile[];
+  PackDesc d;
+  d.src = w; d.dst = dst; d.taps = taps; d.rows = rows; d.cols = cols; d.cols_pad = cols_pad;
+  d.s_tap = s_tap; d.s_row = s_row; d.s_col = s_col; d.tiles_c = gridDim.x; d.first_block = 0; d.taps_magic = taps_magic;
+  pack_tile(d, blockIdx.y * gridDim.x + blockIdx.x, tile);
+}
+
+// all stale weight packs of a net in ONE launch: block -> (descriptor, tile) by binary search over first_block
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int n_descs) {
+  extern __shared__ float tile[];
+  int lo = 0, hi = n_descs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackDesc d = descs[lo];
+  pack_tile(d, (int)blockIdx.x - d.first_block, tile);
+}
+
 // One block per output channel n: writes the gamma-folded bf16 weight rows [tap][n][:] and the per-tap partial sums
 //   Pg[tap] = sum_c bf16(w*gamma)   Pb[tap] = sum_c w*beta
 // then combines them into the 16 border classes (which of the 3x3 taps see real pixels).
@@ -1174,14 +1239,47 @@ int sbm_conv_fold_groupnorm(const float* w, void* dst, float* tab, int32_t kh, i
   return 0;
 }
 
+int sbm_pack_weights_multi(const sbm_pack_desc* descs_dev, int32_t n_descs, int32_t n_blocks, int32_t max_taps,
+                           void* stream) {
+  SBM_CHECK_ARG(descs_dev && n_descs > 0 && n_blocks > 0 && max_taps > 0 && max_taps <= 64,
+                "sbm_pack_weights_multi: bad args");
+  const size_t smem = (size_t)(max_taps | 1) * 32 * 33 * sizeof(float);
+  SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_pack_weights_multi: too many taps");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(sbm::pack_weights_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    configured = smem;
+  }
+  sbm::pack_weights_multi_kernel<<<n_blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const sbm::PackDesc*>(descs_dev), n_descs);
+  SBM_CUDA_OK(cudaGetLastError());
+  sbm::g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
 int sbm_pack_weight_bf16(const float* w, void* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
                          int64_t s_tap, int64_t s_row, int64_t s_col, void* stream) {
   SBM_CHECK_ARG(w && dst && taps > 0 && rows > 0 && cols > 0 && cols_pad >= cols, "sbm_pack_weight_bf16: bad args");
-  const int64_t total = (int64_t)taps * rows * cols_pad;
-  const int threads = 256;
-  const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, (int64_t)sbm::sm_count() * 8);
-  sbm::pack_weight_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, static_cast<__nv_bfloat16*>(dst), taps, rows, cols, cols_pad, s_tap, s_row, s_col);
+  if ((int64_t)rows * cols >= 4096 && taps <= 16) {
+    const size_t smem = (size_t)(taps | 1) * 32 * 33 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(sbm::pack_weight_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      configured = smem;
+    }
+    dim3 grid((cols_pad + 31) / 32, (rows + 31) / 32);
+    sbm::pack_weight_tiled_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(dst), taps, rows, cols, cols_pad, s_tap, s_row, s_col,
+        (uint32_t)(taps > 1 ? ((1ull << 32) + taps - 1) / taps : 0));
+  } else {
+    const int64_t total = (int64_t)taps * rows * cols_pad;
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>((total + threads - 1) / threads, (int64_t)sbm::sm_count() * 8);
+    sbm::pack_weight_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(dst), taps, rows, cols, cols_pad, s_tap, s_row, s_col);
+  }
   SBM_CUDA_OK(cudaGetLastError());
   sbm::g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

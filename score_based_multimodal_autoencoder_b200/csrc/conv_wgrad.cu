@@ -316,6 +316,32 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// Tiled variant (both sides coalesced): packed rows are read along their column axis, the parameter layout is
+// written in ITS contiguous order (taps, then whichever of row / col has the smaller stride).
+__global__ void __launch_bounds__(256)
+unpack_wgrad_tiled_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int rows, int cols,
+                          int cols_pad, int64_t s_tap, int64_t s_row, int64_t s_col, uint32_t taps_magic) {
+  extern __shared__ float tile[];  // [32 rows][33][TP], TP = taps | 1
+  const int TP = taps | 1;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int n = taps * 1024;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int cc = e & 31, rr = (e >> 5) & 31, t = e >> 10;
+    const int r = r0 + rr, c = c0 + cc;
+    tile[(rr * 33 + cc) * TP + t] = (r < rows && c < cols) ? src[((int64_t)t * rows + r) * cols_pad + c] : 0.f;
+  }
+  __syncthreads();
+  const bool col_inner = llabs(s_col) <= llabs(s_row);
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int rc = taps == 1 ? e : (int)__umulhi((uint32_t)e, taps_magic);  // e / taps (exact for e < 2^16)
+    const int t = e - rc * taps;
+    const int inner = rc & 31, outer = rc >> 5;
+    const int rr = col_inner ? outer : inner, cc = col_inner ? inner : outer;
+    const int r = r0 + rr, c = c0 + cc;
+    if (r < rows && c < cols) dst[t * s_tap + (int64_t)r * s_row + (int64_t)c * s_col] = tile[(rr * 33 + cc) * TP + t];
+  }
+}
+
 }  // namespace sbm
 
 extern "C" {
@@ -327,10 +353,24 @@ int sbm_conv_wgrad(const sbm_wgrad_args* a, void* stream) {
 int sbm_unpack_wgrad(const float* src, float* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
                      int64_t s_tap, int64_t s_row, int64_t s_col, void* stream) {
   SBM_CHECK_ARG(src && dst && taps > 0 && rows > 0 && cols > 0, "sbm_unpack_wgrad: bad args");
-  const int64_t total = (int64_t)taps * rows * cols;
-  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sbm::sm_count() * 8);
-  sbm::unpack_wgrad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, taps, rows, cols, cols_pad,
-                                                                                  s_tap, s_row, s_col);
+  if ((int64_t)rows * cols >= 4096 && taps <= 16) {
+    const size_t smem = (size_t)(taps | 1) * 32 * 33 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(sbm::unpack_wgrad_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+      configured = smem;
+    }
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    sbm::unpack_wgrad_tiled_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(src, dst, taps, rows, cols,
+                                                                                           cols_pad, s_tap, s_row, s_col,
+                                                                                           (uint32_t)(taps > 1 ? ((1ull << 32) + taps - 1) / taps : 0));
+  } else {
+    const int64_t total = (int64_t)taps * rows * cols;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sbm::sm_count() * 8);
+    sbm::unpack_wgrad_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, taps, rows, cols, cols_pad,
+                                                                                    s_tap, s_row, s_col);
+  }
   SBM_CUDA_OK(cudaGetLastError());
   sbm::g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;

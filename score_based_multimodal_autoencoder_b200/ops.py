@@ -17,6 +17,60 @@ def pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
+class _ZeroArena:
+    """The backward pass needs ~400 small zero-initialised accumulators (split-K weight gradients, bias / GroupNorm
+    parameter gradients, reduction scratch).  Instead of one fill kernel each, a backward pass takes them from ONE
+    freshly allocated zeroed buffer (sized from the previous pass), i.e. one fill launch.  The buffer is new every
+    pass, so gradients that alias it stay valid for as long as they are referenced."""
+
+    def __init__(self):
+        self.buf, self.off, self.used = None, 0, 0
+
+    def begin(self, size_hint: int, device) -> None:
+        self.buf = torch.zeros(size_hint, dtype=torch.float32, device=device) if size_hint > 0 else None
+        self.off, self.used = 0, 0
+
+    def end(self) -> int:
+        used, self.buf = self.used, None
+        return used
+
+    def take(self, shape, dtype, device):
+        n = 1
+        for d in shape:
+            n *= d
+        words = (n * torch.empty((), dtype=dtype).element_size() + 3) // 4
+        words = (words + 3) // 4 * 4  # 16-byte aligned slices
+        self.used += words
+        if self.buf is None or self.buf.device != device or self.off + words > self.buf.numel():
+            return torch.zeros(shape, dtype=dtype, device=device)
+        raw = self.buf[self.off:self.off + words]
+        self.off += words
+        return raw.view(dtype)[:n].view(shape)
+
+
+_arena: _ZeroArena | None = None
+
+
+def arena_begin(size_hint: int, device) -> None:
+    global _arena
+    _arena = _ZeroArena()
+    _arena.begin(size_hint, device)
+
+
+def arena_end() -> int:
+    global _arena
+    used = _arena.end() if _arena is not None else 0
+    _arena = None
+    return used
+
+
+def _zeros(shape, dtype, device):
+    shape = tuple(shape) if isinstance(shape, (tuple, list)) else (shape,)
+    if _arena is not None:
+        return _arena.take(shape, dtype, torch.device(device))
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
 def pack_weight(w: torch.Tensor, taps: int, rows: int, cols: int, s_tap: int, s_row: int, s_col: int,
                 out: torch.Tensor | None = None) -> torch.Tensor:
     """fp32 weight (any strided view described by element strides) -> bf16 [taps, rows, pad8(cols)]."""
@@ -27,7 +81,38 @@ def pack_weight(w: torch.Tensor, taps: int, rows: int, cols: int, s_tap: int, s_
     L.check(L.lib().sbm_pack_weight_bf16(L.ptr(w), L.ptr(out), C.c_int32(taps), C.c_int32(rows), C.c_int32(cols),
                                          C.c_int32(cols_pad), C.c_int64(s_tap), C.c_int64(s_row), C.c_int64(s_col),
                                          L.stream_ptr()), "sbm_pack_weight_bf16")
+    # how to redo this pack in place (pack_weights_multi): `w` keeps the source storage alive / addressable
+    out._pack_spec = (w, taps, rows, cols, cols_pad, s_tap, s_row, s_col)
     return out
+
+
+_multi_tables: dict = {}
+
+
+def pack_weights_multi(packs) -> None:
+    """Re-run the packs of `packs` (tensors returned by pack_weight, refreshed IN PLACE from their current source
+    values) as ONE kernel launch.  The device descriptor table is cached per set of (source, destination) pointers."""
+    if not packs:
+        return
+    key = tuple((t._pack_spec[0].data_ptr(), t.data_ptr()) for t in packs)
+    hit = _multi_tables.get(key)
+    if hit is None:
+        arr = (L.PackDesc * len(packs))()
+        blocks, max_taps = 0, 1
+        for i, t in enumerate(packs):
+            w, taps, rows, cols, cols_pad, s_tap, s_row, s_col = t._pack_spec
+            tiles_c = (cols_pad + 31) // 32
+            arr[i] = L.PackDesc(w.data_ptr(), t.data_ptr(), taps, rows, cols, cols_pad, s_tap, s_row, s_col, tiles_c,
+                                blocks, ((1 << 32) + taps - 1) // taps if taps > 1 else 0, 0)
+            blocks += tiles_c * ((rows + 31) // 32)
+            max_taps = max(max_taps, taps)
+        dev = packs[0].device
+        table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        hit = (table, len(packs), blocks, max_taps)
+        _multi_tables[key] = hit
+    table, n, blocks, max_taps = hit
+    L.check(L.lib().sbm_pack_weights_multi(L.ptr(table), C.c_int32(n), C.c_int32(blocks), C.c_int32(max_taps),
+                                           L.stream_ptr()), "sbm_pack_weights_multi")
 
 
 def pack_conv2d_weight(w: torch.Tensor, out=None) -> torch.Tensor:
@@ -197,7 +282,7 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, *, kind: int, kh: int, kw: int
     """Packed fp32 weight gradient [kh*kw, cout, pad8(cin)] of conv_igemm(x, ...) given dy (both bf16 channels-last)."""
     assert x.dtype == torch.bfloat16 and dy.dtype == torch.bfloat16
     b, h, w, _ = x.shape
-    dwpk = torch.zeros((kh * kw, cout, pad8(cin)), dtype=torch.float32, device=x.device)
+    dwpk = _zeros((kh * kw, cout, pad8(cin)), torch.float32, x.device)
     a = L.WgradArgs()
     a.kind, a.kh, a.kw = kind, kh, kw
     a.batch, a.h, a.w = b, h, w
@@ -239,7 +324,7 @@ def _rows(t: torch.Tensor) -> int:
 
 
 def colsum(x: torch.Tensor, c: int) -> torch.Tensor:
-    out = torch.zeros(c, dtype=torch.float32, device=x.device)
+    out = _zeros(c, torch.float32, x.device)
     L.check(L.lib().sbm_colsum(L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), C.c_int64(_rows(x)), C.c_int32(c),
                                L.ptr(out), L.stream_ptr()), "sbm_colsum")
     return out
@@ -250,9 +335,9 @@ def groupnorm_bwd(x, dy, c, stats, gamma, *, groups=1, in_act=0, addend=None, wa
     """-> (dx_f32 | None, dx_bf16 | None, dgamma, dbeta).  out_act: activation applied after the norm (needs beta)."""
     b, h, w, _ = x.shape
     dev = x.device
-    bst = torch.zeros((b, groups, 2), dtype=torch.float32, device=dev)
-    dgamma = torch.zeros(c, dtype=torch.float32, device=dev)
-    dbeta = torch.zeros(c, dtype=torch.float32, device=dev)
+    bst = _zeros((b, groups, 2), torch.float32, dev)
+    dgamma = _zeros(c, torch.float32, dev)
+    dbeta = _zeros(c, torch.float32, dev)
     of = torch.empty((b, h, w, pad8(c)), dtype=torch.float32, device=dev) if want_f32 else None
     ob = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=dev) if want_bf16 else None
     L.check(L.lib().sbm_groupnorm_bwd(
@@ -279,8 +364,8 @@ def dwconv7_bwd_input(dy, c, w, addend=None):
 def dwconv7_wgrad(x, dy, c, dcond=None, ldc=0, want_db=True):
     """-> (dw [c,1,7,7], db [c] | None); dcond (a [B, >=c] slice view) is overwritten with sum_p dy."""
     b, h, wd, _ = x.shape
-    dw = torch.zeros((c, 1, 7, 7), dtype=torch.float32, device=x.device)
-    db = torch.zeros(c, dtype=torch.float32, device=x.device) if want_db else None
+    dw = _zeros((c, 1, 7, 7), torch.float32, x.device)
+    db = _zeros(c, torch.float32, x.device) if want_db else None
     L.check(L.lib().sbm_dwconv7_wgrad(L.ptr(x), C.c_int64(x.stride(2)), L.ptr(dy), C.c_int64(dy.stride(2)), L.ptr(dw),
                                       L.ptr(db), L.ptr(dcond), C.c_int64(ldc), C.c_int32(b), C.c_int32(h),
                                       C.c_int32(wd), C.c_int32(c), L.stream_ptr()), "sbm_dwconv7_wgrad")

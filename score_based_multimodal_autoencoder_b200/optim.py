@@ -122,7 +122,8 @@ class GraphedTrainStep:
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            for _ in range(max(warmup, 1)):
+            # >= 2 eager steps: the second one builds the device tables (multi-tensor re-pack, Adam) the capture re-uses
+            for _ in range(max(warmup, 2)):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)

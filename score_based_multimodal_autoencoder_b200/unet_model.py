@@ -167,15 +167,47 @@ class Unet(nn.Module):
         self.fold_input_norm = True
 
     # ------------------------------------------------------------------ packed-weight cache
+    @staticmethod
+    def _sig(params):
+        return tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+
     def _cached(self, key, params, build):
-        sig = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+        sig = self._sig(params)
         hit = self._packed.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
         with torch.no_grad():
             val = build()
-        self._packed[key] = (sig, val)
+        self._packed[key] = (sig, val, params)
         return val
+
+    def _refresh_packed(self):
+        """Bring every stale bf16 weight pack up to date IN PLACE with one multi-tensor launch (an optimizer step
+        invalidates all ~180 of them; re-packing one by one is 180 tiny launches per training step).  Packs whose
+        source is not a live view of the parameters (concatenated copies, folded GroupNorm tables) are left to the lazy
+        per-use rebuild of `_cached`."""
+        todo = []
+        for key, (sig, val, params) in self._packed.items():
+            cur = self._sig(params)
+            if cur == sig:
+                continue
+            packs = [val] if isinstance(val, torch.Tensor) else list(getattr(val[0], "_subpacks", ())) if isinstance(val, tuple) else []
+            ok = bool(packs)
+            storages = {p.untyped_storage().data_ptr() for p in params if p is not None}
+            for t in packs:
+                spec = getattr(t, "_pack_spec", None)
+                if spec is None or spec[0].untyped_storage().data_ptr() not in storages:
+                    ok = False
+            if ok:
+                todo.append((key, cur, val, params, packs))
+        if not todo:
+            return
+        with torch.no_grad():
+            ops.pack_weights_multi([t for _, _, _, _, packs in todo for t in packs])
+            for key, cur, val, params, _ in todo:
+                if isinstance(val, tuple) and hasattr(val[0], "_bias_sources"):  # concatenated bias of the cond GEMM
+                    torch.cat([b.detach().float() for b in val[0]._bias_sources], out=val[1])
+                self._packed[key] = (cur, val, params)
 
     def _w_conv(self, conv: nn.Conv2d):
         return self._cached(id(conv), (conv.weight,), lambda: ops.pack_conv2d_weight(conv.weight))
@@ -205,11 +237,14 @@ class Unet(nn.Module):
             wpk = torch.empty((1, total, pad8(self.time_dim)), dtype=torch.bfloat16, device=params[0].device)
             off = 0
             offsets = {}
+            subpacks = []
             for b in blocks:
-                ops.pack_linear_weight(b.mlp[1].weight, out=wpk[:, off:off + b.dim])
+                subpacks.append(ops.pack_linear_weight(b.mlp[1].weight, out=wpk[:, off:off + b.dim]))
                 offsets[id(b)] = off
                 off += b.dim
             bias = torch.cat([b.mlp[1].bias.detach().float() for b in blocks]).contiguous()
+            wpk._subpacks = subpacks                      # for the in-place multi-tensor refresh
+            wpk._bias_sources = [b.mlp[1].bias for b in blocks]
             return wpk, bias, offsets, total
 
         return self._cached("cond", params, build)

@@ -300,7 +300,7 @@ def test_graphed_train_step_equals_eager_steps():
     opt = FusedAdam(m_e.parameters(), lr=5e-4)
     sh.manual_seed(99)
     eager = []
-    for b in batches[:3] + batches:  # the graphed run spends its 3 warm-up steps on batches[0..2] too
+    for b in [batches[0], batches[0]] + batches:  # the graphed run spends its 2 warm-up steps on batches[0]
         loss = sh.loss_fn(b, m_e, sde, likelihood_weighting=False, rng="philox")
         opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -310,11 +310,10 @@ def test_graphed_train_step_equals_eager_steps():
     torch.manual_seed(0)
     m_g = Unet(**kw).cuda().train()
     sh.manual_seed(99)
-    # warm-up consumes batches[0] three times in GraphedTrainStep; feed the same sequence as the eager run instead
-    step = GraphedTrainStep(m_g, sde, batches[0], lr=5e-4, warmup=1)
-    got = [step(b).item() for b in batches[1:3] + batches]
-    # eager[0] used batches[0] (= the graphed warm-up step); compare from the second step on
-    for a, b in zip(got, eager[1:]):
+    step = GraphedTrainStep(m_g, sde, batches[0], lr=5e-4, warmup=2)
+    got = [step(b).item() for b in batches]
+    # eager[0:2] used batches[0] (= the graphed warm-up steps); compare from the third step on
+    for a, b in zip(got, eager[2:]):
         assert abs(a - b) <= 2e-3 * abs(b), (got, eager)
     # Adam's normalised update turns split-K summation-order noise on near-zero gradients into O(lr) differences on
     # single elements, so compare the tensors in norm
