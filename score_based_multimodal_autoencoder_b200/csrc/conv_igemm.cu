@@ -1053,8 +1053,8 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   dim3 grid((unsigned)m_tiles, (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
   g_last_variant = BN;
   switch (BN) {
-    case 32: return launch_conv<32, 6>(tmA, tmB, p, grid, stream);
-    case 64: return launch_conv<64, 6>(tmA, tmB, p, grid, stream);
+    case 32: return launch_conv<32, 10>(tmA, tmB, p, grid, stream);  // small tiles: deeper ring, the K loop is TMA-latency bound
+    case 64: return launch_conv<64, 8>(tmA, tmB, p, grid, stream);
     case 128: return launch_conv<128, 6>(tmA, tmB, p, grid, stream);
     default: return launch_conv<256, 4>(tmA, tmB, p, grid, stream);
   }
@@ -1097,24 +1097,57 @@ __device__ __forceinline__ void pack_tile(const PackDesc& d, int tile, float* ti
   const int r0 = (tile / d.tiles_c) * 32, c0 = (tile % d.tiles_c) * 32;
   const bool col_inner = llabs(d.s_col) <= llabs(d.s_row);
   const int n = taps * 1024;
+  if (d.s_tap == 1 && d.s_col == taps && (taps & 1) && (d.s_row & 3) == 0 && c0 + 32 <= cols &&
+      (reinterpret_cast<uintptr_t>(d.src) & 15) == 0) {
+    // nn.Conv2d layout [O][I][taps] with odd taps: a tile row is ONE contiguous run of 32*taps floats that maps 1:1
+    // onto the shared-memory row (TP == taps) -> 16-byte loads
+    const int run4 = taps * 8;  // float4s per row
+    for (int e = threadIdx.x; e < 32 * run4; e += 256) {
+      const int rr = e / run4, j4 = e - rr * run4;
+      const int r = r0 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) v = __ldg(reinterpret_cast<const float4*>(d.src + (int64_t)r * d.s_row + (int64_t)c0 * taps) + j4);
+      float* tp = tile_smem + rr * 33 * TP + j4 * 4;
+      tp[0] = v.x; tp[1] = v.y; tp[2] = v.z; tp[3] = v.w;
+    }
+  } else {
 #pragma unroll 4
-  for (int e = threadIdx.x; e < n; e += 256) {
-    const int rc = taps == 1 ? e : (int)__umulhi((uint32_t)e, d.taps_magic);  // e / taps (exact for e < 2^16)
-    const int t = e - rc * taps;
-    const int inner = rc & 31, outer = rc >> 5;
-    const int rr = col_inner ? outer : inner, cc = col_inner ? inner : outer;
-    const int r = r0 + rr, c = c0 + cc;
-    float v = 0.f;
-    if (r < rows && c < cols) v = __ldg(d.src + t * d.s_tap + (int64_t)r * d.s_row + (int64_t)c * d.s_col);
-    tile_smem[(rr * 33 + cc) * TP + t] = v;
+    for (int e = threadIdx.x; e < n; e += 256) {
+      const int rc = taps == 1 ? e : (int)__umulhi((uint32_t)e, d.taps_magic);  // e / taps (exact for e < 2^16)
+      const int t = e - rc * taps;
+      const int inner = rc & 31, outer = rc >> 5;
+      const int rr = col_inner ? outer : inner, cc = col_inner ? inner : outer;
+      const int r = r0 + rr, c = c0 + cc;
+      float v = 0.f;
+      if (r < rows && c < cols) v = __ldg(d.src + t * d.s_tap + (int64_t)r * d.s_row + (int64_t)c * d.s_col);
+      tile_smem[(rr * 33 + cc) * TP + t] = v;
+    }
   }
   __syncthreads();
+  if ((cols_pad & 7) == 0 && (reinterpret_cast<uintptr_t>(d.dst) & 15) == 0) {
+    // 8 consecutive columns (one 16-byte store) per thread
+    for (int e = threadIdx.x; e < taps * 128; e += 256) {
+      const int c8 = e & 3, rr = (e >> 2) & 31, t = e >> 7;
+      const int r = r0 + rr, c = c0 + c8 * 8;
+      if (r < rows && c < cols_pad) {
+        uint32_t wds[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = tile_smem[(rr * 33 + c8 * 8 + 2 * k) * TP + t], hi = tile_smem[(rr * 33 + c8 * 8 + 2 * k + 1) * TP + t];
+          __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+          wds[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(d.dst + ((int64_t)t * rows + r) * cols_pad + c) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+      }
+    }
+  } else {
 #pragma unroll 4
-  for (int e = threadIdx.x; e < n; e += 256) {
-    const int cc = e & 31, rr = (e >> 5) & 31, t = e >> 10;
-    const int r = r0 + rr, c = c0 + cc;
-    if (r < rows && c < cols_pad)
-      d.dst[((int64_t)t * rows + r) * cols_pad + c] = __float2bfloat16_rn(tile_smem[(rr * 33 + cc) * TP + t]);
+    for (int e = threadIdx.x; e < n; e += 256) {
+      const int cc = e & 31, rr = (e >> 5) & 31, t = e >> 10;
+      const int r = r0 + rr, c = c0 + cc;
+      if (r < rows && c < cols_pad)
+        d.dst[((int64_t)t * rows + r) * cols_pad + c] = __float2bfloat16_rn(tile_smem[(rr * 33 + cc) * TP + t]);
+    }
   }
 }
 

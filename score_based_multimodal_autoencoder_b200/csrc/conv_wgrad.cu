@@ -26,10 +26,11 @@ namespace sbm {
 extern std::atomic<unsigned long long> g_launches;
 
 constexpr int kWgBM = 128;   // output channels per CTA
-constexpr int kWgBN = 128;   // input channels per CTA
 constexpr int kWgPix = 64;   // pixels per K block
-constexpr int kWgStages = 6;
 constexpr int kWgMaxTaps = 16;
+// input channels per CTA = template parameter BN (128 or 256).  The kernel streams both operands from L2 once per
+// 64-pixel block: (128 + BN) * 64 * 2 bytes for 2 * 128 * BN * 64 FLOP, i.e. 64 FLOP/B at BN = 128 and 85 FLOP/B at
+// BN = 256 -- the wide tile is what keeps layers with >= 256 input channels off the L2-bandwidth floor.
 
 struct WgTap {
   int8_t x_dh, x_dw, y_dh, y_dw;
@@ -46,18 +47,23 @@ struct WgParams {
   WgTap taps[kWgMaxTaps];
 };
 
+template <int BN>
 struct WgSmem {
-  static constexpr int kYBytes = kWgBM * kWgPix * 2;  // 2 atoms of 64 ch x 64 px
-  static constexpr int kXBytes = kWgBN * kWgPix * 2;
+  static constexpr int kStages = BN == 128 ? 6 : 4;
+  static constexpr int kYBytes = kWgBM * kWgPix * 2;  // atoms of 64 ch x 64 px
+  static constexpr int kXBytes = BN * kWgPix * 2;
   static constexpr int kStageBytes = kYBytes + kXBytes;
-  static constexpr int kBarOffset = kWgStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * kWgStages + 1) * 8 + 16 + 1024;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(256, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ WgParams p) {
-  using L = WgSmem;
+  using L = WgSmem<BN>;
+  constexpr int kWgBN = BN;
+  constexpr int kWgStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
@@ -212,6 +218,7 @@ static int conv_wgrad_impl(const sbm_wgrad_args* a, cudaStream_t stream) {
 
   WgParams p;
   memset(&p, 0, sizeof(p));
+  const int kWgBN = a->cin >= 256 ? 256 : 128;  // input channels per CTA (see the note at the top)
   int gh, gw, ntaps = 0;
   cuuint64_t xdim[5], xstr[4], ydim[5], ystr[4];
   if (a->kind == SBM_CONV_S1) {
@@ -289,13 +296,24 @@ static int conv_wgrad_impl(const sbm_wgrad_args* a, cudaStream_t stream) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_wgrad: dy tensor map encode failed (%d)", (int)cr);
 
-  static bool configured = false;
-  if (!configured) {
-    SBM_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::kTotal));
-    configured = true;
-  }
   dim3 grid((unsigned)(p.n_i_tiles * n_o_tiles), (unsigned)ntaps, (unsigned)splits);
-  conv_wgrad_kernel<<<grid, 256, WgSmem::kTotal, stream>>>(tmX, tmY, p);
+  if (kWgBN == 256) {
+    static bool configured = false;
+    if (!configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WgSmem<256>::kTotal));
+      configured = true;
+    }
+    conv_wgrad_kernel<256><<<grid, 256, WgSmem<256>::kTotal, stream>>>(tmX, tmY, p);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       WgSmem<128>::kTotal));
+      configured = true;
+    }
+    conv_wgrad_kernel<128><<<grid, 256, WgSmem<128>::kTotal, stream>>>(tmX, tmY, p);
+  }
   SBM_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return 0;
