@@ -171,9 +171,9 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
     float4 xv[2], sv[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
-      if (qs[u] < n_quads) {
-        xv[u] = x[qs[u]];
-        sv[u] = score[qs[u]];
+      if (qs[u] < n_quads) {  // read-once / write-once streams: keep them out of the way of L2-resident data
+        xv[u] = __ldcs(x + qs[u]);
+        sv[u] = __ldcs(score + qs[u]);
       }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -194,8 +194,8 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
         const float gs = g * sq;
         out.x += gs * z.x; out.y += gs * z.y; out.z += gs * z.z; out.w += gs * z.w;
       }
-      if (x_mean_out) x_mean_out[q] = mean;
-      x_out[q] = apply_impute(im, icoef, out, q, q - b * eqd.d);
+      if (x_mean_out) __stcs(x_mean_out + q, mean);
+      __stcs(x_out + q, apply_impute(im, icoef, out, q, q - b * eqd.d));
     }
   }
 }
@@ -297,8 +297,8 @@ corrector_update_kernel(const float4* __restrict__ x, const float4* __restrict__
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       if (qs[u] < n_quads) {
-        xv[u] = x[qs[u]];
-        gv[u] = grad[qs[u]];
+        xv[u] = __ldcs(x + qs[u]);
+        gv[u] = __ldcs(grad + qs[u]);
       }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -317,8 +317,8 @@ corrector_update_kernel(const float4* __restrict__ x, const float4* __restrict__
       const float4 mean = make_float4(xv[u].x + step * gv[u].x, xv[u].y + step * gv[u].y, xv[u].z + step * gv[u].z,
                                       xv[u].w + step * gv[u].w);
       const float4 out = make_float4(mean.x + ns * z.x, mean.y + ns * z.y, mean.z + ns * z.z, mean.w + ns * z.w);
-      if (x_mean_out) x_mean_out[q] = mean;
-      x_out[q] = apply_impute(im, icoef, out, q, q - b * eqd.d);
+      if (x_mean_out) __stcs(x_mean_out + q, mean);
+      __stcs(x_out + q, apply_impute(im, icoef, out, q, q - b * eqd.d));
     }
   }
   if (reset_acc) {
@@ -462,6 +462,17 @@ static int ew_grid(int64_t n_items) {
   const int64_t want = (n_items + 255) / 256;
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
 }
+// Grid of a grid-stride kernel = exactly one resident wave (SMs x blocks that fit per SM): with a fixed cap like 8
+// blocks per SM a kernel whose registers allow only 5 runs 1.6 waves and idles ~20 % of the machine in the second one.
+template <typename K>
+static int wave_grid(K kernel, int64_t n_items, int per_thread = 1) {
+  static int per_sm = 0;  // one static per kernel type
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+  }
+  const int64_t want = (n_items + 256 * per_thread - 1) / (256 * per_thread);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * per_sm));
+}
 static int check_latent(const sbm_latent_shape* ls, const char* who) {
   SBM_CHECK_ARG(ls && ls->batch > 0 && ls->mods > 0 && ls->mods <= 32 && ls->dd > 0, "%s: bad latent shape", who);
   SBM_CHECK_ARG(ls->dd % 4 == 0, "%s: D*D = %d must be a multiple of 4 (vectorised latent access)", who, ls->dd);
@@ -526,7 +537,7 @@ int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const flo
   SBM_CHECK_ARG(noise || rng || probability_flow, "sbm_predictor_step: need injected noise or an rng");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  predictor_kernel<<<ew_grid((nq + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
+  predictor_kernel<<<wave_grid(predictor_kernel, nq, 2), 256, 0, (cudaStream_t)stream>>>(
       (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,
       (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,
       rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
@@ -544,7 +555,9 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
   const int EQ = E / 4;
   const int S = (EQ % 32 == 0) ? 1 : ((2 * EQ) % 32 == 0 ? 2 : ((4 * EQ) % 32 == 0 ? 4 : 1));
   const int groups = (ls->batch + S - 1) / S;
-  const int blocks = std::max(1, std::min((groups + 7) / 8, sm_count() * 8));
+  const int blocks = S == 1 ? wave_grid(corrector_norms_kernel<1>, (int64_t)groups * 32)
+                            : (S == 2 ? wave_grid(corrector_norms_kernel<2>, (int64_t)groups * 32)
+                                      : wave_grid(corrector_norms_kernel<4>, (int64_t)groups * 32));
   const uint64_t seed = rng ? rng->seed : 0, draw = rng ? rng->draw : 0;
   const uint64_t* ddev = rng ? rng->draw_dev : nullptr;
   const uint64_t qoff = rng ? rng->sample_offset * (uint64_t)EQ : 0;
@@ -572,7 +585,7 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
   SBM_CHECK_ARG(global_batch >= ls->batch, "sbm_corrector_update: global_batch < local batch");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  corrector_update_kernel<<<ew_grid((nq + 1) / 2), 256, 0, (cudaStream_t)stream>>>(
+  corrector_update_kernel<<<wave_grid(corrector_update_kernel, nq, 2), 256, 0, (cudaStream_t)stream>>>(
       (const float4*)x, (const float4*)grad, t, (const float4*)noise, acc2, alphas, (float4*)x_out,
       (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,
       1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,
@@ -604,7 +617,7 @@ int sbm_dsm_perturb(const sbm_latent_shape* ls, const sbm_sde* sde, const float*
   SBM_CHECK_ARG((u && z) || rng, "sbm_dsm_perturb: need injected (u, z) or an rng");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  dsm_perturb_kernel<<<ew_grid(nq), 256, 0, (cudaStream_t)stream>>>(
+  dsm_perturb_kernel<<<wave_grid(dsm_perturb_kernel, nq), 256, 0, (cudaStream_t)stream>>>(
       x0, u, z, xt, z_out, t_out, std_out, g2_out, nq, E, to_sdep(sde), sde->T, eps, rng ? rng->seed : 0,
       rng ? rng->draw : 0, rng ? rng->draw + 1 : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset : 0);
   SBM_CUDA_OK(cudaGetLastError());
