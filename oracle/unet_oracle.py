@@ -84,8 +84,15 @@ def _residual_prenorm(sd, p, x, fn):
 
 
 def unet_forward(sd: dict, x: torch.Tensor, time: torch.Tensor, *, dim: int, dim_mults=(1, 2, 4, 8)) -> torch.Tensor:
-    """unet_model.py:275-323 (power-of-two inputs only: the padding branch :276-284 is a no-op for 8x8/16x16)."""
+    """unet_model.py:275-323, including the zero padding of non-power-of-two extents (:276-284) and the final crop
+    (:318-322)."""
     n_levels = len(dim_mults)
+    pw = int((2 ** math.ceil(math.log2(x.shape[-1])) - x.shape[-1]) // 2)
+    ph = int((2 ** math.ceil(math.log2(x.shape[-2])) - x.shape[-2]) // 2)
+    if pw or ph:
+        y = unet_forward(sd, F.pad(x, (pw, pw, ph, ph)), time, dim=dim, dim_mults=dim_mults)
+        y = y[..., pw:-pw] if pw else y
+        return y[..., ph:-ph, :] if ph else y
     x = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
     t = sinusoidal_embedding(time, dim)
     t = F.linear(t, sd["time_mlp.1.weight"], sd["time_mlp.1.bias"])

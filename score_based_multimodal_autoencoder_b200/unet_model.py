@@ -12,6 +12,7 @@ GroupNorm statistics in fp64.  There is no CPU / eager fallback: a CPU tensor ra
 """
 from __future__ import annotations
 
+import math
 from functools import partial
 
 import torch
@@ -267,7 +268,7 @@ class Unet(nn.Module):
         st1 = self._stats(b, dev)
         cptr = cond[:, :, :, cond_off:] if (cond is not None and blk.mlp is not None) else None
         st2 = self._stats(b, dev)
-        if self.fold_input_norm and isinstance(blk.net[0], nn.GroupNorm):
+        if self.fold_input_norm and isinstance(blk.net[0], nn.GroupNorm) and h == w and w <= 16:
             # depthwise output stored once as bf16 (statistics from the unrounded values); the first GroupNorm is
             # folded into the 3x3 convolution like the second one
             hdw = ops.dwconv7(xf, c_in, blk.ds_conv.weight, blk.ds_conv.bias, cptr, ldc, st1, out_dtype=torch.bfloat16)
@@ -359,10 +360,21 @@ class Unet(nn.Module):
     def forward(self, x, time=None):
         if not x.is_cuda:
             raise L.SbmError("Unet.forward needs CUDA tensors: the B200 path has no CPU fallback")
+        # non-power-of-two extents are zero-padded symmetrically and the output cropped (unet_model.py:276-284, 318-322)
+        pw = int((2 ** math.ceil(math.log2(x.shape[-1])) - x.shape[-1]) // 2)
+        ph = int((2 ** math.ceil(math.log2(x.shape[-2])) - x.shape[-2]) // 2)
+        if pw or ph:
+            x = torch.nn.functional.pad(x, (pw, pw, ph, ph))
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .autograd import unet_forward_train
-            return unet_forward_train(self, x, time)
-        return self._forward_infer(x, time)
+            y = unet_forward_train(self, x, time)
+        else:
+            y = self._forward_infer(x, time)
+        if pw:
+            y = y[..., pw:-pw]
+        if ph:
+            y = y[..., ph:-ph, :]
+        return y
 
     @torch.no_grad()
     def _forward_infer(self, x, time):
@@ -371,8 +383,9 @@ class Unet(nn.Module):
             raise ValueError(f"expected {self.channels} latent channels, got {m}")
         for s in (hh, ww):
             if s & (s - 1):
-                # the reference zero-pads to the next power of two (unet_model.py:276-284); latents are 8x8 / 16x16
-                raise NotImplementedError("latent extent must be a power of two")
+                # forward() pads to the next power of two like the reference; an odd deficit (e.g. 7) stays unpadded
+                # there too and crashes in its first down-sampling conv
+                raise ValueError("latent extent must pad to a power of two (unet_model.py:276-284)")
         dev = x.device
         x = x.contiguous().float()
         time = time.contiguous().float()

@@ -74,3 +74,21 @@ def test_unet_weight_update_invalidates_packed_cache():
         y2 = m(x, t)
     assert not torch.allclose(y0, y1)
     assert rel_l2(y2 * 2, y1) < 1e-2
+
+
+@pytest.mark.parametrize("hw", [(6, 6), (12, 8)])
+def test_unet_pads_non_power_of_two_latents_like_the_reference(hw):
+    """unet_model.py:276-284, 318-322: extents are zero-padded symmetrically to the next power of two and the output is
+    cropped (the oracle's padding branch is pinned against the real reference: relative error 0.0)."""
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    kw = dict(dim=32, channels=5, dim_mults=(1, 2))
+    shapes = {k: tuple(v.shape) for k, v in Unet(**kw).state_dict().items()}
+    m, sd = _build(kw, shapes)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 5, *hw, generator=g)
+    t = torch.rand(4, generator=g) * 0.999 + 1e-3
+    with torch.no_grad():
+        y = m(x.cuda(), t.cuda())
+        ref = uo.unet_forward(sd, x, t, dim=32, dim_mults=(1, 2))
+    assert y.shape == ref.shape == x.shape
+    assert rel_l2(y, ref) < BF16_NET_TOL
