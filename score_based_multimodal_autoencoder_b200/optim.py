@@ -130,7 +130,8 @@ class GraphedTrainStep:
         n0 = L.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads (e.g. the NCCL watchdog polling events) may touch CUDA while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._body()
         self.launches_per_step = L.launch_count() - n0
         # capture does not execute: the counters still hold the post-warm-up state the first replay must start from

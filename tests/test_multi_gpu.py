@@ -18,6 +18,6 @@ def test_sharded_sampling_and_data_parallel_gradients_nccl():
         port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tools", "check_multi_gpu.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(ROOT, "tools", "check_multi_gpu.py")], capture_output=True, text=True, timeout=240)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0 and "OK" in r.stdout
