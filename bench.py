@@ -323,10 +323,7 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
         return loss
 
     graphed, step = None, eager_step
-    # N > 1: the captured step would contain the NCCL all-reduces.  That ran on 2 GPUs (31.5 vs 38.4 ms/step) but a
-    # second capture in one process hung once, so until that is understood the multi-GPU leg stays on the eager loop
-    # unless SBM_GRAPH_DDP=1.
-    if use_graph and (world == 1 or os.environ.get("SBM_GRAPH_DDP") == "1"):
+    if use_graph:
         # the whole step (loss_fn + backward [+ bucketed NCCL all-reduces] + FusedAdam) replayed as ONE CUDA graph;
         # per-step state (Philox draw id, Adam step count) lives on the device
         from score_based_multimodal_autoencoder_b200.optim import GraphedTrainStep
@@ -363,15 +360,21 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
     n0 = L.launch_count()
     ms = timed(lambda: step(z))
     launches = graphed.launches_per_step if graphed is not None else (L.launch_count() - n0) // steps
+    launches = int(launches)
     # end to end: H2D of the latent batch and D2H of the loss every step (the reference does loss.item() per step)
     ms_e2e = timed(lambda: step(z_host.to(device, non_blocking=True)).item())
     loss_val = float(step(z).item())
+    used_graph = graphed is not None
+    # a captured graph that contains NCCL kernels must be destroyed BEFORE the process group (destroying the
+    # communicator first dead-locks at exit)
+    step = graphed = None
+    torch.cuda.synchronize()
     gb = shape[0] * world
     return {"metric": "dsm_train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms,
             "n_gpus": world, "scaling": "weak", "global_batch": gb, "latents_per_sec": gb * 1e3 / ms,
             "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": z_host.numel() * 4 * world,
                     "d2h_bytes_per_step": 4 * world},
-            "gpu_launches_per_step": int(launches), "loss": loss_val, "cuda_graph": graphed is not None,
+            "gpu_launches_per_step": launches, "loss": loss_val, "cuda_graph": used_graph,
             "model_tflops_per_gpu": 3 * fwd_gf * 1e9 * shape[0] / (ms * 1e-3) / 1e12,
             "grad_allreduce": None if world == 1 else {"backend": "nccl", "bucket_mb": 64,
                                                        "bytes_per_step": sum(p.numel() for p in model.parameters()) * 4,

@@ -102,7 +102,10 @@ class GraphedTrainStep:
         for batch in loader: loss = step(batch)                          # copy-in + one graph launch; loss: 0-d tensor
 
     Semantics = the eager sequence `loss = loss_fn(batch, model, sde, ...); opt.zero_grad(); loss.backward();
-    opt.step()` with in-kernel Philox (t, z) draws; verified step-for-step against it (tests/test_backward_gpu.py)."""
+    opt.step()` with in-kernel Philox (t, z) draws; verified step-for-step against it (tests/test_backward_gpu.py).
+    `model` may be a `DataParallelScoreNet`: the bucketed NCCL all-reduces are captured with the step (verified on 2
+    GPUs).  In that case call `close()` (or drop the object) BEFORE `dist.destroy_process_group()`: tearing the
+    communicator down while a graph still holds its kernels dead-locks at exit."""
 
     def __init__(self, model, sde, example_batch, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, loss_kwargs=None, warmup=3,
                  optimizer=None):
@@ -146,6 +149,13 @@ class GraphedTrainStep:
         L.check(L.lib().sbm_train_tick(L.ptr(self.opt.step_dev), L.ptr(self.draw_dev), C.c_uint64(2), L.stream_ptr()),
                 "sbm_train_tick")
         return loss
+
+    def close(self):
+        """Release the captured graph (required before destroying the process group when it holds NCCL kernels)."""
+        self.graph = None
+        self.loss = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def __call__(self, batch):
         self.batch.copy_(batch, non_blocking=True)

@@ -2,7 +2,8 @@
   1. batch-sharded conditional PC sampling in exact mode (2-scalar all-reduce per corrector step) + final gather
      == the unsharded batch on one GPU;
   2. data-parallel DSM step: rank-averaged gradients (bucketed all-reduce issued from inside the backward pass)
-     == gradients of the same loss over the concatenated batch on one GPU.
+     == gradients of the same loss over the concatenated batch on one GPU;
+  3. the data-parallel training step captured as ONE CUDA graph (NCCL all-reduces inside) == the eager DDP loop.
 Usage: python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tools/check_multi_gpu.py
 """
 import os
@@ -68,12 +69,41 @@ def main():
     lsum = loss.detach().clone()
     dist.all_reduce(lsum)
     e3 = abs(lsum.item() / world - loss_full.item()) / abs(loss_full.item())
-    ok = e1 < 1e-5 and e2 < 2e-3 and e3 < 1e-5 and 1e-7 < e1b < 0.2
+    # ---- 3. the data-parallel training step as ONE CUDA graph (NCCL all-reduces captured) == the eager DDP loop
+    from score_based_multimodal_autoencoder_b200.optim import FusedAdam, GraphedTrainStep
+    batches = [torch.randn(8, 5, 8, 8, generator=torch.Generator().manual_seed(100 + 7 * rank + k)).to(dev) for k in range(5)]
+
+    def fresh():
+        torch.manual_seed(0)
+        mm = Unet(**kw).to(dev).train()
+        return mm, D.DataParallelScoreNet(mm, bucket_mb=0.25)
+
+    m_e, d_e = fresh()
+    opt = FusedAdam(m_e.parameters(), lr=5e-4)
+    sh.manual_seed(31, sample_offset=rank * 8)
+    eager = []
+    for b in [batches[0], batches[0]] + batches:
+        l = sh.loss_fn(b, d_e, sde, likelihood_weighting=False, rng="philox")
+        opt.zero_grad(set_to_none=True)
+        l.backward()
+        opt.step()
+        eager.append(l.item())
+    m_g, d_g = fresh()
+    sh.manual_seed(31, sample_offset=rank * 8)
+    gstep = GraphedTrainStep(d_g, sde, batches[0], lr=5e-4, warmup=2)
+    got = [gstep(b).item() for b in batches]
+    gstep.close()  # before destroy_process_group: the graph holds NCCL kernels
+    e4 = max(abs(a - b) / abs(b) for a, b in zip(got, eager[2:]))
+    num = sum(((pe.double() - pg.double()) ** 2).sum() for pe, pg in zip(m_e.parameters(), m_g.parameters()))
+    den = sum((pe.double() ** 2).sum() for pe in m_e.parameters())
+    e4 = max(e4, (num / den).sqrt().item())
+    ok = e1 < 1e-5 and e2 < 2e-3 and e3 < 1e-5 and 1e-7 < e1b < 0.2 and e4 < 5e-3
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"multi-gpu check (world {world}): sharded exact sampling rel-max {e1:.2e} (independent shards {e1b:.2e}), "
-              f"DDP grads rel-L2 {e2:.2e} over {nb} buckets, loss {e3:.2e} -> {'OK' if t.item() == 1 else 'FAIL'}", flush=True)
+              f"DDP grads rel-L2 {e2:.2e} over {nb} buckets, loss {e3:.2e}, graphed DDP step vs eager {e4:.2e} -> "
+              f"{'OK' if t.item() == 1 else 'FAIL'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if t.item() == 1 else 1)
 
