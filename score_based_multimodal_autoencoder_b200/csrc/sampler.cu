@@ -109,7 +109,7 @@ __device__ __forceinline__ void sde_drift_diff(const SdeP& s, float t, float& dr
     const float beta = s.b0 + t * (s.b1 - s.b0);
     drift_coef = -0.5f * beta;
     if (s.kind == SBM_SDE_VP) {
-      g = sqrtf(beta);
+      g = fast_sqrt(beta);  // MUFU.SQRT: 1 ulp, far inside the 1e-5 parity tolerance of the step kernels
     } else {
       const float discount = 1.f - expf(-2.f * s.b0 * t - (s.b1 - s.b0) * t * t);
       g = sqrtf(beta * discount);
@@ -244,7 +244,10 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
         sg[0] += q0 + q1;
         sn[0] += n0 + n1;
       } else {
-        const int s0 = q / EQ, s1i = (q + 32) / EQ;
+        // sample index inside the group by comparison (S <= 4): an integer division per trip costs more than the sums
+        const int qb = q + 32;
+        const int s0 = (q >= EQ) + (q >= 2 * EQ) + (q >= 3 * EQ);
+        const int s1i = (qb >= EQ) + (qb >= 2 * EQ) + (qb >= 3 * EQ);
 #pragma unroll
         for (int k = 0; k < S; ++k) {
           if (s0 == k) { sg[k] += q0; sn[k] += n0; }

@@ -17,6 +17,9 @@ def pad8(c: int) -> int:
     return (c + 7) // 8 * 8
 
 
+_ITEMSIZE = {torch.float32: 4, torch.float64: 8, torch.bfloat16: 2, torch.int32: 4, torch.int64: 8}
+
+
 class _ZeroArena:
     """The backward pass needs ~400 small zero-initialised accumulators (split-K weight gradients, bias / GroupNorm
     parameter gradients, reduction scratch).  Instead of one fill kernel each, a backward pass takes them from ONE
@@ -38,7 +41,7 @@ class _ZeroArena:
         n = 1
         for d in shape:
             n *= d
-        words = (n * torch.empty((), dtype=dtype).element_size() + 3) // 4
+        words = (n * _ITEMSIZE[dtype] + 3) // 4
         words = (words + 3) // 4 * 4  # 16-byte aligned slices
         self.used += words
         if self.buf is None or self.buf.device != device or self.off + words > self.buf.numel():
