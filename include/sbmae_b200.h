@@ -216,6 +216,10 @@ int sbm_dsm_perturb(const sbm_latent_shape* ls, const sbm_sde* sde, const float*
 int sbm_dsm_loss(const sbm_latent_shape* ls, const float* score, const float* z, const float* std, const float* g2,
                  float* dscore, double* loss_acc, int32_t likelihood_weighting, int32_t reduce_mean,
                  int64_t global_batch, void* stream);
+/* nn.Dropout(p), training mode (unet_openai.py:265), IN PLACE on channels-last x[rows][C] (SBM_F32 / SBM_BF16, row
+ * stride ld elements, ld % 8 == 0): x *= keep/(1-p), keep = Philox uniform of (seed, draw [+ *draw_dev], element) >= p.
+ * The mask is never stored: the same call on the gradient of the output is the backward. */
+int sbm_dropout(void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t C, float p, const sbm_rng* rng, void* stream);
 int sbm_scale_by_scalar(const float* in, const float* scalar_dev, float* out, int64_t n, void* stream);
 int sbm_f64_to_f32(const double* in, float* out, int32_t n, void* stream);
 

@@ -11,7 +11,11 @@ of closures; the backward replays it.  Every gradient comes from libsbmae_b200 k
   * the `h + emb_out[..., None, None]` row bias (unet_openai.py:303) back-propagates through a per-sample column sum
     into ONE gradient GEMM for all `emb_layers` projections; `QKVAttention` through `sbm_softmax_attn_bwd`; nearest-2x
     up-sampling through a 2x2 block sum.
-Dropout (unet_openai.py:265) must be 0 in training mode here (the reference's 0.1 needs a mask kernel: not built).
+Dropout (unet_openai.py:265, p = 0.1 in train_lat_celebhq_unet_cont2_cond.py:653) = `sbm_dropout` in place on the
+GroupNorm32+SiLU output (the conv / weight-gradient operand) and, with the same Philox coordinates, on the gradient
+coming back from the conv: the mask is regenerated, never stored.  The per-forward draw id lives in device memory
+(`UNetModel._dropout_ctr`, snapshotted then advanced at the start of every training forward) so a captured CUDA graph
+draws fresh masks on every replay.
 """
 from __future__ import annotations
 
@@ -82,6 +86,11 @@ class _OPlan(_Plan):
         h = ops.conv_igemm(a, m._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out, bias=conv1.bias,
                            rowbias=cond[:, :, :, off:off + c_out])
         a2, st2 = self._gn32(h, c_out, gn2, L.ACT_SILU)
+        drop = self.drop
+        p_drop = float(blk.dropout) if drop is not None else 0.0
+        layer_id = m._res_index[id(blk)]
+        if p_drop > 0:
+            ops.dropout_(a2, c_out, p_drop, drop[0], layer_id, drop[1])
         sk = blk.skip_connection
         has_skip = isinstance(sk, nn.Conv2d)
         if has_skip:
@@ -100,6 +109,8 @@ class _OPlan(_Plan):
             g = out.g
             _, g_b = ops.add(g, None, c_out, want_bf16=True)
             da2 = self._conv2d_bwd(conv2, a2, g_b, g, c_out, c_out, 3)
+            if p_drop > 0:
+                ops.dropout_(da2, c_out, p_drop, drop[0], layer_id, drop[1])
             dh, dh_b = self._gn32_bwd(gn2, h, da2, c_out, st2, L.ACT_SILU, want_bf16=True)
             ops.colsum_per_sample(dh, c_out, dcond[:, 0, 0, off:off + c_out])   # d emb_out = sum over the pixels
             da = self._conv2d_bwd(conv1, a, dh_b, dh, c_in, c_out, 3)
@@ -145,6 +156,7 @@ class _OPlan(_Plan):
         dev = x.device
         ted, mc = m.time_embed_dim, m.model_channels
         with_z = z is not None
+        self.drop = m._dropout_draw() if (m.training and m.dropout > 0) else None
 
         # ---- embedding path (pre-activations kept for the SiLU backward)
         te = ops.time_embed(timesteps, mc, 1)

@@ -27,6 +27,7 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/sbmae_b200.h"
 #include "common.cuh"
@@ -1006,12 +1007,18 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   const int64_t M = (int64_t)a->batch << log_ohw;
   const int m_tiles = (int)((M + kBM - 1) / kBM);
   // small problems (one tile per CTA, less than a wave): narrower tiles spread the K loop and the epilogue over more SMs
-  while (BN > 64 && (int64_t)m_tiles * ((a->cout + BN - 1) / BN) * nphase < sm_count()) BN >>= 1;
-  // CTA-pair kernel: 256 x BN tiles; worth it once there is at least one full wave of pairs
+  // (stop at kNarrowPct % of a wave: a 128-wide tile list that covers 86 % of the SMs beats 64-wide tiles in 1.7 waves,
+  // whose A tiles are re-read from L2 by twice as many CTAs)
+  static const int kNarrowPct = [] { const char* e = getenv("SBM_NARROW_PCT"); return e ? atoi(e) : 75; }();
+  while (BN > 64 && (int64_t)m_tiles * ((a->cout + BN - 1) / BN) * nphase * 100 < (int64_t)sm_count() * kNarrowPct)
+    BN >>= 1;
+  // CTA-pair kernel: 256 x BN tiles; worth it once the tile pairs cover ~40 % of the SM pairs (measured on the 2x2-level
+  // layers: 64 pair tiles on 74 SM pairs run 1.3x faster than 128 single-CTA tiles -- half the weight traffic per CTA)
   // (a cout tail is fine: weight rows beyond cout are TMA zero fill, the epilogue clips the columns)
   const int n_tiles_pair = (a->cout + BN - 1) / BN;
+  static const int kPairPct = [] { const char* e = getenv("SBM_PAIR_PCT"); return e ? atoi(e) : 80; }();
   const bool use_pair = !g_force_single && (BN == 256 || BN == 128) && !a->out_nchw &&
-                        (int64_t)((m_tiles + 1) / 2) * n_tiles_pair * nphase >= sm_count() / 2;
+                        (int64_t)((m_tiles + 1) / 2) * n_tiles_pair * nphase * 200 >= (int64_t)sm_count() * kPairPct;
   const int ntaps_total = a->kh * a->kw;
   const cuuint64_t bdim[3] = {(cuuint64_t)a->cin, (cuuint64_t)a->cout, (cuuint64_t)ntaps_total};
   const cuuint64_t bstr[2] = {(cuuint64_t)a->cin_pad * 2, (cuuint64_t)a->cout * a->cin_pad * 2};

@@ -863,7 +863,7 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
   // 256 pixels (32 KB) per step: 1 sample of 16x16, 4 of 8x8, 16 of 4x4, ...
   const int spb = std::max(1, std::min(B, 256 / (H * W)));
   const size_t smem = (size_t)2 * spb * H * W * kDwCh * sizeof(float);
-  static size_t configured = 0;
+  static size_t configured = 0, configured_occ = 0;
   if (smem > 48 * 1024 && smem > configured) {
     SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_pipe_kernel<W, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
@@ -871,8 +871,17 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
   }
   const int chunks = (C + kDwCh - 1) / kDwCh;
   const int nsteps = (B + spb - 1) / spb;
-  // 2-3 resident blocks per SM; a block walks several steps when there is enough work (so the prefetch overlaps)
-  int gy = std::max(1, std::min(nsteps, ((W <= 8 ? 3 : 2) * sm_count() + chunks - 1) / chunks));
+  // exactly ONE wave of resident blocks (2-3 per SM), each walking several steps so the prefetch overlaps: the grid
+  // is rounded DOWN to the resident slots -- a handful of blocks spilling into a second wave would run their whole
+  // share of the steps after everyone else has finished (measured: 300 blocks on 296 slots cost 1.5x)
+  static int per_sm = 0;
+  if (per_sm == 0 || smem > configured_occ) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_pipe_kernel<W, TOut>, 256, smem) != cudaSuccess ||
+        per_sm <= 0)
+      per_sm = 1;
+    configured_occ = smem;
+  }
+  int gy = std::max(1, std::min(nsteps, per_sm * sm_count() / chunks));
   dim3 grid(chunks, gy);
   dwconv7_pipe_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H,
                                                         spb, flip, addend, ldadd);
@@ -1058,7 +1067,7 @@ int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, i
   }
   const size_t smem = ((size_t)3 * n * 33 + 32 * 33) * sizeof(float);
   SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_linear_attn_fwd: n=%d too large", n);
-  static size_t configured = 0;
+  static size_t configured = 0, configured_occ = 0;
   if (smem > 48 * 1024 && smem > configured) {
     SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -1075,7 +1084,7 @@ int sbm_softmax_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, 
   SBM_CHECK_ARG(qkv && out && B > 0 && n > 0 && heads > 0 && dh > 0, "sbm_softmax_attn_fwd: bad args");
   const size_t smem = ((size_t)n * (n + 1) + 2 * (size_t)n * 33) * sizeof(float);
   SBM_CHECK_ARG(smem <= 200 * 1024, "sbm_softmax_attn_fwd: n=%d too large for the shared-memory score tile", n);
-  static size_t configured = 0;
+  static size_t configured = 0, configured_occ = 0;
   if (smem > 48 * 1024 && smem > configured) {
     SBM_CUDA_OK(cudaFuncSetAttribute(softmax_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

@@ -154,6 +154,48 @@ __device__ __forceinline__ float2 impute_coef(const Impute& im, const SdeP& s) {
   return make_float2(mc, sd);
 }
 
+// nn.Dropout(p) in training mode (unet_openai.py:265), in place on a channels-last activation x[rows][C] (fp32 or
+// bf16, row stride ld): x *= keep / (1 - p), keep = (uniform >= p).  The uniform of element (row, c) is word (c & 3) of
+// Philox(seed, draw, quad = (row * C8 + c) / 4) with C8 = C rounded up to 8, so the SAME call on the gradient of the
+// output is the backward (the mask is regenerated, never stored).  One channel octet per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(T* __restrict__ x, int64_t ld, int64_t n_oct, FastDiv c8d, int C, float p, float inv_keep,
+               uint64_t seed, uint64_t draw, const uint64_t* draw_dev) {
+  if (draw_dev) draw += *draw_dev;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t thr = (uint32_t)(p * 16777216.0f);  // keep iff (word >> 8) >= p * 2^24  (torch.rand's 24-bit uniform)
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n_oct; o += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t row = fdiv((uint32_t)o, c8d);
+    const int c0 = ((uint32_t)o - row * c8d.d) * 8;
+    const uint64_t quad = (uint64_t)o * 2;
+    const uint4 r0 = Philox::round10(make_uint4((uint32_t)quad, (uint32_t)(quad >> 32), (uint32_t)draw,
+                                                (uint32_t)(draw >> 32)), key);
+    const uint4 r1 = Philox::round10(make_uint4((uint32_t)(quad + 1), (uint32_t)((quad + 1) >> 32), (uint32_t)draw,
+                                                (uint32_t)(draw >> 32)), key);
+    const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    T* px = x + (int64_t)row * ld + c0;
+    if constexpr (sizeof(T) == 2) {
+      uint4 v = *reinterpret_cast<uint4*>(px);
+      __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        e[j] = (c0 + j < C && (w[j] >> 8) >= thr) ? __float2bfloat16(__bfloat162float(e[j]) * inv_keep)
+                                                  : __float2bfloat16(0.f);
+      *reinterpret_cast<uint4*>(px) = v;
+    } else {
+      float4 a = *reinterpret_cast<float4*>(px), b = *reinterpret_cast<float4*>(px + 4);
+      float* e[2] = {reinterpret_cast<float*>(&a), reinterpret_cast<float*>(&b)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        e[j >> 2][j & 3] = (c0 + j < C && (w[j] >> 8) >= thr) ? e[j >> 2][j & 3] * inv_keep : 0.f;
+      *reinterpret_cast<float4*>(px) = a;
+      *reinterpret_cast<float4*>(px + 4) = b;
+    }
+  }
+}
+
+
 // ------------------------------------------------------------------------------ predictor
 // One thread = one quad (4 consecutive latent elements), two quads in flight per loop trip.
 __global__ void __launch_bounds__(256)
@@ -505,6 +547,29 @@ extern "C" {
 int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem_offset, float scale, void* stream) {
   SBM_CHECK_ARG(out && n > 0 && n % 4 == 0 && elem_offset % 4 == 0, "sbm_randn: n and offset must be multiples of 4");
   randn_kernel<<<ew_grid(n / 4), 256, 0, (cudaStream_t)stream>>>(out, n / 4, seed, draw, elem_offset / 4, scale);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_dropout(void* x, int32_t dtype, int64_t ld, int64_t rows, int32_t C, float p, const sbm_rng* rng,
+                void* stream) {
+  SBM_CHECK_ARG(x && rows > 0 && C > 0 && rng, "sbm_dropout: bad args");
+  SBM_CHECK_ARG(p >= 0.f && p < 1.f, "sbm_dropout: p = %g must be in [0, 1)", (double)p);
+  SBM_CHECK_ARG(dtype == SBM_F32 || dtype == SBM_BF16, "sbm_dropout: dtype");
+  const int c8 = (C + 7) / 8;
+  SBM_CHECK_ARG(ld >= (int64_t)c8 * 8 && ld % 8 == 0, "sbm_dropout: row stride %lld must cover C rounded up to 8",
+                (long long)ld);
+  const int64_t n_oct = rows * c8;
+  SBM_CHECK_ARG(n_oct < (int64_t(1) << 32), "sbm_dropout: more than 2^32 channel octets");
+  const float inv_keep = 1.f / (1.f - p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == SBM_BF16)
+    dropout_kernel<__nv_bfloat16><<<wave_grid(dropout_kernel<__nv_bfloat16>, n_oct), 256, 0, st>>>(
+        (__nv_bfloat16*)x, ld, n_oct, make_fastdiv((uint32_t)c8), C, p, inv_keep, rng->seed, rng->draw, rng->draw_dev);
+  else
+    dropout_kernel<float><<<wave_grid(dropout_kernel<float>, n_oct), 256, 0, st>>>(
+        (float*)x, ld, n_oct, make_fastdiv((uint32_t)c8), C, p, inv_keep, rng->seed, rng->draw, rng->draw_dev);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;

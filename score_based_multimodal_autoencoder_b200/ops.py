@@ -251,6 +251,16 @@ def groupnorm_apply(x: torch.Tensor, c: int, stats: torch.Tensor, gamma, beta, *
         L.stream_ptr()), "sbm_groupnorm_apply")
 
 
+def dropout_(x: torch.Tensor, c: int, p: float, seed: int, draw: int, draw_dev=None) -> torch.Tensor:
+    """nn.Dropout(p) in training mode, IN PLACE on a channels-last [B, H, W, ld] tensor (fp32 / bf16); the mask is a
+    function of (seed, draw + *draw_dev, element), so the same call on the gradient of the output is the backward."""
+    b, h, w, _ = x.shape
+    r = L.Rng(seed & 0xFFFFFFFFFFFFFFFF, draw, 0, draw_dev.data_ptr() if draw_dev is not None else None)
+    L.check(L.lib().sbm_dropout(L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), C.c_int64(b * h * w),
+                                C.c_int32(c), C.c_float(p), C.byref(r), L.stream_ptr()), "sbm_dropout")
+    return x
+
+
 def time_embed(t: torch.Tensor, dim: int, mode: int) -> torch.Tensor:
     b = t.shape[0]
     ld = pad8(dim)

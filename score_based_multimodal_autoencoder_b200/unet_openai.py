@@ -16,11 +16,12 @@ sm_100a kernels through the C ABI (ops.py -> libsbmae_b200.so):
     of a pre-planned concat buffer.
 
 With autograd enabled the forward runs through `autograd_openai.py` (one autograd node, hand-written backward): the
-z-conditioned DSM training of `train_lat_celebhq_unet_cont2_cond.py`; dropout must be 0 there.
+z-conditioned DSM training of `train_lat_celebhq_unet_cont2_cond.py`; train-mode dropout = `sbm_dropout` (Philox masks).
 There is no CPU / eager fallback.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
@@ -220,6 +221,9 @@ class UNetModel(nn.Module):
                                  zero_module(conv_nd(dims, model_channels, out_channels, 3, padding=1)))
         self._packed: dict = {}
         self._res_blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+        self._res_index = {id(blk): i for i, blk in enumerate(self._res_blocks)}
+        self._dropout_seed = None
+        self._dropout_ctr = None
 
     @property
     def inner_dtype(self):  # unet_openai.py:531-536
@@ -331,14 +335,35 @@ class UNetModel(nn.Module):
             raise NotImplementedError("class-conditional embedding is not used by any reference score-net command")
         if not x.is_cuda:
             raise L.SbmError("UNetModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in train() mode is not built (mask kernel): call eval() for sampling "
-                                      "or construct the net with dropout=0 for training")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        # train() mode with dropout > 0 always takes the training plan (it owns the mask kernel), also under no_grad
+        if (self.training and self.dropout > 0) or (torch.is_grad_enabled()
+                                                    and any(p.requires_grad for p in self.parameters())):
             from .autograd_openai import unet_openai_forward_train
             return unet_openai_forward_train(self, x, timesteps, z)
         with torch.no_grad():
             return self._forward_infer(x, timesteps, z)
+
+    # ------------------------------------------------------------------ dropout stream
+    _DRAWS_PER_FORWARD = 4096  # > number of ResBlocks: draw id = forward index * 4096 + ResBlock index
+
+    def set_dropout_seed(self, seed: int) -> None:
+        """Philox key of the dropout masks (default: torch.initial_seed() at the first training forward; give every
+        data-parallel rank its own)."""
+        self._dropout_seed = int(seed)
+
+    def _dropout_draw(self):
+        """-> (seed, device scalar holding this forward's draw base).  The counter is snapshotted and advanced on the
+        stream (inside a captured graph too), so the backward of THIS forward regenerates the same masks."""
+        dev = next(self.parameters()).device
+        if getattr(self, "_dropout_seed", None) is None:
+            self._dropout_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + 0x5D) & 0xFFFFFFFFFFFFFFFF
+        ctr = getattr(self, "_dropout_ctr", None)
+        if ctr is None or ctr.device != dev:
+            ctr = self._dropout_ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        snap = ctr.clone()
+        L.check(L.lib().sbm_train_tick(None, L.ptr(ctr), C.c_uint64(self._DRAWS_PER_FORWARD), L.stream_ptr()),
+                "sbm_train_tick")
+        return self._dropout_seed, snap
 
     def _forward_infer(self, x, timesteps, z):
         b, m, hh, ww = x.shape

@@ -145,3 +145,22 @@ def test_unet_openai_state_dict_schema_matches_reference_golden():
     assert got == {k: tuple(v) for k, v in g["shapes"].items()}
     with pytest.raises(Exception):
         m(g["x"], g["t"])  # CPU tensors: no fallback
+
+
+def test_oracle_philox_known_answers_and_dropout_mask():
+    """oracle/philox.py against the Random123 known-answer vectors of Philox4x32-10 (kat_vectors: zero, all-ones and
+    pi-digit counter / key), and the statistics of the dropout mask derived from it."""
+    import numpy as np
+
+    from oracle.philox import dropout_keep, philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(np.array(ctr, dtype=np.uint32), key)
+        assert tuple(int(v) for v in got) == want
+    keep = dropout_keep(0x1234ABCD5678, 3, 4096, 20, 0.1)
+    assert keep.shape == (4096, 20) and abs(keep.mean() - 0.9) < 5e-3
+    assert not np.array_equal(keep, dropout_keep(0x1234ABCD5678, 4, 4096, 20, 0.1))
+    assert dropout_keep(1, 0, 64, 8, 0.0).all()

@@ -161,3 +161,121 @@ def test_unet_openai_training_gradients_vs_reference_golden():
         # the emb_layers / conv-bias gradients in front of a GroupNorm are sums that cancel almost completely (the norm
         # removes per-group constants), so bf16 noise weighs more on them: bound the bulk tightly, the worst loosely
         assert rels[int(0.9 * len(rels))] <= 5e-2 and worst <= 0.2, (worst, worst_k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c", [64, 20])
+def test_dropout_kernel_mask_is_bit_exact_with_the_oracle(dtype, c):
+    """sbm_dropout against oracle/philox.py (integer work: every keep / drop decision must agree), on a strided
+    channels-last view, with the draw id split between the host argument and the device counter."""
+    import numpy as np
+
+    from oracle.philox import dropout_keep
+    from score_based_multimodal_autoencoder_b200 import ops
+    b, h, w, p, seed = 3, 4, 8, 0.1, 0x1234ABCD5678
+    ld = ops.pad8(c)
+    buf = torch.zeros((b, h, w, ld + 16), dtype=dtype, device="cuda")
+    x = buf[..., 8:8 + ld]
+    x[..., :c] = 1.0
+    ctr = torch.tensor([4096 * 5], dtype=torch.int64, device="cuda")
+    ops.dropout_(x, c, p, seed, 7, ctr)
+    keep = torch.from_numpy(dropout_keep(seed, 4096 * 5 + 7, b * h * w, c, p)).view(b, h, w, c)
+    got = x[..., :c].float().cpu()
+    assert torch.equal(got != 0, keep)
+    want = torch.tensor(1.0 / (1.0 - p)).to(dtype).float()
+    assert torch.equal(got[keep], want.expand_as(got[keep]))
+    assert buf[..., :8].abs().sum() == 0 and buf[..., 8 + ld:].abs().sum() == 0     # nothing outside the view
+    # the same call on another tensor (the gradient) applies the same mask
+    gbuf = torch.randn((b, h, w, ld), device="cuda").to(dtype)
+    g0 = gbuf.clone()
+    ops.dropout_(gbuf, c, p, seed, 4096 * 5 + 7, None)
+    exp = torch.where(keep.cuda(), (g0[..., :c].float() * (1.0 / (1.0 - p))).to(dtype), torch.zeros((), dtype=dtype, device="cuda"))
+    assert torch.equal(gbuf[..., :c], exp)
+
+
+def test_unet_openai_dropout_training_vs_reference_golden():
+    """train() mode with dropout = 0.1 (the net train_lat_celebhq_unet_cont2_cond.py:651-653 trains): loss and
+    gradients against the UNMODIFIED reference module whose nn.Dropout was fed the same Philox masks
+    (tests/golden/unet_openai_train_dropout.pt, oracle/gen_golden_openai_train.py)."""
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    g = golden("unet_openai_train_dropout.pt")
+    m, _ = _build(g["kwargs"], g["shapes"])
+    m.train()
+    m.set_dropout_seed(g["seed"])
+    assert len(m._res_blocks) == g["n_masks"]
+    sde = sh.VPSDE(0.1, 20.0, 1000)
+    loss = sh.loss_fn(g["batch"].cuda(), m, sde, reduce_mean=True, likelihood_weighting=False, u=g["u"].cuda(),
+                      z=g["z"].cuda(), z_cond=g["zc"].cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = g["loss"].item()
+    print(f"dropout loss {loss.item():.6f} vs reference {ref:.6f} (eval-mode {g['loss_eval_mode'].item():.6f})")
+    assert abs(loss.item() - ref) <= 2e-3 * abs(ref)
+    assert abs(loss.item() - ref) < 0.25 * abs(g["loss_eval_mode"].item() - ref)    # the masks were applied
+    params = dict(m.named_parameters())
+    rels = []
+    for k, r in g["grads"].items():
+        got = params[k].grad
+        assert got is not None, k
+        if r["norm"].item() < 1e-5 * g["grad_norm"].item():
+            assert got.norm().item() < 1e-4 * g["grad_norm"].item(), k
+            continue
+        head = got.flatten()[:256].float().cpu()
+        rels.append((((head - r["head"]).norm() / (r["head"].norm() + 1e-12)).item(), k))
+        assert abs(got.norm().item() - r["norm"].item()) <= 8e-2 * r["norm"].item(), k
+    gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters() if p.grad is not None)).item()
+    rels.sort()
+    print(f"total grad norm {gn:.5e} vs {g['grad_norm'].item():.5e}; head rel-L2 median {rels[len(rels) // 2][0]:.3e}, "
+          f"p90 {rels[int(0.9 * len(rels))][0]:.3e}, worst {rels[-1]}")
+    assert abs(gn - g["grad_norm"].item()) <= 3e-2 * g["grad_norm"].item()
+    assert rels[int(0.9 * len(rels))][0] <= 5e-2 and rels[-1][0] <= 0.2
+
+    # a second forward draws new masks (device counter advanced); eval() is deterministic and mask-free;
+    # train() under no_grad (sampling without calling eval(), as plt scripts may) still applies dropout
+    x = g["batch"].cuda()
+    t = torch.full((x.shape[0],), 0.5, device="cuda")
+    with torch.no_grad():
+        y1, y2 = m(x, t, z=g["zc"].cuda()), m(x, t, z=g["zc"].cuda())
+        m.eval()
+        e1, e2 = m(x, t, z=g["zc"].cuda()), m(x, t, z=g["zc"].cuda())
+    assert not torch.equal(y1, y2) and torch.equal(e1, e2)
+    assert 1e-3 < rel_l2(y1, e1) < 0.5
+
+
+def test_unet_openai_dropout_in_a_captured_training_step():
+    """GraphedTrainStep with dropout 0.1: the mask draw id lives in device memory (snapshot + advance inside the graph),
+    so every replay draws fresh masks and the replayed run equals the eager loop step for step (same seeds)."""
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    from score_based_multimodal_autoencoder_b200.optim import FusedAdam, GraphedTrainStep
+    g = golden("unet_openai_train_dropout.pt")
+    sde = sh.VPSDE(0.1, 20.0, 1000)
+    gen = torch.Generator().manual_seed(11)
+    batches = [torch.randn(6, 3, 8, 8, generator=gen).cuda() for _ in range(5)]
+    zc = g["zc"].cuda()
+
+    m_e, _ = _build(g["kwargs"], g["shapes"])
+    m_e.train()
+    m_e.set_dropout_seed(99)
+    opt = FusedAdam(m_e.parameters(), lr=1e-4)
+    sh.manual_seed(5)
+    eager = []
+    for b in [batches[0], batches[0]] + batches:
+        loss = sh.loss_fn(b, m_e, sde, likelihood_weighting=False, rng="philox", z_cond=zc)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        eager.append(loss.item())
+
+    m_g, _ = _build(g["kwargs"], g["shapes"])
+    m_g.train()
+    m_g.set_dropout_seed(99)
+    sh.manual_seed(5)
+    step = GraphedTrainStep(m_g, sde, batches[0], lr=1e-4, warmup=2,
+                            loss_kwargs=dict(likelihood_weighting=False, z_cond=zc))
+    got = [step(b).item() for b in batches]
+    again = step(batches[-1]).item()
+    step.close()
+    print(got, eager[2:], again)
+    for a, b in zip(got, eager[2:]):
+        assert abs(a - b) <= 3e-3 * abs(b), (got, eager)
+    assert again != got[-1]      # same batch, next replay: new t / z / masks

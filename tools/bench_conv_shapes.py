@@ -17,6 +17,9 @@ SHAPES = [  # H, cin, cout, k
 ]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 MODES = [("staged", 0)] + ([("direct", 1)] if os.environ.get("SBM_AB_EPILOGUE") else [])
+if os.environ.get("SBM_LOWRES"):
+    SHAPES = [(2, 1024, 512, 3), (2, 512, 1024, 3), (2, 1024, 1024, 3), (2, 512, 512, 3), (4, 1024, 512, 3), (4, 512, 1024, 3),
+              (1, 1024, 512, 3), (1, 512, 1024, 3), (2, 512, 384, 1), (4, 512, 384, 1)]
 if os.environ.get("SBM_SMALLK"):
     SHAPES = [(16, 147, 170, 1), (16, 170, 256, 1), (16, 256, 384, 1), (16, 128, 256, 1), (8, 512, 384, 1), (8, 128, 512, 1),
               (16, 512, 256, 1), (16, 256, 512, 3)]
@@ -43,6 +46,7 @@ for (H, cin, cout, k) in SHAPES:
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1) * 1e3)
             t = sorted(ts[1:])[len(ts[1:]) // 2]
+            v = L.lib().sbm_conv_last_variant()
             print(f"H={H:2d} {cin:4d}->{cout:4d} k={k} M={B * H * H:6d} taps={taps} {mode:6s} {label:16s}: {t:8.1f} us  "
-                  f"{flops / t / 1e6:7.1f} TFLOP/s", flush=True)
+                  f"{flops / t / 1e6:7.1f} TFLOP/s  BN={v & 0xFFFF}{' pair' if v & (1 << 16) else ''}", flush=True)
     L.lib().sbm_conv_force_direct_epilogue(0)
