@@ -82,8 +82,13 @@ int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 int sbm_conv_force_single_cta(int32_t on);
 /* A/B switch: 1 = per-thread global stores in the CTA-pair kernel instead of the TMA-staged epilogue */
 int sbm_conv_force_direct_epilogue(int32_t on);
-/* which kernel the calling thread's last sbm_conv_igemm used: N tile | CTA-pair << 16 | staged epilogue << 17 */
+/* which kernel the calling thread's last sbm_conv_igemm used: N tile | CTA-pair << 16 | staged epilogue << 17 |
+ * pixel-major tiling << 18 */
 int sbm_conv_last_variant(void);
+/* pixel-major tiling of stride-1 'same' convolutions (a tile = 128 samples at ONE output pixel, so taps that only read
+ * zero padding there are skipped): -1 = decide by work estimate (default), 0 = never, 1 = whenever the CTA-pair kernel
+ * runs the layer.  Results are bit-identical either way (the skipped products are exact zeros).  Returns the old mode */
+int sbm_conv_pixel_major(int32_t mode);
 
 /* Weight gradient of sbm_conv_igemm: dwpk[tap][o][i] += sum_pixels dy[p][o] * x[p shifted by tap][i]  (fp32, split-K
  * atomics: the caller zeroes dwpk).  x = the forward input operand (bf16), dy = gradient of the forward output (bf16,

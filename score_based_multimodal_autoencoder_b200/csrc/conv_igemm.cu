@@ -38,6 +38,7 @@ namespace sbm {
 std::atomic<unsigned long long> g_launches{0};
 static bool g_force_single = false;  // debugging / A-B timing switch (sbm_conv_force_single_cta)
 static thread_local int g_last_variant = 0;  // BN | pair << 16 | staged << 17 of the last launch (bench bookkeeping)
+static int g_pixel_major = [] { const char* e = getenv("SBM_PIXEL_MAJOR"); return e ? atoi(e) : -1; }();       // -1: by work estimate, 0: never, 1: whenever the CTA-pair kernel runs the layer
 static bool g_force_direct = false;  // A-B switch: per-thread global stores instead of the TMA-staged epilogue
 
 constexpr int kBM = 128;
@@ -78,7 +79,14 @@ struct ConvKernelParams {
   const double* gn_stats;   // [batch][2] (sum, sum of squares) of the input tensor, or NULL
   const float* gn_tab;      // [2][16][cout]: Sg then Tb
   double gn_inv_count;
-  float gn_eps, pad1;
+  float gn_eps;
+  // pixel-major tiling (stride-1 'same' convolutions at large batch): the 128 rows of a tile are 128 SAMPLES at ONE
+  // output pixel, so the taps that read zero padding at that pixel are skipped for the whole tile
+  int32_t pm;
+  int32_t pm_blocks;        // 256-sample blocks in the batch
+  int32_t pm_global;        // tile order: 1 = (pixel rank, block) -- cost-sorted over the whole list, for short lists;
+                            // 0 = (block, pixel rank) -- a block's pixels stay together (DRAM page / L2 locality)
+  uint8_t pm_pix[256];      // output pixels (i * W + j) ordered by falling tap count: the tile list is cost-sorted
   TapTable taps[4];
 };
 
@@ -569,11 +577,28 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto tile_origin = [&](int t, int& ph, int& nt, int& b0, int& oh0) {
+  // tile t -> phase, N tile, first sample, first output row (and, pixel-major: the output column pj of the tile)
+  auto tile_origin = [&](int t, int& ph, int& nt, int& b0, int& oh0, int& pj) {
     ph = t / per_phase;
     const int rem = t - ph * per_phase;
     const int mp = rem / sch.n_tiles;
     nt = rem - mp * sch.n_tiles;
+    pj = 0;
+    if (p.pm) {  // m-pair index -> (pixel rank, 256-sample block); interior pixels (most taps) first, corners last
+      int pr, sb;
+      if (p.pm_global) {
+        pr = mp / p.pm_blocks;
+        sb = mp - pr * p.pm_blocks;
+      } else {
+        sb = mp >> log_ohw;
+        pr = mp & ((1 << log_ohw) - 1);
+      }
+      const int px = p.pm_pix[pr];
+      b0 = (sb << 8) + ((int)rank << 7);
+      oh0 = px >> p.log_ow;
+      pj = px & ((1 << p.log_ow) - 1);
+      return;
+    }
     const int mt = 2 * mp + (int)rank;
     if (log_ohw >= 7) {
       const int tiles_per_img = 1 << (log_ohw - 7);
@@ -584,29 +609,44 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       oh0 = 0;
     }
   };
+  // k-th tile of this cluster.  Pixel-major tile lists are sorted by falling cost and dealt out in snake order (round
+  // k runs over the clusters forwards, round k+1 backwards), which evens out the per-cluster sums of unequal tiles
+  auto tile_of_round = [&](int k) -> int {
+    return k * npairs + ((p.pm && (k & 1)) ? npairs - 1 - pair : pair);
+  };
+  // taps of the table that read at least one real pixel for this tile (pixel-major: the tile is one output pixel)
+  auto tap_mask = [&](const TapTable& tt, int oh0, int pj) -> uint32_t {
+    if (!p.pm) return (1u << tt.ntaps) - 1u;
+    uint32_t m = 0;
+    for (int k = 0; k < tt.ntaps; ++k)
+      if ((unsigned)(oh0 + tt.dh[k]) < (1u << p.log_oh) && (unsigned)(pj + tt.dw[k]) < (1u << p.log_ow)) m |= 1u << k;
+    return m;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA loads its own operand halves)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = pair; t < sch.total; t += npairs) {
-        int ph, nt, b0, oh0;
-        tile_origin(t, ph, nt, b0, oh0);
+      for (int k = 0; k * npairs < sch.total; ++k) {
+        const int t = tile_of_round(k);
+        if (t >= sch.total) continue;
+        int ph, nt, b0, oh0, pj;
+        tile_origin(t, ph, nt, b0, oh0, pj);
         const TapTable& tt = p.taps[ph];
         const int n0 = nt * BN + (int)rank * (BN / 2);
-        const int num_kb = tt.ntaps * p.cblocks;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.cblocks;
-          const int cb = kb - tap * p.cblocks;
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          uint8_t* sb = sa + L::kABytes;
-          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-          const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
-          ptx::tma_load_5d_2sm(sa, &tmA, lead_bar, cb * kBK, tt.dw[tap], tt.q[tap], oh0 + tt.dh[tap], b0);
-          ptx::tma_load_3d_2sm(sb, &tmB, lead_bar, cb * kBK, n0, tt.wtap[tap]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (uint32_t tm = tap_mask(tt, oh0, pj); tm != 0; tm &= tm - 1) {
+          const int tap = __ffs(tm) - 1;
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+            const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+            ptx::tma_load_5d_2sm(sa, &tmA, lead_bar, cb * kBK, pj + tt.dw[tap], tt.q[tap], oh0 + tt.dh[tap], b0);
+            ptx::tma_load_3d_2sm(sb, &tmB, lead_bar, cb * kBK, n0, tt.wtap[tap]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -616,9 +656,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       constexpr uint32_t idesc = ptx::make_idesc_bf16(256, BN);
       int stage = 0, astage = 0;
       uint32_t phase = 0, aphase = 0;
-      for (int t = pair; t < sch.total; t += npairs) {
-        const int ph = t / per_phase;
-        const int num_kb = p.taps[ph].ntaps * p.cblocks;
+      for (int k = 0; k * npairs < sch.total; ++k) {
+        const int t = tile_of_round(k);
+        if (t >= sch.total) continue;
+        int ph, nt, b0, oh0, pj;
+        tile_origin(t, ph, nt, b0, oh0, pj);
+        const int num_kb = __popc(tap_mask(p.taps[ph], oh0, pj)) * p.cblocks;
         ptx::mbar_wait(&tempty_bar[astage], aphase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t tacc = tmem_base + (uint32_t)(astage * BN);
@@ -645,14 +688,15 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int ew = e & 3;      // TMEM lane quarter
     const int hc = e >> 2;     // column half
     const int r = ew * 32 + lane;
-    const int j = r & ((1 << p.log_ow) - 1);
-    const int i = (r >> p.log_ow) & ((1 << p.log_th) - 1);
-    const int bl = r >> (p.log_ow + p.log_th);
+    // row r of a tile = pixel (i, j) of local image bl (pixel-major: sample r at the tile's pixel)
+    const int j_r = p.pm ? 0 : (r & ((1 << p.log_ow) - 1));
+    const int i = p.pm ? 0 : ((r >> p.log_ow) & ((1 << p.log_th) - 1));
+    const int bl = p.pm ? r : (r >> (p.log_ow + p.log_th));
     const uint32_t lead_tempty0 = ptx::mapa_u32(ptx::smem_u32(&tempty_bar[0]), 0);
     // staged path: this warp's 32 rows are one TMA box (columns, ow-run, 1, rows, images) starting at
-    const int sub_j = (ew * 32) & ((1 << p.log_ow) - 1);
-    const int sub_i = ((ew * 32) >> p.log_ow) & ((1 << p.log_th) - 1);
-    const int sub_b = (ew * 32) >> (p.log_ow + p.log_th);
+    const int sub_j = p.pm ? 0 : ((ew * 32) & ((1 << p.log_ow) - 1));
+    const int sub_i = p.pm ? 0 : (((ew * 32) >> p.log_ow) & ((1 << p.log_th) - 1));
+    const int sub_b = p.pm ? ew * 32 : ((ew * 32) >> (p.log_ow + p.log_th));
     uint8_t* wst = smem + L::kStagingOffset + e * kStgPerWarp;
     uint64_t* rbar = res_bar + 3 * e;
     const bool has_res = p.residual != nullptr;
@@ -660,17 +704,20 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint32_t nchunk = 0;  // chunks this warp has staged so far (buffer rotation + barrier parity)
     int astage = 0;
     uint32_t aphase = 0;
-    for (int t = pair; t < sch.total; t += npairs) {
-      int ph, nt, b0, oh0;
-      tile_origin(t, ph, nt, b0, oh0);
+    for (int k = 0; k * npairs < sch.total; ++k) {
+        const int t = tile_of_round(k);
+        if (t >= sch.total) continue;
+      int ph, nt, b0, oh0, pj;
+      tile_origin(t, ph, nt, b0, oh0, pj);
       const TapTable& tt = p.taps[ph];
       const int b = b0 + bl;
       const int oh = oh0 + i;
+      const int j = pj + j_r;
       const bool row_ok = b < p.batch;
       float s1 = 0.f, s2 = 0.f;
       const GnRow gr = gn_row(p, b, oh, j, row_ok);
       if constexpr (kStaged) {
-        const int cj = sub_j, ci = oh0 + sub_i, cb = b0 + sub_b, cq = tt.out_q;
+        const int cj = pj + sub_j, ci = oh0 + sub_i, cb = b0 + sub_b, cq = tt.out_q;
         const int ncol0 = nt * BN + hc * (BN / 2);
         const int nch = min((BN / 2) / kEC, max(0, (p.cout - ncol0 + kEC - 1) / kEC));
         if (has_res && nch > 0 && lane == 0) {
@@ -733,7 +780,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty0 + (uint32_t)astage * 8u);
       if (p.stats != nullptr) {
         if (!row_ok) { s1 = 0.f; s2 = 0.f; }
-        const int seg = log_ohw >= 5 ? 32 : (1 << log_ohw);
+        const int seg = p.pm ? 1 : (log_ohw >= 5 ? 32 : (1 << log_ohw));   // rows of this warp that share a sample
         for (int o = seg >> 1; o > 0; o >>= 1) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
           s2 += __shfl_xor_sync(0xffffffffu, s2, o);
@@ -817,7 +864,8 @@ static int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
 // Tensor map over an output-geometry tensor (output / residual / bf16 copy) whose box is the 32 rows x kEC columns one
 // epilogue warp produces per chunk: dims (c, j, q, i, b); q addresses the output-parity phase of a transposed conv.
 static bool encode_rowbox_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensorMap* tm, const void* base, int dtype,
-                              int64_t ld, int cout, int ow, int oh, int batch, int sp, int log_ow, int log_th) {
+                              int64_t ld, int cout, int ow, int oh, int batch, int sp, int log_ow, int log_th,
+                              bool pm = false) {
   const cuuint64_t esz = (dtype == SBM_F32) ? 4 : 2;
   const cuuint64_t OWf = (cuuint64_t)sp * ow, OHf = (cuuint64_t)sp * oh;
   const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)ow, sp == 2 ? OWf + 2 : 1, (cuuint64_t)oh,
@@ -828,7 +876,9 @@ static bool encode_rowbox_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensor
   const int bw = std::min(ow, 32);
   const int bh = std::min(th, 32 / bw);
   const int bb = 32 / (bw * bh);
-  const cuuint32_t box[5] = {(cuuint32_t)kEC, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)bb};
+  // pixel-major tiles: the warp's 32 rows are 32 samples at one pixel
+  const cuuint32_t box[5] = {(cuuint32_t)kEC, pm ? 1u : (cuuint32_t)bw, 1u, pm ? 1u : (cuuint32_t)bh,
+                             pm ? 32u : (cuuint32_t)bb};
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   const CUresult cr = encode(tm, dtype == SBM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                              5, const_cast<void*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -989,36 +1039,81 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   if (a->out2) vec = vec && ((a->ldo2 * 2) % 16 == 0) && ((reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
   p.vec_ok = vec ? 1 : 0;
 
+  // ---- tile shape
+  const int64_t M = (int64_t)a->batch << log_ohw;
+  static const int kNarrowPct = [] { const char* e = getenv("SBM_NARROW_PCT"); return e ? atoi(e) : 75; }();
+  static const int kPairPct = [] { const char* e = getenv("SBM_PAIR_PCT"); return e ? atoi(e) : 80; }();
+  int BN = 0;
+  auto choose = [&](int m_tiles_) -> bool {  // sets BN; returns whether the CTA-pair kernel runs this tile list
+    if (a->cout <= 32) BN = 32;
+    else if (a->cout <= 64) BN = 64;
+    else if (a->cout <= 128) BN = 128;
+    else if (a->cout % 256 == 0 || a->cout > 512) BN = 256;
+    else BN = (a->cout % 128 == 0) ? 128 : 256;
+    // small problems (one tile per CTA, less than a wave): narrower tiles spread the K loop and the epilogue over more
+    // SMs (stop at kNarrowPct % of a wave: a 128-wide tile list that covers 86 % of the SMs beats 64-wide tiles in 1.7
+    // waves, whose A tiles are re-read from L2 by twice as many CTAs)
+    while (BN > 64 && (int64_t)m_tiles_ * ((a->cout + BN - 1) / BN) * nphase * 100 < (int64_t)sm_count() * kNarrowPct)
+      BN >>= 1;
+    // CTA-pair kernel: 256 x BN tiles; worth it once the tile pairs cover ~40 % of the SM pairs (measured on the
+    // 2x2-level layers: 64 pair tiles on 74 SM pairs run 1.3x faster than 128 single-CTA tiles -- half the weight
+    // traffic per CTA).  A cout tail is fine: weight rows beyond cout are TMA zero fill, the epilogue clips the columns
+    return !g_force_single && (BN == 256 || BN == 128) && !a->out_nchw &&
+           (int64_t)((m_tiles_ + 1) / 2) * ((a->cout + BN - 1) / BN) * nphase * 200 >= (int64_t)sm_count() * kPairPct;
+  };
+  // Pixel-major tiling (see ConvKernelParams::pm): a 'same' convolution computes taps on zero padding for every border
+  // pixel -- 8 % of the MMAs of a 3x3 at 16x16, 16 % at 8x8, 31 % at 4x4, 56 % at 2x2.  With the 128 rows of a tile
+  // taken along the BATCH at one output pixel, those taps are skipped for the whole tile (and never loaded).  Used when
+  // the saving outweighs the rows wasted by rounding the batch up to 256-sample blocks.
+  int m_tiles = (int)((M + kBM - 1) / kBM);
+  bool pm = false;
+  if (a->kind == SBM_CONV_S1 && p.taps[0].ntaps > 1 && g_pixel_major != 0) {
+    int64_t valid = 0;
+    for (int i = 0; i < oh; ++i)
+      for (int j = 0; j < ow; ++j)
+        for (int k = 0; k < p.taps[0].ntaps; ++k)
+          valid += (i + p.taps[0].dh[k] >= 0 && i + p.taps[0].dh[k] < oh && j + p.taps[0].dw[k] >= 0 &&
+                    j + p.taps[0].dw[k] < ow) ? 1 : 0;
+    const int blocks = (a->batch + 255) / 256;
+    const double work_pm = (double)blocks * 256 * valid;                            // MMA rows x taps
+    const double work_std = (double)m_tiles * kBM * p.taps[0].ntaps;
+    if (g_pixel_major == 1 || work_pm < 0.97 * work_std) {
+      const int m_tiles_pm = 2 * blocks * oh * ow;
+      if (oh * ow <= 256 && choose(m_tiles_pm)) {
+        pm = true;
+        m_tiles = m_tiles_pm;
+        p.pm_blocks = blocks;
+        // few rounds per cluster: balance matters most -> global cost order; many rounds: keep a block's pixels together
+        p.pm_global = ((int64_t)(m_tiles_pm / 2) * ((a->cout + BN - 1) / BN) <= 4 * (int64_t)(sm_count() / 2)) ? 1 : 0;
+        if (const char* e = getenv("SBM_PM_GLOBAL")) p.pm_global = atoi(e);
+        int n = 0;
+        for (int want = p.taps[0].ntaps; want >= 1; --want)     // counting sort by valid taps, raster order inside
+          for (int i = 0; i < oh; ++i)
+            for (int j = 0; j < ow; ++j) {
+              int v = 0;
+              for (int k = 0; k < p.taps[0].ntaps; ++k)
+                v += (i + p.taps[0].dh[k] >= 0 && i + p.taps[0].dh[k] < oh && j + p.taps[0].dw[k] >= 0 &&
+                      j + p.taps[0].dw[k] < ow) ? 1 : 0;
+              if (v == want) p.pm_pix[n++] = (uint8_t)(i * ow + j);
+            }
+      }
+    }
+  }
+  const bool use_pair = pm ? true : choose(m_tiles);
+  const int n_tiles_pair = (a->cout + BN - 1) / BN;
+  p.pm = pm ? 1 : 0;
+
   // ---- tensor maps
   CUtensorMap tmA, tmB;
-  const cuuint32_t abox[5] = {(cuuint32_t)kBK, (cuuint32_t)ow, 1u, (cuuint32_t)(1 << log_th), (cuuint32_t)nb};
+  const cuuint32_t abox_std[5] = {(cuuint32_t)kBK, (cuuint32_t)ow, 1u, (cuuint32_t)(1 << log_th), (cuuint32_t)nb};
+  const cuuint32_t abox_pm[5] = {(cuuint32_t)kBK, 1u, 1u, 1u, (cuuint32_t)kBM};
+  const cuuint32_t* abox = pm ? abox_pm : abox_std;
   const cuuint32_t ones5[5] = {1, 1, 1, 1, 1};
   CUresult cr = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(a->x), adim, astr, abox, ones5,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_igemm: activation tensor map encode failed (CUresult %d)", (int)cr);
 
-  int BN;
-  if (a->cout <= 32) BN = 32;
-  else if (a->cout <= 64) BN = 64;
-  else if (a->cout <= 128) BN = 128;
-  else if (a->cout % 256 == 0 || a->cout > 512) BN = 256;
-  else BN = (a->cout % 128 == 0) ? 128 : 256;
-  const int64_t M = (int64_t)a->batch << log_ohw;
-  const int m_tiles = (int)((M + kBM - 1) / kBM);
-  // small problems (one tile per CTA, less than a wave): narrower tiles spread the K loop and the epilogue over more SMs
-  // (stop at kNarrowPct % of a wave: a 128-wide tile list that covers 86 % of the SMs beats 64-wide tiles in 1.7 waves,
-  // whose A tiles are re-read from L2 by twice as many CTAs)
-  static const int kNarrowPct = [] { const char* e = getenv("SBM_NARROW_PCT"); return e ? atoi(e) : 75; }();
-  while (BN > 64 && (int64_t)m_tiles * ((a->cout + BN - 1) / BN) * nphase * 100 < (int64_t)sm_count() * kNarrowPct)
-    BN >>= 1;
-  // CTA-pair kernel: 256 x BN tiles; worth it once the tile pairs cover ~40 % of the SM pairs (measured on the 2x2-level
-  // layers: 64 pair tiles on 74 SM pairs run 1.3x faster than 128 single-CTA tiles -- half the weight traffic per CTA)
-  // (a cout tail is fine: weight rows beyond cout are TMA zero fill, the epilogue clips the columns)
-  const int n_tiles_pair = (a->cout + BN - 1) / BN;
-  static const int kPairPct = [] { const char* e = getenv("SBM_PAIR_PCT"); return e ? atoi(e) : 80; }();
-  const bool use_pair = !g_force_single && (BN == 256 || BN == 128) && !a->out_nchw &&
-                        (int64_t)((m_tiles + 1) / 2) * n_tiles_pair * nphase * 200 >= (int64_t)sm_count() * kPairPct;
   const int ntaps_total = a->kh * a->kw;
   const cuuint64_t bdim[3] = {(cuuint64_t)a->cin, (cuuint64_t)a->cout, (cuuint64_t)ntaps_total};
   const cuuint64_t bstr[2] = {(cuuint64_t)a->cin_pad * 2, (cuuint64_t)a->cout * a->cin_pad * 2};
@@ -1036,15 +1131,15 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
     if (staged) {
       const int sp_i = (int)sp;
       staged = encode_rowbox_map(encode, &em.out, a->out, a->out_dtype, a->ldo, a->cout, ow, oh, a->batch, sp_i, log_ow,
-                                 log_th);
+                                 log_th, pm);
       if (staged && a->residual)
         staged = encode_rowbox_map(encode, &em.res, a->residual, a->res_dtype, a->ldr, a->cout, ow, oh, a->batch, sp_i,
-                                   log_ow, log_th);
+                                   log_ow, log_th, pm);
       if (staged && a->out2)
         staged = encode_rowbox_map(encode, &em.out2, a->out2, SBM_BF16, a->ldo2, a->cout, ow, oh, a->batch, sp_i,
-                                   log_ow, log_th);
+                                   log_ow, log_th, pm);
     }
-    g_last_variant = BN | (1 << 16) | (staged ? (1 << 17) : 0);
+    g_last_variant = BN | (1 << 16) | (staged ? (1 << 17) : 0) | (pm ? (1 << 18) : 0);
     if (staged) {
       if (!a->residual) em.res = em.out;
       if (!a->out2) em.out2 = em.out;
@@ -1256,6 +1351,11 @@ int sbm_conv_force_single_cta(int32_t on) {
 }
 
 int sbm_conv_last_variant(void) { return sbm::g_last_variant; }
+int sbm_conv_pixel_major(int32_t mode) {
+  const int old = sbm::g_pixel_major;
+  sbm::g_pixel_major = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  return old;
+}
 
 int sbm_conv_force_direct_epilogue(int32_t on) {
   sbm::g_force_direct = on != 0;

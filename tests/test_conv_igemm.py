@@ -332,3 +332,90 @@ def test_conv_folded_groupnorm(case):
     assert rel < 2.5e-3, rel
     ref_s = torch.stack([got.sum(dim=(1, 2, 3)), (got * got).sum(dim=(1, 2, 3))], dim=1)
     assert torch.allclose(st_out, ref_s, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("case", [
+    # B,   H,  W, cin, cout, k, options
+    (256, 16, 16, 64, 256, 3, "f32_res_out2"),      # one 256-sample block, all border classes of a 16x16 map
+    (300,  8,  8, 72, 256, 3, "bf16_gelu_stats"),   # ragged batch: second sample block is mostly out of bounds
+    (512,  4,  4, 128, 384, 3, "gnfold_res"),       # BN=128 pair, GroupNorm folded (per-pixel border class)
+    (1024, 2,  2, 64, 512, 3, "rowbias_silu"),      # every pixel a corner: 4 of 9 taps
+    (256,  8, 16, 64, 320, 3, "cat_views"),         # non-square map, cout tail, strided output views
+    (256,  4,  4, 64, 256, 1, "f32_res_out2"),      # 1x1 kernel: nothing to skip, must stay on the standard tiling
+], ids=lambda c: "x".join(map(str, c)))
+def test_conv_pixel_major_tiling(case):
+    """Pixel-major tiling (a tile = 128 samples at one output pixel; taps that only read zero padding there are skipped)
+    against float64 torch and BIT-FOR-BIT against the standard tiling: the skipped products are exact zeros."""
+    L, ops = _mods()
+    B, H, W, cin, cout, k, opt = case
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(B * 131 + H * 7 + cout)
+    x = (torch.randn(B, cin, H, W, generator=g) * 1.3 + 0.4).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(B, H, W, cout, generator=g).to(dev)
+    rb = torch.randn(B, cout, generator=g).to(dev)
+    xb = _nhwc_bf16(x, ops.pad8(cin))
+    xd = x.double()
+    outs = []
+    for mode in (0, 1):
+        L.lib().sbm_conv_pixel_major(mode)
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        kw = dict(kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout, stats=stats)
+        out2 = None
+        if opt == "gnfold_res":
+            gamma = (1.0 + 0.3 * torch.randn(cin, generator=torch.Generator().manual_seed(1))).to(dev)
+            beta = (0.2 * torch.randn(cin, generator=torch.Generator().manual_seed(2))).to(dev)
+            wpk, tab = ops.fold_groupnorm_conv(w, bias, gamma, beta)
+            gst = torch.stack([xd.sum(dim=(1, 2, 3)), (xd * xd).sum(dim=(1, 2, 3))], dim=1).contiguous()
+            out = ops.conv_igemm(xb, wpk, residual=res, gn_stats=gst, gn_tab=tab, **kw)
+            ref = F.conv2d(F.group_norm(xd, 1, gamma.double(), beta.double(), eps=1e-5), w.double(), bias.double(),
+                           padding=k // 2).permute(0, 2, 3, 1) + res.double()
+            tol = 6e-3
+        else:
+            wq = w.to(torch.bfloat16).float()
+            wpk = ops.pack_conv2d_weight(wq)
+            pre = F.conv2d(xd, wq.double(), bias.double(), padding=k // 2).permute(0, 2, 3, 1)
+            if opt == "f32_res_out2":
+                out2 = torch.zeros(B, H, W, ops.pad8(cout), dtype=torch.bfloat16, device=dev)
+                out = ops.conv_igemm(xb, wpk, bias=bias, residual=res, out2=out2, **kw)
+                ref, tol = pre + res.double(), 3e-5
+            elif opt == "bf16_gelu_stats":
+                out = ops.conv_igemm(xb, wpk, bias=bias, act=L.ACT_GELU, out_dtype=torch.bfloat16, **kw)
+                ref, tol = _gelu64(pre), 5e-3
+            elif opt == "rowbias_silu":
+                out = ops.conv_igemm(xb, wpk, bias=bias, act=L.ACT_SILU, rowbias=rb, **kw)
+                pr = pre + rb.double()[:, None, None, :]
+                ref, tol = pr * torch.sigmoid(pr), 3e-5
+            else:  # cat_views
+                cat_f = torch.full((B, H, W, 2 * ops.pad8(cout)), 3.0, dtype=torch.float32, device=dev)
+                cat_b = torch.full((B, H, W, 2 * ops.pad8(cout)), 3.0, dtype=torch.bfloat16, device=dev)
+                o0 = ops.pad8(cout)
+                out = ops.conv_igemm(xb, wpk, bias=bias, residual=res, out=cat_f[..., o0:], out2=cat_b[..., o0:], **kw)
+                out2 = cat_b[..., o0:]
+                ref, tol = pre + res.double(), 3e-5
+                torch.cuda.synchronize()
+                assert (cat_f[..., :o0] == 3.0).all() and (cat_b[..., :o0] == 3.0).all()
+        torch.cuda.synchronize()
+        variant = L.lib().sbm_conv_last_variant()
+        assert bool(variant & (1 << 18)) == (mode == 1 and k > 1), (mode, hex(variant))
+        got = out[..., :cout].double()
+        assert (got - ref).abs().max().item() <= tol * ref.abs().max().item(), (case, mode)
+        ref_s = torch.stack([got.sum(dim=(1, 2, 3)), (got * got).sum(dim=(1, 2, 3))], dim=1)
+        assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3), (case, mode)
+        outs.append((out[..., :cout].clone(), None if out2 is None else out2[..., :cout].clone()))
+    L.lib().sbm_conv_pixel_major(-1)
+    assert torch.equal(outs[0][0], outs[1][0])
+    if outs[0][1] is not None:
+        assert torch.equal(outs[0][1], outs[1][1])
+    # the A/B switch of the per-thread-store epilogue takes the same tiling
+    if opt == "f32_res_out2" and k == 3:
+        L.lib().sbm_conv_pixel_major(1)
+        L.lib().sbm_conv_force_direct_epilogue(1)
+        o3 = ops.conv_igemm(xb, wpk, bias=bias, residual=res, kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout)
+        torch.cuda.synchronize()
+        v = L.lib().sbm_conv_last_variant()
+        L.lib().sbm_conv_force_direct_epilogue(0)
+        L.lib().sbm_conv_pixel_major(-1)
+        assert (v & (1 << 18)) and not (v & (1 << 17))
+        assert torch.equal(o3[..., :cout], outs[0][0])
