@@ -336,6 +336,188 @@ dwconv7_pipe_kernel(const float* __restrict__ x, int64_t ldx, const float* __res
   }
 }
 
+// ---- packed-fp32 variant (Blackwell FFMA2: fma.rn.f32x2 = two IEEE fp32 FMAs per instruction).
+// The scalar kernel above is ISSUE-bound (ncu: 58 % of its instructions are FFMA, issue slots 71 % busy, FMA pipe 47 %).
+// Here a lane owns a channel PAIR (x, weights and accumulators are 64-bit register pairs), so every multiply-add
+// instruction does two, the x loads are 8-byte and the stores 4/8-byte.  A warp covers 16 channel pairs x 2 output rows:
+// lanes 0-15 and 16-31 work on different rows (of two samples at the same row when the step holds several samples, so
+// the two halves skip the same padding rows; rows oh, oh+1 of one sample at 16x16).  The 49 taps live in shared memory
+// ([tap][32 channels]) and are re-read per kernel row (7 pair loads per 100 FFMA2).  Same accumulation order as the
+// scalar kernel: results are bit-identical.
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
+template <int W, typename TOut>
+__global__ void __launch_bounds__(256, 3)
+dwconv7_f2_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                  const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
+                  TOut* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C, int H, int spb,
+                  int flip, const float* __restrict__ addend, int64_t ldadd) {
+  extern __shared__ __align__(16) float sm[];
+  const int HW = H * W;
+  const int slab = spb * HW * kDwCh;           // floats per buffer (spb samples per step)
+  float* wsm = sm + 2 * slab;                  // [49][32] taps of this block's channels
+  const int c0 = blockIdx.x * kDwCh;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int cp = lane & 15, half = lane >> 4;
+  const int c = c0 + 2 * cp;
+  const bool ok0 = c < C, ok1 = c + 1 < C;
+  const int nsteps = (B + spb - 1) / spb;
+  const int log_hw = 31 - __clz(HW);           // maps are powers of two
+
+  auto prefetch = [&](int step, float* buf) {
+    const int chunks = spb * HW * 8;
+    for (int i = tid; i < chunks; i += 256) {
+      const int q = i & 7, pix = i >> 3;
+      const int b = step * spb + (pix >> log_hw);
+      if (b < B && c0 + q * 4 < C)
+        cp_async16(buf + pix * kDwCh + q * 4, x + ((int64_t)step * spb * HW + pix) * ldx + c0 + q * 4);
+    }
+    cp_async_commit();
+  };
+
+  for (int i = tid; i < 49 * kDwCh; i += 256) {
+    const int tap = i >> 5, ch = i & 31;
+    wsm[i] = (c0 + ch < C) ? __ldg(w + (int64_t)(c0 + ch) * 49 + (flip ? 48 - tap : tap)) : 0.f;
+  }
+  const float2 bias2 = make_float2((ok0 && bias) ? __ldg(bias + c) : 0.f, (ok1 && bias) ? __ldg(bias + c + 1) : 0.f);
+
+  // work items of a step: (sample pair, row) when the step holds >= 2 samples, else row pairs of the one sample
+  const bool by_sample = spb >= 2;
+  const int items = by_sample ? ((spb + 1) >> 1) * H : (H + 1) >> 1;
+  const int per_warp = (items + 7) >> 3;
+
+  int step = blockIdx.y;
+  if (step < nsteps) prefetch(step, sm);
+  int cur = 0;
+  for (; step < nsteps; step += gridDim.y) {
+    const int nxt = step + gridDim.y;
+    if (nxt < nsteps) {
+      prefetch(nxt, sm + (cur ^ 1) * slab);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();   // (also orders the tap staging before the first use)
+    {
+      const int it_begin = warp * per_warp, it_end = min(items, it_begin + per_warp);
+      int cur_ls = -1;
+      float s1 = 0.f, s2 = 0.f;
+      float2 add2 = make_float2(0.f, 0.f);
+      auto flush = [&](int ls_) {   // executed by the whole warp (it_begin/it_end are warp-uniform)
+        float t1 = s1, t2 = s2;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+          t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        }
+        if (stats != nullptr && ls_ >= 0 && ls_ < spb && cp == 0) {
+          const int bb = step * spb + ls_;
+          if (bb < B) {
+            atomicAdd(stats + 2 * (int64_t)bb, (double)t1);
+            atomicAdd(stats + 2 * (int64_t)bb + 1, (double)t2);
+          }
+        }
+        s1 = 0.f;
+        s2 = 0.f;
+      };
+      for (int it = it_begin; it < it_end; ++it) {
+        int ls, oh;
+        if (by_sample) {
+          const int sp2 = it / H;
+          oh = it - sp2 * H;
+          ls = 2 * sp2 + half;
+        } else {
+          ls = 0;
+          oh = 2 * it + half;
+        }
+        const int b = step * spb + ls;
+        const bool row_ok = ls < spb && b < B && oh < H;
+        const int ls_key = by_sample ? (it / H) : 0;   // warp-uniform: the sample pair
+        if (ls_key != cur_ls) {
+          flush(by_sample ? 2 * cur_ls + half : cur_ls);
+          cur_ls = ls_key;
+          add2 = bias2;
+          if (cond != nullptr && ls < spb && b < B) {
+            if (ok0) add2.x += __ldg(cond + (int64_t)b * ldc + c);
+            if (ok1) add2.y += __ldg(cond + (int64_t)b * ldc + c + 1);
+          }
+        }
+        const float* sx = sm + cur * slab + ls * HW * kDwCh + 2 * cp;
+        unsigned long long acc[W];
+#pragma unroll
+        for (int i = 0; i < W; ++i) acc[i] = 0ull;
+#pragma unroll
+        for (int kh = 0; kh < 7; ++kh) {
+          const int ih = oh + kh - 3;
+          if (ih < 0 || ih >= H || !row_ok) continue;
+          unsigned long long wr[7];
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw)
+            wr[kw] = *reinterpret_cast<const unsigned long long*>(wsm + (kh * 7 + kw) * kDwCh + 2 * cp);
+          const float* row = sx + (ih * W) * kDwCh;
+#pragma unroll
+          for (int iw = 0; iw < W; ++iw) {
+            const unsigned long long v = *reinterpret_cast<const unsigned long long*>(row + iw * kDwCh);
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+              const int ow = iw - kw + 3;
+              if (ow >= 0 && ow < W) acc[ow] = ffma2(v, wr[kw], acc[ow]);
+            }
+          }
+        }
+        if (row_ok && ok0) {
+          const int64_t prow = (int64_t)b * HW + oh * W;
+          TOut* op = out + prow * ldo + c;
+          const float* ap = addend != nullptr ? addend + prow * ldadd + c : nullptr;
+#pragma unroll
+          for (int i = 0; i < W; ++i) {
+            float2 r = unpack2(acc[i]);
+            r.x += add2.x;
+            r.y += add2.y;
+            if (ap != nullptr) {
+              if (ok1) {
+                const float2 a2 = *reinterpret_cast<const float2*>(ap + (int64_t)i * ldadd);
+                r.x += a2.x;
+                r.y += a2.y;
+              } else {
+                r.x += ap[(int64_t)i * ldadd];
+              }
+            }
+            if constexpr (sizeof(TOut) == 2) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(r.x, r.y);
+              if (ok1) *reinterpret_cast<__nv_bfloat162*>(op + (int64_t)i * ldo) = h2;
+              else op[(int64_t)i * ldo] = __low2bfloat16(h2);
+              r = __bfloat1622float2(h2);   // the statistics describe the tensor the next GEMM reads
+            } else {
+              if (ok1) *reinterpret_cast<float2*>(op + (int64_t)i * ldo) = r;
+              else op[(int64_t)i * ldo] = r.x;
+            }
+            s1 += r.x;
+            s2 = fmaf(r.x, r.x, s2);
+            if (ok1) {
+              s1 += r.y;
+              s2 = fmaf(r.y, r.y, s2);
+            }
+          }
+        }
+      }
+      flush(by_sample ? 2 * cur_ls + half : cur_ls);
+    }
+    __syncthreads();  // every warp is done with this buffer before the next prefetch overwrites it
+    cur ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------ group statistics
 // stats[b][g] += (sum, sumsq) over the pixels x channels of group g.  grid = (chunks, groups, B)
 __global__ void __launch_bounds__(256)
@@ -862,10 +1044,18 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
                                const float* addend, int64_t ldadd, cudaStream_t st) {
   // 256 pixels (32 KB) per step: 1 sample of 16x16, 4 of 8x8, 16 of 4x4, ...
   const int spb = std::max(1, std::min(B, 256 / (H * W)));
-  const size_t smem = (size_t)2 * spb * H * W * kDwCh * sizeof(float);
+  // packed-fp32 kernel: needs even strides and 8-byte aligned rows for its pair loads / stores
+  static const bool f2_env = [] { const char* e = getenv("SBM_DWCONV_F32X2"); return e ? atoi(e) != 0 : true; }();
+  const auto al = [](const void* ptr, int64_t ld, int bytes) {
+    return ptr == nullptr || ((ld % 2 == 0) && (reinterpret_cast<uintptr_t>(ptr) % bytes == 0));
+  };
+  const bool f2 = f2_env && al(out, ldo, 2 * (int)sizeof(TOut)) && al(addend, ldadd, 8);
+  const size_t smem = (size_t)2 * spb * H * W * kDwCh * sizeof(float) + (f2 ? 49 * kDwCh * sizeof(float) : 0);
   static size_t configured = 0, configured_occ = 0;
   if (smem > 48 * 1024 && smem > configured) {
     SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_pipe_kernel<W, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_f2_kernel<W, TOut>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
     configured = smem;
   }
@@ -874,17 +1064,24 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
   // exactly ONE wave of resident blocks (2-3 per SM), each walking several steps so the prefetch overlaps: the grid
   // is rounded DOWN to the resident slots -- a handful of blocks spilling into a second wave would run their whole
   // share of the steps after everyone else has finished (measured: 300 blocks on 296 slots cost 1.5x)
-  static int per_sm = 0;
+  static int per_sm = 0, per_sm_f2 = 0;
   if (per_sm == 0 || smem > configured_occ) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_pipe_kernel<W, TOut>, 256, smem) != cudaSuccess ||
         per_sm <= 0)
       per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f2, dwconv7_f2_kernel<W, TOut>, 256, smem) != cudaSuccess ||
+        per_sm_f2 <= 0)
+      per_sm_f2 = 1;
     configured_occ = smem;
   }
-  int gy = std::max(1, std::min(nsteps, per_sm * sm_count() / chunks));
+  int gy = std::max(1, std::min(nsteps, (f2 ? per_sm_f2 : per_sm) * sm_count() / chunks));
   dim3 grid(chunks, gy);
-  dwconv7_pipe_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H,
-                                                        spb, flip, addend, ldadd);
+  if (f2)
+    dwconv7_f2_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H, spb,
+                                                        flip, addend, ldadd);
+  else
+    dwconv7_pipe_kernel<W, TOut><<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, (TOut*)out, ldo, stats, B, C, H,
+                                                          spb, flip, addend, ldadd);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -104,6 +104,35 @@ def test_groupnorm_backward(groups, in_act, C, H):
     assert torch.allclose(db, beta.grad.float(), rtol=2e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("H,C,B", [(16, 170, 3), (16, 40, 2), (8, 64, 7), (8, 512, 9), (4, 33, 21), (2, 64, 70), (1, 70, 300)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_dwconv7_forward(H, C, B, out_dtype):
+    """Depthwise 7x7 + bias + per-sample time condition + GroupNorm statistics (unet_model.py:103-105) against float64
+    torch: ragged batches (odd sample counts per shared-memory step), odd channel counts, both output types."""
+    L, ops = _mods()
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 1000 + C + B)
+    x = torch.randn(B, C, H, H, generator=g).to(dev)
+    w = (torch.randn(C, 1, 7, 7, generator=g) / 7).to(dev)
+    bias = torch.randn(C, generator=g).to(dev)
+    cond = torch.randn(B, C, generator=g).to(dev)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=3, groups=C) + cond.double()[:, :, None, None]
+    ld = ops.pad8(C)
+    xn = torch.full((B, H, H, ld), 3.0, device=dev)
+    xn[..., :C] = _nhwc(x)
+    condp = torch.zeros(B, ld, device=dev)
+    condp[:, :C] = cond
+    stats = torch.zeros(B, 1, 2, dtype=torch.float64, device=dev)
+    out = ops.dwconv7(xn, C, w.contiguous(), bias, condp, ld, stats, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    got = out[..., :C].double()
+    refn = _nhwc(ref)
+    tol = 1e-5 if out_dtype == torch.float32 else 5e-3
+    assert (got - refn).abs().max().item() <= tol * refn.abs().max().item()
+    ref_s = torch.stack([got.sum(dim=(1, 2, 3)), (got * got).sum(dim=(1, 2, 3))], dim=-1).view(B, 1, 2)
+    assert torch.allclose(stats, ref_s, rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("H,C", [(16, 40), (8, 64), (4, 33), (2, 64), (1, 70)])
 def test_dwconv7_backward(H, C):
     L, ops = _mods()
