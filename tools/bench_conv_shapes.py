@@ -35,7 +35,11 @@ for (H, cin, cout, k) in SHAPES:
     outf = torch.empty(B, H, H, ops.pad8(cout), dtype=torch.float32, device=dev)
     for mode, flag in MODES:
         L.lib().sbm_conv_force_direct_epilogue(flag)
-        for label, kw in [("bf16+gelu+stats", dict(act=L.ACT_GELU, out=out, stats=st)), ("fp32+bf16copy", dict(out=outf, out2=out))]:
+        labels = [("bf16+gelu+stats", dict(act=L.ACT_GELU, out=out, stats=st)), ("fp32+bf16copy", dict(out=outf, out2=out))]
+        if os.environ.get("SBM_STATS_AB"):
+            labels = [("bf16+gelu+stats", dict(act=L.ACT_GELU, out=out, stats=st)), ("bf16+gelu", dict(act=L.ACT_GELU, out=out)),
+                      ("bf16+stats", dict(out=out, stats=st)), ("bf16", dict(out=out))]
+        for label, kw in labels:
             ts = []
             for it in range(6):
                 flush.zero_()
