@@ -410,25 +410,34 @@ dwconv7_f2_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
     __syncthreads();   // (also orders the tap staging before the first use)
     {
       const int it_begin = warp * per_warp, it_end = min(items, it_begin + per_warp);
-      int cur_ls = -1;
       float s1 = 0.f, s2 = 0.f;
-      float2 add2 = make_float2(0.f, 0.f);
-      auto flush = [&](int ls_) {   // executed by the whole warp (it_begin/it_end are warp-uniform)
+      double d1 = 0.0, d2 = 0.0;
+      int cur_key = -1, cur_ls = -1;
+      // GroupNorm statistics: every ROW is summed the same way (fp32 over its channels and pixels, half-warp
+      // reduction), the row totals are accumulated in fp64 and flushed once per sample -- so the numbers do not depend
+      // on how the batch size groups rows into steps and warps, and a batch shard reproduces the unsharded result
+      auto row_done = [&]() {     // executed by the whole warp (the item loop bounds are warp-uniform)
         float t1 = s1, t2 = s2;
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) {
           t1 += __shfl_xor_sync(0xffffffffu, t1, o);
           t2 += __shfl_xor_sync(0xffffffffu, t2, o);
         }
-        if (stats != nullptr && ls_ >= 0 && ls_ < spb && cp == 0) {
-          const int bb = step * spb + ls_;
-          if (bb < B) {
-            atomicAdd(stats + 2 * (int64_t)bb, (double)t1);
-            atomicAdd(stats + 2 * (int64_t)bb + 1, (double)t2);
-          }
-        }
+        d1 += (double)t1;
+        d2 += (double)t2;
         s1 = 0.f;
         s2 = 0.f;
+      };
+      auto flush = [&]() {
+        if (stats != nullptr && cur_ls >= 0 && cur_ls < spb && cp == 0) {
+          const int bb = step * spb + cur_ls;
+          if (bb < B) {
+            atomicAdd(stats + 2 * (int64_t)bb, d1);
+            atomicAdd(stats + 2 * (int64_t)bb + 1, d2);
+          }
+        }
+        d1 = 0.0;
+        d2 = 0.0;
       };
       for (int it = it_begin; it < it_end; ++it) {
         int ls, oh;
@@ -440,17 +449,18 @@ dwconv7_f2_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
           ls = 0;
           oh = 2 * it + half;
         }
+        const int key = by_sample ? it / H : 0;   // warp-uniform: the sample (pair) this item belongs to
+        if (key != cur_key) {
+          flush();
+          cur_key = key;
+          cur_ls = ls;
+        }
         const int b = step * spb + ls;
         const bool row_ok = ls < spb && b < B && oh < H;
-        const int ls_key = by_sample ? (it / H) : 0;   // warp-uniform: the sample pair
-        if (ls_key != cur_ls) {
-          flush(by_sample ? 2 * cur_ls + half : cur_ls);
-          cur_ls = ls_key;
-          add2 = bias2;
-          if (cond != nullptr && ls < spb && b < B) {
-            if (ok0) add2.x += __ldg(cond + (int64_t)b * ldc + c);
-            if (ok1) add2.y += __ldg(cond + (int64_t)b * ldc + c + 1);
-          }
+        float2 add2 = bias2;
+        if (cond != nullptr && row_ok) {
+          if (ok0) add2.x += __ldg(cond + (int64_t)b * ldc + c);
+          if (ok1) add2.y += __ldg(cond + (int64_t)b * ldc + c + 1);
         }
         const float* sx = sm + cur * slab + ls * HW * kDwCh + 2 * cp;
         unsigned long long acc[W];
@@ -510,8 +520,9 @@ dwconv7_f2_kernel(const float* __restrict__ x, int64_t ldx, const float* __restr
             }
           }
         }
+        row_done();
       }
-      flush(by_sample ? 2 * cur_ls + half : cur_ls);
+      flush();
     }
     __syncthreads();  // every warp is done with this buffer before the next prefetch overwrites it
     cur ^= 1;
