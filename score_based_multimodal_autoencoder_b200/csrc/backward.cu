@@ -602,14 +602,42 @@ adam_kernel(const sbm_adam_tensor* __restrict__ tensors, const int2* __restrict_
   const int64_t start = (int64_t)ck.y * chunk_elems;
   const int64_t end = min(start + (int64_t)chunk_elems, t.n);
   const float step = lr / bc1;
-  for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) {
-    const float g = t.grad[i] * grad_scale;
-    const float m = beta1 * t.exp_avg[i] + (1.f - beta1) * g;
-    const float v = beta2 * t.exp_avg_sq[i] + (1.f - beta2) * g * g;
+  auto upd = [&](float g, float& m, float& v, float& p) {
+    g *= grad_scale;
+    m = beta1 * m + (1.f - beta1) * g;
+    v = beta2 * v + (1.f - beta2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= step * (m / denom);
+  };
+  int64_t i0 = start;
+  // 16-byte path: 4 elements per thread, the four streams' loads issued together (28 B/element of HBM traffic)
+  if (((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad) |
+        reinterpret_cast<uintptr_t>(t.exp_avg) | reinterpret_cast<uintptr_t>(t.exp_avg_sq)) & 15) == 0 &&
+      (start & 3) == 0) {
+    const int64_t nq = (end - start) >> 2;
+    float4* p4 = reinterpret_cast<float4*>(t.param + start);
+    const float4* g4 = reinterpret_cast<const float4*>(t.grad + start);
+    float4* m4 = reinterpret_cast<float4*>(t.exp_avg + start);
+    float4* v4 = reinterpret_cast<float4*>(t.exp_avg_sq + start);
+    for (int64_t q = threadIdx.x; q < nq; q += blockDim.x) {
+      const float4 g = __ldcs(g4 + q);
+      float4 m = m4[q], v = v4[q], p = p4[q];
+      upd(g.x, m.x, v.x, p.x);
+      upd(g.y, m.y, v.y, p.y);
+      upd(g.z, m.z, v.z, p.z);
+      upd(g.w, m.w, v.w, p.w);
+      m4[q] = m;
+      v4[q] = v;
+      p4[q] = p;
+    }
+    i0 = start + (nq << 2);
+  }
+  for (int64_t i = i0 + threadIdx.x; i < end; i += blockDim.x) {
+    float m = t.exp_avg[i], v = t.exp_avg_sq[i], p = t.param[i];
+    upd(t.grad[i], m, v, p);
     t.exp_avg[i] = m;
     t.exp_avg_sq[i] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    t.param[i] -= step * (m / denom);
+    t.param[i] = p;
   }
 }
 
