@@ -369,12 +369,37 @@ class Unet(nn.Module):
             from .autograd import unet_forward_train
             y = unet_forward_train(self, x, time)
         else:
-            y = self._forward_infer(x, time)
+            y = self._forward_chunked(x, time)
         if pw:
             y = y[..., pw:-pw]
         if ph:
             y = y[..., ph:-ph, :]
         return y
+
+    # widest activation of one sample-chunk, in elements: batches beyond it (the 4k-64k sweep of BASELINE configs[4]) run
+    # through the net in slices -- exact, since GroupNorm(1, C) and both attentions are per-sample
+    max_chunk_elems = 1 << 29
+
+    def max_batch(self, hh, ww):
+        widest = hh * ww * max(self.init_dim, max(blk.hidden for blk in self._convnext_blocks()))
+        return max(1, self.max_chunk_elems // widest)
+
+    def _convnext_blocks(self):
+        return [mod for mod in self.modules() if isinstance(mod, ConvNextBlock)]
+
+    @torch.no_grad()
+    def _forward_chunked(self, x, time):
+        b = x.shape[0]
+        mb = self.max_batch(x.shape[-2], x.shape[-1])
+        if b <= mb:
+            return self._forward_infer(x, time)
+        n = -(-b // mb)
+        step = -(-b // n)
+        step = -(-step // 256) * 256 if step >= 256 else step   # whole 256-sample blocks for the pixel-major tiling
+        out = torch.empty((b, self.out_dim, x.shape[-2], x.shape[-1]), dtype=torch.float32, device=x.device)
+        for lo in range(0, b, step):
+            out[lo:lo + step] = self._forward_infer(x[lo:lo + step], time[lo:lo + step])
+        return out
 
     @torch.no_grad()
     def _forward_infer(self, x, time):

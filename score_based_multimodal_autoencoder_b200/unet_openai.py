@@ -341,7 +341,19 @@ class UNetModel(nn.Module):
             from .autograd_openai import unet_openai_forward_train
             return unet_openai_forward_train(self, x, timesteps, z)
         with torch.no_grad():
-            return self._forward_infer(x, timesteps, z)
+            # large batches run in slices (exact: GroupNorm32 and the attention are per-sample)
+            b = x.shape[0]
+            widest = x.shape[-2] * x.shape[-1] * self.model_channels * max(self.channel_mult) * 2
+            mb = max(1, self.max_chunk_elems // widest)
+            if b <= mb:
+                return self._forward_infer(x, timesteps, z)
+            out = torch.empty((b, self.out_channels, x.shape[-2], x.shape[-1]), dtype=torch.float32, device=x.device)
+            for lo in range(0, b, mb):
+                out[lo:lo + mb] = self._forward_infer(x[lo:lo + mb], timesteps[lo:lo + mb],
+                                                      None if z is None else z[lo:lo + mb])
+            return out
+
+    max_chunk_elems = 1 << 29
 
     # ------------------------------------------------------------------ dropout stream
     _DRAWS_PER_FORWARD = 4096  # > number of ResBlocks: draw id = forward index * 4096 + ResBlock index

@@ -92,3 +92,19 @@ def test_unet_pads_non_power_of_two_latents_like_the_reference(hw):
         ref = uo.unet_forward(sd, x, t, dim=32, dim_mults=(1, 2))
     assert y.shape == ref.shape == x.shape
     assert rel_l2(y, ref) < BF16_NET_TOL
+
+
+def test_unet_large_batch_runs_in_slices_with_identical_results():
+    """Batches beyond Unet.max_batch() (the 4k-64k sweep of BASELINE configs[4]) are walked in slices; the net has no
+    cross-sample coupling, so the result equals the one-shot forward bit for bit."""
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    torch.manual_seed(0)
+    m = Unet(dim=32, channels=5, dim_mults=(1, 2)).cuda().eval()
+    x = torch.randn(700, 5, 8, 8, device="cuda")
+    t = torch.rand(700, device="cuda")
+    with torch.no_grad():
+        y0 = m(x, t)
+        m.max_chunk_elems = 300 * 8 * 8 * 64          # -> slices of 256 samples (whole 256-sample blocks)
+        assert m.max_batch(8, 8) < 700
+        y1 = m(x, t)
+    assert y1.shape == y0.shape and torch.equal(y0, y1)
