@@ -5,6 +5,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from tests.util import rel_l2
+
 pytestmark = pytest.mark.gpu
 
 
@@ -161,7 +163,7 @@ def test_dwconv7_backward(H, C):
     assert torch.allclose(dcond[:, 0, 0, 8:8 + C], cond.grad.float(), rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("n_side", [1, 2, 4, 16])
+@pytest.mark.parametrize("n_side", [1, 2, 4, 8, 16])
 def test_linear_attention_backward(n_side):
     L, ops = _mods()
     dev = torch.device("cuda")
@@ -182,6 +184,8 @@ def test_linear_attention_backward(n_side):
     dqkv = ops.linear_attn_bwd(qkv_t, do.float().reshape(B, n_side, n_side, -1).contiguous(), heads, d ** -0.5)
     torch.cuda.synchronize()
     assert (fwd.float().reshape(B, n, -1) - out_n.detach().float()).abs().max().item() <= 1e-2 * out_n.abs().max().item()
+    # bf16 output of an fp32 / tf32 computation: the error is rounding noise, not a layout slip
+    assert rel_l2(fwd.float().reshape(B, n, -1), out_n.detach().float()) < 4e-3
     ref = qkv.grad.float()
     got = dqkv.float().reshape(B, n, -1)
     assert (got - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item() + 1e-6
@@ -227,7 +231,7 @@ def test_dsm_training_step_gradients_vs_reference_golden():
     from oracle.det_weights import fill_state_dict
     from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
     from score_based_multimodal_autoencoder_b200.unet_model import Unet
-    from tests.util import golden
+    from tests.util import golden, rel_l2
     g = golden("dsm_loss.pt")
     net = golden("unet_poly.pt")
     m = Unet(**net["kwargs"])
