@@ -360,6 +360,20 @@ def em_predictor(x, t, score_fn, sde, probability_flow=False, cl_g=None, cl_s=No
     return _predictor_kernel(sde, x, score, t, noise=noise, rng=r, probability_flow=probability_flow)
 
 
+def rd_predictor(x, t, score_fn, sde, probability_flow=False, z_cond=None, *, noise=None):
+    """Reverse-diffusion (ancestral) predictor step -> (x, x_mean):
+        (rev_f, rev_G) = sde.reverse(score_fn, probability_flow).discretize(x, t);  x_mean = x - rev_f;
+        x = x_mean + rev_G * z.
+    The reference ships this discretisation (sde_helper2.py:236-253, 319-324, 373-381) but no caller (SURVEY.md 8a-6);
+    this is the API-complete thin wrapper over the SDE classes' tensor expressions -- a handful of elementwise torch
+    ops on the caller's device next to the score-net call, not a fused kernel and not on the measured path."""
+    fn = score_fn if z_cond is None else (lambda a, b: _call_score(score_fn, a, b, z_cond))
+    z = torch.randn_like(x) if noise is None else noise     # drawn before the net call, like em_predictor (:47)
+    rev_f, rev_G = sde.reverse(fn, probability_flow).discretize(x, t)
+    x_mean = x - rev_f
+    return x_mean + _bc(rev_G) * z, x_mean
+
+
 def corrector(x, t, score_fn, sde, n_steps, target_snr, cl_g=None, cl_s=None, target=None, given=None, all_mods=None,
               z_cond=None, *, noise=None, rng="torch", global_batch=None, reduce_fn=None):
     """Langevin corrector (sde_helper2.py:54-106) -> (x, x_mean).  Two fused kernels per Langevin step

@@ -51,6 +51,14 @@ def test_oracle_sde_objects_and_host_classes():
         if "disc_f" in c:
             f, G = sde.discretize(c["x"], c["t"])
             assert torch.allclose(f, c["disc_f"], rtol=1e-6, atol=1e-7) and torch.allclose(G, c["disc_G"], rtol=1e-6)
+            # reverse-diffusion predictor built on it (sde_helper2.py:319-324): x_mean = x - (f - G^2 s), x = x_mean + G z
+            score_fn = lambda a, b: -0.5 * a
+            zn = torch.full_like(c["x"], 0.25)
+            xn, xm = sh.rd_predictor(c["x"], c["t"], score_fn, sde, noise=zn)
+            Gb = c["disc_G"][:, None, None, None]
+            want_mean = c["x"] - (c["disc_f"] - Gb ** 2 * score_fn(c["x"], c["t"]))
+            assert torch.allclose(xm, want_mean, rtol=1e-6, atol=1e-7)
+            assert torch.allclose(xn, want_mean + Gb * zn, rtol=1e-6, atol=1e-7)
         if "alphas" in c:
             assert torch.equal(sde.alphas, c["alphas"])
             assert torch.equal(sde.sqrt_1m_alphas_cumprod, c["sqrt_1m_alphas_cumprod"])
