@@ -32,4 +32,5 @@ with torch.no_grad():
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-print(f"forward B={B}: {e0.elapsed_time(e1) / iters:.3f} ms  (SBM_NARROW_PCT={os.environ.get('SBM_NARROW_PCT', '100')})")
+knobs = " ".join(k + "=" + v for k, v in os.environ.items() if k.startswith("SBM_")) or "defaults"
+print(f"forward B={B}: {e0.elapsed_time(e1) / iters:.3f} ms  ({knobs})")
