@@ -90,9 +90,9 @@ int sbm_conv_last_variant(void);
  * runs the layer.  Results are bit-identical either way (the skipped products are exact zeros).  Returns the old mode */
 int sbm_conv_pixel_major(int32_t mode);
 
-/* Weight gradient of sbm_conv_igemm: dwpk[tap][o][i] += sum_pixels dy[p][o] * x[p shifted by tap][i]  (fp32, split-K
- * atomics: the caller zeroes dwpk).  x = the forward input operand (bf16), dy = gradient of the forward output (bf16,
- * output geometry).  Backward of the nn.Conv2d / nn.ConvTranspose2d / nn.Linear weights under loss.backward()
+/* Weight gradient of sbm_conv_igemm: dwpk[tap][o][i] += sum_pixels dy[p][o] * x[p shifted by tap][i]  (fp32; split-K
+ * partial tiles are ADDED into dwpk by TMA reduce-add boxes, so the caller zeroes dwpk).  x = the forward input
+ * operand (bf16), dy = gradient of the forward output (bf16, output geometry).  Backward of the nn.Conv2d / nn.ConvTranspose2d / nn.Linear weights under loss.backward()
  * (train_lat_celebhq_unet_cont2.py:98-100). */
 typedef struct sbm_wgrad_args {
   int32_t kind, kh, kw;
