@@ -172,3 +172,16 @@ def test_oracle_philox_known_answers_and_dropout_mask():
     assert keep.shape == (4096, 20) and abs(keep.mean() - 0.9) < 5e-3
     assert not np.array_equal(keep, dropout_keep(0x1234ABCD5678, 4, 4096, 20, 0.1))
     assert dropout_keep(1, 0, 64, 8, 0.0).all()
+
+
+def test_docs_name_only_declared_entry_points_and_cover_all_of_them():
+    """INTEGRATION.md is the binding guide: every `sbm_*` it (or DESIGN.md) names is declared in include/sbmae_b200.h,
+    and every declared entry point appears in INTEGRATION.md's table."""
+    hdr = open(os.path.join(ROOT, "include", "sbmae_b200.h")).read()
+    known = set(re.findall(r"\b(sbm_[a-z0-9_]+)\b", hdr))
+    declared = set(re.findall(r"\b(sbm_[a-z0-9_]+)\s*\(", hdr))
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for doc in ("INTEGRATION.md", "DESIGN.md"):
+        named = set(re.findall(r"\b(sbm_[a-z0-9_]+)\b", open(os.path.join(ROOT, doc)).read()))
+        assert not (named - known), (doc, sorted(named - known))
+    assert not [n for n in declared if n not in integ], sorted(n for n in declared if n not in integ)
