@@ -1,0 +1,71 @@
+"""Generate tests/golden/res_ae.pt: latents and reconstructions of the UNMODIFIED reference `ResAE` / `ResVAE`
+(h_vae_model_copy.py) in eval mode with deterministic non-trivial weights and BatchNorm running statistics, for the
+PolyMNIST configuration of train_poly_unet_cont.py:548-560 (32x32 inputs, three down-sampling RBlocks) at reduced batch.
+`torchvision` (imported but unused by that file) is absent here: an empty module stands in for it.
+
+Run in the build container only:  python -m oracle.gen_golden_vae"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+
+from . import vae_oracle as vo
+from .det_weights import fill_state_dict
+from .gen_golden import OUT, REF
+
+ENC = [(64, 64, 64, 2), (64, 128, 128, 2), (128, 256, 256, 2)]
+DEC = [(256, 128, 128, 2), (128, 128, 64, 2), (64, 64, 64, 2)]
+SIZE_IN, SIZE_Z, IMG_CH = 32, 64, 3
+
+
+def main():
+    if "torchvision" not in sys.modules:
+        sys.modules["torchvision"] = types.ModuleType("torchvision")
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import h_vae_model_copy as hv
+    out = {"enc": ENC, "dec": DEC, "size_in": SIZE_IN, "size_z": SIZE_Z, "img_ch": IMG_CH}
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(5, IMG_CH, SIZE_IN, SIZE_IN, generator=g)
+    for name, cls in (("ae", hv.ResAE), ("vae", hv.ResVAE)):
+        torch.manual_seed(0)
+        ref = cls(ENC, DEC, SIZE_IN, SIZE_Z, IMG_CH)
+        sd0 = ref.state_dict()
+        shapes = {k: tuple(v.shape) for k, v in sd0.items() if v.dtype.is_floating_point}
+        sd = fill_state_dict(shapes)
+        for k in shapes:                      # running variances must be positive, running means moderate
+            if k.endswith("running_var"):
+                sd[k] = sd[k].abs() + 0.5
+        full = dict(sd0)
+        full.update(sd)
+        ref.load_state_dict(full)
+        ref.eval()
+        with torch.no_grad():
+            if name == "ae":
+                z = ref.encoder(x)
+                logvar = None
+            else:
+                z, logvar = ref.encoder(x)
+            rec = ref.decoder(z)
+            z_o = vo.ae_encode(sd, x, ENC)
+            rec_o = vo.ae_decode(sd, z, ENC, DEC, SIZE_IN)
+        e1 = ((z_o - z).abs().max() / z.abs().max()).item()
+        e2 = ((rec_o - rec).abs().max() / rec.abs().max()).item()
+        print(f"{name}: latent {tuple(z.shape)} oracle rel-max {e1:.2e}; reconstruction {tuple(rec.shape)} rel-max {e2:.2e}")
+        assert e1 < 1e-5 and e2 < 1e-5
+        if logvar is not None:
+            lv_o = vo.res_encoder(sd, x, ENC)[1]
+            assert ((lv_o - logvar).abs().max() / logvar.abs().max()).item() < 1e-5
+        out[name] = {"shapes": shapes, "z": z.clone(), "rec": rec.clone(),
+                     "logvar": None if logvar is None else logvar.clone()}
+    out["x"] = x
+    path = os.path.join(OUT, "res_ae.pt")
+    torch.save(out, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  fp32 CPU restatement of the unimodal residual encoders /
+decoders either side of the score-model path -- `RBlock`, `ResEncoder`, `ResDecoder`, `ResAE.encoder/decoder`,
+`ResVAE.encoder/decoder` of h_vae_model_copy.py:9-174 -- in eval mode (BatchNorm uses its running statistics), the
+mode every sampling / DSM-training script of the reference runs them in (train_poly_unet_cont.py:556-571: the
+autoencoders are loaded from checkpoints and frozen).  SURVEY.md 8f-1: the next row after the score-model path; this
+oracle and its golden (tests/golden/res_ae.pt, made by oracle/gen_golden_vae.py from the unmodified reference) are the
+parity anchor for it.  State-dict keys are the reference's."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def _bn(sd, p, x, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (h_vae_model_copy.py:19,22,47)."""
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        training=False, eps=eps)
+
+
+def rblock(sd, p, x, in_width, out_width, down_rate=None, up_rate=None):
+    """h_vae_model_copy.py:9-39: conv3x3 -> BN -> LeakyReLU(0.2) -> conv3x3 -> BN, 1x1 `size_conv` on the skip when the
+    widths differ, LeakyReLU(0.2) AFTER the sum, then average pooling / nearest up-sampling."""
+    h = F.conv2d(x, sd[p + ".conv.0.weight"], None, padding=1)
+    h = F.leaky_relu(_bn(sd, p + ".conv.1", h), 0.2)
+    h = _bn(sd, p + ".conv.4", F.conv2d(h, sd[p + ".conv.3.weight"], None, padding=1))
+    if in_width != out_width:
+        x = F.conv2d(x, sd[p + ".size_conv.weight"], None)
+    h = F.leaky_relu(x + h, 0.2)
+    if down_rate is not None:
+        h = F.avg_pool2d(h, down_rate)
+    if up_rate is not None:
+        h = F.interpolate(h, scale_factor=up_rate, mode="nearest")
+    return h
+
+
+def res_encoder(sd, x, channel_list, p="enc"):
+    """h_vae_model_copy.py:41-72 -> (mu, logvar)."""
+    h = F.conv2d(x, sd[p + ".ch_enc.0.weight"], sd[p + ".ch_enc.0.bias"], padding=2)
+    h = F.avg_pool2d(F.leaky_relu(_bn(sd, p + ".ch_enc.1", h), 0.2), 2)
+    for i, (cin, _mid, cout, rate) in enumerate(channel_list):
+        h = rblock(sd, f"{p}.r_blocks.{i}", h, cin, cout, down_rate=rate)
+    mu, logvar = h.chunk(2, dim=1)
+    mu = F.linear(mu.reshape(mu.shape[0], -1), sd[p + ".mu_lin.weight"], sd[p + ".mu_lin.bias"])
+    logvar = F.linear(logvar.reshape(logvar.shape[0], -1), sd[p + ".logvar_lin.weight"], sd[p + ".logvar_lin.bias"])
+    return mu, logvar
+
+
+def res_decoder(sd, x, channel_list, p="dec"):
+    """h_vae_model_copy.py:74-90."""
+    h = x
+    for i, (cin, _mid, cout, rate) in enumerate(channel_list):
+        h = rblock(sd, f"{p}.r_blocks.{i}", h, cin, cout, up_rate=rate)
+    c = channel_list[-1][2]
+    h = rblock(sd, f"{p}.ch_dec.0", h, c, c)
+    return F.conv2d(h, sd[p + ".ch_dec.1.weight"], sd[p + ".ch_dec.1.bias"], padding=2)
+
+
+def ae_encode(sd, x, enc_channel_list):
+    """ResAE.encoder (h_vae_model_copy.py:164-166) / the mean of ResVAE.encoder (:118-120): the latent the score model
+    is trained on (train_poly_unet_cont.py:257-268 stacks these per modality)."""
+    return res_encoder(sd, x, enc_channel_list)[0]
+
+
+def ae_decode(sd, z, enc_channel_list, dec_channel_list, size_in):
+    """ResAE.decoder / ResVAE.decoder (h_vae_model_copy.py:127-130, 168-171): Linear -> ReLU -> view -> ResDecoder."""
+    init = size_in
+    for c in enc_channel_list:
+        init //= c[3]
+    ch = enc_channel_list[-1][2]
+    lin = ch * init * init
+    side = lin // ch // init
+    h = F.relu(F.linear(z, sd["z_lin.weight"], sd["z_lin.bias"]))
+    return res_decoder(sd, h.view(z.shape[0], ch, side, side), dec_channel_list)

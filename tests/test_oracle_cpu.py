@@ -185,3 +185,22 @@ def test_docs_name_only_declared_entry_points_and_cover_all_of_them():
         named = set(re.findall(r"\b(sbm_[a-z0-9_]+)\b", open(os.path.join(ROOT, doc)).read()))
         assert not (named - known), (doc, sorted(named - known))
     assert not [n for n in declared if n not in integ], sorted(n for n in declared if n not in integ)
+
+
+def test_oracle_residual_autoencoders_match_reference_golden():
+    """oracle/vae_oracle.py (the encoders / decoders either side of the score-model path) against the
+    unmodified reference ResAE / ResVAE in eval mode (tests/golden/res_ae.pt, oracle/gen_golden_vae.py)."""
+    from oracle import vae_oracle as vo
+    g = golden("res_ae.pt")
+    for name in ("ae", "vae"):
+        c = g[name]
+        sd = fill_state_dict(c["shapes"])
+        for k in c["shapes"]:
+            if k.endswith("running_var"):
+                sd[k] = sd[k].abs() + 0.5
+        mu, logvar = vo.res_encoder(sd, g["x"], g["enc"])
+        assert torch.allclose(mu, c["z"], rtol=1e-5, atol=1e-6)
+        if c["logvar"] is not None:
+            assert torch.allclose(logvar, c["logvar"], rtol=1e-5, atol=1e-6)
+        rec = vo.ae_decode(sd, c["z"], g["enc"], g["dec"], g["size_in"])
+        assert rec.shape == g["x"].shape and torch.allclose(rec, c["rec"], rtol=1e-5, atol=1e-5)
