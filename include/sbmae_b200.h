@@ -279,6 +279,16 @@ int sbm_ema_step(const sbm_ema_tensor* tensors_dev, const int32_t* chunks_dev, i
  * (Philox draw id of sbm_dsm_perturb, which consumes 2 per step).  One 1-thread kernel. */
 int sbm_train_tick(int32_t* step_dev, uint64_t* draw_dev, uint64_t draw_inc, void* stream);
 
+/* ------------------------------------------------------------------ residual autoencoders */
+/* RBlock tail `self.sf(x + xhat)` + `down_pool` / `up_pool` (h_vae_model_copy.py:26-39), ResEncoder.ch_enc's
+ * LeakyReLU + AvgPool2d(2) (:48-50) and, with slope 0, the ReLU after z_lin (:128): y = LeakyReLU_slope(x) then
+ * mode 0 nothing | 1 average pooling by `rate` | 2 nearest up-sampling by `rate`.  x: channels-last [B,H,W,ldx]
+ * (SBM_F32 / SBM_BF16); out_bf16: channels-last rows of ldo elements (channel padding zeroed) and / or, mode 0 only,
+ * out_nchw_f32 [B][C][H][W]. */
+int sbm_lrelu_resample(const void* x, int32_t in_dtype, int64_t ldx, void* out_bf16, int64_t ldo, float* out_nchw_f32,
+                       int32_t B, int32_t H, int32_t W, int32_t C, float slope, int32_t mode, int32_t rate,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

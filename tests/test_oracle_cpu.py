@@ -204,3 +204,14 @@ def test_oracle_residual_autoencoders_match_reference_golden():
             assert torch.allclose(logvar, c["logvar"], rtol=1e-5, atol=1e-6)
         rec = vo.ae_decode(sd, c["z"], g["enc"], g["dec"], g["size_in"])
         assert rec.shape == g["x"].shape and torch.allclose(rec, c["rec"], rtol=1e-5, atol=1e-5)
+
+
+def test_res_autoencoder_state_dict_schema_matches_reference_golden():
+    """The drop-in ResAE / ResVAE expose the reference's parameter and BatchNorm-buffer names and shapes, so its
+    checkpoints load (h_vae_model_copy.py:92-174)."""
+    from score_based_multimodal_autoencoder_b200 import h_vae_model_copy as hv
+    g = golden("res_ae.pt")
+    for name, cls in (("ae", hv.ResAE), ("vae", hv.ResVAE)):
+        m = cls(g["enc"], g["dec"], g["size_in"], g["size_z"], g["img_ch"])
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+        assert got == g[name]["shapes"]

@@ -1,0 +1,99 @@
+"""GPU parity of the drop-in residual autoencoders (score_based_multimodal_autoencoder_b200/h_vae_model_copy.py,
+SURVEY.md 8f-1) against the golden outputs of the unmodified reference `ResAE` / `ResVAE` in eval mode
+(tests/golden/res_ae.pt) and against the fp32 CPU oracle at another batch size.  bf16 GEMM operands and bf16
+activations between blocks, fp32 accumulation: rel-L2 <= 2e-2 of the fp32 reference."""
+import pytest
+import torch
+
+from oracle import vae_oracle as vo
+from oracle.det_weights import fill_state_dict
+from tests.util import golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _build(name, g):
+    from score_based_multimodal_autoencoder_b200 import h_vae_model_copy as hv
+    cls = hv.ResAE if name == "ae" else hv.ResVAE
+    m = cls(g["enc"], g["dec"], g["size_in"], g["size_z"], g["img_ch"])
+    sd = fill_state_dict(g[name]["shapes"])
+    for k in g[name]["shapes"]:
+        if k.endswith("running_var"):
+            sd[k] = sd[k].abs() + 0.5
+    full = dict(m.state_dict())
+    full.update(sd)
+    m.load_state_dict(full)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("name", ["ae", "vae"])
+def test_res_autoencoder_matches_reference_golden(name):
+    g = golden("res_ae.pt")
+    m, _ = _build(name, g)
+    x = g["x"].cuda()
+    if name == "ae":
+        z = m.encoder(x)
+    else:
+        z, logvar = m.encoder(x)
+        assert rel_l2(logvar, g[name]["logvar"]) < TOL
+    rec = m.decoder(g[name]["z"].cuda())
+    e_z, e_r = rel_l2(z, g[name]["z"]), rel_l2(rec, g[name]["rec"])
+    print(f"{name}: latent rel-L2 {e_z:.3e}, reconstruction rel-L2 {e_r:.3e}")
+    assert z.shape == g[name]["z"].shape and rec.shape == g[name]["rec"].shape and rec.dtype == torch.float32
+    assert e_z < TOL and e_r < TOL
+    # whole round trip through the module's own forward
+    out = m(x)
+    out = out if name == "ae" else out[0]
+    assert out.shape == x.shape and torch.isfinite(out).all()
+
+
+def test_res_autoencoder_matches_oracle_at_another_batch_and_rejects_train_mode():
+    g = golden("res_ae.pt")
+    m, sd = _build("ae", g)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(37, g["img_ch"], g["size_in"], g["size_in"], generator=gen)
+    z_ref = vo.ae_encode(sd, x, g["enc"])
+    z = m.encoder(x.cuda())
+    rec = m.decoder(z_ref.cuda())
+    rec_ref = vo.ae_decode(sd, z_ref, g["enc"], g["dec"], g["size_in"])
+    assert rel_l2(z, z_ref) < TOL and rel_l2(rec, rec_ref) < TOL
+    # per-sample independence (eval-mode BatchNorm is a fixed affine map)
+    assert rel_l2(m.encoder(x[:3].cuda()), z[:3]) < 1e-5
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.encoder(x.cuda())
+    m.eval()
+    from score_based_multimodal_autoencoder_b200 import _lib as L
+    with pytest.raises(L.SbmError):
+        m.encoder(x)
+
+
+@pytest.mark.parametrize("case", [(3, 8, 8, 40, 0, 1, torch.float32), (2, 16, 16, 64, 1, 2, torch.float32),
+                                  (2, 8, 8, 24, 1, 4, torch.bfloat16), (3, 4, 4, 64, 2, 2, torch.float32),
+                                  (2, 2, 2, 16, 2, 4, torch.bfloat16)])
+def test_lrelu_resample_kernel(case):
+    """sbm_lrelu_resample against torch: LeakyReLU then AvgPool2d / nearest up-sampling, both input types, NCHW output."""
+    import torch.nn.functional as F
+    from score_based_multimodal_autoencoder_b200 import ops
+    from score_based_multimodal_autoencoder_b200.h_vae_model_copy import lrelu_resample
+    B, H, W, Cc, mode, rate, dt = case
+    gen = torch.Generator().manual_seed(B * 100 + H + Cc)
+    x = torch.randn(B, Cc, H, W, generator=gen).cuda()
+    ld = ops.pad8(Cc)
+    xn = torch.full((B, H, W, ld), float("nan"), device="cuda", dtype=dt)
+    xn[..., :Cc] = x.permute(0, 2, 3, 1).to(dt)
+    xr = xn[..., :Cc].float().permute(0, 3, 1, 2)
+    ref = F.leaky_relu(xr, 0.2)
+    if mode == 1:
+        ref = F.avg_pool2d(ref, rate)
+    elif mode == 2:
+        ref = F.interpolate(ref, scale_factor=rate, mode="nearest")
+    out = lrelu_resample(xn, Cc, 0.2, mode, rate)
+    torch.cuda.synchronize()
+    assert out.shape[1:3] == ref.shape[2:] and out.dtype == torch.bfloat16
+    assert torch.equal(out[..., :Cc].float(), ref.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    assert (out[..., Cc:] == 0).all()
+    if mode == 0:
+        o2 = lrelu_resample(xn, Cc, 0.2, nchw=True)
+        assert torch.equal(o2, ref)
