@@ -62,6 +62,34 @@ def main():
         out[name] = {"shapes": shapes, "z": z.clone(), "rec": rec.clone(),
                      "logvar": None if logvar is None else logvar.clone()}
     out["x"] = x
+    # ---- family "N" (CelebA-HQ image modality, train_lat_celebhq_unet_cont2.py:427-431) at reduced size
+    enc_n, dec_n, size_n, z_n = [(64, 128, 128, 4), (128, 256, 256, 4)], [(256, 256, 128, 4), (128, 128, 64, 4)], 64, 256
+    xn = torch.rand(2, IMG_CH, size_n, size_n, generator=g)
+    out["N"] = {"enc": enc_n, "dec": dec_n, "size_in": size_n, "size_z": z_n, "x": xn}
+    for name, cls in (("aen", hv.ResAEN), ("vaen", hv.ResVAEN)):
+        torch.manual_seed(0)
+        ref = cls(enc_n, dec_n, size_n, z_n, IMG_CH)
+        sd0 = ref.state_dict()
+        shapes = {k: tuple(v.shape) for k, v in sd0.items() if v.dtype.is_floating_point}
+        sd = fill_state_dict(shapes)
+        for k in shapes:
+            if k.endswith("running_var"):
+                sd[k] = sd[k].abs() + 0.5
+        full = dict(sd0)
+        full.update(sd)
+        ref.load_state_dict(full)
+        ref.eval()
+        with torch.no_grad():
+            z = ref.encoder(xn)
+            z = z if name == "aen" else z[0]
+            rec = ref.decoder(z)
+            z_o = vo.ae_encode(sd, xn, enc_n, family="N")
+            rec_o = vo.ae_decode(sd, z, enc_n, dec_n, size_n, family="N")
+        e1 = ((z_o - z).abs().max() / z.abs().max()).item()
+        e2 = ((rec_o - rec).abs().max() / rec.abs().max()).item()
+        print(f"{name}: latent {tuple(z.shape)} oracle rel-max {e1:.2e}; reconstruction {tuple(rec.shape)} rel-max {e2:.2e}")
+        assert e1 < 1e-5 and e2 < 1e-5
+        out["N"][name] = {"shapes": shapes, "z": z.clone(), "rec": rec.clone()}
     path = os.path.join(OUT, "res_ae.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -204,6 +204,18 @@ def test_oracle_residual_autoencoders_match_reference_golden():
             assert torch.allclose(logvar, c["logvar"], rtol=1e-5, atol=1e-6)
         rec = vo.ae_decode(sd, c["z"], g["enc"], g["dec"], g["size_in"])
         assert rec.shape == g["x"].shape and torch.allclose(rec, c["rec"], rtol=1e-5, atol=1e-5)
+    # the CelebA-HQ variants ResAEN / ResVAEN (GELU blocks, bilinear up-sampling, sigmoid output): oracle pinned for the
+    # next round's CUDA side
+    n = g["N"]
+    for name in ("aen", "vaen"):
+        c = n[name]
+        sd = fill_state_dict(c["shapes"])
+        for k in c["shapes"]:
+            if k.endswith("running_var"):
+                sd[k] = sd[k].abs() + 0.5
+        assert torch.allclose(vo.ae_encode(sd, n["x"], n["enc"], family="N"), c["z"], rtol=1e-5, atol=1e-6)
+        rec = vo.ae_decode(sd, c["z"], n["enc"], n["dec"], n["size_in"], family="N")
+        assert torch.allclose(rec, c["rec"], rtol=1e-5, atol=1e-6) and rec.min() >= 0 and rec.max() <= 1
 
 
 def test_res_autoencoder_state_dict_schema_matches_reference_golden():
