@@ -288,6 +288,11 @@ int sbm_train_tick(int32_t* step_dev, uint64_t* draw_dev, uint64_t draw_inc, voi
 int sbm_lrelu_resample(const void* x, int32_t in_dtype, int64_t ldx, void* out_bf16, int64_t ldo, float* out_nchw_f32,
                        int32_t B, int32_t H, int32_t W, int32_t C, float slope, int32_t mode, int32_t rate,
                        void* stream);
+/* superset for the CelebA-HQ variants RBlockN / ResDecoderN (h_vae_model_copy.py:347-428): act 0 = LeakyReLU(slope),
+ * 1 = exact GELU; mode 3 = BILINEAR up-sampling by `rate` (nn.Upsample(mode='bilinear'), align_corners=False). */
+int sbm_act_resample(const void* x, int32_t in_dtype, int64_t ldx, void* out_bf16, int64_t ldo, float* out_nchw_f32,
+                     int32_t B, int32_t H, int32_t W, int32_t C, int32_t act, float slope, int32_t mode, int32_t rate,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,5 @@
-"""Drop-in for the reference's residual autoencoders `ResAE` / `ResVAE` (h_vae_model_copy.py:9-174) -- the encoders
+"""Drop-in for the reference's residual autoencoders `ResAE` / `ResVAE` (h_vae_model_copy.py:9-174) and their CelebA-HQ
+variants `ResAEN` / `ResVAEN` (:347-590: GELU blocks, bilinear up-sampling, sigmoid output) -- the encoders
 that turn each modality into the latents the score model is trained on, and the decoders that turn sampled latents
 back into images (train_poly_unet_cont.py:548-571, 257-268) -- in EVAL mode, the mode every score-model script of the
 reference runs them in (loaded from a checkpoint and frozen).  SURVEY.md 8f-1: the first row either side of the path.
@@ -24,17 +25,24 @@ from . import ops
 from .ops import pad8
 
 
-def lrelu_resample(x: torch.Tensor, c: int, slope: float, mode: int = 0, rate: int = 1, nchw: bool = False):
-    """LeakyReLU_slope(x) then (mode 0) nothing / (1) AvgPool2d(rate) / (2) nearest up-sampling by rate.
-    x: channels-last [B,H,W,ld] fp32 or bf16 -> bf16 channels-last, or fp32 NCHW when `nchw` (mode 0)."""
+ACT_LRELU, ACT_GELU = 0, 1
+MODE_SAME, MODE_AVGPOOL, MODE_NEAREST, MODE_BILINEAR = 0, 1, 2, 3
+
+
+def lrelu_resample(x: torch.Tensor, c: int, slope: float, mode: int = 0, rate: int = 1, nchw: bool = False,
+                   act: int = ACT_LRELU):
+    """act(x) -- LeakyReLU_slope or exact GELU -- then (mode 0) nothing / (1) AvgPool2d(rate) / (2) nearest or
+    (3) bilinear up-sampling by rate.  x: channels-last [B,H,W,ld] fp32 or bf16 -> bf16 channels-last, or fp32 NCHW
+    when `nchw` (mode 0)."""
     b, h, w, _ = x.shape
-    oh, ow = (h // rate, w // rate) if mode == 1 else ((h * rate, w * rate) if mode == 2 else (h, w))
+    oh, ow = (h // rate, w // rate) if mode == 1 else ((h * rate, w * rate) if mode >= 2 else (h, w))
     out_b = None if nchw else torch.empty((b, oh, ow, pad8(c)), dtype=torch.bfloat16, device=x.device)
     out_n = torch.empty((b, c, h, w), dtype=torch.float32, device=x.device) if nchw else None
-    L.check(L.lib().sbm_lrelu_resample(
+    L.check(L.lib().sbm_act_resample(
         L.ptr(x), C.c_int32(L.BF16 if x.dtype == torch.bfloat16 else L.F32), C.c_int64(x.stride(2)), L.ptr(out_b),
         C.c_int64(out_b.stride(2) if out_b is not None else 0), L.ptr(out_n), C.c_int32(b), C.c_int32(h), C.c_int32(w),
-        C.c_int32(c), C.c_float(slope), C.c_int32(mode), C.c_int32(max(rate, 1)), L.stream_ptr()), "sbm_lrelu_resample")
+        C.c_int32(c), C.c_int32(act), C.c_float(slope), C.c_int32(mode), C.c_int32(max(rate, 1)), L.stream_ptr()),
+        "sbm_act_resample")
     return out_n if nchw else out_b
 
 
@@ -46,49 +54,71 @@ class _Holder(nn.Module):
 
 
 class RBlock(_Holder):  # h_vae_model_copy.py:9-39
+    _act, _up_mode = ACT_LRELU, MODE_NEAREST      # LeakyReLU(0.2), nn.Upsample(nearest)
+
     def __init__(self, in_width, middle_width, out_width, down_rate=None, up_rate=None, residual=True):
         super().__init__()
         self.down_rate, self.up_rate, self.residual = down_rate, up_rate, residual
         self.in_width, self.middle_width, self.out_width = in_width, middle_width, out_width
         self.conv = nn.Sequential(
-            nn.Conv2d(in_width, middle_width, 3, 1, 1, bias=False), nn.BatchNorm2d(middle_width), nn.LeakyReLU(0.2),
+            nn.Conv2d(in_width, middle_width, 3, 1, 1, bias=False), nn.BatchNorm2d(middle_width),
+            nn.GELU() if self._act == ACT_GELU else nn.LeakyReLU(0.2),
             nn.Conv2d(middle_width, out_width, 3, 1, 1, bias=False), nn.BatchNorm2d(out_width))
-        self.sf = nn.LeakyReLU(0.2)
+        self.sf = nn.GELU() if self._act == ACT_GELU else nn.LeakyReLU(0.2)
         self.size_conv = nn.Conv2d(in_width, out_width, 1, 1, 0, bias=False)
 
 
+class RBlockN(RBlock):  # h_vae_model_copy.py:347-377: GELU, bilinear up-sampling
+    _act, _up_mode = ACT_GELU, MODE_BILINEAR
+
+
 class ResEncoder(_Holder):  # h_vae_model_copy.py:41-72
+    _block, _stem_slope = RBlock, 0.2
+
     def __init__(self, channel_list, size_in=64, size_z=64, img_ch=3):
         super().__init__()
         self.img_ch, self.channel_list, self.size_z, self.size_in = img_ch, channel_list, size_z, size_in
         self.ch_enc = nn.Sequential(nn.Conv2d(img_ch, channel_list[0][0], 5, 1, 2), nn.BatchNorm2d(channel_list[0][0]),
-                                    nn.LeakyReLU(0.2), nn.AvgPool2d(2))
+                                    nn.LeakyReLU(self._stem_slope), nn.AvgPool2d(2))
         init_size = size_in // 2
         for i in channel_list:
             init_size = init_size // i[3]
         self.final_side = init_size
         self.size_z_lin = (init_size * init_size) * (channel_list[-1][2] // 2)
-        self.r_blocks = nn.ModuleList([RBlock(*i) for i in channel_list])
+        self.r_blocks = nn.ModuleList([self._block(*i) for i in channel_list])
         self.mu_lin = nn.Linear(self.size_z_lin, size_z)
         self.logvar_lin = nn.Linear(self.size_z_lin, size_z)
 
 
+class ResEncoderN(ResEncoder):  # h_vae_model_copy.py:379-409: LeakyReLU(0.1) stem, RBlockN
+    _block, _stem_slope = RBlockN, 0.1
+
+
 class ResDecoder(_Holder):  # h_vae_model_copy.py:74-90
+    _block, _sigmoid = RBlock, False
+
     def __init__(self, channel_list, size_in=64, size_z=64, img_ch=3):
         super().__init__()
         self.img_ch, self.channel_list, self.size_z = img_ch, channel_list, size_z
-        self.r_blocks = nn.ModuleList([RBlock(i[0], i[1], i[2], None, i[3], True) for i in channel_list])
+        self.r_blocks = nn.ModuleList([self._block(i[0], i[1], i[2], None, i[3], True) for i in channel_list])
         c = channel_list[-1][2]
-        self.ch_dec = nn.Sequential(RBlock(c, c, c), nn.Conv2d(c, img_ch, 5, 1, 2))
+        tail = [RBlock(c, c, c), nn.Conv2d(c, img_ch, 5, 1, 2)] + ([nn.Sigmoid()] if self._sigmoid else [])
+        self.ch_dec = nn.Sequential(*tail)
+
+
+class ResDecoderN(ResDecoder):  # h_vae_model_copy.py:411-428: RBlockN up-blocks, plain RBlock + conv + Sigmoid tail
+    _block, _sigmoid = RBlockN, True
 
 
 class _ResBase(nn.Module):
+    _enc_cls, _dec_cls = ResEncoder, ResDecoder
+
     def __init__(self, enc_channel_list, dec_channel_list, size_in=64, size_z=64, img_ch=3):
         super().__init__()
         self.enc_channel_list, self.dec_channel_list = enc_channel_list, dec_channel_list
         self.size_z, self.size_in, self.img_ch = size_z, size_in, img_ch
-        self.enc = ResEncoder(enc_channel_list, size_in, size_z, img_ch)
-        self.dec = ResDecoder(dec_channel_list, size_in, size_z, img_ch)
+        self.enc = self._enc_cls(enc_channel_list, size_in, size_z, img_ch)
+        self.dec = self._dec_cls(dec_channel_list, size_in, size_z, img_ch)
         init_size = size_in
         for i in enc_channel_list:
             init_size = init_size // i[3]
@@ -158,8 +188,9 @@ class _ResBase(nn.Module):
         """x_b: bf16 channels-last -> bf16 channels-last (after the block's pooling / up-sampling)."""
         c_in, c_mid, c_out = blk.in_width, blk.middle_width, blk.out_width
         w1, b1 = self._conv_bn(blk.conv[0], blk.conv[1])
+        act, up = blk._act, blk._up_mode
         h = ops.conv_igemm(x_b, w1, kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_mid, bias=b1)
-        a = lrelu_resample(h, c_mid, 0.2)
+        a = lrelu_resample(h, c_mid, 0.2, act=act)
         if c_in != c_out:
             res = ops.conv_igemm(x_b, self._conv_plain(blk.size_conv), kind=L.CONV_S1, kh=1, kw=1, cin=c_in, cout=c_out)
         else:
@@ -167,10 +198,10 @@ class _ResBase(nn.Module):
         w2, b2 = self._conv_bn(blk.conv[3], blk.conv[4])
         h2 = ops.conv_igemm(a, w2, kind=L.CONV_S1, kh=3, kw=3, cin=c_mid, cout=c_out, bias=b2, residual=res)
         if blk.down_rate is not None:
-            return lrelu_resample(h2, c_out, 0.2, 1, blk.down_rate)
+            return lrelu_resample(h2, c_out, 0.2, MODE_AVGPOOL, blk.down_rate, act=act)
         if blk.up_rate is not None:
-            return lrelu_resample(h2, c_out, 0.2, 2, blk.up_rate)
-        return lrelu_resample(h2, c_out, 0.2)
+            return lrelu_resample(h2, c_out, 0.2, up, blk.up_rate, act=act)
+        return lrelu_resample(h2, c_out, 0.2, act=act)
 
     @torch.no_grad()
     def _encode(self, x):
@@ -182,7 +213,7 @@ class _ResBase(nn.Module):
         w0, b0 = self._conv_bn(enc.ch_enc[0], enc.ch_enc[1], im2col=True)
         a0 = ops.stem_im2col(x, 5, 5)
         h = ops.conv_igemm(a0, w0, kind=L.CONV_S1, kh=1, kw=1, cin=self.img_ch * 25, cout=c0, bias=b0)
-        cur = lrelu_resample(h, c0, 0.2, 1, 2)
+        cur = lrelu_resample(h, c0, enc._stem_slope, MODE_AVGPOOL, 2)
         for blk in enc.r_blocks:
             cur = self._rblock(blk, cur)
         ch = enc.channel_list[-1][2]
@@ -218,8 +249,9 @@ class _ResBase(nn.Module):
         feat = lrelu_resample(h2, c, 0.2, nchw=True)
         oc = self.dec.ch_dec[1]
         cols = ops.stem_im2col(feat, 5, 5)
-        return ops.conv_igemm(cols, self._conv_plain(oc, im2col=True), kind=L.CONV_S1, kh=1, kw=1, cin=c * 25,
-                              cout=self.img_ch, bias=oc.bias, nchw=True)
+        y = ops.conv_igemm(cols, self._conv_plain(oc, im2col=True), kind=L.CONV_S1, kh=1, kw=1, cin=c * 25,
+                           cout=self.img_ch, bias=oc.bias, nchw=True)
+        return torch.sigmoid_(y) if self.dec._sigmoid else y       # ResDecoderN's nn.Sigmoid on the [B, img_ch, H, W] image
 
     def sample(self, amount, device):
         return self.decoder(torch.randn(amount, self.size_z).to(device))
@@ -231,6 +263,10 @@ class ResAE(_ResBase):  # h_vae_model_copy.py:145-174
 
     def forward(self, m):
         return self.decoder(self.encoder(m))
+
+
+class ResAEN(ResAE):  # h_vae_model_copy.py:549-590 (CelebA-HQ image modality, train_lat_celebhq_unet_cont2.py:427-431)
+    _enc_cls, _dec_cls = ResEncoderN, ResDecoderN
 
 
 class ResVAE(_ResBase):  # h_vae_model_copy.py:92-143
@@ -245,3 +281,7 @@ class ResVAE(_ResBase):  # h_vae_model_copy.py:92-143
         mu, logvar = self.encoder(m)
         z = self.reparametrize(mu, logvar)
         return self.decoder(z), mu, logvar
+
+
+class ResVAEN(ResVAE):  # h_vae_model_copy.py:457-503
+    _enc_cls, _dec_cls = ResEncoderN, ResDecoderN

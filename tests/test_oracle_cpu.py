@@ -227,3 +227,8 @@ def test_res_autoencoder_state_dict_schema_matches_reference_golden():
         m = cls(g["enc"], g["dec"], g["size_in"], g["size_z"], g["img_ch"])
         got = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
         assert got == g[name]["shapes"]
+    n = g["N"]
+    for name, cls in (("aen", hv.ResAEN), ("vaen", hv.ResVAEN)):
+        m = cls(n["enc"], n["dec"], n["size_in"], n["size_z"], 3)
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+        assert got == n[name]["shapes"]

@@ -15,8 +15,8 @@ TOL = 2e-2
 
 def _build(name, g):
     from score_based_multimodal_autoencoder_b200 import h_vae_model_copy as hv
-    cls = hv.ResAE if name == "ae" else hv.ResVAE
-    m = cls(g["enc"], g["dec"], g["size_in"], g["size_z"], g["img_ch"])
+    cls = {"ae": hv.ResAE, "vae": hv.ResVAE, "aen": hv.ResAEN, "vaen": hv.ResVAEN}[name]
+    m = cls(g["enc"], g["dec"], g["size_in"], g["size_z"], g.get("img_ch", 3))
     sd = fill_state_dict(g[name]["shapes"])
     for k in g[name]["shapes"]:
         if k.endswith("running_var"):
@@ -46,6 +46,47 @@ def test_res_autoencoder_matches_reference_golden(name):
     out = m(x)
     out = out if name == "ae" else out[0]
     assert out.shape == x.shape and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("name", ["aen", "vaen"])
+def test_res_autoencoder_celeba_variants_match_reference_golden(name):
+    """ResAEN / ResVAEN (GELU blocks, bilinear up-sampling by 4, LeakyReLU(0.1) stem, sigmoid output) against the
+    unmodified reference (tests/golden/res_ae.pt, key "N")."""
+    n = golden("res_ae.pt")["N"]
+    m, _ = _build(name, n)
+    z = m.encoder(n["x"].cuda())
+    z = z if name == "aen" else z[0]
+    rec = m.decoder(n[name]["z"].cuda())
+    e_z, e_r = rel_l2(z, n[name]["z"]), rel_l2(rec, n[name]["rec"])
+    print(f"{name}: latent rel-L2 {e_z:.3e}, reconstruction rel-L2 {e_r:.3e}")
+    assert z.shape == n[name]["z"].shape and rec.shape == n[name]["rec"].shape
+    assert e_z < TOL and e_r < TOL and rec.min() >= 0 and rec.max() <= 1
+
+
+@pytest.mark.parametrize("case", [(2, 4, 4, 64, 4, torch.float32), (3, 8, 8, 24, 2, torch.bfloat16),
+                                  (2, 2, 2, 16, 4, torch.float32), (2, 1, 1, 8, 2, torch.float32)])
+def test_gelu_bilinear_resample_kernel(case):
+    """sbm_act_resample: exact GELU then bilinear up-sampling (nn.Upsample(mode='bilinear')) / average pooling."""
+    import torch.nn.functional as F
+    from score_based_multimodal_autoencoder_b200 import ops
+    from score_based_multimodal_autoencoder_b200 import h_vae_model_copy as hv
+    B, H, W, Cc, rate, dt = case
+    gen = torch.Generator().manual_seed(B * 10 + H + Cc)
+    x = torch.randn(B, Cc, H, W, generator=gen).cuda()
+    xn = torch.full((B, H, W, ops.pad8(Cc)), float("nan"), device="cuda", dtype=dt)
+    xn[..., :Cc] = x.permute(0, 2, 3, 1).to(dt)
+    xr = xn[..., :Cc].float().permute(0, 3, 1, 2)
+    act = F.gelu(xr.double())
+    up = F.interpolate(act, scale_factor=rate, mode="bilinear").permute(0, 2, 3, 1)
+    out = hv.lrelu_resample(xn, Cc, 0.0, hv.MODE_BILINEAR, rate, act=hv.ACT_GELU)
+    torch.cuda.synchronize()
+    assert out.shape[1:3] == up.shape[1:3]
+    assert (out[..., :Cc].double() - up).abs().max().item() <= 5e-3 * up.abs().max().item() + 1e-6
+    assert (out[..., Cc:] == 0).all()
+    if H % 2 == 0:
+        pool = F.avg_pool2d(act, 2).permute(0, 2, 3, 1)
+        o2 = hv.lrelu_resample(xn, Cc, 0.0, hv.MODE_AVGPOOL, 2, act=hv.ACT_GELU)
+        assert (o2[..., :Cc].double() - pool).abs().max().item() <= 5e-3 * pool.abs().max().item() + 1e-6
 
 
 def test_res_autoencoder_matches_oracle_at_another_batch_and_rejects_train_mode():
