@@ -76,3 +76,31 @@ def ae_decode(sd, z, enc_channel_list, dec_channel_list, size_in, family=""):
     side = lin // ch // init
     h = F.relu(F.linear(z, sd["z_lin.weight"], sd["z_lin.bias"]))
     return res_decoder(sd, h.view(z.shape[0], ch, side, side), dec_channel_list, family=family)
+
+
+def attr_mlp(sd, x, p, n_layers, last_plain=False, eps=1e-5):
+    """`enc_net` / `dec_net` of CelebAAttrNewBN[AE] (h_vae_model.py:718-755, 833-868): Linear -> BatchNorm1d (eval) -> ReLU
+    blocks at Sequential indices 0, 3, 6, ...; with `last_plain` the final Linear has no norm / activation."""
+    h = x
+    for i in range(n_layers):
+        k = 3 * i
+        h = F.linear(h, sd[f"{p}.{k}.weight"], sd[f"{p}.{k}.bias"])
+        if last_plain and i == n_layers - 1:
+            break
+        h = F.batch_norm(h, sd[f"{p}.{k + 1}.running_mean"], sd[f"{p}.{k + 1}.running_var"], sd[f"{p}.{k + 1}.weight"],
+                         sd[f"{p}.{k + 1}.bias"], training=False, eps=eps)
+        h = F.relu(h)
+    return h
+
+
+def attr_encode(sd, x):
+    """CelebAAttrNewBN.encoder (h_vae_model.py:757-760) -> (mu, logvar | None for the AE variant, :870-873)."""
+    h = attr_mlp(sd, x, "enc_net", 5)
+    mu = F.linear(h, sd["mu_lin.weight"], sd["mu_lin.bias"])
+    logvar = F.linear(h, sd["logvar_lin.weight"], sd["logvar_lin.bias"]) if "logvar_lin.weight" in sd else None
+    return mu, logvar
+
+
+def attr_decode(sd, z):
+    """CelebAAttrNewBN.decoder (h_vae_model.py:767-768)."""
+    return attr_mlp(sd, z, "dec_net", 6, last_plain=True)

@@ -9,7 +9,7 @@ import torch
 
 from oracle import sde_oracle as so
 from oracle import unet_oracle as uo
-from oracle.det_weights import fill_state_dict
+from oracle.det_weights import fill_autoencoder_state_dict, fill_state_dict
 from tests.util import ROOT, golden, rel_l2
 
 
@@ -194,26 +194,26 @@ def test_oracle_residual_autoencoders_match_reference_golden():
     g = golden("res_ae.pt")
     for name in ("ae", "vae"):
         c = g[name]
-        sd = fill_state_dict(c["shapes"])
-        for k in c["shapes"]:
-            if k.endswith("running_var"):
-                sd[k] = sd[k].abs() + 0.5
+        sd = fill_autoencoder_state_dict(c["shapes"], gain=1.0)
         mu, logvar = vo.res_encoder(sd, g["x"], g["enc"])
         assert torch.allclose(mu, c["z"], rtol=1e-5, atol=1e-6)
         if c["logvar"] is not None:
             assert torch.allclose(logvar, c["logvar"], rtol=1e-5, atol=1e-6)
         rec = vo.ae_decode(sd, c["z"], g["enc"], g["dec"], g["size_in"])
         assert rec.shape == g["x"].shape and torch.allclose(rec, c["rec"], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(vo.ae_decode(sd, g["zz"], g["enc"], g["dec"], g["size_in"]), c["rec_zz"], rtol=1e-5, atol=1e-5)
+        # the fixtures are input-sensitive (a golden whose outputs barely depend on the inputs pins only the biases)
+        assert ((c["z"] - c["z"].mean(0)).norm() / c["z"].norm()).item() > 0.03
+        assert ((c["rec_zz"] - c["rec_zz"].mean(0)).norm() / c["rec_zz"].norm()).item() > 0.1
     # the CelebA-HQ variants ResAEN / ResVAEN (GELU blocks, bilinear up-sampling, sigmoid output): oracle pinned for the
     # next round's CUDA side
     n = g["N"]
     for name in ("aen", "vaen"):
         c = n[name]
-        sd = fill_state_dict(c["shapes"])
-        for k in c["shapes"]:
-            if k.endswith("running_var"):
-                sd[k] = sd[k].abs() + 0.5
+        sd = fill_autoencoder_state_dict(c["shapes"], gain=1.0)
         assert torch.allclose(vo.ae_encode(sd, n["x"], n["enc"], family="N"), c["z"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(vo.ae_decode(sd, n["zz"], n["enc"], n["dec"], n["size_in"], family="N"), c["rec_zz"],
+                              rtol=1e-5, atol=1e-6)
         rec = vo.ae_decode(sd, c["z"], n["enc"], n["dec"], n["size_in"], family="N")
         assert torch.allclose(rec, c["rec"], rtol=1e-5, atol=1e-6) and rec.min() >= 0 and rec.max() <= 1
 
@@ -232,3 +232,24 @@ def test_res_autoencoder_state_dict_schema_matches_reference_golden():
         m = cls(n["enc"], n["dec"], n["size_in"], n["size_z"], 3)
         got = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
         assert got == n[name]["shapes"]
+
+
+def test_oracle_attribute_autoencoders_and_schema_match_reference_golden():
+    """oracle/vae_oracle.py `attr_*` against the unmodified reference CelebAAttrNewBN / CelebAAttrNewBNAE
+    (tests/golden/attr_ae.pt, oracle/gen_golden_attr.py), and the drop-in classes' state_dict schema."""
+    from oracle import vae_oracle as vo
+    from score_based_multimodal_autoencoder_b200 import h_vae_model as hm
+    g = golden("attr_ae.pt")
+    for name in ("vae", "ae"):
+        c = g[name]
+        sd = fill_autoencoder_state_dict(c["shapes"], gain=1.6)
+        mu, logvar = vo.attr_encode(sd, g["x"])
+        assert torch.allclose(mu, c["z"], rtol=1e-5, atol=1e-6)
+        assert (logvar is None) == (c["logvar"] is None)
+        if logvar is not None:
+            assert torch.allclose(logvar, c["logvar"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(vo.attr_decode(sd, g["zz"]), c["rec"], rtol=1e-5, atol=1e-5)
+        assert ((c["z"] - c["z"].mean(0)).norm() / c["z"].norm()).item() > 0.2      # not a dead ReLU net
+        m = hm.CelebAAttrNewBN(g["size_z"]) if name == "vae" else hm.CelebAAttrNewBNAE(g["size_z"])
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+        assert got == c["shapes"]

@@ -6,21 +6,25 @@ import pytest
 import torch
 
 from oracle import vae_oracle as vo
-from oracle.det_weights import fill_state_dict
+from oracle.det_weights import fill_autoencoder_state_dict, structured_images
 from tests.util import golden, rel_l2
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-2
+TOL = 2e-2        # whole output
+TOL_VAR = 8e-2    # input-dependent part only (output minus its batch mean): a broken data path shows up here as ~1
+
+
+def rel_var(a, b):
+    """error relative to the INPUT-DEPENDENT part of the reference (b minus its mean over the batch)."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / (b - b.mean(0, keepdim=True)).norm()).item()
 
 
 def _build(name, g):
     from score_based_multimodal_autoencoder_b200 import h_vae_model_copy as hv
     cls = {"ae": hv.ResAE, "vae": hv.ResVAE, "aen": hv.ResAEN, "vaen": hv.ResVAEN}[name]
     m = cls(g["enc"], g["dec"], g["size_in"], g["size_z"], g.get("img_ch", 3))
-    sd = fill_state_dict(g[name]["shapes"])
-    for k in g[name]["shapes"]:
-        if k.endswith("running_var"):
-            sd[k] = sd[k].abs() + 0.5
+    sd = fill_autoencoder_state_dict(g[name]["shapes"], gain=1.0)
     full = dict(m.state_dict())
     full.update(sd)
     m.load_state_dict(full)
@@ -38,10 +42,13 @@ def test_res_autoencoder_matches_reference_golden(name):
         z, logvar = m.encoder(x)
         assert rel_l2(logvar, g[name]["logvar"]) < TOL
     rec = m.decoder(g[name]["z"].cuda())
-    e_z, e_r = rel_l2(z, g[name]["z"]), rel_l2(rec, g[name]["rec"])
-    print(f"{name}: latent rel-L2 {e_z:.3e}, reconstruction rel-L2 {e_r:.3e}")
+    rec_zz = m.decoder(g["zz"].cuda())
+    e_z, e_r, e_rz = rel_l2(z, g[name]["z"]), rel_l2(rec, g[name]["rec"]), rel_l2(rec_zz, g[name]["rec_zz"])
+    v_z, v_rz = rel_var(z, g[name]["z"]), rel_var(rec_zz, g[name]["rec_zz"])
+    print(f"{name}: latent rel-L2 {e_z:.3e} (input-dependent part {v_z:.3e}), reconstruction {e_r:.3e}, "
+          f"reconstruction of random latents {e_rz:.3e} (input-dependent part {v_rz:.3e})")
     assert z.shape == g[name]["z"].shape and rec.shape == g[name]["rec"].shape and rec.dtype == torch.float32
-    assert e_z < TOL and e_r < TOL
+    assert e_z < TOL and e_r < TOL and e_rz < TOL and v_z < TOL_VAR and v_rz < TOL_VAR
     # whole round trip through the module's own forward
     out = m(x)
     out = out if name == "ae" else out[0]
@@ -57,10 +64,14 @@ def test_res_autoencoder_celeba_variants_match_reference_golden(name):
     z = m.encoder(n["x"].cuda())
     z = z if name == "aen" else z[0]
     rec = m.decoder(n[name]["z"].cuda())
-    e_z, e_r = rel_l2(z, n[name]["z"]), rel_l2(rec, n[name]["rec"])
-    print(f"{name}: latent rel-L2 {e_z:.3e}, reconstruction rel-L2 {e_r:.3e}")
+    rec_zz = m.decoder(n["zz"].cuda())
+    e_z, e_r, e_rz = rel_l2(z, n[name]["z"]), rel_l2(rec, n[name]["rec"]), rel_l2(rec_zz, n[name]["rec_zz"])
+    v_z, v_rz = rel_var(z, n[name]["z"]), rel_var(rec_zz, n[name]["rec_zz"])
+    print(f"{name}: latent rel-L2 {e_z:.3e} (input-dependent part {v_z:.3e}), reconstruction {e_r:.3e}, "
+          f"reconstruction of random latents {e_rz:.3e} (input-dependent part {v_rz:.3e})")
     assert z.shape == n[name]["z"].shape and rec.shape == n[name]["rec"].shape
-    assert e_z < TOL and e_r < TOL and rec.min() >= 0 and rec.max() <= 1
+    assert e_z < TOL and e_r < TOL and e_rz < TOL and v_z < TOL_VAR and v_rz < TOL_VAR
+    assert rec.min() >= 0 and rec.max() <= 1
 
 
 @pytest.mark.parametrize("case", [(2, 4, 4, 64, 4, torch.float32), (3, 8, 8, 24, 2, torch.bfloat16),
@@ -92,13 +103,14 @@ def test_gelu_bilinear_resample_kernel(case):
 def test_res_autoencoder_matches_oracle_at_another_batch_and_rejects_train_mode():
     g = golden("res_ae.pt")
     m, sd = _build("ae", g)
-    gen = torch.Generator().manual_seed(3)
-    x = torch.rand(37, g["img_ch"], g["size_in"], g["size_in"], generator=gen)
+    x = structured_images(37, g["img_ch"], g["size_in"], 3)
+    zz = torch.randn(37, g["size_z"], generator=torch.Generator().manual_seed(4))
     z_ref = vo.ae_encode(sd, x, g["enc"])
     z = m.encoder(x.cuda())
-    rec = m.decoder(z_ref.cuda())
-    rec_ref = vo.ae_decode(sd, z_ref, g["enc"], g["dec"], g["size_in"])
+    rec = m.decoder(zz.cuda())
+    rec_ref = vo.ae_decode(sd, zz, g["enc"], g["dec"], g["size_in"])
     assert rel_l2(z, z_ref) < TOL and rel_l2(rec, rec_ref) < TOL
+    assert rel_var(z, z_ref) < TOL_VAR and rel_var(rec, rec_ref) < TOL_VAR
     # per-sample independence (eval-mode BatchNorm is a fixed affine map)
     assert rel_l2(m.encoder(x[:3].cuda()), z[:3]) < 1e-5
     m.train()
