@@ -9,17 +9,14 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle.det_weights import fill_state_dict  # noqa: E402  (parity numbers only: the checker, not the thing measured)
+from oracle.det_weights import fill_autoencoder_state_dict  # noqa: E402  (parity numbers only: the checker, not the thing measured)
 from score_based_multimodal_autoencoder_b200 import _lib as L  # noqa: E402
 from score_based_multimodal_autoencoder_b200.h_vae_model_copy import ResAE  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 g = torch.load(os.path.join(ROOT, "tests", "golden", "res_ae.pt"))
 m = ResAE(g["enc"], g["dec"], g["size_in"], g["size_z"], g["img_ch"])
-sd = fill_state_dict(g["ae"]["shapes"])
-for k in g["ae"]["shapes"]:
-    if k.endswith("running_var"):
-        sd[k] = sd[k].abs() + 0.5
+sd = fill_autoencoder_state_dict(g["ae"]["shapes"], gain=1.0)
 full = dict(m.state_dict())
 full.update(sd)
 m.load_state_dict(full)
