@@ -253,3 +253,14 @@ def test_oracle_attribute_autoencoders_and_schema_match_reference_golden():
         m = hm.CelebAAttrNewBN(g["size_z"]) if name == "vae" else hm.CelebAAttrNewBNAE(g["size_z"])
         got = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
         assert got == c["shapes"]
+
+
+def test_only_tests_smoke_and_bench_import_the_oracle():
+    """oracle/ is the checker: nothing under the package or tools/ may import it (bench.py: cpu_baseline / --impl
+    reference only; __graft_entry__: build() compiles nothing from it, smoke() checks against it)."""
+    for sub in ("score_based_multimodal_autoencoder_b200", "tools"):
+        d = os.path.join(ROOT, sub)
+        for fn in os.listdir(d):
+            if fn.endswith(".py"):
+                src = open(os.path.join(d, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, (sub, fn)
