@@ -264,3 +264,55 @@ def test_only_tests_smoke_and_bench_import_the_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(d, fn)).read()
                 assert "import oracle" not in src and "from oracle" not in src, (sub, fn)
+
+
+def test_autoencoder_host_plans_on_emulated_kernels_match_the_oracle():
+    """The host side of the autoencoder plans (BatchNorm folding, weight permutations, slicing, call order) run against
+    torch stand-ins of the kernels (tests/emulation.py) and compared with the fp32 oracle on input-sensitive weights:
+    whole output and, separately, the input-dependent part of it (a broken data path shows up there as ~1)."""
+    from oracle import vae_oracle as vo
+    from oracle.det_weights import structured_images
+    from score_based_multimodal_autoencoder_b200 import h_vae_model as hm
+    from score_based_multimodal_autoencoder_b200 import h_vae_model_copy as hc
+    from tests.emulation import emulated_kernels
+
+    def rel_var(a, b):
+        a, b = a.double(), b.double()
+        return ((a - b).norm() / (b - b.mean(0, keepdim=True)).norm()).item()
+
+    def load(m, gain):
+        shapes = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.dtype.is_floating_point}
+        sd = fill_autoencoder_state_dict(shapes, gain)
+        full = dict(m.state_dict())
+        full.update(sd)
+        m.load_state_dict(full)
+        return m.eval(), sd
+
+    poly = ([(64, 64, 64, 2), (64, 128, 128, 2), (128, 256, 256, 2)], [(256, 128, 128, 2), (128, 128, 64, 2), (64, 64, 64, 2)])
+    with emulated_kernels(), torch.no_grad():
+        for fam, cls, (enc, dec), size, zdim, nb in (("", hc.ResVAE, poly, 32, 64, 4),
+                                                     ("N", hc.ResVAEN, ([(64, 128, 128, 4), (128, 256, 256, 4)],
+                                                                        [(256, 256, 128, 4), (128, 128, 64, 4)]), 64, 256, 3)):
+            m, sd = load(cls(enc, dec, size, zdim, 3), 1.0)
+            x = structured_images(nb, 3, size, 11)
+            zz = torch.randn(nb, zdim, generator=torch.Generator().manual_seed(3))
+            mu, lv = m.encoder(x)
+            rec = m.decoder(zz)
+            mu_o, lv_o = vo.res_encoder(sd, x, enc, family=fam)
+            rec_o = vo.ae_decode(sd, zz, enc, dec, size, family=fam)
+            assert rel_l2(mu, mu_o) < 1e-2 and rel_l2(lv, lv_o) < 1e-2 and rel_l2(rec, rec_o) < 1e-2, fam
+            assert rel_var(mu, mu_o) < 8e-2 and rel_var(rec, rec_o) < 8e-2, fam
+        for m in (hm.CelebAAttrNewBN(256), hm.CelebAAttrNewBNAE(256)):
+            m, sd = load(m, 1.6)
+            x = (torch.rand(16, 18, generator=torch.Generator().manual_seed(5)) > 0.5).float()
+            zz = torch.randn(16, 256, generator=torch.Generator().manual_seed(6))
+            z = m.encoder(x)
+            z = z[0] if isinstance(z, tuple) else z
+            rec = m.decoder(zz)
+            z_o, rec_o = vo.attr_encode(sd, x)[0], vo.attr_decode(sd, zz)
+            assert rel_l2(z, z_o) < 1e-2 and rel_l2(rec, rec_o) < 1e-2
+            assert rel_var(z, z_o) < 6e-2 and rel_var(rec, rec_o) < 6e-2
+    # the real kernel wrappers are back: a CPU tensor is refused again
+    from score_based_multimodal_autoencoder_b200 import _lib as L
+    with pytest.raises(L.SbmError):
+        hm.CelebAAttrNewBNAE(64).eval().decoder(torch.zeros(2, 64))
