@@ -199,11 +199,23 @@ int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem
 int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                        const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
                        const sbm_rng* rng, const sbm_impute* impute, void* stream);
+/* reverse-diffusion (ancestral) predictor: (f, G) = sde.discretize(x, t), rev_f = f - G^2 s [*0.5], x_mean = x - rev_f,
+ * x' = x_mean + G z  (sde_helper2.py:236-253 base rule = subVPSDE, :373-381 VPSDE/DDPM, :465-473 VESDE/SMLD, :319-324
+ * RSDE.discretize).  table = device copy of sde.discrete_betas (VPSDE) / sde.discrete_sigmas (VESDE), NULL for subVPSDE.
+ * Same kernel, traffic (12 B / element) and epilogues as sbm_predictor_step. */
+int sbm_rd_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
+                          const float* t, const float* table, const float* noise, float* x_out, float* x_mean_out,
+                          int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, void* stream);
 /* corrector, sde_helper2.py:96-98: acc2[0] += sum_b ||grad_b||, acc2[1] += sum_b ||noise_b||.  acc2 is a buffer of
  * THREE doubles, zero before the first call (the third is a completion ticket used by reset_acc below); multi-GPU
- * exact mode all-reduces acc2[0..1] between the two calls */
+ * exact mode all-reduces acc2[0..1] between the two calls.  noise = injected buffer; else rng = Philox stream; with
+ * BOTH NULL only acc2[0] is accumulated (4 B / element, memory-bound) and acc2[1] comes from sbm_noise_norm */
 int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
                         double* acc2, void* stream);
+/* acc2[1] += sum_b ||noise_b|| of the Philox draw `rng` (sde_helper2.py:96, 98).  Touches no latent memory: the draw is
+ * a function of (seed, draw id, element index), so the samplers run this on a side stream beside the score-net
+ * forward and the norms kernel proper never regenerates the stream */
+int sbm_noise_norm(const sbm_latent_shape* ls, const sbm_rng* rng, double* acc2, void* stream);
 /* corrector, sde_helper2.py:56-60,99-101: step = (snr * mean||noise|| / mean||grad||)^2 * 2 * alpha[t];
  * x_mean = x + step*grad; x' = x_mean + sqrt(2 step) * noise.  alphas = device copy of sde.alphas (NULL: alpha = 1) */
 int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* grad,

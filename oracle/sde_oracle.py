@@ -84,6 +84,38 @@ def em_predictor_step(s: SdeSpec, x, t, score, z, probability_flow=False):
     return x_new, x_mean
 
 
+def discretize(s: SdeSpec, x, t):
+    """(f, G[B]) of the discretised forward SDE, x_{i+1} = x_i + f + G z.
+    subVP: the base class's Euler-Maruyama rule, sde_helper2.py:236-253 (f = drift/N, G = diffusion*sqrt(1/N));
+    VP: DDPM rule, :373-381 (f = sqrt(alpha_i) x - x, G = sqrt(beta_i), i = (t(N-1)/T).long());
+    VE: SMLD rule, :465-473 (f = 0, G = sqrt(sigma_i^2 - sigma_{i-1}^2), sigma_{-1} = 0)."""
+    if s.kind == "subvp":
+        dt = 1 / s.N
+        drift, diffusion = sde_coeffs(s, x, t)
+        return drift * dt, diffusion * torch.sqrt(torch.tensor(dt))
+    timestep = (t * (s.N - 1) / s.T).long()
+    if s.kind == "vp":
+        betas = torch.linspace(s.b0 / s.N, s.b1 / s.N, s.N)
+        beta = betas[timestep]
+        alpha = (1.0 - betas)[timestep]
+        return _bc(torch.sqrt(alpha)) * x - x, torch.sqrt(beta)
+    sigmas = torch.exp(torch.linspace(np.log(s.b0), np.log(s.b1), s.N))
+    sigma = sigmas[timestep]
+    adjacent = torch.where(timestep == 0, torch.zeros_like(t), sigmas[timestep - 1])
+    return torch.zeros_like(x), torch.sqrt(sigma ** 2 - adjacent ** 2)
+
+
+def rd_predictor_step(s: SdeSpec, x, t, score, z, probability_flow=False):
+    """Reverse-diffusion predictor over RSDE.discretize (sde_helper2.py:319-324): rev_f = f - G^2 score [*0.5],
+    rev_G = 0 if ODE else G; x_mean = x - rev_f; x = x_mean + rev_G z.  (The reference ships the discretisation
+    without a caller; the update is the standard ancestral rule it was written for.)"""
+    f, G = discretize(s, x, t)
+    rev_f = f - _bc(G) ** 2 * score * (0.5 if probability_flow else 1.0)
+    rev_G = torch.zeros_like(G) if probability_flow else G
+    x_mean = x - rev_f
+    return x_mean + _bc(rev_G) * z, x_mean
+
+
 def corrector_alpha(s: SdeSpec, t: torch.Tensor) -> torch.Tensor:
     """sde_helper2.py:56-60: alpha looked up by truncating t*(N-1)/T to an integer index."""
     if s.kind in ("vp", "subvp"):
@@ -128,7 +160,7 @@ def timesteps(s: SdeSpec, eps: float) -> torch.Tensor:
 
 def pc_sampler(s: SdeSpec, score_fn, x0, noise_pred, noise_corr, *, z_obs=None, obs_mask=None, eps=1e-3,
                noise_obs=True, pc=True, n_steps=1, target_snr=0.16, predictor_first=True, probability_flow=False,
-               num_steps=None, return_trace=False):
+               num_steps=None, return_trace=False, predictor="euler"):
     """N-step predictor-corrector sampler with observed-latent imputation.
 
     predictor_first=True  : train_lat_celebhq_unet_cont2.py:287-316 (calc_perf), train_poly_unet_cont.py:444-471
@@ -140,6 +172,7 @@ def pc_sampler(s: SdeSpec, score_fn, x0, noise_pred, noise_corr, *, z_obs=None, 
     B = x0.shape[0]
     ts = timesteps(s, eps)
     steps = s.N if num_steps is None else num_steps
+    rule = {"euler": em_predictor_step, "reverse_diffusion": rd_predictor_step}[predictor]
     x = x0.clone()
     x_mean = x0.clone()
     trace = []
@@ -150,7 +183,7 @@ def pc_sampler(s: SdeSpec, score_fn, x0, noise_pred, noise_corr, *, z_obs=None, 
             x = impute_observed(s, x, z_obs, obs_mask, vec_t, noise_obs)
 
         def predictor(x):
-            return em_predictor_step(s, x, vec_t, score_fn(x, vec_t), noise_pred[i], probability_flow)
+            return rule(s, x, vec_t, score_fn(x, vec_t), noise_pred[i], probability_flow)
 
         def corrector(x):
             xm = x
@@ -176,9 +209,42 @@ def pc_sampler(s: SdeSpec, score_fn, x0, noise_pred, noise_corr, *, z_obs=None, 
     return (out, trace) if return_trace else out
 
 
-def dsm_loss(s: SdeSpec, batch, score_fn, u, z, *, reduce_mean=True, likelihood_weighting=False, eps=1e-5):
-    """Denoising score matching loss.  sde_helper2.py:152-186 (importance-sampled-t branch excluded).
-    u = torch.rand(B) and z = torch.randn_like(batch) are the reference's two draws, in that order."""
+def likelihood_importance_cum_weight(t, beta_0, beta_1, eps=1e-5):
+    """sde_helper2.py:129-134 (jax.numpy -> numpy)."""
+    e1 = 0.5 * eps * (eps - 2) * beta_0 - 0.5 * eps ** 2 * beta_1
+    e2 = 0.5 * t * (t - 2) * beta_0 - 0.5 * t ** 2 * beta_1
+    term1 = np.where(np.abs(e1) <= 1e-3, -e1, 1.0 - np.exp(e1))
+    term2 = np.where(np.abs(e2) <= 1e-3, -e2, 1.0 - np.exp(e2))
+    return 0.5 * (-2 * np.log(term1) + 2 * np.log(term2) + beta_0 * (-2 * eps + eps ** 2 - (t - 2) * t)
+                  + beta_1 * (-eps ** 2 + t ** 2))
+
+
+def importance_sampled_t(s: SdeSpec, u01: torch.Tensor, eps=1e-5, steps=100) -> torch.Tensor:
+    """sde_helper2.py:136-148: quantile = Uniform(0, Z).sample((B,)) (= u01 * Z with u01 = the underlying torch.rand
+    draw, float32), then 100 bisection steps of the cumulative weight on [eps, T] in float32."""
+    Z = likelihood_importance_cum_weight(s.T, s.b0, s.b1, eps)
+    quantile = (0.0 + u01 * (float(Z) - 0.0)).numpy()
+    lb = np.ones_like(quantile) * eps
+    ub = np.ones_like(quantile) * s.T
+    for _ in range(steps):
+        mid = (lb + ub) / 2.0
+        value = likelihood_importance_cum_weight(mid, s.b0, s.b1, eps=eps)
+        lb = np.where(value <= quantile, mid, lb)
+        ub = np.where(value <= quantile, ub, mid)
+    return torch.tensor(np.array((lb + ub) / 2.0))
+
+
+def dsm_loss(s: SdeSpec, batch, score_fn, u, z, *, reduce_mean=True, likelihood_weighting=False, eps=1e-5, t_is=None):
+    """Denoising score matching loss.  sde_helper2.py:152-186.
+    u = torch.rand(B) and z = torch.randn_like(batch) are the reference's two draws, in that order.
+    t_is: the importance-sampled times of the `likelihood_weighting and im_sample` branch (:164-165, 177-179;
+    `importance_sampled_t`): t = t_is, loss = red((score * std + z)^2) without the g^2 weight."""
+    if t_is is not None:
+        t = t_is.to(batch.dtype)
+        mean, std = marginal_prob(s, batch, t)
+        score = score_fn(mean + _bc(std) * z, t)
+        losses = torch.square(score * _bc(std) + z).reshape(batch.shape[0], -1)
+        return torch.mean(torch.mean(losses, dim=-1) if reduce_mean else 0.5 * torch.sum(losses, dim=-1))
     t = u * (s.T - eps) + eps
     mean, std = marginal_prob(s, batch, t)
     perturbed = mean + _bc(std) * z

@@ -410,6 +410,11 @@ class _Plan:
 class UnetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, time, *params):
+        if x.requires_grad or time.requires_grad:
+            # the hand-written backward produces PARAMETER gradients only; silently returning a zero input gradient
+            # would corrupt e.g. a score Jacobian or an encoder trained through the latent
+            raise L.SbmError("Unet: gradients w.r.t. the input latent / time are not implemented on the B200 path "
+                             "(detach the input, or differentiate the parameters only)")
         plan = _Plan(model)
         with torch.no_grad():
             out = plan.forward(x.contiguous().float(), time.contiguous().float())
@@ -420,6 +425,9 @@ class UnetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         plan = ctx.plan
+        if plan is None:
+            raise L.SbmError("Unet: the backward tape was already consumed (a second backward through the same forward, "
+                             "e.g. retain_graph=True, is not supported: run the forward again)")
         with torch.no_grad():
             plan.backward(dout)
         grads = tuple(plan.pg.get(p) for p in ctx.params)

@@ -361,6 +361,9 @@ class _OPlan(_Plan):
 class UNetModelFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, timesteps, z, *params):
+        if x.requires_grad or timesteps.requires_grad or (z is not None and z.requires_grad):
+            raise L.SbmError("UNetModel: gradients w.r.t. the input latent / timesteps / conditioning code z are not "
+                             "implemented on the B200 path (detach them, or differentiate the parameters only)")
         plan = _OPlan(model)
         with torch.no_grad():
             out = plan.forward(x.contiguous().float(), timesteps.contiguous().float(),
@@ -372,6 +375,9 @@ class UNetModelFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         plan = ctx.plan
+        if plan is None:
+            raise L.SbmError("UNetModel: the backward tape was already consumed (a second backward through the same "
+                             "forward is not supported: run the forward again)")
         with torch.no_grad():
             plan.backward(dout)
         grads = tuple(plan.pg.get(p) for p in ctx.params)

@@ -128,6 +128,37 @@ __device__ __forceinline__ void sde_marginal(const SdeP& s, float t, float& mean
   }
 }
 
+// sde.discretize(x, t) -> f = fc-rule applied to x, G.  VP: DDPM rule from the discrete_betas table
+// (sde_helper2.py:373-381: f = sqrt(alpha_i) x - x, G = sqrt(beta_i), alpha_i = 1 - beta_i in fp32 like the table the
+// reference builds, :337-338); VE: SMLD rule from the discrete_sigmas table (:465-473: f = 0,
+// G = sqrt(sigma_i^2 - sigma_{i-1}^2), sigma_{-1} = 0); subVP has no override and takes the Euler-Maruyama rule of the
+// base class (:236-253: f = drift / N, G = diffusion * sqrt(1/N)).  i = (t (N-1) / T).long().
+__device__ __forceinline__ void rd_discretize(const SdeP& s, float t, float T, const float* __restrict__ table,
+                                              float& fc, float& G) {
+  if (s.kind == SBM_SDE_SUBVP) {
+    float dc, g;
+    sde_drift_diff(s, t, dc, g);
+    const float dtp = 1.f / (float)s.N;
+    fc = dc * dtp;
+    G = g * sqrtf(dtp);
+    return;
+  }
+  const int i = min(max((int)(t * (float)(s.N - 1) / T), 0), s.N - 1);
+  if (s.kind == SBM_SDE_VP) {
+    const float beta = __ldg(table + i);
+    fc = sqrtf(1.f - beta);
+    G = sqrtf(beta);
+  } else {
+    const float sigma = __ldg(table + i);
+    const float adj = i == 0 ? 0.f : __ldg(table + i - 1);
+    fc = 0.f;
+    G = sqrtf(sigma * sigma - adj * adj);
+  }
+}
+__device__ __forceinline__ float rd_f(const SdeP& s, float fc, float x) {
+  return s.kind == SBM_SDE_VP ? __fsub_rn(__fmul_rn(fc, x), x) : fc * x;
+}
+
 struct Impute {
   const float* z_obs;   // clean latents [B,M,D,D] or NULL (no imputation)
   uint32_t mask;        // bit m set = modality channel m observed
@@ -202,7 +233,8 @@ __global__ void __launch_bounds__(256)
 predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score, const float* __restrict__ t,
                  const float4* __restrict__ noise, float4* __restrict__ x_out, float4* __restrict__ x_mean_out,
                  uint32_t n_quads, FastDiv eqd, SdeP s, int ode, uint64_t seed, uint64_t draw,
-                 const uint64_t* draw_dev, uint64_t quad_offset, Impute im) {
+                 const uint64_t* draw_dev, uint64_t quad_offset, Impute im, int rd, const float* __restrict__ table,
+                 float T) {
   if (draw_dev) draw += *draw_dev;
   const float dt = -1.f / (float)s.N;
   const float sq = sqrtf(-dt);
@@ -222,18 +254,33 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
       const uint32_t q = qs[u];
       if (q >= n_quads) break;
       const uint32_t b = fdiv(q, eqd);
-      float dc, g;
-      sde_drift_diff(s, __ldg(t + b), dc, g);
-      const float g2 = g * g * (ode ? 0.5f : 1.f);
       float4 mean;
-      mean.x = xv[u].x + (dc * xv[u].x - g2 * sv[u].x) * dt;
-      mean.y = xv[u].y + (dc * xv[u].y - g2 * sv[u].y) * dt;
-      mean.z = xv[u].z + (dc * xv[u].z - g2 * sv[u].z) * dt;
-      mean.w = xv[u].w + (dc * xv[u].w - g2 * sv[u].w) * dt;
+      float gs;  // coefficient of the noise
+      if (!rd) {
+        float dc, g;
+        sde_drift_diff(s, __ldg(t + b), dc, g);
+        const float g2 = g * g * (ode ? 0.5f : 1.f);
+        mean.x = xv[u].x + (dc * xv[u].x - g2 * sv[u].x) * dt;
+        mean.y = xv[u].y + (dc * xv[u].y - g2 * sv[u].y) * dt;
+        mean.z = xv[u].z + (dc * xv[u].z - g2 * sv[u].z) * dt;
+        mean.w = xv[u].w + (dc * xv[u].w - g2 * sv[u].w) * dt;
+        gs = g * sq;
+      } else {
+        // reverse-diffusion (ancestral) rule: (f, G) = sde.discretize(x, t); rev_f = f - G^2 s [*0.5];
+        // x_mean = x - rev_f; x' = x_mean + G z   (sde_helper2.py:236-253, 319-324, 373-381, 465-473)
+        float fc, G;  // f = fc * x
+        rd_discretize(s, __ldg(t + b), T, table, fc, G);
+        const float G2 = G * G * (ode ? 0.5f : 1.f);
+        // f is formed the way the reference does (sqrt(alpha) * x - x: two roundings), then x - (f - G^2 s)
+        mean.x = xv[u].x - (rd_f(s, fc, xv[u].x) - G2 * sv[u].x);
+        mean.y = xv[u].y - (rd_f(s, fc, xv[u].y) - G2 * sv[u].y);
+        mean.z = xv[u].z - (rd_f(s, fc, xv[u].z) - G2 * sv[u].z);
+        mean.w = xv[u].w - (rd_f(s, fc, xv[u].w) - G2 * sv[u].w);
+        gs = G;
+      }
       float4 out = mean;
       if (!ode) {
         const float4 z = noise ? noise[q] : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
-        const float gs = g * sq;
         out.x += gs * z.x; out.y += gs * z.y; out.z += gs * z.z; out.w += gs * z.w;
       }
       if (x_mean_out) __stcs(x_mean_out + q, mean);
@@ -246,12 +293,17 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
 // norms: acc[0] += sum_b ||grad_b||, acc[1] += sum_b ||noise_b||  (fp64 accumulators).  One warp reduces S consecutive
 // samples at a time, S chosen so that S * (E/4) quads are a multiple of 32: every lane is busy on every trip (a
 // PolyMNIST latent has 80 quads, i.e. 2.5 warp trips per sample).
-template <int S>
+// GRAD: read the score and accumulate acc[0].  NM: noise source of acc[1]: 0 none, 1 injected buffer, 2 Philox.
+// The Philox noise norm does not depend on any data (it is a function of seed, draw id and element index), and
+// regenerating the stream is pure ALU work: <true, 2> made this kernel issue-bound at 0.35 of the HBM roofline (ncu,
+// round 1).  The samplers therefore run <false, 2> (no memory traffic at all) on a side stream next to the score-net
+// forward whose output <true, 0> then reduces at memory speed.
+template <int S, bool GRAD, int NM>
 __global__ void __launch_bounds__(256)
 corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict__ noise, double* __restrict__ acc,
                        int B, int EQ, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
                        uint64_t quad_offset) {
-  if (draw_dev) draw += *draw_dev;
+  if (NM == 2 && draw_dev) draw += *draw_dev;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int groups = (B + S - 1) / S;
@@ -264,42 +316,41 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
     float sg[S], sn[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) { sg[k] = 0.f; sn[k] = 0.f; }
-    for (int q = lane; q < total; q += 64) {
-      const bool two = q + 32 < total;
-      const float4 g0 = grad[base + q];
-      const float4 g1 = two ? grad[base + q + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
-      float n0, n1 = 0.f;
-      if (noise) {
-        const float4 z0 = noise[base + q];
-        n0 = z0.x * z0.x + z0.y * z0.y + z0.z * z0.z + z0.w * z0.w;
-        if (two) {
-          const float4 z1 = noise[base + q + 32];
-          n1 = z1.x * z1.x + z1.y * z1.y + z1.z * z1.z + z1.w * z1.w;
-        }
-      } else {
-        n0 = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q));
-        if (two) n1 = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + q + 32));
-      }
-      const float q0 = g0.x * g0.x + g0.y * g0.y + g0.z * g0.z + g0.w * g0.w;
-      const float q1 = g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w;
-      if (S == 1) {
-        sg[0] += q0 + q1;
-        sn[0] += n0 + n1;
-      } else {
-        // sample index inside the group by comparison (S <= 4): an integer division per trip costs more than the sums
-        const int qb = q + 32;
-        const int s0 = (q >= EQ) + (q >= 2 * EQ) + (q >= 3 * EQ);
-        const int s1i = (qb >= EQ) + (qb >= 2 * EQ) + (qb >= 3 * EQ);
+    for (int q = lane; q < total; q += 128) {
+      float4 gv[4];
+      float nv[4];
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
-          if (s0 == k) { sg[k] += q0; sn[k] += n0; }
-          if (two && s1i == k) { sg[k] += q1; sn[k] += n1; }
+      for (int u = 0; u < 4; ++u) {  // four 16-byte loads in flight per lane
+        const int qq = q + 32 * u;
+        const bool on = qq < total;
+        gv[u] = (GRAD && on) ? __ldcs(grad + base + qq) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nv[u] = 0.f;
+        if (NM == 1 && on) {
+          const float4 z = __ldcs(noise + base + qq);
+          nv[u] = z.x * z.x + z.y * z.y + z.z * z.z + z.w * z.w;
+        }
+        if (NM == 2 && on) nv[u] = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + qq));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int qq = q + 32 * u;
+        const float gq = gv[u].x * gv[u].x + gv[u].y * gv[u].y + gv[u].z * gv[u].z + gv[u].w * gv[u].w;
+        if (S == 1) {
+          sg[0] += gq;
+          sn[0] += nv[u];
+        } else {
+          // sample index inside the group by comparison (S <= 4): an integer division per trip costs more than the
+          // sums; out-of-range quads carry zeros
+          const int si = (qq >= EQ) + (qq >= 2 * EQ) + (qq >= 3 * EQ);
+#pragma unroll
+          for (int k = 0; k < S; ++k)
+            if (si == k) { sg[k] += gq; sn[k] += nv[u]; }
         }
       }
     }
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      const float tg = warp_sum(sg[k]), tn = warp_sum(sn[k]);
+      const float tg = GRAD ? warp_sum(sg[k]) : 0.f, tn = NM ? warp_sum(sn[k]) : 0.f;
       if (k < ns) {
         a0 += (double)sqrtf(tg);
         a1 += (double)sqrtf(tn);
@@ -511,10 +562,24 @@ static int ew_grid(int64_t n_items) {
 // blocks per SM a kernel whose registers allow only 5 runs 1.6 waves and idles ~20 % of the machine in the second one.
 template <typename K>
 static int wave_grid(K kernel, int64_t n_items, int per_thread = 1) {
-  static int per_sm = 0;  // one static per kernel type
-  if (per_sm == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+  // occupancy per kernel FUNCTION (template instantiations of one kernel share the pointer type K, not the pointer)
+  static std::atomic<const void*> keys[16];
+  static std::atomic<int> vals[16];
+  int per_sm = 0;
+  for (int i = 0; i < 16; ++i) {
+    const void* k = keys[i].load(std::memory_order_acquire);
+    if (k == (const void*)kernel) { per_sm = vals[i].load(std::memory_order_relaxed); break; }
+    if (k == nullptr) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+      const void* expect = nullptr;
+      vals[i].store(per_sm, std::memory_order_relaxed);  // a racing thread stores the same value for the same kernel
+      if (!keys[i].compare_exchange_strong(expect, (const void*)kernel, std::memory_order_release) &&
+          expect != (const void*)kernel)
+        continue;  // slot taken by another kernel meanwhile: keep looking (per_sm is already known)
+      break;
+    }
   }
+  if (per_sm <= 0) per_sm = 4;
   const int64_t want = (n_items + 256 * per_thread - 1) / (256 * per_thread);
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * per_sm));
 }
@@ -536,6 +601,46 @@ static Impute to_impute(const sbm_impute* im, int dd) {
   r.ddq = make_fastdiv((uint32_t)(dd / 4));
   if (r.mask == 0u) r.z_obs = nullptr;
   return r;
+}
+
+template <int S, bool GRAD, int NM>
+static int launch_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
+                        double* acc2, void* stream) {
+  const int EQ = ls->mods * ls->dd / 4;
+  const int groups = (ls->batch + S - 1) / S;
+  // a group moves S*EQ quads; size the grid by 128-quad warp trips so that a small batch still spreads over the SMs
+  const int blocks = wave_grid(corrector_norms_kernel<S, GRAD, NM>, (int64_t)groups * 32);
+  corrector_norms_kernel<S, GRAD, NM><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, rng ? rng->seed : 0, rng ? rng->draw : 0,
+      rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)EQ : 0);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+template <bool GRAD, int NM>
+static int dispatch_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
+                          double* acc2, void* stream) {
+  const int EQ = ls->mods * ls->dd / 4;
+  const int S = (EQ % 32 == 0) ? 1 : ((2 * EQ) % 32 == 0 ? 2 : ((4 * EQ) % 32 == 0 ? 4 : 1));
+  if (S == 1) return launch_norms<1, GRAD, NM>(ls, grad, noise, rng, acc2, stream);
+  if (S == 2) return launch_norms<2, GRAD, NM>(ls, grad, noise, rng, acc2, stream);
+  return launch_norms<4, GRAD, NM>(ls, grad, noise, rng, acc2, stream);
+}
+
+static int launch_predictor(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
+                            const float* t, const float* noise, float* x_out, float* x_mean_out,
+                            int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, int rd,
+                            const float* table, void* stream) {
+  const int E = ls->mods * ls->dd;
+  const int64_t nq = (int64_t)ls->batch * E / 4;
+  predictor_kernel<<<wave_grid(predictor_kernel, nq, 2), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,
+      (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,
+      rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
+      to_impute(impute, ls->dd), rd, table, sde->T);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
 }
 
 }  // namespace sbm
@@ -603,45 +708,35 @@ int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const flo
   if (check_latent(ls, "sbm_predictor_step")) return 1;
   SBM_CHECK_ARG(sde && x && score && t && x_out, "sbm_predictor_step: null pointer");
   SBM_CHECK_ARG(noise || rng || probability_flow, "sbm_predictor_step: need injected noise or an rng");
-  const int E = ls->mods * ls->dd;
-  const int64_t nq = (int64_t)ls->batch * E / 4;
-  predictor_kernel<<<wave_grid(predictor_kernel, nq, 2), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,
-      (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,
-      rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
-      to_impute(impute, ls->dd));
-  SBM_CUDA_OK(cudaGetLastError());
-  count_launch_s();
-  return 0;
+  return launch_predictor(ls, sde, x, score, t, noise, x_out, x_mean_out, probability_flow, rng, impute, 0, nullptr,
+                          stream);
+}
+
+int sbm_rd_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
+                          const float* t, const float* table, const float* noise, float* x_out, float* x_mean_out,
+                          int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, void* stream) {
+  if (check_latent(ls, "sbm_rd_predictor_step")) return 1;
+  SBM_CHECK_ARG(sde && x && score && t && x_out, "sbm_rd_predictor_step: null pointer");
+  SBM_CHECK_ARG(noise || rng || probability_flow, "sbm_rd_predictor_step: need injected noise or an rng");
+  SBM_CHECK_ARG(table || sde->kind == SBM_SDE_SUBVP,
+                "sbm_rd_predictor_step: VPSDE needs the discrete_betas table, VESDE the discrete_sigmas table");
+  return launch_predictor(ls, sde, x, score, t, noise, x_out, x_mean_out, probability_flow, rng, impute, 1, table,
+                          stream);
 }
 
 int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
                         double* acc2, void* stream) {
   if (check_latent(ls, "sbm_corrector_norms")) return 1;
-  SBM_CHECK_ARG(grad && acc2 && (noise || rng), "sbm_corrector_norms: null pointer");
-  const int E = ls->mods * ls->dd;
-  const int EQ = E / 4;
-  const int S = (EQ % 32 == 0) ? 1 : ((2 * EQ) % 32 == 0 ? 2 : ((4 * EQ) % 32 == 0 ? 4 : 1));
-  const int groups = (ls->batch + S - 1) / S;
-  const int blocks = S == 1 ? wave_grid(corrector_norms_kernel<1>, (int64_t)groups * 32)
-                            : (S == 2 ? wave_grid(corrector_norms_kernel<2>, (int64_t)groups * 32)
-                                      : wave_grid(corrector_norms_kernel<4>, (int64_t)groups * 32));
-  const uint64_t seed = rng ? rng->seed : 0, draw = rng ? rng->draw : 0;
-  const uint64_t* ddev = rng ? rng->draw_dev : nullptr;
-  const uint64_t qoff = rng ? rng->sample_offset * (uint64_t)EQ : 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (S == 1)
-    corrector_norms_kernel<1><<<blocks, 256, 0, st>>>((const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, seed,
-                                                      draw, ddev, qoff);
-  else if (S == 2)
-    corrector_norms_kernel<2><<<blocks, 256, 0, st>>>((const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, seed,
-                                                      draw, ddev, qoff);
-  else
-    corrector_norms_kernel<4><<<blocks, 256, 0, st>>>((const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, seed,
-                                                      draw, ddev, qoff);
-  SBM_CUDA_OK(cudaGetLastError());
-  count_launch_s();
-  return 0;
+  SBM_CHECK_ARG(grad && acc2, "sbm_corrector_norms: null pointer");
+  if (noise) return dispatch_norms<true, 1>(ls, grad, noise, nullptr, acc2, stream);
+  if (rng) return dispatch_norms<true, 2>(ls, grad, nullptr, rng, acc2, stream);
+  return dispatch_norms<true, 0>(ls, grad, nullptr, nullptr, acc2, stream);  // acc2[1] comes from sbm_noise_norm
+}
+
+int sbm_noise_norm(const sbm_latent_shape* ls, const sbm_rng* rng, double* acc2, void* stream) {
+  if (check_latent(ls, "sbm_noise_norm")) return 1;
+  SBM_CHECK_ARG(rng && acc2, "sbm_noise_norm: null pointer");
+  return dispatch_norms<false, 2>(ls, nullptr, nullptr, rng, acc2, stream);
 }
 
 int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* grad,

@@ -106,6 +106,16 @@ class GradReducer:
         self.begin()
 
     def begin(self):
+        # `loss.backward()` hands autograd VIEWS of the flat buffer; AccumulateGrad adopts them as `p.grad`.  If such a
+        # gradient is still alive when the next backward starts (zero_grad(set_to_none=False), a manual p.grad.zero_(),
+        # gradient accumulation over several backward passes), writing this pass's gradient into the slot would
+        # overwrite `p.grad` in place and autograd would then add the slot to itself (every gradient doubled from the
+        # second pass on).  Detach those gradients from the buffer first: autograd then accumulates into the private copy.
+        base = self.flat.untyped_storage().data_ptr()
+        for p in self.params:
+            g = p.grad
+            if g is not None and g.untyped_storage().data_ptr() == base:
+                p.grad = g.clone()
         self._pending = [c for _, _, c in self.buckets]
         self._seen = set()
         self._works = []
@@ -115,7 +125,8 @@ class GradReducer:
         """Called by the backward pass with the final gradient of `p`; returns the view that will hold the average."""
         off, n = self.slot[p]
         view = self.flat[off:off + n].view(p.shape)
-        view.copy_(g)
+        if g.data_ptr() != view.data_ptr():  # producers may write straight into `grad_view(p)`
+            view.copy_(g)
         if p in self._seen:
             raise RuntimeError("GradReducer: a parameter reported its gradient twice in one backward pass")
         self._seen.add(p)

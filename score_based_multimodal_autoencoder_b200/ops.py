@@ -97,8 +97,12 @@ def pack_weights_multi(packs) -> None:
     values) as ONE kernel launch.  The device descriptor table is cached per set of (source, destination) pointers."""
     if not packs:
         return
-    key = tuple((t._pack_spec[0].data_ptr(), t.data_ptr()) for t in packs)
+    # full pack geometry in the key: after a model is freed the allocator may hand the same addresses to tensors of
+    # another shape; bounded (a training run keeps re-using ONE table per model)
+    key = tuple((t._pack_spec[0].data_ptr(), t.data_ptr()) + tuple(t._pack_spec[1:]) for t in packs)
     hit = _multi_tables.get(key)
+    if hit is None and len(_multi_tables) >= 16:
+        _multi_tables.pop(next(iter(_multi_tables)))
     if hit is None:
         arr = (L.PackDesc * len(packs))()
         blocks, max_taps = 0, 1

@@ -31,6 +31,8 @@ class FusedAdam(torch.optim.Optimizer):
         ps = [p for p in group["params"] if p.grad is not None]
         for p in ps:
             st = self.state[p]
+            if "step" in st and not isinstance(st["step"], int):
+                st["step"] = int(st["step"])  # a torch.optim.Adam checkpoint stores the step as a float tensor
             if not st:
                 st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, dtype=torch.float32)
@@ -39,7 +41,8 @@ class FusedAdam(torch.optim.Optimizer):
                 raise L.SbmError("FusedAdam needs contiguous fp32 CUDA parameters")
             if not p.grad.is_contiguous():
                 p.grad = p.grad.contiguous()
-        sig = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        sig = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == sig:
             return hit[1:]
@@ -74,6 +77,7 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        stepped = False
         for gi, group in enumerate(self.param_groups):
             if not any(p.grad is not None for p in group["params"]):
                 continue
@@ -83,6 +87,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self.state[p]["step"] = step
             if self.capturable and self.step_dev is None:
                 self.step_dev = torch.full((1,), step - 1, dtype=torch.int32, device=ps[0].device)
+            stepped = True
             b1, b2 = group["betas"]
             L.check(L.lib().sbm_adam_step(L.ptr(t_dev), L.ptr(c_dev), C.c_int32(n_chunks), C.c_int32(_CHUNK),
                                           C.c_float(group["lr"]), C.c_float(b1), C.c_float(b2), C.c_float(group["eps"]),
@@ -92,7 +97,39 @@ class FusedAdam(torch.optim.Optimizer):
             # the kernel wrote the parameters through raw pointers: tell autograd (and the score net's packed-weight
             # cache, keyed by `_version`) that they changed
             torch.autograd.graph.increment_version(ps)
+        if self.capturable and stepped:
+            # the device counter is what the kernel's bias correction reads: advance it HERE (eager loops and captured
+            # graphs alike), once per step whatever the number of parameter groups
+            L.check(L.lib().sbm_train_tick(L.ptr(self.step_dev), None, C.c_uint64(0), L.stream_ptr()), "sbm_train_tick")
         return loss
+
+    def _sync_host_steps(self):
+        """Graph replays advance only the device counter: bring the host-side `state[p]['step']` up to date."""
+        if self.capturable and self.step_dev is not None:
+            n = int(self.step_dev.item())
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = n
+
+    def state_dict(self):
+        self._sync_host_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        # the moment tensors were replaced: drop the raw-pointer tables that still point at the old ones, and restart
+        # the device step counter from the loaded step
+        self._tables.clear()
+        step = 0
+        for st in self.state.values():
+            if "step" in st:
+                st["step"] = int(st["step"])
+                step = max(step, st["step"])
+            for k in ("exp_avg", "exp_avg_sq"):
+                if k in st:
+                    st[k] = st[k].float().contiguous()
+        if self.capturable and self.step_dev is not None:
+            self.step_dev.fill_(step)
 
 
 class GraphedTrainStep:
@@ -146,8 +183,8 @@ class GraphedTrainStep:
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.opt.step()
-        L.check(L.lib().sbm_train_tick(L.ptr(self.opt.step_dev), L.ptr(self.draw_dev), C.c_uint64(2), L.stream_ptr()),
-                "sbm_train_tick")
+        # (the Adam step count is advanced by FusedAdam.step itself)
+        L.check(L.lib().sbm_train_tick(None, L.ptr(self.draw_dev), C.c_uint64(2), L.stream_ptr()), "sbm_train_tick")
         return loss
 
     def close(self):

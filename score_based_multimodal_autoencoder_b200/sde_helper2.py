@@ -80,6 +80,19 @@ class SDE(abc.ABC):
     def _c(self) -> L.SdeC:
         return L.SdeC(_KIND[self._kind], float(self.beta_0), float(self.beta_1), int(self.N), float(self.T))
 
+    def _disc_table_on(self, device):
+        """Device copy of the table `discretize` indexes: discrete_betas (VPSDE) / discrete_sigmas (VESDE); None for
+        subVPSDE, which has no override and takes the base class's Euler-Maruyama rule (sde_helper2.py:236-253)."""
+        src = getattr(self, "discrete_sigmas", None) if self._kind == "ve" else (
+            self.discrete_betas if self._kind == "vp" else None)
+        if src is None:
+            return None
+        key = ("disc", str(device))
+        tab = self._dev_tables.get(key)
+        if tab is None:
+            tab = self._dev_tables[key] = src.to(device=device, dtype=torch.float32).contiguous()
+        return tab
+
     def _alphas_on(self, device):
         """Device-resident copy of `alphas` (the reference re-uploads the table on every corrector call,
         sde_helper2.py:58)."""
@@ -103,9 +116,8 @@ class _ReverseSDE:
         return self._fwd.T
 
     def sde(self, x, t, cl_g=None, cl_s=None, target=None, given=None, all_mods=None):
-        _reject_guidance(cl_g, given)
         drift, diffusion = self._fwd.sde(x, t)
-        score = self._score_fn(x, t)
+        score = _guided(self._score_fn(x, t), x, t, cl_g, cl_s, given, all_mods)
         drift = drift - _bc(diffusion) ** 2 * score * (0.5 if self.probability_flow else 1.0)
         # the reference returns the float 0. here (sde_helper2.py:316), which its own em_predictor cannot index;
         # a zero vector keeps the contract usable
@@ -241,13 +253,6 @@ class VESDE(SDE):
 
 
 # ======================================================================================= helpers
-def _reject_guidance(cl_g, given):
-    if cl_g is not None and given is not None and given:
-        raise NotImplementedError(
-            "classifier/EBM guidance (sde_helper2.py:65-94, 283-312) needs the ClwithTime2/3 energy nets, which the "
-            "reference repository does not contain; pass cl_g=None (the shipped default, --use-clg 0)")
-
-
 def _latent_shape(x) -> L.LatentShape:
     if x.dim() != 4:
         raise ValueError("latent must be [B, M, D, D]")
@@ -295,32 +300,66 @@ def _impute_struct(z_obs, obs_mask, noise_obs, t_next, t_next_dev=None):
                     t_next_dev.data_ptr() if t_next_dev is not None else None)
 
 
+_PREDICTORS = ("euler", "reverse_diffusion")
+
+
 def _predictor_kernel(sde, x, score, t, *, noise=None, rng=None, probability_flow=False, impute=None, want_mean=True,
-                      out=None):
+                      out=None, predictor="euler"):
+    """One fused launch: Euler-Maruyama (`sbm_predictor_step`) or reverse-diffusion (`sbm_rd_predictor_step`) rule."""
     ls = _latent_shape(x)
     x_new = out if out is not None else torch.empty_like(x)
     x_mean = torch.empty_like(x) if want_mean else None
     sc = sde._c()
-    L.check(L.lib().sbm_predictor_step(C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(score), L.ptr(t), L.ptr(noise),
-                                       L.ptr(x_new), L.ptr(x_mean), C.c_int32(1 if probability_flow else 0),
-                                       C.byref(rng) if rng is not None else None,
-                                       C.byref(impute) if impute is not None else None, L.stream_ptr()),
-            "sbm_predictor_step")
+    common = (L.ptr(noise), L.ptr(x_new), L.ptr(x_mean), C.c_int32(1 if probability_flow else 0),
+              C.byref(rng) if rng is not None else None, C.byref(impute) if impute is not None else None,
+              L.stream_ptr())
+    if predictor == "euler":
+        L.check(L.lib().sbm_predictor_step(C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(score), L.ptr(t), *common),
+                "sbm_predictor_step")
+    elif predictor == "reverse_diffusion":
+        L.check(L.lib().sbm_rd_predictor_step(C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(score), L.ptr(t),
+                                              L.ptr(sde._disc_table_on(x.device)), *common), "sbm_rd_predictor_step")
+    else:
+        raise ValueError(f"predictor must be one of {_PREDICTORS}, got {predictor!r}")
     return x_new, x_mean
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(dev):
+    s = _side_streams.get(dev.index)
+    if s is None:
+        s = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def _fork_noise_norm(x, rng, acc):
+    """acc[1] += sum_b ||noise_b|| of the Philox draw `rng`, on a side stream: the draw depends on no data, so it runs
+    beside the score-net forward that produces the other operand of the corrector's step size (sde_helper2.py:96-99).
+    Returns the stream to join (`torch.cuda.current_stream().wait_stream(side)`) before the norms are consumed."""
+    ls = _latent_shape(x)
+    side = _side_stream(x.device)
+    side.wait_stream(torch.cuda.current_stream())
+    L.check(L.lib().sbm_noise_norm(C.byref(ls), C.byref(rng), L.ptr(acc), C.c_void_p(side.cuda_stream)),
+            "sbm_noise_norm")
+    return side
+
+
 def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, impute=None, want_mean=True,
-                       global_batch=None, reduce_fn=None, acc=None, out=None):
+                       global_batch=None, reduce_fn=None, acc=None, out=None, noise_norm_done=False):
     """norms kernel -> (optional cross-rank sum of the two batch norms) -> update kernel.  `acc` is a zeroed buffer of
-    3 doubles (2 sums + a completion ticket); the update kernel re-zeroes it, so a reused `acc` never needs a memset."""
+    3 doubles (2 sums + a completion ticket); the update kernel re-zeroes it, so a reused `acc` never needs a memset.
+    `noise_norm_done`: acc[1] already holds the Philox noise norm (`_fork_noise_norm`), the norms kernel reads the
+    score only."""
     ls = _latent_shape(x)
     if acc is None:
         acc = torch.zeros(3, dtype=torch.float64, device=x.device)
     elif acc.numel() < 3:
         raise L.SbmError("corrector accumulator needs 3 doubles (2 sums + ticket)")
     rp = C.byref(rng) if rng is not None else None
-    L.check(L.lib().sbm_corrector_norms(C.byref(ls), L.ptr(grad), L.ptr(noise), rp, L.ptr(acc), L.stream_ptr()),
-            "sbm_corrector_norms")
+    L.check(L.lib().sbm_corrector_norms(C.byref(ls), L.ptr(grad), L.ptr(noise), None if noise_norm_done else rp,
+                                        L.ptr(acc), L.stream_ptr()), "sbm_corrector_norms")
     if reduce_fn is not None:  # multi-GPU exact mode: sum the two batch norms over ranks
         reduce_fn(acc[:2])
     x_new = out if out is not None else torch.empty_like(x)
@@ -343,11 +382,18 @@ def _call_score(score_fn, x, t, z_cond):
     return score_fn(x, t) if z_cond is None else score_fn(x, t, z=z_cond)
 
 
+def _guided(score, x, t, cl_g, cl_s, given, all_mods):
+    """Classifier / EBM guidance of the score (sde_helper2.py:65-94, 283-312); a no-op without `cl_g` or `given`."""
+    if cl_g is None or given is None or not given:
+        return score
+    from .guidance import apply_guidance
+    return apply_guidance(score, x, t, cl_g, cl_s, given, all_mods)
+
+
 def em_predictor(x, t, score_fn, sde, probability_flow=False, cl_g=None, cl_s=None, target=None, given=None,
                  all_mods=None, z_cond=None, *, noise=None, rng="torch"):
     """Euler-Maruyama reverse-SDE predictor step (sde_helper2.py:45-52) -> (x, x_mean).
     One fused kernel after the score-net call; the noise is drawn BEFORE the net call like the reference."""
-    _reject_guidance(cl_g, given)
     _need_cuda(x, t)
     x, t = _f32c(x), _f32c(t)
     r = None
@@ -357,21 +403,28 @@ def em_predictor(x, t, score_fn, sde, probability_flow=False, cl_g=None, cl_s=No
         else:
             r = _rng.next()
     score = _f32c(_call_score(score_fn, x, t, z_cond))
+    score = _guided(score, x, t, cl_g, cl_s, given, all_mods)
     return _predictor_kernel(sde, x, score, t, noise=noise, rng=r, probability_flow=probability_flow)
 
 
-def rd_predictor(x, t, score_fn, sde, probability_flow=False, z_cond=None, *, noise=None):
+def rd_predictor(x, t, score_fn, sde, probability_flow=False, z_cond=None, *, noise=None, rng="torch"):
     """Reverse-diffusion (ancestral) predictor step -> (x, x_mean):
         (rev_f, rev_G) = sde.reverse(score_fn, probability_flow).discretize(x, t);  x_mean = x - rev_f;
         x = x_mean + rev_G * z.
-    The reference ships this discretisation (sde_helper2.py:236-253, 319-324, 373-381) but no caller (SURVEY.md 8a-6);
-    this is the API-complete thin wrapper over the SDE classes' tensor expressions -- a handful of elementwise torch
-    ops on the caller's device next to the score-net call, not a fused kernel and not on the measured path."""
-    fn = score_fn if z_cond is None else (lambda a, b: _call_score(score_fn, a, b, z_cond))
-    z = torch.randn_like(x) if noise is None else noise     # drawn before the net call, like em_predictor (:47)
-    rev_f, rev_G = sde.reverse(fn, probability_flow).discretize(x, t)
-    x_mean = x - rev_f
-    return x_mean + _bc(rev_G) * z, x_mean
+    The reference ships this discretisation (sde_helper2.py:236-253, 319-324, 373-381, 465-473) without a caller
+    (SURVEY.md 8a-6); here it is a mode of the fused predictor kernel (`sbm_rd_predictor_step`, same 12 B / element)
+    and selectable in the N-step samplers with `predictor="reverse_diffusion"`."""
+    _need_cuda(x, t)
+    x, t = _f32c(x), _f32c(t)
+    r = None
+    if noise is None and not probability_flow:
+        if rng == "torch":
+            noise = torch.randn_like(x)     # drawn before the net call, like em_predictor (:47)
+        else:
+            r = _rng.next()
+    score = _f32c(_call_score(score_fn, x, t, z_cond))
+    return _predictor_kernel(sde, x, score, t, noise=noise, rng=r, probability_flow=probability_flow,
+                             predictor="reverse_diffusion")
 
 
 def corrector(x, t, score_fn, sde, n_steps, target_snr, cl_g=None, cl_s=None, target=None, given=None, all_mods=None,
@@ -379,21 +432,25 @@ def corrector(x, t, score_fn, sde, n_steps, target_snr, cl_g=None, cl_s=None, ta
     """Langevin corrector (sde_helper2.py:54-106) -> (x, x_mean).  Two fused kernels per Langevin step
     (batch-coupled norms, then the update); the noise is drawn AFTER the net call like the reference.
     `noise`: optional [n_steps, B, M, D, D] injected noise."""
-    _reject_guidance(cl_g, given)
     _need_cuda(x, t)
     x, t = _f32c(x), _f32c(t)
     x_mean = x
+    acc = torch.zeros(3, dtype=torch.float64, device=x.device)
     for i in range(n_steps):
-        grad = _f32c(_call_score(score_fn, x, t, z_cond))
-        nz, r = None, None
+        nz, r, side = None, None, None
         if noise is not None:
             nz = noise[i] if noise.dim() == 5 else noise
-        elif rng == "torch":
-            nz = torch.randn_like(x)
-        else:
+        elif rng != "torch":
             r = _rng.next()
+            side = _fork_noise_norm(x, r, acc)
+        grad = _f32c(_call_score(score_fn, x, t, z_cond))
+        grad = _guided(grad, x, t, cl_g, cl_s, given, all_mods)
+        if nz is None and r is None:
+            nz = torch.randn_like(x)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         x, x_mean = _corrector_kernels(sde, x, grad, t, target_snr, noise=nz, rng=r, global_batch=global_batch,
-                                       reduce_fn=reduce_fn)
+                                       reduce_fn=reduce_fn, acc=acc, noise_norm_done=side is not None)
     return x, x_mean
 
 
@@ -407,162 +464,295 @@ def _obs_mask_from(given, all_mods) -> int:
     return mask
 
 
+class _PCRun:
+    """The per-step arithmetic of one predictor-corrector run over fixed buffers.
+
+    Semantics = the reference's inline loop (train_lat_celebhq_unet_cont2.py:287-316 for predictor_first=True,
+    :173-200 / sde_helper2.py:121-128 for predictor_first=False).  Per step: 2 score-net forwards + the fused
+    elementwise kernels (predictor, corrector norms, corrector update; the Philox noise norm beside the net on a side
+    stream); the imputation of the observed channels for step i+1 is an epilogue of the last kernel of step i.
+    `z_obs` / `z_cond` are the buffers the steps READ (static copies when the step is captured into a CUDA graph)."""
+
+    def __init__(self, model, sde, B, dev, *, z_obs, obs_mask, z_cond, eps, noise_obs, pc, n_steps, target_snr,
+                 predictor_first, probability_flow, predictor, global_batch, reduce_fn, guidance=None):
+        if predictor not in _PREDICTORS:
+            raise ValueError(f"predictor must be one of {_PREDICTORS}, got {predictor!r}")
+        self.model, self.sde, self.dev, self.B = model, sde, dev, B
+        self.z_obs, self.obs_mask, self.z_cond = z_obs, obs_mask, z_cond
+        self.conditional = z_obs is not None and obs_mask != 0
+        self.noise_obs, self.pc, self.n_steps, self.target_snr = noise_obs, pc, n_steps, target_snr
+        self.predictor_first, self.probability_flow, self.predictor = predictor_first, probability_flow, predictor
+        self.global_batch, self.reduce_fn, self.guidance = global_batch, reduce_fn, guidance
+        self.N = sde.N
+        self.ts = torch.linspace(sde.T, eps, sde.N, device=dev)
+        self.ts_host = self.ts.tolist()
+        self.t_vec = torch.empty(B, device=dev, dtype=torch.float32)
+        self.acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.n_draws = (0 if probability_flow else 1) + (n_steps if pc else 0)
+
+    def _score(self, x):
+        s = _call_score(self.model, x, self.t_vec, self.z_cond)
+        if self.guidance is not None:
+            cl_g, cl_s, given, all_mods = self.guidance
+            s = _guided(_f32c(s), x, self.t_vec, cl_g, cl_s, given, all_mods)
+        return s
+
+    def impute(self, x, t, noise_obs):
+        """x[:, observed] <- (noised) clean latents, in place (first step / finishing)."""
+        if not self.conditional:
+            return
+        ls, sc = _latent_shape(x), self.sde._c()
+        im = _impute_struct(self.z_obs, self.obs_mask, noise_obs, t)
+        L.check(L.lib().sbm_impute_observed(C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(x), C.byref(im),
+                                            L.stream_ptr()), "sbm_impute_observed")
+
+    def step(self, i, x, *, last, graph_state=None, noise_pred=None, noise_corr=None, torch_rng=False):
+        """Runs step i on x -> (x, x_mean or None).  `graph_state` = (t_next_dev, draw_dev) when the step is being
+        captured for replay (t_vec is then maintained by sbm_sampler_tick)."""
+        t_next_dev, draw_dev = graph_state if graph_state is not None else (None, None)
+        t_vec, sde, pf = self.t_vec, self.sde, self.probability_flow
+        if graph_state is None:
+            t_vec.fill_(self.ts_host[i])
+        im = None
+        if self.conditional and not last:
+            im = _impute_struct(self.z_obs, self.obs_mask, self.noise_obs, self.ts_host[min(i + 1, self.N - 1)],
+                                t_next_dev)
+        inject = noise_pred is not None
+
+        def predictor(x, impute, want_mean):
+            nz = noise_pred[i] if inject else None
+            if torch_rng and not pf:
+                nz = torch.randn_like(x)  # reference order: drawn BEFORE the net call (sde_helper2.py:47)
+            r = None if (nz is not None or pf) else _rng.next(draw_dev)
+            score = self._score(x)
+            return _predictor_kernel(sde, x, score, t_vec, noise=nz, rng=r, probability_flow=pf, impute=impute,
+                                     want_mean=want_mean, predictor=self.predictor)
+
+        def langevin(x, impute, want_mean):
+            xm = x
+            for k in range(self.n_steps):
+                nz = noise_corr[i, k] if inject else None
+                r, side = None, None
+                if nz is None and not torch_rng:
+                    r = _rng.next(draw_dev)
+                    side = _fork_noise_norm(x, r, self.acc)
+                grad = self._score(x)
+                if torch_rng:
+                    nz = torch.randn_like(x)  # reference order: drawn AFTER the net call (sde_helper2.py:96)
+                if side is not None:
+                    torch.cuda.current_stream().wait_stream(side)
+                final_k = k == self.n_steps - 1
+                x, xm = _corrector_kernels(sde, x, grad, t_vec, self.target_snr, noise=nz, rng=r,
+                                           impute=impute if final_k else None, want_mean=want_mean and final_k,
+                                           global_batch=self.global_batch, reduce_fn=self.reduce_fn, acc=self.acc,
+                                           noise_norm_done=side is not None)
+            return x, xm
+
+        if self.predictor_first:
+            if self.pc:
+                x, _ = predictor(x, None, False)
+                return langevin(x, im, last)
+            return predictor(x, im, last)
+        if self.pc:
+            x, _ = langevin(x, None, False)
+        return predictor(x, im, last)
+
+
 @torch.no_grad()
 def pc_sampler(x0, model, sde, *, z_obs=None, obs_mask=0, eps=1e-3, noise_obs=True, pc=True, n_steps=1,
                target_snr=0.16, predictor_first=True, probability_flow=False, noise_pred=None, noise_corr=None,
                num_steps=None, global_batch=None, reduce_fn=None, use_graph=False, return_state=False,
-               rng="philox", z_cond=None):
-    """N-step predictor-corrector sampler over a stacked latent [B,M,D,D] with observed-modality imputation.
+               rng="philox", z_cond=None, predictor="euler", cl_g=None, cl_s=None, given=None, all_mods=None):
+    """N-step predictor-corrector sampler over a stacked latent [B,M,D,D] with observed-modality imputation
+    (see `_PCRun`).  Returns the last x_mean with the observed channels set to the clean latents.
 
-    Semantics = the reference's inline loop (train_lat_celebhq_unet_cont2.py:287-316 for predictor_first=True,
-    :173-200 / sde_helper2.py:121-128 for predictor_first=False).  Per step: 2 score-net forwards + 3 fused
-    elementwise kernels (predictor, corrector norms, corrector update); the imputation of the observed channels
-    for step i+1 is an epilogue of the last kernel of step i.  Returns the last x_mean with the observed
-    channels set to the clean latents.
-    """
+    predictor : "euler" (em_predictor, the reference's sampler) or "reverse_diffusion" (the discretize() rule);
+    use_graph : replay ONE captured CUDA graph per step; the capture is cached across calls (same model weights,
+                shapes and options), so repeated calls cost a copy-in plus the replays;
+    cl_g, cl_s, given, all_mods : classifier / EBM guidance of both score evaluations (sde_helper2.py:65-94, 283-312)."""
     _need_cuda(x0)
     dev = x0.device
-    x = _f32c(x0).clone()
-    B = x.shape[0]
-    N = sde.N
-    steps = N if num_steps is None else num_steps
-    ts = torch.linspace(sde.T, eps, N, device=dev)
-    ts_host = ts.tolist()
-    conditional = z_obs is not None and obs_mask != 0
-    if conditional:
-        z_obs = _f32c(z_obs)
-        ls = _latent_shape(x)
-        sc = sde._c()
-        im0 = _impute_struct(z_obs, obs_mask, noise_obs, ts_host[0])
-        L.check(L.lib().sbm_impute_observed(C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(x), C.byref(im0),
-                                            L.stream_ptr()), "sbm_impute_observed")
+    B = x0.shape[0]
+    steps = sde.N if num_steps is None else num_steps
     inject = noise_pred is not None
     torch_rng = (rng == "torch") and not inject
-    t_vec = torch.empty(B, device=dev, dtype=torch.float32)
-    acc = torch.zeros(3, dtype=torch.float64, device=dev)
+    guidance = (cl_g, cl_s, given, all_mods) if (cl_g is not None and given) else None
+    opts = dict(obs_mask=obs_mask if z_obs is not None else 0, eps=eps, noise_obs=noise_obs, pc=pc, n_steps=n_steps,
+                target_snr=target_snr, predictor_first=predictor_first, probability_flow=probability_flow,
+                predictor=predictor, global_batch=global_batch, reduce_fn=reduce_fn, guidance=guidance)
+    if use_graph and steps >= 1 and not inject and not torch_rng and guidance is None:
+        return _graph_cache.run(model, sde, x0, z_obs, z_cond, steps, opts, return_state)
+    x = _f32c(x0).clone()
+    run = _PCRun(model, sde, B, dev, z_obs=_f32c(z_obs) if opts["obs_mask"] else None,
+                 z_cond=z_cond, **opts)
+    run.impute(x, run.ts_host[0], noise_obs)
     x_mean = x
-
-    def one_step(i, x, *, last, graph_state=None):
-        """Runs step i; `graph_state` = (t_next_dev, draw_dev) when the step is being captured for replay."""
-        t_next_dev, draw_dev = graph_state if graph_state is not None else (None, None)
-        if graph_state is None:
-            t_vec.fill_(ts_host[i])
-        im = None
-        if conditional and not last:
-            im = _impute_struct(z_obs, obs_mask, noise_obs, ts_host[min(i + 1, N - 1)], t_next_dev)
-
-        def predictor(x, impute, want_mean):
-            nz = noise_pred[i] if inject else None
-            if torch_rng and not probability_flow:
-                nz = torch.randn_like(x)  # reference order: drawn BEFORE the net call (sde_helper2.py:47)
-            r = None if (nz is not None or probability_flow) else _rng.next(draw_dev)
-            score = _call_score(model, x, t_vec, z_cond)
-            return _predictor_kernel(sde, x, score, t_vec, noise=nz, rng=r, probability_flow=probability_flow,
-                                     impute=impute, want_mean=want_mean)
-
-        def langevin(x, impute, want_mean):
-            xm = x
-            for k in range(n_steps):
-                grad = _call_score(model, x, t_vec, z_cond)
-                nz = noise_corr[i, k] if inject else None
-                if torch_rng:
-                    nz = torch.randn_like(x)  # reference order: drawn AFTER the net call (sde_helper2.py:96)
-                r = None if nz is not None else _rng.next(draw_dev)
-                final_k = k == n_steps - 1
-                x, xm = _corrector_kernels(sde, x, grad, t_vec, target_snr, noise=nz, rng=r,
-                                           impute=impute if final_k else None, want_mean=want_mean and final_k,
-                                           global_batch=global_batch, reduce_fn=reduce_fn, acc=acc)
-            return x, xm
-
-        if predictor_first:
-            if pc:
-                x, _ = predictor(x, None, False)
-                return langevin(x, im, last)
-            return predictor(x, im, last)
-        if pc:
-            x, _ = langevin(x, None, False)
-        return predictor(x, im, last)
-
-    if use_graph and steps > 2 and not inject and not torch_rng:
-        x, x_mean = _graph_replay(one_step, x, steps, ts, t_vec, n_draws=(1 if not probability_flow else 0) +
-                                  (n_steps if pc else 0))
-    else:
-        for i in range(steps):
-            last = i == steps - 1
-            x, xm = one_step(i, x, last=last)
-            if last:
-                x_mean = xm
+    for i in range(steps):
+        last = i == steps - 1
+        x, xm = run.step(i, x, last=last, noise_pred=noise_pred, noise_corr=noise_corr, torch_rng=torch_rng)
+        if last:
+            x_mean = xm
     out = x_mean
-    if conditional:
-        ls = _latent_shape(out)
-        sc = sde._c()
-        imf = _impute_struct(z_obs, obs_mask, False, 0.0)
-        L.check(L.lib().sbm_impute_observed(C.byref(ls), C.byref(sc), L.ptr(out), L.ptr(out), C.byref(imf),
-                                            L.stream_ptr()), "sbm_impute_observed")
+    run.impute(out, 0.0, False)
     return (out, x) if return_state else out
 
 
-def _graph_replay(one_step, x, steps, ts, t_vec, n_draws):
-    """Capture ONE predictor-corrector step (2 net forwards + the fused sampler kernels) into a CUDA graph and replay
-    it for steps 0..steps-2; every per-step quantity (t, t_next, Philox draw id) lives in device memory and is
-    advanced by the sbm_sampler_tick kernel inside the graph.  The last step runs eagerly (it alone writes x_mean
-    and skips the imputation)."""
-    dev = x.device
-    B = x.shape[0]
-    step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-    draw_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-    t_next_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-    x_static = x.clone()
-    base_draw = _rng.draw
+class _PCGraph:
+    """ONE predictor-corrector step (2 net forwards + the fused sampler kernels) captured as a CUDA graph over static
+    buffers, plus the variant for the final step (writes x_mean, skips the imputation, finishes with the clean
+    observed latents).  Every per-step quantity (t, t_next, Philox draw id) lives in device memory and is advanced by
+    the sbm_sampler_tick kernel inside the graph, so the same graph serves all N steps (graph replay equals the eager
+    loop bit for bit -- tests/test_sampler_gpu.py)."""
 
-    def tick(advance):
-        L.check(L.lib().sbm_sampler_tick(L.ptr(ts), C.c_int32(ts.numel()), L.ptr(step_dev), L.ptr(draw_dev),
-                                         L.ptr(t_vec), C.c_int32(B), L.ptr(t_next_dev), C.c_int32(advance),
-                                         C.c_uint64(n_draws), L.stream_ptr()), "sbm_sampler_tick")
+    def __init__(self, model, sde, x0, z_obs, z_cond, opts):
+        dev = x0.device
+        B = x0.shape[0]
+        self.x = torch.empty_like(x0, dtype=torch.float32).contiguous()
+        self.out = torch.empty_like(self.x)
+        self.z_obs = torch.empty_like(self.x) if opts["obs_mask"] else None
+        self.z_cond = torch.empty_like(z_cond) if z_cond is not None else None
+        self.run = _PCRun(model, sde, B, dev, z_obs=self.z_obs, z_cond=self.z_cond, **opts)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.draw_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.t_next_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.graphs = {}
+        self.launches = {}
+        self.seed = (_rng.seed, _rng.sample_offset)
 
-    def body():
-        tick(0)
-        _rng.draw = base_draw  # the device counter supplies the per-step offset
-        xn, _ = one_step(0, x_static, last=False, graph_state=(t_next_dev, draw_dev))
-        x_static.copy_(xn)
-        tick(1)
+    def _tick(self, advance):
+        r = self.run
+        L.check(L.lib().sbm_sampler_tick(L.ptr(r.ts), C.c_int32(r.ts.numel()), L.ptr(self.step_dev),
+                                         L.ptr(self.draw_dev), L.ptr(r.t_vec), C.c_int32(r.B), L.ptr(self.t_next_dev),
+                                         C.c_int32(advance), C.c_uint64(r.n_draws), L.stream_ptr()),
+                "sbm_sampler_tick")
 
-    # warm-up on a side stream (packs weights, sizes the allocator), then restore the state and capture
-    s = torch.cuda.Stream(device=dev)
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        body()
-    torch.cuda.current_stream().wait_stream(s)
-    x_static.copy_(x)
-    step_dev.zero_()
-    draw_dev.zero_()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        body()
-    x_static.copy_(x)
-    step_dev.zero_()
-    draw_dev.zero_()
-    for _ in range(steps - 1):
+    def _body(self, last):
+        self._tick(0)
+        host_draw = _rng.draw
+        _rng.draw = 0  # the device counter carries the whole draw id
+        try:
+            xn, xm = self.run.step(0, self.x, last=last, graph_state=(self.t_next_dev, self.draw_dev))
+        finally:
+            _rng.draw = host_draw
+        self.x.copy_(xn)
+        if last:
+            self.out.copy_(xm)
+            self.run.impute(self.out, 0.0, False)
+        self._tick(1)
+
+    def _capture(self, last):
+        dev = self.x.device
+        keep = (self.x.clone(), self.step_dev.clone(), self.draw_dev.clone())
+        # warm-up on a side stream (packs weights, sizes the allocator), then restore the state and capture
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._body(last)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(dev)
+        n0 = L.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._body(last)
+        self.launches[last] = L.launch_count() - n0
+        self.x.copy_(keep[0])
+        self.step_dev.copy_(keep[1])
+        self.draw_dev.copy_(keep[2])
+        self.graphs[last] = g
+        return g
+
+    def sample(self, x0, z_obs, z_cond, steps, return_state):
+        r = self.run
+        self.x.copy_(x0)
+        if self.z_obs is not None:
+            self.z_obs.copy_(z_obs)
+        if self.z_cond is not None:
+            self.z_cond.copy_(z_cond)
+        self.step_dev.zero_()
+        self.draw_dev.fill_(_rng.draw)
+        r.impute(self.x, r.ts_host[0], r.noise_obs)
+        if steps > 1:
+            g = self.graphs.get(False) or self._capture(False)
+            for _ in range(steps - 1):
+                g.replay()
+        g = self.graphs.get(True) or self._capture(True)
         g.replay()
-    # final step, eager
-    _rng.draw = base_draw + (steps - 1) * n_draws
-    x_fin, x_mean = one_step(steps - 1, x_static, last=True)
-    return x_fin, x_mean
+        _rng.draw += steps * r.n_draws
+        out = self.out.clone()
+        return (out, self.x.clone()) if return_state else out
+
+
+class _GraphCache:
+    """Captured sampler steps, kept across calls.  An entry is valid for one (model, weight versions, SDE, latent shape,
+    sampler options, Philox seed / shard offset); a changed weight re-captures in place.  Bounded (LRU): a captured
+    CelebA-sized step owns a private pool of a few GB of activations."""
+
+    max_entries = 4
+
+    def __init__(self):
+        self.entries: dict = {}
+
+    @staticmethod
+    def _weights_sig(model):
+        params = getattr(model, "parameters", None)
+        if params is None:
+            return None
+        return tuple((p.data_ptr(), p._version) for p in params())
+
+    def run(self, model, sde, x0, z_obs, z_cond, steps, opts, return_state):
+        import weakref
+        x0 = _f32c(x0)
+        conditional = bool(opts["obs_mask"])
+        key = (id(model), type(sde).__name__, float(sde.beta_0), float(sde.beta_1), int(sde.N), tuple(x0.shape),
+               str(x0.device), None if z_cond is None else (tuple(z_cond.shape), z_cond.dtype),
+               tuple((k, id(v) if callable(v) else v) for k, v in sorted(opts.items()) if k != "guidance"),
+               _rng.seed, _rng.sample_offset)
+        sig = self._weights_sig(model)
+        hit = self.entries.pop(key, None)
+        if hit is not None and (hit[0]() is not model or hit[1] != sig):
+            hit = None  # another object at the same address, or the weights changed: capture again
+        if hit is None:
+            try:
+                ref = weakref.ref(model)
+            except TypeError:  # plain functions / lambdas used as score nets in tests
+                ref = (lambda m: (lambda: m))(model)
+            hit = (ref, sig, _PCGraph(model, sde, x0, z_obs if conditional else None, z_cond, opts))
+        self.entries[key] = hit  # most recent last
+        while len(self.entries) > self.max_entries:
+            self.entries.pop(next(iter(self.entries)))
+        return hit[2].sample(x0, _f32c(z_obs) if conditional else None, z_cond, steps, return_state)
+
+    def clear(self):
+        self.entries.clear()
+
+    def launches_per_step(self):
+        """kernels per replayed step of the most recently used entry: {False: mid step, True: final step}"""
+        if not self.entries:
+            return {}
+        return dict(next(reversed(self.entries.values()))[2].launches)
+
+
+_graph_cache = _GraphCache()
+
+
+def clear_graph_cache():
+    """Drop every cached sampler graph (and the activation pools they own)."""
+    _graph_cache.clear()
 
 
 def uncond_sampler(sample_shape, model, device, sde, eps=1e-3, probability_flow=False, pc=False, n_steps=1,
-                   target_snr=0.16, cl_g=None, cl_s=None, target=None, *, rng="philox", use_graph=False):
-    """sde_helper2.py:115-128: prior -> N x (corrector if pc; predictor) -> x_mean."""
-    if cl_g is not None:
-        raise NotImplementedError("guidance is not part of the B200 path (see _reject_guidance)")
+                   target_snr=0.16, cl_g=None, cl_s=None, target=None, *, rng="philox", use_graph=False,
+                   predictor="euler"):
+    """sde_helper2.py:115-128: prior -> N x (corrector if pc; predictor) -> x_mean.  `cl_g` is accepted and inert, as
+    in the reference: uncond_sampler passes no `given` to its step functions (:125-126), so guidance never fires."""
     device = torch.device(device)
     if rng == "torch":
         x = sde.prior_sampling(sample_shape).to(device)  # CPU draw + H2D, exactly like the reference (:118)
         return pc_sampler(x, model, sde, eps=eps, pc=pc, n_steps=n_steps, target_snr=target_snr,
-                          predictor_first=False, probability_flow=probability_flow, rng="torch")
+                          predictor_first=False, probability_flow=probability_flow, rng="torch", predictor=predictor)
     x = randn(sample_shape, device, scale=float(sde.sigma_max) if isinstance(sde, VESDE) else 1.0)
     return pc_sampler(x, model, sde, eps=eps, pc=pc, n_steps=n_steps, target_snr=target_snr, predictor_first=False,
-                      probability_flow=probability_flow, use_graph=use_graph)
+                      probability_flow=probability_flow, use_graph=use_graph, predictor=predictor)
 
 
 def randn(shape, device, scale=1.0):
@@ -580,12 +770,14 @@ def randn(shape, device, scale=1.0):
 def cond_sampler(z_obs, given, all_mods, model, sde, eps=1e-3, noise_obs=True, pc=True, n_steps=1, target_snr=0.16,
                  pc_order="predictor_first", probability_flow=False, *, x_init=None, dim=None, use_graph=False,
                  global_batch=None, reduce_fn=None, noise_pred=None, noise_corr=None, num_steps=None, rng="philox",
-                 z_cond=None):
+                 z_cond=None, predictor="euler", cl_g=None, cl_s=None):
     """Conditional generation: sample the missing modalities given the observed ones.
 
     z_obs   : dict {mod: [B, size_z]} of clean encoder latents for the observed modalities (the reference's
               `z[mod]`), or an already stacked [B, M, D, D] tensor (only the `given` channels are read);
-    given   : string of observed modality keys (e.g. '0', '12'); all_mods: string of all keys in channel order
+    given   : string of observed modality keys (e.g. '0', '12'); all_mods: string of all keys in channel order;
+    cl_g, cl_s : optional classifier / EBM guidance (dict of pair energies or one index-conditioned energy net and its
+              scale, train_lat_celebhq_unet_cont2.py:305-312)
     Returns the stacked latent [B, M, D, D]: missing channels = final x_mean, observed channels = clean latents
     (train_lat_celebhq_unet_cont2.py:314-316)."""
     mask = _obs_mask_from(given, all_mods)
@@ -609,7 +801,7 @@ def cond_sampler(z_obs, given, all_mods, model, sde, eps=1e-3, noise_obs=True, p
                       n_steps=n_steps, target_snr=target_snr, predictor_first=(pc_order == "predictor_first"),
                       probability_flow=probability_flow, use_graph=use_graph, global_batch=global_batch,
                       reduce_fn=reduce_fn, noise_pred=noise_pred, noise_corr=noise_corr, num_steps=num_steps, rng=rng,
-                      z_cond=z_cond)
+                      z_cond=z_cond, predictor=predictor, cl_g=cl_g, cl_s=cl_s, given=given, all_mods=all_mods)
 
 
 # ======================================================================================= DSM loss

@@ -282,6 +282,48 @@ def test_fused_adam_matches_torch_adam():
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
 
 
+def test_fused_adam_capturable_eager_loop_state_dict_and_resume():
+    """(1) FusedAdam(capturable=True) in a plain eager loop advances its device step counter itself (bias
+    correction not frozen at step 1); (2) state_dict() reports the true step; (3) load_state_dict of a torch.optim.Adam
+    checkpoint works (float-tensor steps) and the kernel then writes the LOADED moment tensors."""
+    from score_based_multimodal_autoencoder_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(1)
+    shapes = [(300, 17), (70000,)]
+    p_ref = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    p_cap = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    o_ref = torch.optim.Adam(p_ref, lr=5e-4)
+    o_cap = FusedAdam(p_cap, lr=5e-4, capturable=True)
+    grads = [[torch.randn(s, generator=g).cuda() for s in shapes] for _ in range(9)]
+    for it in range(6):
+        for a, b, gr in zip(p_ref, p_cap, grads[it]):
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o_ref.step()
+        o_cap.step()
+    for a, b in zip(p_ref, p_cap):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    sd = o_cap.state_dict()
+    assert all(int(st["step"]) == 6 for st in sd["state"].values())
+    # resume a fresh FusedAdam from torch.optim.Adam's checkpoint and continue in lock-step
+    p_new = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    o_new = FusedAdam(p_new, lr=5e-4)
+    for b, gr in zip(p_new, grads[0]):   # one throw-away step so that tables / moments exist before the load
+        b.grad = gr.clone()
+    o_new.step()
+    with torch.no_grad():
+        for b, a in zip(p_new, p_ref):
+            b.copy_(a)
+    o_new.load_state_dict(o_ref.state_dict())
+    for it in range(6, 9):
+        for a, b, gr in zip(p_ref, p_new, grads[it]):
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o_ref.step()
+        o_new.step()
+    for a, b in zip(p_ref, p_new):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    for a, b in zip(p_ref, p_new):
+        assert torch.allclose(o_ref.state[a]["exp_avg_sq"], o_new.state[b]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+
+
 # DSM-loss curve of the UNMODIFIED reference (unet_model.Unet(dim=32, channels=5, dim_mults=(1,2)) under torch.manual_seed(0),
 # torch.optim.Adam(lr=5e-4), fixed batch / u / z from torch.Generator().manual_seed(3), fp32 CPU), generated in the build
 # container with the reference modules imported from /root/reference (same recipe as oracle/gen_golden.py).
@@ -354,6 +396,8 @@ def test_graphed_train_step_equals_eager_steps():
     den = sum((pe.double() ** 2).sum() for pe in m_e.parameters())
     assert (num / den).sqrt().item() < 5e-3
     assert step.launches_per_step > 100
+    # graph replays advance only the device counter; state_dict() still reports the true number of steps
+    assert all(int(st["step"]) == 2 + len(batches) for st in step.opt.state_dict()["state"].values())
 
 
 def test_update_ema_matches_reference_semantics():

@@ -116,3 +116,43 @@ def _ddp_wrapper(rank, world):
 
 def test_data_parallel_wrapper_broadcasts_and_keeps_schema_gloo():
     _run(_ddp_wrapper)
+
+
+class _SinkFn(torch.autograd.Function):
+    """Stand-in for the score net's autograd node: reports the gradient through the reducer like autograd._Plan does."""
+
+    @staticmethod
+    def forward(ctx, red, p, scale):
+        ctx.red, ctx.p, ctx.scale = red, p, scale
+        return (p * scale).sum()
+
+    @staticmethod
+    def backward(ctx, dout):
+        ctx.red.begin()
+        g = ctx.red.grad_ready(ctx.p, torch.full(ctx.p.shape, ctx.scale) * dout)
+        ctx.red.finish()
+        return None, g, None
+
+
+def test_grad_reducer_views_survive_zero_grad_in_place_and_accumulation():
+    """p.grad aliases the flat bucket buffer after the first backward; a second backward with the gradient
+    still alive (set_to_none=False, or accumulation) must not double it."""
+    p = torch.nn.Parameter(torch.zeros(5))
+    red = D.GradReducer([p])
+    opt = torch.optim.SGD([p], lr=0.0)
+    seen = []
+    for _ in range(3):
+        opt.zero_grad(set_to_none=False)
+        _SinkFn.apply(red, p, 1.0).backward()
+        seen.append(p.grad.clone())
+    assert all(torch.equal(g, torch.ones(5)) for g in seen), seen
+    # gradient accumulation: two backward passes per step add up
+    opt.zero_grad(set_to_none=True)
+    _SinkFn.apply(red, p, 2.0).backward()
+    _SinkFn.apply(red, p, 3.0).backward()
+    assert torch.equal(p.grad, torch.full((5,), 5.0))
+    # the default mode still hands out the zero-copy view
+    opt.zero_grad(set_to_none=True)
+    _SinkFn.apply(red, p, 4.0).backward()
+    assert torch.equal(p.grad, torch.full((5,), 4.0))
+    assert p.grad.untyped_storage().data_ptr() == red.flat.untyped_storage().data_ptr()

@@ -51,19 +51,29 @@ def test_oracle_sde_objects_and_host_classes():
         if "disc_f" in c:
             f, G = sde.discretize(c["x"], c["t"])
             assert torch.allclose(f, c["disc_f"], rtol=1e-6, atol=1e-7) and torch.allclose(G, c["disc_G"], rtol=1e-6)
-            # reverse-diffusion predictor built on it (sde_helper2.py:319-324): x_mean = x - (f - G^2 s), x = x_mean + G z
-            score_fn = lambda a, b: -0.5 * a
-            zn = torch.full_like(c["x"], 0.25)
-            xn, xm = sh.rd_predictor(c["x"], c["t"], score_fn, sde, noise=zn)
-            Gb = c["disc_G"][:, None, None, None]
-            want_mean = c["x"] - (c["disc_f"] - Gb ** 2 * score_fn(c["x"], c["t"]))
-            assert torch.allclose(xm, want_mean, rtol=1e-6, atol=1e-7)
-            assert torch.allclose(xn, want_mean + Gb * zn, rtol=1e-6, atol=1e-7)
+            fo, Go = so.discretize(spec, c["x"], c["t"])
+            assert torch.equal(fo, c["disc_f"]) and torch.equal(Go, c["disc_G"])
         if "alphas" in c:
             assert torch.equal(sde.alphas, c["alphas"])
             assert torch.equal(sde.sqrt_1m_alphas_cumprod, c["sqrt_1m_alphas_cumprod"])
             assert torch.equal(spec.alphas(), c["alphas"])
         assert isinstance(sde, sh.SDE) and sde.T == 1 and sde.N == c["N"]
+
+
+def test_oracle_reverse_diffusion_predictor_matches_reference_golden():
+    """oracle discretize / rd_predictor_step == the unmodified reference's sde.reverse(...).discretize based update
+    (oracle/gen_golden_rd.py), all three SDE kinds, SDE and ODE; the host classes' discretize() agree too."""
+    from score_based_multimodal_autoencoder_b200 import sde_helper2 as sh
+    cls = {"vp": sh.VPSDE, "subvp": sh.subVPSDE, "ve": sh.VESDE}
+    for c in golden("rd_predictor.pt"):
+        spec = so.SdeSpec(c["kind"], c["a"], c["b"], c["N"])
+        f, G = so.discretize(spec, c["x"], c["t"])
+        assert torch.equal(f, c["disc_f"]) and torch.equal(G, c["disc_G"])
+        f2, G2 = cls[c["kind"]](c["a"], c["b"], c["N"]).discretize(c["x"], c["t"])
+        assert torch.allclose(f2, c["disc_f"], rtol=1e-6, atol=1e-7) and torch.allclose(G2, c["disc_G"], rtol=1e-6)
+        for pf, key in ((False, "sde"), (True, "ode")):
+            xn, xm = so.rd_predictor_step(spec, c["x"], c["t"], c["score"], c["z"], pf)
+            assert torch.equal(xn, c[key]["x"]) and torch.equal(xm, c[key]["x_mean"])
 
 
 def test_oracle_sampler_steps_and_loops():

@@ -62,6 +62,39 @@ def test_step_kernels_all_sdes_vs_oracle(kind, a, b):
     assert rel_max(xc, rc) < STEP_TOL and rel_max(xcm, rcm) < STEP_TOL
 
 
+def test_reverse_diffusion_predictor_matches_reference_golden():
+    """sbm_rd_predictor_step (a mode of the fused predictor kernel) vs the update built on the unmodified reference's
+    sde.reverse(score_fn, pf).discretize (tests/golden/rd_predictor.pt): VP (two tables), subVP, VE; SDE and ODE."""
+    sh = _sh()
+    for c in golden("rd_predictor.pt"):
+        sde = _mk(c["kind"], c["a"], c["b"], c["N"])
+        score = c["score"].cuda()
+        fn = lambda xx, tt: score
+        xn, xm = sh.rd_predictor(c["x"].cuda(), c["t"].cuda(), fn, sde, noise=c["z"].cuda())
+        assert rel_max(xn, c["sde"]["x"]) < STEP_TOL and rel_max(xm, c["sde"]["x_mean"]) < STEP_TOL, c["kind"]
+        xo, xom = sh.rd_predictor(c["x"].cuda(), c["t"].cuda(), fn, sde, probability_flow=True)
+        assert rel_max(xo, c["ode"]["x"]) < STEP_TOL and rel_max(xom, c["ode"]["x_mean"]) < STEP_TOL, c["kind"]
+        assert torch.equal(xo, xom)
+
+
+@pytest.mark.parametrize("kind,a,b", [("vp", 0.1, 20.0), ("subvp", 0.1, 20.0), ("ve", 0.01, 50.0)])
+def test_reverse_diffusion_predictor_all_sdes_vs_oracle(kind, a, b):
+    sh = _sh()
+    N = 50
+    sde = _mk(kind, a, b, N)
+    spec = so.SdeSpec(kind, a, b, N)
+    g = torch.Generator().manual_seed(4)
+    B = 33
+    x = torch.randn(B, 3, 16, 16, generator=g)
+    t = torch.rand(B, generator=g) * 0.999 + 1e-3
+    score = torch.randn(B, 3, 16, 16, generator=g)
+    z = torch.randn(B, 3, 16, 16, generator=g)
+    fn = lambda xx, tt: score.cuda()
+    xp, xm = sh.rd_predictor(x.cuda(), t.cuda(), fn, sde, noise=z.cuda())
+    rp, rm = so.rd_predictor_step(spec, x, t, score, z)
+    assert rel_max(xp, rp) < STEP_TOL and rel_max(xm, rm) < STEP_TOL
+
+
 def _toy_score(x, t):
     # smooth, per-sample, batch-independent stand-in for the net: isolates the sampler arithmetic
     return -x * (0.5 + t[:, None, None, None]) + 0.1 * torch.sin(3.0 * x)
@@ -90,6 +123,34 @@ def test_pc_sampler_loop_logic_vs_oracle(given, pf, nobs):
     for i, on in enumerate(mask):
         if on:
             assert torch.equal(out[:, i].cpu(), z0[:, i])
+
+
+@pytest.mark.parametrize("kind,a,b,pf", [("vp", 1.0, 5.0, True), ("vp", 0.1, 20.0, False), ("ve", 0.01, 50.0, True),
+                                         ("subvp", 0.1, 20.0, True)])
+def test_pc_sampler_reverse_diffusion_loop_vs_oracle(kind, a, b, pf):
+    """predictor="reverse_diffusion" selected in the N-step conditional sampler (imputation epilogue included)."""
+    sh = _sh()
+    N, B, M, D = 12, 9, 5, 8
+    sde = _mk(kind, a, b, N)
+    spec = so.SdeSpec(kind, a, b, N)
+    g = torch.Generator().manual_seed(12)
+    z0 = torch.randn(B, M, D, D, generator=g)
+    npred = torch.randn(N, B, M, D, D, generator=g)
+    ncorr = torch.randn(N, 1, B, M, D, D, generator=g)
+    mask = [m in "02" for m in "01234"]
+    ref = so.pc_sampler(spec, _toy_score, z0, npred, ncorr, z_obs=z0, obs_mask=mask, predictor_first=pf,
+                        predictor="reverse_diffusion")
+    out = sh.cond_sampler(z0.cuda(), "02", "01234", _toy_score, sde, x_init=z0.cuda(), noise_pred=npred.cuda(),
+                          pc_order="predictor_first" if pf else "corrector_first", noise_corr=ncorr.cuda(),
+                          predictor="reverse_diffusion")
+    assert rel_max(out, ref) < 1e-4
+    # and through the cached CUDA graph with the in-kernel Philox stream: graph == eager
+    sh.manual_seed(5)
+    e = sh.cond_sampler(z0.cuda(), "02", "01234", _toy_score, sde, x_init=z0.cuda(), predictor="reverse_diffusion")
+    sh.manual_seed(5)
+    gr = sh.cond_sampler(z0.cuda(), "02", "01234", _toy_score, sde, x_init=z0.cuda(), predictor="reverse_diffusion",
+                         use_graph=True)
+    assert rel_max(gr, e) < 1e-5
 
 
 def test_cond_loops_with_bf16_net_vs_reference_golden():
