@@ -223,6 +223,15 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
                          float* x_mean_out, float target_snr, int64_t global_batch, const sbm_rng* rng,
                          const sbm_impute* impute, int32_t reset_acc /* 1: zero acc2 once every block has read it */,
                          void* stream);
+/* classifier / EBM guidance (sde_helper2.py:65-94, 283-312).  gather: new_x = cat(x[:, m1], x[:, m2]).view(B, 2*dd)
+ * as bf16 rows of `ld` elements (the energy net's GEMM operand; padding zeroed).  apply: score[:, m1] -= cl_s *
+ * grad[:, 0:dd], score[:, m2] -= cl_s * grad[:, dd:2dd] in place (grad = d mean(E) / d new_x, fp32 rows of ldg
+ * elements); a negative m1 / m2 skips that half (train_poly_unet_cont.py:87).  The energy net itself (two hidden
+ * layers) and its input gradient run on sbm_conv_igemm / sbm_time_embed / sbm_act_bwd. */
+int sbm_guidance_gather(const sbm_latent_shape* ls, const float* x, int32_t m1, int32_t m2, void* out_bf16, int32_t ld,
+                        void* stream);
+int sbm_guidance_apply(const sbm_latent_shape* ls, float* score, const float* grad, int64_t ldg, int32_t m1, int32_t m2,
+                       float cl_s, void* stream);
 int sbm_impute_observed(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, float* x_out,
                         const sbm_impute* impute, void* stream);
 /* loss_fn, sde_helper2.py:167-170: t = u*(T-eps)+eps; xt = mean(x0,t) + std(t)*z.  u,z injected or drawn (rng) */

@@ -554,6 +554,38 @@ __global__ void sampler_tick_kernel(const float* __restrict__ ts, int n_ts, int*
   }
 }
 
+// ------------------------------------------------------------------------------ classifier / EBM guidance glue
+// new_x = cat(x[:, m1], x[:, m2]).view(B, 2*DD) (sde_helper2.py:70-71, 288-289) as the bf16 GEMM operand of the energy
+// net: out[b][0:DD] = x[b][m1], out[b][DD:2DD] = x[b][m2], row stride ld (padding zeroed).
+__global__ void __launch_bounds__(256)
+guidance_gather_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int M, int DD, int m1,
+                       int m2, int ld) {
+  const int64_t total = (int64_t)B * ld;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % ld);
+    const int64_t b = idx / ld;
+    float v = 0.f;
+    if (j < 2 * DD) v = x[(b * M + (j < DD ? m1 : m2)) * DD + (j < DD ? j : j - DD)];
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+// score[:, m1] -= cl_s * g[:, 0:DD]; score[:, m2] -= cl_s * g[:, DD:2DD]  (sde_helper2.py:75-76, 293-294); m < 0 skips
+// that half (train_poly_unet_cont.py:87 updates the predicted modality only).  g: fp32 rows of stride ldg.
+__global__ void __launch_bounds__(256)
+guidance_apply_kernel(float* __restrict__ score, const float* __restrict__ g, int B, int M, int DD, int m1, int m2,
+                      int64_t ldg, float cl_s) {
+  const int64_t total = (int64_t)B * 2 * DD;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % (2 * DD));
+    const int64_t b = idx / (2 * DD);
+    const int m = j < DD ? m1 : m2;
+    if (m < 0) continue;
+    score[(b * M + m) * DD + (j < DD ? j : j - DD)] -= cl_s * g[b * ldg + j];
+  }
+}
+
 static int ew_grid(int64_t n_items) {
   const int64_t want = (n_items + 255) / 256;
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
@@ -753,6 +785,30 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
       (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,
       1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,
       rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd), reset_acc);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_guidance_gather(const sbm_latent_shape* ls, const float* x, int32_t m1, int32_t m2, void* out_bf16, int32_t ld,
+                        void* stream) {
+  if (check_latent(ls, "sbm_guidance_gather")) return 1;
+  SBM_CHECK_ARG(x && out_bf16 && m1 >= 0 && m1 < ls->mods && m2 >= 0 && m2 < ls->mods && ld >= 2 * ls->dd,
+                "sbm_guidance_gather: bad args");
+  guidance_gather_kernel<<<ew_grid((int64_t)ls->batch * ld), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)out_bf16, ls->batch, ls->mods, ls->dd, m1, m2, ld);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_guidance_apply(const sbm_latent_shape* ls, float* score, const float* grad, int64_t ldg, int32_t m1, int32_t m2,
+                       float cl_s, void* stream) {
+  if (check_latent(ls, "sbm_guidance_apply")) return 1;
+  SBM_CHECK_ARG(score && grad && m1 < ls->mods && m2 < ls->mods && (m1 >= 0 || m2 >= 0) && ldg >= 2 * ls->dd,
+                "sbm_guidance_apply: bad args");
+  guidance_apply_kernel<<<ew_grid((int64_t)ls->batch * 2 * ls->dd), 256, 0, (cudaStream_t)stream>>>(
+      score, grad, ls->batch, ls->mods, ls->dd, m1, m2, ldg, cl_s);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;

@@ -21,8 +21,17 @@ out = torch.empty_like(x)
 
 
 def pc_kernels():
-    x1, _ = sh._predictor_kernel(sde, x, s, t, rng=rng.next(), want_mean=False, out=out)
-    sh._corrector_kernels(sde, x1, s, t, 0.16, rng=rng.next(), want_mean=False, acc=acc, out=out)
+    # as the samplers run them: the Philox noise-norm kernel (no memory traffic) on a side stream, joined before the
+    # score-norm kernel; set SBM_PROFILE_FUSED_NORMS=1 for the round-1 single norms kernel that regenerates the noise
+    r_pred, r_corr = rng.next(), rng.next()
+    if os.environ.get("SBM_PROFILE_FUSED_NORMS") == "1":
+        x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
+        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out)
+        return
+    side = sh._fork_noise_norm(x, r_corr, acc)
+    x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True)
 
 
 def dsm():
