@@ -223,6 +223,12 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
                          float* x_mean_out, float target_snr, int64_t global_batch, const sbm_rng* rng,
                          const sbm_impute* impute, int32_t reset_acc /* 1: zero acc2 once every block has read it */,
                          void* stream);
+/* legacy annealed-Langevin evaluators (eval_lat_celeba_hq_all.py:268-275, fid_upd10.py:279-290): for every modality
+ * channel m whose bit in obs_mask is clear, x' = x + coef_a[m] * score + coef_b[m] * noise; observed channels are copied
+ * through.  coef_a / coef_b: HOST arrays of ls->mods floats (the per-level step sizes, folded on the host). */
+int sbm_langevin_axpy_step(const sbm_latent_shape* ls, const float* x, const float* score, const float* noise,
+                           const float* coef_a, const float* coef_b, uint32_t obs_mask, float* x_out,
+                           const sbm_rng* rng, void* stream);
 /* classifier / EBM guidance (sde_helper2.py:65-94, 283-312).  gather: new_x = cat(x[:, m1], x[:, m2]).view(B, 2*dd)
  * as bf16 rows of `ld` elements (the energy net's GEMM operand; padding zeroed).  apply: score[:, m1] -= cl_s *
  * grad[:, 0:dd], score[:, m2] -= cl_s * grad[:, dd:2dd] in place (grad = d mean(E) / d new_x, fp32 rows of ldg

@@ -269,3 +269,45 @@ def prior_logp(s: SdeSpec, z: torch.Tensor) -> torch.Tensor:
     if s.kind == "ve":
         return -n / 2.0 * math.log(2 * math.pi * s.b1 ** 2) - torch.sum(z ** 2, dim=(1, 2, 3)) / (2 * s.b1 ** 2)
     return -n / 2.0 * math.log(2 * math.pi) - torch.sum(z ** 2, dim=(1, 2, 3)) / 2.0
+
+
+def annealed_langevin(model, z_all, obs_mask, er, c, sigmas, n_comp, noise, num_levels=None):
+    """Legacy annealed-Langevin evaluator, eval_lat_celeba_hq_all.py:258-275, on the stacked latent [B,M,D,D]
+    (the reference keeps a dict of [B,size_z] latents and re-stacks it before every net call: same values).
+    er, c: per-channel lists; sigmas: float64 numpy levels; noise: [levels, n_comp, B, M, D, D] (the reference draws one
+    randn_like per missing modality: channel m of noise[s, i] stands for that draw).  Restated from an inline script
+    loop (not an importable function): pinned by reading, not by running the reference."""
+    x = z_all.clone()
+    sig = torch.tensor(sigmas)                                           # float64, :222
+    B = x.shape[0]
+    levels = len(sigmas) if num_levels is None else num_levels
+    for s_in in range(levels):
+        sigma_index = torch.tensor([s_in] * B)
+        cur = sig[sigma_index].float()
+        for i in range(n_comp):
+            sm_out = model(x, sigma_index) / cur.view(B, 1, 1, 1)
+            new = x.clone()
+            for m, on in enumerate(obs_mask):
+                if not on:
+                    alpha = er[m] * (sig[s_in] ** 2) / (sig[-1] ** 2)
+                    new[:, m] = x[:, m] + (alpha * sm_out[:, m]) + c[m] * (torch.sqrt(2 * alpha) * noise[s_in, i][:, m])
+            x = new.float()
+    return x
+
+
+def langevin_refine(sm_model, z_all, obs_mask, n_comp, lr1, lr2, schedule, noise):
+    """Fixed-step evaluator, fid_upd10.py:279-290 (inline script loop, restated).  noise: [draws, B, M, D, D]."""
+    x = z_all.clone()
+    B = x.shape[0]
+    k = 0
+    for i in range(n_comp):
+        sm_out = sm_model(x.view(B, -1)).view_as(x)
+        steps = [lr1] if not schedule else [lr1 * ((i + 1) / n_comp)] + ([1 * ((i + 1) / n_comp)] if i == n_comp - 1 else [])
+        for a in steps:
+            new = x.clone()
+            for m, on in enumerate(obs_mask):
+                if not on:
+                    new[:, m] = x[:, m] + (a * sm_out[:, m]) + lr2 * noise[k][:, m]
+            x = new
+            k += 1
+    return x

@@ -554,6 +554,36 @@ __global__ void sampler_tick_kernel(const float* __restrict__ ts, int n_ts, int*
   }
 }
 
+// ------------------------------------------------------------------------------ legacy annealed-Langevin evaluators
+// eval_lat_celeba_hq_all.py:268-275 and fid_upd10.py:279-290: for every modality channel m that is NOT observed
+//   x' = x + a[m] * score + b[m] * noise          (observed channels are copied through)
+// with a[m] = er[m] sigma_i^2 / sigma_last^2 / sigma_i, b[m] = c[m] sqrt(2 er[m] sigma_i^2 / sigma_last^2) for the
+// annealed sampler and a = lr1 (i+1)/n_comp, b = lr2 for the fixed-step one.  12 B / element like the predictor.
+struct ModCoef {
+  float a[32], b[32];
+};
+__global__ void __launch_bounds__(256)
+langevin_axpy_kernel(const float4* __restrict__ x, const float4* __restrict__ score, const float4* __restrict__ noise,
+                     float4* __restrict__ x_out, uint32_t n_quads, FastDiv eqd, FastDiv ddq, uint32_t obs_mask,
+                     ModCoef cf, uint64_t seed, uint64_t draw, const uint64_t* draw_dev, uint64_t quad_offset) {
+  if (draw_dev) draw += *draw_dev;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x) {
+    const uint32_t b = fdiv(q, eqd);
+    const uint32_t m = fdiv(q - b * eqd.d, ddq);
+    float4 xv = __ldcs(x + q);
+    if (!((obs_mask >> m) & 1u)) {
+      const float4 sv = __ldcs(score + q);
+      const float4 z = noise ? noise[q] : philox_normal4(seed, draw, quad_offset + (uint64_t)q);
+      const float a = cf.a[m], bb = cf.b[m];
+      xv.x = xv.x + a * sv.x + bb * z.x;
+      xv.y = xv.y + a * sv.y + bb * z.y;
+      xv.z = xv.z + a * sv.z + bb * z.z;
+      xv.w = xv.w + a * sv.w + bb * z.w;
+    }
+    __stcs(x_out + q, xv);
+  }
+}
+
 // ------------------------------------------------------------------------------ classifier / EBM guidance glue
 // new_x = cat(x[:, m1], x[:, m2]).view(B, 2*DD) (sde_helper2.py:70-71, 288-289) as the bf16 GEMM operand of the energy
 // net: out[b][0:DD] = x[b][m1], out[b][DD:2DD] = x[b][m2], row stride ld (padding zeroed).
@@ -785,6 +815,27 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
       (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,
       1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,
       rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd), reset_acc);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_s();
+  return 0;
+}
+
+int sbm_langevin_axpy_step(const sbm_latent_shape* ls, const float* x, const float* score, const float* noise,
+                           const float* coef_a, const float* coef_b, uint32_t obs_mask, float* x_out,
+                           const sbm_rng* rng, void* stream) {
+  if (check_latent(ls, "sbm_langevin_axpy_step")) return 1;
+  SBM_CHECK_ARG(x && score && x_out && coef_a && coef_b && (noise || rng), "sbm_langevin_axpy_step: null pointer");
+  ModCoef cf;
+  for (int m = 0; m < 32; ++m) {  // HOST arrays of ls->mods coefficients
+    cf.a[m] = m < ls->mods ? coef_a[m] : 0.f;
+    cf.b[m] = m < ls->mods ? coef_b[m] : 0.f;
+  }
+  const int E = ls->mods * ls->dd;
+  const int64_t nq = (int64_t)ls->batch * E / 4;
+  langevin_axpy_kernel<<<wave_grid(langevin_axpy_kernel, nq), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)score, (const float4*)noise, (float4*)x_out, (uint32_t)nq,
+      make_fastdiv((uint32_t)(E / 4)), make_fastdiv((uint32_t)(ls->dd / 4)), obs_mask, cf, rng ? rng->seed : 0,
+      rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;

@@ -326,3 +326,25 @@ def test_autoencoder_host_plans_on_emulated_kernels_match_the_oracle():
     from score_based_multimodal_autoencoder_b200 import _lib as L
     with pytest.raises(L.SbmError):
         hm.CelebAAttrNewBNAE(64).eval().decoder(torch.zeros(2, 64))
+
+
+def test_checkpoint_container_round_trip_and_reference_compatibility(tmp_path):
+    """train_lat_celebhq_unet_cont2.py:534-557, :480: {'epoch','model_state_dict','train_loss','val_loss','size_z'}."""
+    import os
+    from score_based_multimodal_autoencoder_b200 import eval_samplers as es
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    torch.manual_seed(0)
+    m = Unet(dim=32, channels=3, dim_mults=(1, 2))
+    p = str(tmp_path / "ck")
+    es.save_checkpoint(p, m, epoch=3, train_loss=0.1, val_loss=0.2, size_z=256)
+    ck = torch.load(p, map_location="cpu", weights_only=False)
+    assert sorted(ck) == ["epoch", "model_state_dict", "size_z", "train_loss", "val_loss"]
+    torch.manual_seed(1)
+    m2 = Unet(dim=32, channels=3, dim_mults=(1, 2))
+    assert es.load_checkpoint(p, m2) == {"epoch": 3, "train_loss": 0.1, "val_loss": 0.2, "size_z": 256}
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    if os.path.isdir("/root/reference"):      # build container: the file loads strictly into the reference's own module
+        from oracle.gen_golden import import_reference
+        _, um, _ = import_reference()
+        ref = um.Unet(dim=32, channels=3, dim_mults=(1, 2))
+        ref.load_state_dict(ck["model_state_dict"], strict=True)
