@@ -523,14 +523,14 @@ def sampler_kernel_roofline(sh, sde, device, batch=65536):
     acc = torch.zeros(3, dtype=torch.float64, device=device)
     out = torch.empty_like(x)
 
+    noise_ss = torch.zeros(batch, device=device)
+
     def pc_kernels():
-        # the sampler forks the Philox noise-norm kernel (no memory traffic) on a side stream BEFORE the score-net call
-        # of the corrector; with no net in this micro-benchmark it is forked before the predictor kernel instead
+        # predictor -> corrector with in-kernel Philox noise, as pc_sampler runs it: the predictor kernel also accumulates
+        # the per-sample sums of squares of the corrector's draw, the norms kernel reads the score + those sums
         r_pred, r_corr = rng.next(), rng.next()
-        side = sh._fork_noise_norm(x, r_corr, acc)
-        x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
-        torch.cuda.current_stream().wait_stream(side)
-        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True)
+        x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out, noise_ss=noise_ss)
+        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_ss=noise_ss)
 
     for _ in range(3):
         pc_kernels()
@@ -571,12 +571,12 @@ def sampler_kernel_roofline(sh, sde, device, batch=65536):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
     nbytes = 28.0 * x.numel()
-    return {"bound": "hbm", "kernel": "predictor + corrector_norms + corrector_update (+ noise_norm beside them)", "achieved": nbytes / (ms * 1e-3) / 1e9,
+    return {"bound": "hbm", "kernel": "predictor (+ fused noise norm) + corrector_norms + corrector_update", "achieved": nbytes / (ms * 1e-3) / 1e9,
             "unit": "GB/s", "us_per_pc_step": ms * 1e3, "batch": batch, "algorithmic_bytes_per_step": nbytes,
             "timed_as": timed_as,
-            "note": "4 launches per PC step: predictor, score norm, update on the critical path (28 B / element) + the "
-                    "Philox noise-norm kernel (0 B) on a side stream, inside the timed region; the update kernel "
-                    "re-zeroes the norm accumulator itself"}
+            "note": "3 launches per PC step (28 B / element): predictor (also regenerates the corrector's Philox draw and "
+                    "leaves its per-sample sums of squares), score norm, update; the update kernel re-zeroes the norm "
+                    "accumulator itself"}
 
 
 # --------------------------------------------------------------------------------------- CPU arms

@@ -9,6 +9,7 @@
 // (seed, draw id) with counter = GLOBAL element index / 4, so a batch shard on any GPU draws the same
 // numbers as the unsharded batch would.  Latent tensors are dense [B, M, D, D] fp32; E = M*D*D per sample.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/sbmae_b200.h"
 #include "common.cuh"
@@ -234,13 +235,19 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
                  const float4* __restrict__ noise, float4* __restrict__ x_out, float4* __restrict__ x_mean_out,
                  uint32_t n_quads, FastDiv eqd, SdeP s, int ode, uint64_t seed, uint64_t draw,
                  const uint64_t* draw_dev, uint64_t quad_offset, Impute im, int rd, const float* __restrict__ table,
-                 float T) {
-  if (draw_dev) draw += *draw_dev;
+                 float T, float* __restrict__ ss_next, uint64_t draw_next) {
+  if (draw_dev) {
+    draw += *draw_dev;
+    draw_next += *draw_dev;
+  }
   const float dt = -1.f / (float)s.N;
   const float sq = sqrtf(-dt);
   const float2 icoef = impute_coef(im, s);
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_quads; q0 += 2 * stride) {
+  // warp-uniform trip count (the fused noise norm below uses full-warp shuffles): the loop runs while the warp's FIRST
+  // quad is in range, lanes past the end are masked inside
+  for (uint32_t w0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); w0 < n_quads; w0 += 2 * stride) {
+    const uint32_t q0 = w0 + (threadIdx.x & 31u);
     const uint32_t qs[2] = {q0, q0 + stride};
     float4 xv[2], sv[2];
 #pragma unroll
@@ -252,7 +259,7 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const uint32_t q = qs[u];
-      if (q >= n_quads) break;
+      if (q >= n_quads) continue;
       const uint32_t b = fdiv(q, eqd);
       float4 mean;
       float gs;  // coefficient of the noise
@@ -285,6 +292,26 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
       }
       if (x_mean_out) __stcs(x_mean_out + q, mean);
       __stcs(x_out + q, apply_impute(im, icoef, out, q, q - b * eqd.d));
+    }
+    // Fused noise norm of the FOLLOWING Langevin step (sde_helper2.py:96, 98): ss_next[b] += sum of squares of the
+    // corrector's Philox draw over this thread's quads.  The draw depends on no data, and this kernel waits on HBM with
+    // ~45 % of its issue slots idle (ncu), so regenerating the stream here is free where a kernel of its own cost 20 us
+    // at 64k latents.  A warp covers 32 consecutive quads = at most two samples (E/4 >= 32, checked by the host): two
+    // masked warp sums, two atomics per warp and trip.
+    if (ss_next != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t q = qs[u];
+        const bool on = q < n_quads;
+        const uint32_t b = on ? fdiv(q, eqd) : 0xffffffffu;
+        const float n = on ? philox_sumsq4(seed, draw_next, quad_offset + (uint64_t)q) : 0.f;
+        const uint32_t b_lo = __shfl_sync(0xffffffffu, b, 0);
+        const float lo = warp_sum(b == b_lo ? n : 0.f), hi = warp_sum((on && b != b_lo) ? n : 0.f);
+        if ((threadIdx.x & 31) == 0 && b_lo != 0xffffffffu) {
+          atomicAdd(ss_next + b_lo, lo);
+          if (hi != 0.f) atomicAdd(ss_next + b_lo + 1, hi);
+        }
+      }
     }
   }
 }
@@ -331,6 +358,7 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
         }
         if (NM == 2 && on) nv[u] = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + qq));
       }
+      (void)noise;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int qq = q + 32 * u;
@@ -350,7 +378,14 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
     }
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      const float tg = GRAD ? warp_sum(sg[k]) : 0.f, tn = NM ? warp_sum(sn[k]) : 0.f;
+      const float tg = GRAD ? warp_sum(sg[k]) : 0.f;
+      float tn = (NM == 1 || NM == 2) ? warp_sum(sn[k]) : 0.f;
+      if (NM == 3 && k < ns) {  // per-sample sums of squares left by the predictor kernel; cleared for the next step
+        float* ss = reinterpret_cast<float*>(const_cast<float4*>(noise));
+        tn = ss[b0 + k];
+        __syncwarp();
+        if (lane == 0) ss[b0 + k] = 0.f;
+      }
       if (k < ns) {
         a0 += (double)sqrtf(tg);
         a1 += (double)sqrtf(tn);
@@ -622,8 +657,14 @@ static int ew_grid(int64_t n_items) {
 }
 // Grid of a grid-stride kernel = exactly one resident wave (SMs x blocks that fit per SM): with a fixed cap like 8
 // blocks per SM a kernel whose registers allow only 5 runs 1.6 waves and idles ~20 % of the machine in the second one.
+// A/B knobs (both OFF by default): give up `g_reserve` block slots per SM in the memory-bound sampler kernels and run the
+// side-stream noise-norm kernel with `g_noise_blocks` blocks per SM so that the two are co-resident.  Measured at 64k
+// latents (profiles/README.md, round 2): 131 us per PC step with both off, 138-152 us with either on -- the stand-alone
+// noise kernel only pays off beside the score net; next to the predictor its work is fused into that kernel instead.
+static int g_reserve = [] { const char* e = getenv("SBM_SAMPLER_RESERVE"); return e ? atoi(e) : 0; }();
+static int g_noise_blocks = [] { const char* e = getenv("SBM_NOISE_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
 template <typename K>
-static int wave_grid(K kernel, int64_t n_items, int per_thread = 1) {
+static int wave_grid(K kernel, int64_t n_items, int per_thread = 1, int reserve = 0) {
   // occupancy per kernel FUNCTION (template instantiations of one kernel share the pointer type K, not the pointer)
   static std::atomic<const void*> keys[16];
   static std::atomic<int> vals[16];
@@ -642,6 +683,7 @@ static int wave_grid(K kernel, int64_t n_items, int per_thread = 1) {
     }
   }
   if (per_sm <= 0) per_sm = 4;
+  if (reserve > 0 && per_sm - reserve >= 3) per_sm -= reserve;
   const int64_t want = (n_items + 256 * per_thread - 1) / (256 * per_thread);
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * per_sm));
 }
@@ -671,7 +713,9 @@ static int launch_norms(const sbm_latent_shape* ls, const float* grad, const flo
   const int EQ = ls->mods * ls->dd / 4;
   const int groups = (ls->batch + S - 1) / S;
   // a group moves S*EQ quads; size the grid by 128-quad warp trips so that a small batch still spreads over the SMs
-  const int blocks = wave_grid(corrector_norms_kernel<S, GRAD, NM>, (int64_t)groups * 32);
+  int blocks = wave_grid(corrector_norms_kernel<S, GRAD, NM>, (int64_t)groups * 32, 1, GRAD && NM == 0 ? g_reserve : 0);
+  if (!GRAD && g_noise_blocks > 0)  // side-stream kernel: co-resident with the memory-bound kernels, not a full wave
+    blocks = std::max(1, std::min(blocks, sm_count() * g_noise_blocks));
   corrector_norms_kernel<S, GRAD, NM><<<blocks, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, rng ? rng->seed : 0, rng ? rng->draw : 0,
       rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)EQ : 0);
@@ -692,14 +736,14 @@ static int dispatch_norms(const sbm_latent_shape* ls, const float* grad, const f
 static int launch_predictor(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                             const float* t, const float* noise, float* x_out, float* x_mean_out,
                             int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, int rd,
-                            const float* table, void* stream) {
+                            const float* table, void* stream, float* ss_next = nullptr, uint64_t draw_next = 0) {
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  predictor_kernel<<<wave_grid(predictor_kernel, nq, 2), 256, 0, (cudaStream_t)stream>>>(
+  predictor_kernel<<<wave_grid(predictor_kernel, nq, 2, g_reserve), 256, 0, (cudaStream_t)stream>>>(
       (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,
       (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,
       rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
-      to_impute(impute, ls->dd), rd, table, sde->T);
+      to_impute(impute, ls->dd), rd, table, sde->T, ss_next, draw_next);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;
@@ -774,6 +818,20 @@ int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const flo
                           stream);
 }
 
+int sbm_predictor_step_fused_noise(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
+                                   const float* t, const float* table, float* x_out, float* x_mean_out,
+                                   int32_t reverse_diffusion, const sbm_rng* rng, const sbm_impute* impute,
+                                   float* noise_ss, uint64_t noise_draw, void* stream) {
+  if (check_latent(ls, "sbm_predictor_step_fused_noise")) return 1;
+  SBM_CHECK_ARG(sde && x && score && t && x_out && rng && noise_ss, "sbm_predictor_step_fused_noise: null pointer");
+  SBM_CHECK_ARG(ls->mods * ls->dd / 4 >= 32,
+                "sbm_predictor_step_fused_noise: needs at least 128 latent elements per sample (use sbm_noise_norm)");
+  SBM_CHECK_ARG(!reverse_diffusion || table || sde->kind == SBM_SDE_SUBVP,
+                "sbm_predictor_step_fused_noise: the reverse-diffusion rule needs the discretisation table");
+  return launch_predictor(ls, sde, x, score, t, nullptr, x_out, x_mean_out, 0, rng, impute, reverse_diffusion ? 1 : 0,
+                          table, stream, noise_ss, noise_draw);
+}
+
 int sbm_rd_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                           const float* t, const float* table, const float* noise, float* x_out, float* x_mean_out,
                           int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, void* stream) {
@@ -795,6 +853,12 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
   return dispatch_norms<true, 0>(ls, grad, nullptr, nullptr, acc2, stream);  // acc2[1] comes from sbm_noise_norm
 }
 
+int sbm_corrector_norms_ss(const sbm_latent_shape* ls, const float* grad, float* noise_ss, double* acc2, void* stream) {
+  if (check_latent(ls, "sbm_corrector_norms_ss")) return 1;
+  SBM_CHECK_ARG(grad && noise_ss && acc2, "sbm_corrector_norms_ss: null pointer");
+  return dispatch_norms<true, 3>(ls, grad, noise_ss, nullptr, acc2, stream);
+}
+
 int sbm_noise_norm(const sbm_latent_shape* ls, const sbm_rng* rng, double* acc2, void* stream) {
   if (check_latent(ls, "sbm_noise_norm")) return 1;
   SBM_CHECK_ARG(rng && acc2, "sbm_noise_norm: null pointer");
@@ -810,7 +874,7 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
   SBM_CHECK_ARG(global_batch >= ls->batch, "sbm_corrector_update: global_batch < local batch");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  corrector_update_kernel<<<wave_grid(corrector_update_kernel, nq, 2), 256, 0, (cudaStream_t)stream>>>(
+  corrector_update_kernel<<<wave_grid(corrector_update_kernel, nq, 2, g_reserve), 256, 0, (cudaStream_t)stream>>>(
       (const float4*)x, (const float4*)grad, t, (const float4*)noise, acc2, alphas, (float4*)x_out,
       (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,
       1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,

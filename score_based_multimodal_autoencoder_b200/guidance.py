@@ -110,11 +110,12 @@ class ClwithTime2(nn.Module):
         # d mean(out) / d h2 = column sums of fc3.weight / (B * n_class): the same row for every sample
         g3 = self._cached("g3", (self.fc3.weight,), lambda: torch.zeros(pad8(hid), device=xb.device).index_add_(
             0, torch.arange(hid, device=xb.device), self.fc3.weight.detach().float().sum(0)))
-        dy = (g3 / float(b * self.n_class)).view(1, 1, 1, -1).expand(b, 1, 1, -1)             # row stride 0
-        _, da2 = ops.act_bwd(dy, a2, hid, L.ACT_SILU)
-        dh1 = ops.conv_igemm(da2, self._wt(self.fc2), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=hid)
-        _, da1 = ops.act_bwd(dh1, a1, hid, L.ACT_SILU)
-        return ops.conv_igemm(da1, self._wt(self.fc1), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=din)
+        # rows = samples along dim 2 (the row stride the kernels read is stride(2)): the broadcast row has stride 0
+        dy = (g3 / float(b * self.n_class)).view(1, 1, 1, -1).expand(1, 1, b, -1)
+        _, da2 = ops.act_bwd(dy, a2.view(1, 1, b, -1), hid, L.ACT_SILU)
+        dh1 = ops.conv_igemm(da2.view(b, 1, 1, -1), self._wt(self.fc2), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=hid)
+        _, da1 = ops.act_bwd(dh1.view(1, 1, b, -1), a1.view(1, 1, b, -1), hid, L.ACT_SILU)
+        return ops.conv_igemm(da1.view(b, 1, 1, -1), self._wt(self.fc1), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=din)
 
     def energy_grad(self, x_flat, t, id1=None, id2=None):
         """d mean(self(x, t)) / d x for x_flat [B, n_mod*size_z] (fp32 CUDA) -> [B, n_mod*size_z] fp32."""
@@ -143,7 +144,8 @@ class ClwithTime3(ClwithTime2):
         b = e.shape[0]
         row = torch.zeros(e.shape[-1], device=e.device)
         row[:self.hidden] = add
-        _, _ = ops.add(e, row.view(1, 1, 1, -1).expand(b, 1, 1, -1), self.hidden, out=e)
+        ev = e.view(1, 1, b, -1)                                  # rows along dim 2, broadcast row with stride 0
+        ops.add(ev, row.view(1, 1, 1, -1).expand(1, 1, b, -1), self.hidden, out=ev)
         return e
 
 

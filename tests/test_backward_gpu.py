@@ -312,7 +312,8 @@ def test_fused_adam_capturable_eager_loop_state_dict_and_resume():
     with torch.no_grad():
         for b, a in zip(p_new, p_ref):
             b.copy_(a)
-    o_new.load_state_dict(o_ref.state_dict())
+    import copy
+    o_new.load_state_dict(copy.deepcopy(o_ref.state_dict()))   # (load_state_dict keeps same-device tensors by reference)
     for it in range(6, 9):
         for a, b, gr in zip(p_ref, p_new, grads[it]):
             a.grad, b.grad = gr.clone(), gr.clone()
