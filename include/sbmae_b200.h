@@ -199,15 +199,6 @@ int sbm_randn(float* out, int64_t n, uint64_t seed, uint64_t draw, uint64_t elem
 int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                        const float* t, const float* noise, float* x_out, float* x_mean_out, int32_t probability_flow,
                        const sbm_rng* rng, const sbm_impute* impute, void* stream);
-/* predictor step (Euler-Maruyama, or reverse-diffusion with reverse_diffusion != 0 and `table` as below) with in-kernel
- * Philox noise that ALSO accumulates noise_ss[b] += sum of squares of sample b's elements of Philox draw `noise_draw`
- * (the draw of the Langevin step that follows, sde_helper2.py:96): the predictor waits on HBM with idle issue slots, so
- * the corrector's noise norm costs no kernel of its own.  noise_ss: [batch] floats, zero before the first call
- * (sbm_corrector_norms_ss clears what it consumes).  Needs mods*dd >= 128. */
-int sbm_predictor_step_fused_noise(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
-                                   const float* t, const float* table, float* x_out, float* x_mean_out,
-                                   int32_t reverse_diffusion, const sbm_rng* rng, const sbm_impute* impute,
-                                   float* noise_ss, uint64_t noise_draw, void* stream);
 /* reverse-diffusion (ancestral) predictor: (f, G) = sde.discretize(x, t), rev_f = f - G^2 s [*0.5], x_mean = x - rev_f,
  * x' = x_mean + G z  (sde_helper2.py:236-253 base rule = subVPSDE, :373-381 VPSDE/DDPM, :465-473 VESDE/SMLD, :319-324
  * RSDE.discretize).  table = device copy of sde.discrete_betas (VPSDE) / sde.discrete_sigmas (VESDE), NULL for subVPSDE.
@@ -221,9 +212,6 @@ int sbm_rd_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const 
  * BOTH NULL only acc2[0] is accumulated (4 B / element, memory-bound) and acc2[1] comes from sbm_noise_norm */
 int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
                         double* acc2, void* stream);
-/* as sbm_corrector_norms with acc2[1] += sum_b sqrt(noise_ss[b]) from the per-sample sums of squares left by
- * sbm_predictor_step_fused_noise; the consumed entries are reset to zero */
-int sbm_corrector_norms_ss(const sbm_latent_shape* ls, const float* grad, float* noise_ss, double* acc2, void* stream);
 /* acc2[1] += sum_b ||noise_b|| of the Philox draw `rng` (sde_helper2.py:96, 98).  Touches no latent memory: the draw is
  * a function of (seed, draw id, element index), so the samplers run this on a side stream beside the score-net
  * forward and the norms kernel proper never regenerates the stream */

@@ -64,6 +64,12 @@ class _Plan:
         o, i = w.shape
         return self.m._cached((id(lin), "dg"), (w,), lambda: ops.pack_weight(w.detach().contiguous(), 1, i, o, 0, 1, i))
 
+    def _slot(self, p):
+        """Data-parallel training: the parameter's slot in the flat bucket buffer, so that the producing kernel writes
+        the gradient there directly (no copy in `grad_ready`); None otherwise."""
+        sink = getattr(self.m, "_grad_sink", None)
+        return sink.grad_view(p) if sink is not None and p not in self.pg else None
+
     def _grad(self, p, g):
         sink = getattr(self.m, "_grad_sink", None)
         if sink is not None:  # data-parallel training: copy into the flat bucket buffer, all-reduce when a bucket fills
@@ -74,7 +80,7 @@ class _Plan:
     def _conv_s1_bwd(self, conv, x_b, dy_b, dy_f32_for_bias, cin, cout, k, want_dx=True, bias_grad=None):
         """gradients of y = conv_kxk_same(x) + bias.  Returns dx fp32 (or None)."""
         dwpk = ops.conv_wgrad(x_b, dy_b, kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout)
-        self._grad(conv.weight, ops.unpack_conv2d_wgrad(dwpk, conv.weight))
+        self._grad(conv.weight, ops.unpack_conv2d_wgrad(dwpk, conv.weight, self._slot(conv.weight)))
         if conv.bias is not None:
             self._grad(conv.bias, bias_grad if bias_grad is not None else ops.colsum(dy_f32_for_bias, cout))
         if not want_dx:
@@ -268,7 +274,7 @@ class _Plan:
             dtg = ops.conv_igemm(dc_b, wct, kind=L.CONV_S1, kh=1, kw=1, cin=total, cout=td)
             d2f, d2b = ops.act_bwd(dtg, t2pre, td, L.ACT_GELU, want_f32=True, want_bf16=True)
             dw3 = ops.conv_wgrad(t1, d2b, kind=L.CONV_S1, kh=1, kw=1, cin=td, cout=td)
-            self._grad(lin3.weight, ops.unpack_linear_wgrad(dw3, lin3.weight))
+            self._grad(lin3.weight, ops.unpack_linear_wgrad(dw3, lin3.weight, self._slot(lin3.weight)))
             self._grad(lin3.bias, ops.colsum(d2f, td))
             dt1 = ops.conv_igemm(d2b, self._dg_linear(lin3), kind=L.CONV_S1, kh=1, kw=1, cin=td, cout=td)
             d1f, d1b = ops.act_bwd(dt1, t1pre, td, L.ACT_GELU, want_f32=True, want_bf16=True)
@@ -323,7 +329,7 @@ class _Plan:
                     g = yn.g
                     _, g_b = ops.add(g, None, c, want_bf16=True)
                     dw = ops.conv_wgrad(xin.bf16, g_b, kind=L.CONV_S2, kh=4, kw=4, cin=c, cout=c)
-                    self._grad(down.weight, ops.unpack_conv2d_wgrad(dw, down.weight))
+                    self._grad(down.weight, ops.unpack_conv2d_wgrad(dw, down.weight, self._slot(down.weight)))
                     self._grad(down.bias, ops.colsum(g, c))
                     dx = ops.conv_igemm(g_b, self._dg_as_convT(down), kind=L.CONVT_4X4_S2, kh=4, kw=4, cin=c, cout=c)
                     _acc(xin, dx)
@@ -365,7 +371,7 @@ class _Plan:
                 g = yn.g
                 _, g_b = ops.add(g, None, cu, want_bf16=True)
                 dw = ops.conv_wgrad(xin.bf16, g_b, kind=L.CONVT_4X4_S2, kh=4, kw=4, cin=cu, cout=cu)
-                self._grad(up.weight, ops.unpack_convT2d_wgrad(dw, up.weight))
+                self._grad(up.weight, ops.unpack_convT2d_wgrad(dw, up.weight, self._slot(up.weight)))
                 self._grad(up.bias, ops.colsum(g, cu))
                 dx = ops.conv_igemm(g_b, self._dg_as_conv(up), kind=L.CONV_S2, kh=4, kw=4, cin=cu, cout=cu)
                 _acc(xin, dx)

@@ -50,7 +50,7 @@ class _OPlan(_Plan):
     def _conv2d_bwd(self, conv, x_b, g_b, g_f32, cin, cout, k, kind=L.CONV_S1, want_dx=True):
         """gradients of a 2-D convolution (stride 1 'same' or 3x3 stride 2): weight, bias, and dx (fp32) if wanted."""
         dwpk = ops.conv_wgrad(x_b, g_b, kind=kind, kh=k, kw=k, cin=cin, cout=cout)
-        self._grad(conv.weight, ops.unpack_conv2d_wgrad(dwpk, conv.weight))
+        self._grad(conv.weight, ops.unpack_conv2d_wgrad(dwpk, conv.weight, self._slot(conv.weight)))
         self._grad(conv.bias, ops.colsum(g_f32, cout))
         if not want_dx:
             return None

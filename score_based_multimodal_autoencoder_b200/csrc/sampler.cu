@@ -9,7 +9,6 @@
 // (seed, draw id) with counter = GLOBAL element index / 4, so a batch shard on any GPU draws the same
 // numbers as the unsharded batch would.  Latent tensors are dense [B, M, D, D] fp32; E = M*D*D per sample.
 #include <atomic>
-#include <cstdlib>
 
 #include "../../include/sbmae_b200.h"
 #include "common.cuh"
@@ -229,37 +228,37 @@ dropout_kernel(T* __restrict__ x, int64_t ld, int64_t n_oct, FastDiv c8d, int C,
 
 
 // ------------------------------------------------------------------------------ predictor
-// One thread = one quad (4 consecutive latent elements), two quads in flight per loop trip.
+// One thread = one quad (4 consecutive latent elements), U quads in flight per loop trip.  The Philox rounds and the
+// Box-Muller transform are one long dependent chain per quad: with U = 2 the kernel issued on 58 % of its cycles at 55 %
+// of DRAM bandwidth (ncu, round 2) -- neither bound, waiting on its own arithmetic latency; more independent quads
+// per thread fill those slots.
+template <int U>
 __global__ void __launch_bounds__(256)
 predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score, const float* __restrict__ t,
                  const float4* __restrict__ noise, float4* __restrict__ x_out, float4* __restrict__ x_mean_out,
                  uint32_t n_quads, FastDiv eqd, SdeP s, int ode, uint64_t seed, uint64_t draw,
                  const uint64_t* draw_dev, uint64_t quad_offset, Impute im, int rd, const float* __restrict__ table,
-                 float T, float* __restrict__ ss_next, uint64_t draw_next) {
-  if (draw_dev) {
-    draw += *draw_dev;
-    draw_next += *draw_dev;
-  }
+                 float T) {
+  if (draw_dev) draw += *draw_dev;
   const float dt = -1.f / (float)s.N;
   const float sq = sqrtf(-dt);
   const float2 icoef = impute_coef(im, s);
   const uint32_t stride = gridDim.x * blockDim.x;
-  // warp-uniform trip count (the fused noise norm below uses full-warp shuffles): the loop runs while the warp's FIRST
-  // quad is in range, lanes past the end are masked inside
-  for (uint32_t w0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); w0 < n_quads; w0 += 2 * stride) {
-    const uint32_t q0 = w0 + (threadIdx.x & 31u);
-    const uint32_t qs[2] = {q0, q0 + stride};
-    float4 xv[2], sv[2];
+  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_quads; q0 += U * stride) {
+    uint32_t qs[U];
+    float4 xv[U], sv[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < U; ++u) {
+      qs[u] = q0 + u * stride;
       if (qs[u] < n_quads) {  // read-once / write-once streams: keep them out of the way of L2-resident data
         xv[u] = __ldcs(x + qs[u]);
         sv[u] = __ldcs(score + qs[u]);
       }
+    }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const uint32_t q = qs[u];
-      if (q >= n_quads) continue;
+      if (q >= n_quads) break;
       const uint32_t b = fdiv(q, eqd);
       float4 mean;
       float gs;  // coefficient of the noise
@@ -293,26 +292,6 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
       if (x_mean_out) __stcs(x_mean_out + q, mean);
       __stcs(x_out + q, apply_impute(im, icoef, out, q, q - b * eqd.d));
     }
-    // Fused noise norm of the FOLLOWING Langevin step (sde_helper2.py:96, 98): ss_next[b] += sum of squares of the
-    // corrector's Philox draw over this thread's quads.  The draw depends on no data, and this kernel waits on HBM with
-    // ~45 % of its issue slots idle (ncu), so regenerating the stream here is free where a kernel of its own cost 20 us
-    // at 64k latents.  A warp covers 32 consecutive quads = at most two samples (E/4 >= 32, checked by the host): two
-    // masked warp sums, two atomics per warp and trip.
-    if (ss_next != nullptr) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const uint32_t q = qs[u];
-        const bool on = q < n_quads;
-        const uint32_t b = on ? fdiv(q, eqd) : 0xffffffffu;
-        const float n = on ? philox_sumsq4(seed, draw_next, quad_offset + (uint64_t)q) : 0.f;
-        const uint32_t b_lo = __shfl_sync(0xffffffffu, b, 0);
-        const float lo = warp_sum(b == b_lo ? n : 0.f), hi = warp_sum((on && b != b_lo) ? n : 0.f);
-        if ((threadIdx.x & 31) == 0 && b_lo != 0xffffffffu) {
-          atomicAdd(ss_next + b_lo, lo);
-          if (hi != 0.f) atomicAdd(ss_next + b_lo + 1, hi);
-        }
-      }
-    }
   }
 }
 
@@ -325,7 +304,7 @@ predictor_kernel(const float4* __restrict__ x, const float4* __restrict__ score,
 // regenerating the stream is pure ALU work: <true, 2> made this kernel issue-bound at 0.35 of the HBM roofline (ncu,
 // round 1).  The samplers therefore run <false, 2> (no memory traffic at all) on a side stream next to the score-net
 // forward whose output <true, 0> then reduces at memory speed.
-template <int S, bool GRAD, int NM>
+template <int S, bool GRAD, int NM, int NU>
 __global__ void __launch_bounds__(256)
 corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict__ noise, double* __restrict__ acc,
                        int B, int EQ, uint64_t seed, uint64_t draw, const uint64_t* draw_dev,
@@ -343,11 +322,11 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
     float sg[S], sn[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) { sg[k] = 0.f; sn[k] = 0.f; }
-    for (int q = lane; q < total; q += 128) {
-      float4 gv[4];
-      float nv[4];
+    for (int q = lane; q < total; q += 32 * NU) {
+      float4 gv[NU];
+      float nv[NU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // four 16-byte loads in flight per lane
+      for (int u = 0; u < NU; ++u) {  // NU 16-byte loads (or Philox chains) in flight per lane
         const int qq = q + 32 * u;
         const bool on = qq < total;
         gv[u] = (GRAD && on) ? __ldcs(grad + base + qq) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -358,9 +337,8 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
         }
         if (NM == 2 && on) nv[u] = philox_sumsq4(seed, draw, quad_offset + (uint64_t)(base + qq));
       }
-      (void)noise;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < NU; ++u) {
         const int qq = q + 32 * u;
         const float gq = gv[u].x * gv[u].x + gv[u].y * gv[u].y + gv[u].z * gv[u].z + gv[u].w * gv[u].w;
         if (S == 1) {
@@ -378,14 +356,7 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
     }
 #pragma unroll
     for (int k = 0; k < S; ++k) {
-      const float tg = GRAD ? warp_sum(sg[k]) : 0.f;
-      float tn = (NM == 1 || NM == 2) ? warp_sum(sn[k]) : 0.f;
-      if (NM == 3 && k < ns) {  // per-sample sums of squares left by the predictor kernel; cleared for the next step
-        float* ss = reinterpret_cast<float*>(const_cast<float4*>(noise));
-        tn = ss[b0 + k];
-        __syncwarp();
-        if (lane == 0) ss[b0 + k] = 0.f;
-      }
+      const float tg = GRAD ? warp_sum(sg[k]) : 0.f, tn = NM ? warp_sum(sn[k]) : 0.f;
       if (k < ns) {
         a0 += (double)sqrtf(tg);
         a1 += (double)sqrtf(tn);
@@ -408,6 +379,7 @@ corrector_norms_kernel(const float4* __restrict__ grad, const float4* __restrict
 
 // acc = {sum ||grad_b||, sum ||noise_b||, ticket}: the last block to finish zeroes it for the next corrector step, so
 // a captured CUDA graph needs no separate memset launch.
+template <int U>
 __global__ void __launch_bounds__(256)
 corrector_update_kernel(const float4* __restrict__ x, const float4* __restrict__ grad, const float* __restrict__ t,
                         const float4* __restrict__ noise, double* __restrict__ acc,
@@ -422,17 +394,19 @@ corrector_update_kernel(const float4* __restrict__ x, const float4* __restrict__
   const float base = r * r * 2.f;
   const float2 icoef = impute_coef(im, s);
   const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_quads; q0 += 2 * stride) {
-    const uint32_t qs[2] = {q0, q0 + stride};
-    float4 xv[2], gv[2];
+  for (uint32_t q0 = blockIdx.x * blockDim.x + threadIdx.x; q0 < n_quads; q0 += U * stride) {
+    uint32_t qs[U];
+    float4 xv[U], gv[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < U; ++u) {
+      qs[u] = q0 + u * stride;
       if (qs[u] < n_quads) {
         xv[u] = __ldcs(x + qs[u]);
         gv[u] = __ldcs(grad + qs[u]);
       }
+    }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const uint32_t q = qs[u];
       if (q >= n_quads) break;
       const uint32_t b = fdiv(q, eqd);
@@ -651,20 +625,19 @@ guidance_apply_kernel(float* __restrict__ score, const float* __restrict__ g, in
   }
 }
 
+// quads in flight per thread of the predictor / update kernels and Philox chains per lane of the noise-norm kernel
+// (A/B: SBM_SAMPLER_UNROLL = 2 | 4, SBM_NOISE_UNROLL = 4 | 8; defaults = the measured best, profiles/README.md)
+static int g_unroll = [] { const char* e = getenv("SBM_SAMPLER_UNROLL"); return e ? atoi(e) : 2; }();
+static int g_noise_unroll = [] { const char* e = getenv("SBM_NOISE_UNROLL"); return e ? atoi(e) : 4; }();
+
 static int ew_grid(int64_t n_items) {
   const int64_t want = (n_items + 255) / 256;
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8));
 }
 // Grid of a grid-stride kernel = exactly one resident wave (SMs x blocks that fit per SM): with a fixed cap like 8
 // blocks per SM a kernel whose registers allow only 5 runs 1.6 waves and idles ~20 % of the machine in the second one.
-// A/B knobs (both OFF by default): give up `g_reserve` block slots per SM in the memory-bound sampler kernels and run the
-// side-stream noise-norm kernel with `g_noise_blocks` blocks per SM so that the two are co-resident.  Measured at 64k
-// latents (profiles/README.md, round 2): 131 us per PC step with both off, 138-152 us with either on -- the stand-alone
-// noise kernel only pays off beside the score net; next to the predictor its work is fused into that kernel instead.
-static int g_reserve = [] { const char* e = getenv("SBM_SAMPLER_RESERVE"); return e ? atoi(e) : 0; }();
-static int g_noise_blocks = [] { const char* e = getenv("SBM_NOISE_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
 template <typename K>
-static int wave_grid(K kernel, int64_t n_items, int per_thread = 1, int reserve = 0) {
+static int wave_grid(K kernel, int64_t n_items, int per_thread = 1) {
   // occupancy per kernel FUNCTION (template instantiations of one kernel share the pointer type K, not the pointer)
   static std::atomic<const void*> keys[16];
   static std::atomic<int> vals[16];
@@ -683,7 +656,6 @@ static int wave_grid(K kernel, int64_t n_items, int per_thread = 1, int reserve 
     }
   }
   if (per_sm <= 0) per_sm = 4;
-  if (reserve > 0 && per_sm - reserve >= 3) per_sm -= reserve;
   const int64_t want = (n_items + 256 * per_thread - 1) / (256 * per_thread);
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * per_sm));
 }
@@ -707,21 +679,25 @@ static Impute to_impute(const sbm_impute* im, int dd) {
   return r;
 }
 
-template <int S, bool GRAD, int NM>
-static int launch_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
-                        double* acc2, void* stream) {
+template <int S, bool GRAD, int NM, int NU>
+static int launch_norms_u(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
+                          double* acc2, void* stream) {
   const int EQ = ls->mods * ls->dd / 4;
   const int groups = (ls->batch + S - 1) / S;
-  // a group moves S*EQ quads; size the grid by 128-quad warp trips so that a small batch still spreads over the SMs
-  int blocks = wave_grid(corrector_norms_kernel<S, GRAD, NM>, (int64_t)groups * 32, 1, GRAD && NM == 0 ? g_reserve : 0);
-  if (!GRAD && g_noise_blocks > 0)  // side-stream kernel: co-resident with the memory-bound kernels, not a full wave
-    blocks = std::max(1, std::min(blocks, sm_count() * g_noise_blocks));
-  corrector_norms_kernel<S, GRAD, NM><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  // a group moves S*EQ quads; size the grid by warp trips so that a small batch still spreads over the SMs
+  const int blocks = wave_grid(corrector_norms_kernel<S, GRAD, NM, NU>, (int64_t)groups * 32);
+  corrector_norms_kernel<S, GRAD, NM, NU><<<blocks, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)grad, (const float4*)noise, acc2, ls->batch, EQ, rng ? rng->seed : 0, rng ? rng->draw : 0,
       rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)EQ : 0);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;
+}
+template <int S, bool GRAD, int NM>
+static int launch_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
+                        double* acc2, void* stream) {
+  if (!GRAD && g_noise_unroll == 8) return launch_norms_u<S, GRAD, NM, (GRAD ? 4 : 8)>(ls, grad, noise, rng, acc2, stream);
+  return launch_norms_u<S, GRAD, NM, 4>(ls, grad, noise, rng, acc2, stream);
 }
 template <bool GRAD, int NM>
 static int dispatch_norms(const sbm_latent_shape* ls, const float* grad, const float* noise, const sbm_rng* rng,
@@ -736,14 +712,17 @@ static int dispatch_norms(const sbm_latent_shape* ls, const float* grad, const f
 static int launch_predictor(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                             const float* t, const float* noise, float* x_out, float* x_mean_out,
                             int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, int rd,
-                            const float* table, void* stream, float* ss_next = nullptr, uint64_t draw_next = 0) {
+                            const float* table, void* stream) {
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  predictor_kernel<<<wave_grid(predictor_kernel, nq, 2, g_reserve), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,
-      (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,
-      rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,
-      to_impute(impute, ls->dd), rd, table, sde->T, ss_next, draw_next);
+#define SBM_LAUNCH_PREDICTOR(U)                                                                                       \
+  predictor_kernel<U><<<wave_grid(predictor_kernel<U>, nq, U), 256, 0, (cudaStream_t)stream>>>(                        \
+      (const float4*)x, (const float4*)score, t, (const float4*)noise, (float4*)x_out, (float4*)x_mean_out,           \
+      (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), probability_flow, rng ? rng->seed : 0,             \
+      rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr, rng ? rng->sample_offset * (uint64_t)(E / 4) : 0,           \
+      to_impute(impute, ls->dd), rd, table, sde->T)
+  if (g_unroll == 4) SBM_LAUNCH_PREDICTOR(4); else SBM_LAUNCH_PREDICTOR(2);
+#undef SBM_LAUNCH_PREDICTOR
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;
@@ -818,20 +797,6 @@ int sbm_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const flo
                           stream);
 }
 
-int sbm_predictor_step_fused_noise(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
-                                   const float* t, const float* table, float* x_out, float* x_mean_out,
-                                   int32_t reverse_diffusion, const sbm_rng* rng, const sbm_impute* impute,
-                                   float* noise_ss, uint64_t noise_draw, void* stream) {
-  if (check_latent(ls, "sbm_predictor_step_fused_noise")) return 1;
-  SBM_CHECK_ARG(sde && x && score && t && x_out && rng && noise_ss, "sbm_predictor_step_fused_noise: null pointer");
-  SBM_CHECK_ARG(ls->mods * ls->dd / 4 >= 32,
-                "sbm_predictor_step_fused_noise: needs at least 128 latent elements per sample (use sbm_noise_norm)");
-  SBM_CHECK_ARG(!reverse_diffusion || table || sde->kind == SBM_SDE_SUBVP,
-                "sbm_predictor_step_fused_noise: the reverse-diffusion rule needs the discretisation table");
-  return launch_predictor(ls, sde, x, score, t, nullptr, x_out, x_mean_out, 0, rng, impute, reverse_diffusion ? 1 : 0,
-                          table, stream, noise_ss, noise_draw);
-}
-
 int sbm_rd_predictor_step(const sbm_latent_shape* ls, const sbm_sde* sde, const float* x, const float* score,
                           const float* t, const float* table, const float* noise, float* x_out, float* x_mean_out,
                           int32_t probability_flow, const sbm_rng* rng, const sbm_impute* impute, void* stream) {
@@ -853,12 +818,6 @@ int sbm_corrector_norms(const sbm_latent_shape* ls, const float* grad, const flo
   return dispatch_norms<true, 0>(ls, grad, nullptr, nullptr, acc2, stream);  // acc2[1] comes from sbm_noise_norm
 }
 
-int sbm_corrector_norms_ss(const sbm_latent_shape* ls, const float* grad, float* noise_ss, double* acc2, void* stream) {
-  if (check_latent(ls, "sbm_corrector_norms_ss")) return 1;
-  SBM_CHECK_ARG(grad && noise_ss && acc2, "sbm_corrector_norms_ss: null pointer");
-  return dispatch_norms<true, 3>(ls, grad, noise_ss, nullptr, acc2, stream);
-}
-
 int sbm_noise_norm(const sbm_latent_shape* ls, const sbm_rng* rng, double* acc2, void* stream) {
   if (check_latent(ls, "sbm_noise_norm")) return 1;
   SBM_CHECK_ARG(rng && acc2, "sbm_noise_norm: null pointer");
@@ -874,11 +833,14 @@ int sbm_corrector_update(const sbm_latent_shape* ls, const sbm_sde* sde, const f
   SBM_CHECK_ARG(global_batch >= ls->batch, "sbm_corrector_update: global_batch < local batch");
   const int E = ls->mods * ls->dd;
   const int64_t nq = (int64_t)ls->batch * E / 4;
-  corrector_update_kernel<<<wave_grid(corrector_update_kernel, nq, 2, g_reserve), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, (const float4*)grad, t, (const float4*)noise, acc2, alphas, (float4*)x_out,
-      (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,
-      1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,
-      rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd), reset_acc);
+#define SBM_LAUNCH_UPDATE(U)                                                                                          \
+  corrector_update_kernel<U><<<wave_grid(corrector_update_kernel<U>, nq, U), 256, 0, (cudaStream_t)stream>>>(          \
+      (const float4*)x, (const float4*)grad, t, (const float4*)noise, acc2, alphas, (float4*)x_out,                   \
+      (float4*)x_mean_out, (uint32_t)nq, make_fastdiv((uint32_t)(E / 4)), to_sdep(sde), sde->T, target_snr,           \
+      1.0 / (double)global_batch, rng ? rng->seed : 0, rng ? rng->draw : 0, rng ? rng->draw_dev : nullptr,            \
+      rng ? rng->sample_offset * (uint64_t)(E / 4) : 0, to_impute(impute, ls->dd), reset_acc)
+  if (g_unroll == 4) SBM_LAUNCH_UPDATE(4); else SBM_LAUNCH_UPDATE(2);
+#undef SBM_LAUNCH_UPDATE
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_s();
   return 0;

@@ -80,8 +80,12 @@ class GradReducer:
     arrives.  Parameters are laid out in REVERSE registration order, which is the order the backward pass of the
     score net produces them, so buckets complete front to back while later kernels are still running."""
 
-    def __init__(self, params, bucket_bytes: int = 64 << 20, group=None):
+    def __init__(self, params, bucket_bytes: int = 64 << 20, group=None, comm_dtype=None):
+        """comm_dtype=torch.bfloat16: a bucket is cast to bf16 before its all-reduce and back to fp32 afterwards (half
+        the bytes on NVLink: 446 MB instead of 891 MB for the CelebA net).  The average then carries bf16
+        rounding (about 3e-3 relative per element); parameters, Adam moments and the flat buffer stay fp32."""
         self.group = group
+        self.comm_dtype = comm_dtype
         self.world, self.rank = _world(group)
         self.params = [p for p in params if p.requires_grad]
         if not self.params:
@@ -90,6 +94,7 @@ class GradReducer:
         dev = order[0].device
         total = sum(p.numel() for p in order)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.comm = torch.zeros(total, dtype=comm_dtype, device=dev) if comm_dtype not in (None, torch.float32) else None
         self.slot, self.bucket_of, self.buckets = {}, {}, []
         off, start, count = 0, 0, 0
         for p in order:
@@ -142,7 +147,11 @@ class GradReducer:
         if self.world == 1:
             return
         op = dist.ReduceOp.AVG if self._use_avg else dist.ReduceOp.SUM
-        self._works.append((dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True), s, e))
+        buf = self.flat[s:e]
+        if self.comm is not None:
+            buf = self.comm[s:e]
+            buf.copy_(self.flat[s:e])  # cast on the producing stream; the collective is ordered after it
+        self._works.append((dist.all_reduce(buf, op=op, group=self.group, async_op=True), s, e))
 
     def finish(self):
         """Flush buckets whose parameters produced no gradient (their slots are zeroed) and make the current stream
@@ -158,6 +167,8 @@ class GradReducer:
                     self._launch(b)
         for work, s, e in self._works:
             work.wait()
+            if self.comm is not None:
+                self.flat[s:e].copy_(self.comm[s:e])
             if not self._use_avg:
                 self.flat[s:e].div_(self.world)
         self._works = []
@@ -172,7 +183,7 @@ class DataParallelScoreNet(nn.Module):
     parameters are broadcast from rank 0 at construction; `loss.backward()` leaves the rank-AVERAGED gradients in
     `p.grad` (views of one flat buffer).  Same call contract as the wrapped net: `ddp(x, t)`."""
 
-    def __init__(self, module: nn.Module, bucket_mb: float = 64.0, process_group=None):
+    def __init__(self, module: nn.Module, bucket_mb: float = 64.0, process_group=None, grad_comm_dtype=None):
         super().__init__()
         self.module = module
         self.process_group = process_group
@@ -181,7 +192,8 @@ class DataParallelScoreNet(nn.Module):
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=dist.get_global_rank(process_group, 0) if process_group else 0,
                                    group=process_group)
-        self.reducer = GradReducer(module.parameters(), int(bucket_mb * (1 << 20)), process_group)
+        self.reducer = GradReducer(module.parameters(), int(bucket_mb * (1 << 20)), process_group,
+                                   comm_dtype=grad_comm_dtype)
         module._grad_sink = self.reducer  # picked up by autograd._Plan
 
     def forward(self, *args, **kwargs):

@@ -311,29 +311,32 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, *, kind: int, kh: int, kw: int
     return dwpk
 
 
-def unpack_wgrad(dwpk: torch.Tensor, like: torch.Tensor, cols: int, s_tap: int, s_row: int, s_col: int) -> torch.Tensor:
-    """Packed gradient -> a tensor shaped like the parameter `like` (strides as in pack_weight)."""
+def unpack_wgrad(dwpk: torch.Tensor, like: torch.Tensor, cols: int, s_tap: int, s_row: int, s_col: int,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+    """Packed gradient -> a tensor shaped like the parameter `like` (strides as in pack_weight).  `out`: a contiguous
+    fp32 destination of that shape (data-parallel training: the parameter's slot in the flat bucket buffer)."""
     taps, rows, cols_pad = dwpk.shape
-    out = torch.empty_like(like, dtype=torch.float32, memory_format=torch.contiguous_format)
+    if out is None:
+        out = torch.empty_like(like, dtype=torch.float32, memory_format=torch.contiguous_format)
     L.check(L.lib().sbm_unpack_wgrad(L.ptr(dwpk), L.ptr(out), C.c_int32(taps), C.c_int32(rows), C.c_int32(cols),
                                      C.c_int32(cols_pad), C.c_int64(s_tap), C.c_int64(s_row), C.c_int64(s_col),
                                      L.stream_ptr()), "sbm_unpack_wgrad")
     return out
 
 
-def unpack_conv2d_wgrad(dwpk, weight):
+def unpack_conv2d_wgrad(dwpk, weight, out=None):
     o, i, kh, kw = weight.shape
-    return unpack_wgrad(dwpk, weight, i, 1, i * kh * kw, kh * kw)
+    return unpack_wgrad(dwpk, weight, i, 1, i * kh * kw, kh * kw, out)
 
 
-def unpack_convT2d_wgrad(dwpk, weight):
+def unpack_convT2d_wgrad(dwpk, weight, out=None):
     i, o, kh, kw = weight.shape
-    return unpack_wgrad(dwpk, weight, i, 1, kh * kw, o * kh * kw)
+    return unpack_wgrad(dwpk, weight, i, 1, kh * kw, o * kh * kw, out)
 
 
-def unpack_linear_wgrad(dwpk, weight):
+def unpack_linear_wgrad(dwpk, weight, out=None):
     o, i = weight.shape
-    return unpack_wgrad(dwpk, weight, i, 0, i, 1)
+    return unpack_wgrad(dwpk, weight, i, 0, i, 1, out)
 
 
 def _rows(t: torch.Tensor) -> int:

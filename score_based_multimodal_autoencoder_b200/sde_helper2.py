@@ -304,26 +304,12 @@ _PREDICTORS = ("euler", "reverse_diffusion")
 
 
 def _predictor_kernel(sde, x, score, t, *, noise=None, rng=None, probability_flow=False, impute=None, want_mean=True,
-                      out=None, predictor="euler", noise_ss=None):
-    """One fused launch: Euler-Maruyama (`sbm_predictor_step`) or reverse-diffusion (`sbm_rd_predictor_step`) rule.
-    noise_ss: [B] float buffer; with in-kernel Philox noise the launch also accumulates the per-sample sum of squares of
-    the NEXT draw (rng.draw + 1 = the Langevin step that follows) into it (`sbm_predictor_step_fused_noise`)."""
+                      out=None, predictor="euler"):
+    """One fused launch: Euler-Maruyama (`sbm_predictor_step`) or reverse-diffusion (`sbm_rd_predictor_step`) rule."""
     ls = _latent_shape(x)
     x_new = out if out is not None else torch.empty_like(x)
     x_mean = torch.empty_like(x) if want_mean else None
     sc = sde._c()
-    if predictor not in _PREDICTORS:
-        raise ValueError(f"predictor must be one of {_PREDICTORS}, got {predictor!r}")
-    if noise_ss is not None:
-        if rng is None or noise is not None or probability_flow:
-            raise L.SbmError("the fused noise norm needs the in-kernel Philox stream of a stochastic predictor")
-        rd = predictor == "reverse_diffusion"
-        L.check(L.lib().sbm_predictor_step_fused_noise(
-            C.byref(ls), C.byref(sc), L.ptr(x), L.ptr(score), L.ptr(t),
-            L.ptr(sde._disc_table_on(x.device)) if rd else None, L.ptr(x_new), L.ptr(x_mean), C.c_int32(1 if rd else 0),
-            C.byref(rng), C.byref(impute) if impute is not None else None, L.ptr(noise_ss), C.c_uint64(rng.draw + 1),
-            L.stream_ptr()), "sbm_predictor_step_fused_noise")
-        return x_new, x_mean
     common = (L.ptr(noise), L.ptr(x_new), L.ptr(x_mean), C.c_int32(1 if probability_flow else 0),
               C.byref(rng) if rng is not None else None, C.byref(impute) if impute is not None else None,
               L.stream_ptr())
@@ -361,23 +347,19 @@ def _fork_noise_norm(x, rng, acc):
 
 
 def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, impute=None, want_mean=True,
-                       global_batch=None, reduce_fn=None, acc=None, out=None, noise_norm_done=False, noise_ss=None):
+                       global_batch=None, reduce_fn=None, acc=None, out=None, noise_norm_done=False):
     """norms kernel -> (optional cross-rank sum of the two batch norms) -> update kernel.  `acc` is a zeroed buffer of
     3 doubles (2 sums + a completion ticket); the update kernel re-zeroes it, so a reused `acc` never needs a memset.
     `noise_norm_done`: acc[1] already holds the Philox noise norm (`_fork_noise_norm`), the norms kernel reads the
-    score only.  `noise_ss`: the per-sample sums of squares of this draw were left by the predictor kernel."""
+    score only."""
     ls = _latent_shape(x)
     if acc is None:
         acc = torch.zeros(3, dtype=torch.float64, device=x.device)
     elif acc.numel() < 3:
         raise L.SbmError("corrector accumulator needs 3 doubles (2 sums + ticket)")
     rp = C.byref(rng) if rng is not None else None
-    if noise_ss is not None:  # per-sample sums of squares of this draw, left by the preceding predictor kernel
-        L.check(L.lib().sbm_corrector_norms_ss(C.byref(ls), L.ptr(grad), L.ptr(noise_ss), L.ptr(acc), L.stream_ptr()),
-                "sbm_corrector_norms_ss")
-    else:
-        L.check(L.lib().sbm_corrector_norms(C.byref(ls), L.ptr(grad), L.ptr(noise), None if noise_norm_done else rp,
-                                            L.ptr(acc), L.stream_ptr()), "sbm_corrector_norms")
+    L.check(L.lib().sbm_corrector_norms(C.byref(ls), L.ptr(grad), L.ptr(noise), None if noise_norm_done else rp,
+                                        L.ptr(acc), L.stream_ptr()), "sbm_corrector_norms")
     if reduce_fn is not None:  # multi-GPU exact mode: sum the two batch norms over ranks
         reduce_fn(acc[:2])
     x_new = out if out is not None else torch.empty_like(x)
@@ -507,7 +489,6 @@ class _PCRun:
         self.t_vec = torch.empty(B, device=dev, dtype=torch.float32)
         self.acc = torch.zeros(3, dtype=torch.float64, device=dev)
         self.n_draws = (0 if probability_flow else 1) + (n_steps if pc else 0)
-        self.noise_ss = torch.zeros(B, device=dev, dtype=torch.float32)
 
     def _score(self, x):
         s = _call_score(self.model, x, self.t_vec, self.z_cond)
@@ -538,11 +519,6 @@ class _PCRun:
                                 t_next_dev)
         inject = noise_pred is not None
 
-        # predictor -> corrector with in-kernel Philox noise: the predictor kernel also produces the noise norm of the
-        # first Langevin step (its draw id is the predictor's + 1); otherwise that norm comes from a side-stream kernel
-        fuse = (self.predictor_first and self.pc and self.n_steps >= 1 and not inject and not torch_rng and not pf
-                and x.shape[1] * x.shape[2] * x.shape[3] >= 128)
-
         def predictor(x, impute, want_mean):
             nz = noise_pred[i] if inject else None
             if torch_rng and not pf:
@@ -550,19 +526,16 @@ class _PCRun:
             r = None if (nz is not None or pf) else _rng.next(draw_dev)
             score = self._score(x)
             return _predictor_kernel(sde, x, score, t_vec, noise=nz, rng=r, probability_flow=pf, impute=impute,
-                                     want_mean=want_mean, predictor=self.predictor,
-                                     noise_ss=self.noise_ss if fuse else None)
+                                     want_mean=want_mean, predictor=self.predictor)
 
         def langevin(x, impute, want_mean):
             xm = x
             for k in range(self.n_steps):
                 nz = noise_corr[i, k] if inject else None
                 r, side = None, None
-                fused_k = fuse and k == 0
                 if nz is None and not torch_rng:
                     r = _rng.next(draw_dev)
-                    if not fused_k:
-                        side = _fork_noise_norm(x, r, self.acc)
+                    side = _fork_noise_norm(x, r, self.acc)
                 grad = self._score(x)
                 if torch_rng:
                     nz = torch.randn_like(x)  # reference order: drawn AFTER the net call (sde_helper2.py:96)
@@ -572,8 +545,7 @@ class _PCRun:
                 x, xm = _corrector_kernels(sde, x, grad, t_vec, self.target_snr, noise=nz, rng=r,
                                            impute=impute if final_k else None, want_mean=want_mean and final_k,
                                            global_batch=self.global_batch, reduce_fn=self.reduce_fn, acc=self.acc,
-                                           noise_norm_done=side is not None,
-                                           noise_ss=self.noise_ss if fused_k else None)
+                                           noise_norm_done=side is not None)
             return x, xm
 
         if self.predictor_first:

@@ -103,6 +103,27 @@ def test_grad_reducer_bucketed_average_gloo():
     _run(_grad_reducer)
 
 
+def _grad_reducer_bf16(rank, world):
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in [(300, 7), (5,), (4000,)]]
+    red = D.GradReducer(params, bucket_bytes=4096, comm_dtype=torch.bfloat16)
+    red.begin()
+    g = torch.Generator().manual_seed(5)
+    full = {i: torch.randn(params[i].shape, generator=g) for i in range(3)}
+    for i in reversed(range(3)):
+        red.grad_ready(params[i], full[i] * (rank + 1))
+    red.finish()
+    scale = sum(r + 1 for r in range(world)) / world
+    for i in range(3):
+        v = red.grad_view(params[i])
+        assert v.dtype == torch.float32
+        assert torch.allclose(v, full[i] * scale, rtol=2e-2, atol=1e-3)      # bf16 on the wire
+        assert not torch.equal(v, full[i] * scale)
+
+
+def test_grad_reducer_bf16_communication_gloo():
+    _run(_grad_reducer_bf16)
+
+
 def _ddp_wrapper(rank, world):
     torch.manual_seed(rank)  # different initial weights per rank: the wrapper must broadcast rank 0's
     net = torch.nn.Linear(6, 3)

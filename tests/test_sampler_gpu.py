@@ -200,11 +200,10 @@ def test_philox_statistics_and_shard_invariance():
 
 @pytest.mark.parametrize("pf,shape", [(True, (16, 5, 8, 8)), (False, (9, 3, 16, 16)), (True, (7, 1, 8, 8))])
 def test_in_kernel_noise_norms_equal_the_materialised_philox_draws(pf, shape):
-    """The corrector's noise norm never reads a noise tensor on the Philox path: predictor -> corrector order takes it
-    from per-sample sums of squares the predictor kernel accumulates (sbm_predictor_step_fused_noise), corrector-first
-    order (and samples under 128 elements) from the side-stream sbm_noise_norm kernel.  Both must equal the norms of the
-    draws themselves: run the sampler once on the in-kernel stream and once with the SAME draws materialised by
-    sbm_randn and injected (that path reduces the noise tensor it is given)."""
+    """The corrector's noise norm never reads a noise tensor on the Philox path: the side-stream sbm_noise_norm kernel
+    re-derives it from the counter-based stream (sum of squares of a Box-Muller pair = -2 ln u, no normals formed).  It
+    must equal the norm of the draws themselves: run the sampler once on the in-kernel stream and once with the SAME
+    draws materialised by sbm_randn and injected (that path reduces the noise tensor it is given)."""
     import ctypes as C
     from score_based_multimodal_autoencoder_b200 import _lib as L
     sh = _sh()

@@ -20,26 +20,18 @@ acc = torch.zeros(3, dtype=torch.float64, device=dev)
 out = torch.empty_like(x)
 
 
-noise_ss = torch.zeros(batch, device=dev)
-
-
 def pc_kernels():
-    # as pc_sampler runs predictor -> corrector: the predictor kernel also leaves the per-sample sums of squares of the
-    # corrector's Philox draw.  SBM_PROFILE_NORMS=fused: the round-1 norms kernel that regenerates the noise itself;
-    # SBM_PROFILE_NORMS=side: the stand-alone noise-norm kernel on a side stream (corrector-first order)
+    # as the samplers run them: the Philox noise-norm kernel (no memory traffic) on a side stream, joined before the
+    # score-norm kernel; set SBM_PROFILE_FUSED_NORMS=1 for the round-1 single norms kernel that regenerates the noise
     r_pred, r_corr = rng.next(), rng.next()
-    mode = os.environ.get("SBM_PROFILE_NORMS", "predictor")
-    if mode == "fused":
+    if os.environ.get("SBM_PROFILE_FUSED_NORMS") == "1":
         x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
         sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out)
-    elif mode == "side":
-        side = sh._fork_noise_norm(x, r_corr, acc)
-        x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
-        torch.cuda.current_stream().wait_stream(side)
-        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True)
-    else:
-        x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out, noise_ss=noise_ss)
-        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_ss=noise_ss)
+        return
+    side = sh._fork_noise_norm(x, r_corr, acc)
+    x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True)
 
 
 def dsm():
