@@ -7,6 +7,7 @@
 //   * linear attention / softmax attention cores (unet_model.py:135-149,162-177; unet_openai.py:345-358)
 // All reductions are fp32 per thread, combined in fp64 (atomicAdd(double)) so the E[x^2]-E[x]^2 form is safe.
 #include <atomic>
+#include <cstdlib>
 
 #include "../../include/sbmae_b200.h"
 #include "common.cuh"
@@ -1021,6 +1022,259 @@ linear_attn_tiled_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
   }
 }
 
+// Tensor-core variant (n = 64 or 256 positions, the 8x8 and 16x16 levels that carry ~90 % of the attention time).
+// The register-tiled kernel above is FMA-issue bound (~5 k instructions per thread, 1.2 TB/s at 16x16: ncu, round 1);
+// here the two 32-wide products run as bf16 mma.sync.m16n8k16 with fp32 accumulation:
+//   load : every thread reads 16-byte chunks of R = n/32 rows of q, k and v straight into registers (no staging)
+//   q    : soft-max over d across the 8 lanes that share a row (3 xor-shuffles), * scale, -> bf16 qb[p][d]
+//   k    : column max / exp / column sums from the registers (lanes with equal tid & 7 share channels: 2 shuffles +
+//          one shared-memory exchange between the warps), exp(k - max) -> bf16 kb[p][d]; 1/sum goes into the context
+//   v    : -> bf16 vb[p][e]
+//   ctx  : warp = one 16x8 tile of ctx[d][e] = sum_p kb[p][d] vb[p][e]   (A, B via ldmatrix.trans), * 1/ksum -> cb
+//   out  : warp = two 16-row tiles of out[p][e] = sum_d qb[p][d] cb[d][e]; the tile is written back over the warp's own
+//          qb rows and leaves with 16-byte coalesced stores
+// Rows are 64 bytes; 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3), which makes every ldmatrix phase
+// (8 rows x 16 bytes) conflict-free.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t swz_off(int row, int col) {  // byte offset of element (row, col) of a [*][32] bf16 tile
+  return (uint32_t)(row * 64 + ((((col >> 3) ^ (row >> 1)) & 3) << 4) + ((col & 7) << 1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int R>  // rows per thread: n = 32 * R
+__global__ void __launch_bounds__(256, 2)
+linear_attn_mma_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                       int heads, float scale) {
+  constexpr int n = 32 * R;
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  uint8_t* qb = attn_smem;                   // [n][32] bf16, swizzled
+  uint8_t* kb = qb + n * 64;
+  uint8_t* vb = kb + n * 64;
+  uint8_t* cb = vb + n * 64;                 // [32][32] bf16 context
+  float (*red)[8][32] = reinterpret_cast<float (*)[8][32]>(cb + 32 * 64);   // [2][8][32] per-warp column maxima / sums
+  float* kinv = reinterpret_cast<float*>(cb + 32 * 64 + 2 * 8 * 32 * 4);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int hid = heads * kHeadDim;
+  const int q8 = tid & 7, p0 = tid >> 3;        // 16-byte chunk (channels 4 q8 .. 4 q8 + 3) of rows p0 + 32 j
+  const float* src = qkv + ((int64_t)b * n + p0) * ldq + h * kHeadDim + q8 * 4;
+
+  // ---- load: 3 R independent 16-byte loads per thread
+  float4 qv[R], kv[R], vv[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const float* s = src + (int64_t)(32 * j) * ldq;
+    qv[j] = __ldg(reinterpret_cast<const float4*>(s));
+    kv[j] = __ldg(reinterpret_cast<const float4*>(s + hid));
+    vv[j] = __ldg(reinterpret_cast<const float4*>(s + 2 * hid));
+  }
+  // ---- v -> bf16; q soft-max over d (8 lanes share a row); k column max over this thread's rows
+  float4 kmax4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int p = p0 + 32 * j;
+    *reinterpret_cast<uint2*>(vb + swz_off(p, q8 * 4)) =
+        make_uint2(pack_bf16x2(vv[j].x, vv[j].y), pack_bf16x2(vv[j].z, vv[j].w));
+    float m = fmaxf(fmaxf(qv[j].x, qv[j].y), fmaxf(qv[j].z, qv[j].w));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    const float e0 = __expf(qv[j].x - m), e1 = __expf(qv[j].y - m), e2 = __expf(qv[j].z - m), e3 = __expf(qv[j].w - m);
+    float ssum = (e0 + e1) + (e2 + e3);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+    const float inv = scale / ssum;
+    *reinterpret_cast<uint2*>(qb + swz_off(p, q8 * 4)) =
+        make_uint2(pack_bf16x2(e0 * inv, e1 * inv), pack_bf16x2(e2 * inv, e3 * inv));
+    kmax4.x = fmaxf(kmax4.x, kv[j].x); kmax4.y = fmaxf(kmax4.y, kv[j].y);
+    kmax4.z = fmaxf(kmax4.z, kv[j].z); kmax4.w = fmaxf(kmax4.w, kv[j].w);
+  }
+  // lanes q8, q8 + 8, q8 + 16, q8 + 24 hold the same channels
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    kmax4.x = fmaxf(kmax4.x, __shfl_xor_sync(0xffffffffu, kmax4.x, o));
+    kmax4.y = fmaxf(kmax4.y, __shfl_xor_sync(0xffffffffu, kmax4.y, o));
+    kmax4.z = fmaxf(kmax4.z, __shfl_xor_sync(0xffffffffu, kmax4.z, o));
+    kmax4.w = fmaxf(kmax4.w, __shfl_xor_sync(0xffffffffu, kmax4.w, o));
+  }
+  if (lane < 8) *reinterpret_cast<float4*>(&red[0][warp][q8 * 4]) = kmax4;
+  __syncthreads();
+  float4 cmax = *reinterpret_cast<const float4*>(&red[0][0][q8 * 4]);
+#pragma unroll
+  for (int w2 = 1; w2 < 8; ++w2) {
+    const float4 t = *reinterpret_cast<const float4*>(&red[0][w2][q8 * 4]);
+    cmax.x = fmaxf(cmax.x, t.x); cmax.y = fmaxf(cmax.y, t.y); cmax.z = fmaxf(cmax.z, t.z); cmax.w = fmaxf(cmax.w, t.w);
+  }
+  // ---- k: exp(k - max) -> bf16, column sums
+  float4 ks = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    const int p = p0 + 32 * j;
+    const float e0 = __expf(kv[j].x - cmax.x), e1 = __expf(kv[j].y - cmax.y), e2 = __expf(kv[j].z - cmax.z),
+                e3 = __expf(kv[j].w - cmax.w);
+    ks.x += e0; ks.y += e1; ks.z += e2; ks.w += e3;
+    *reinterpret_cast<uint2*>(kb + swz_off(p, q8 * 4)) = make_uint2(pack_bf16x2(e0, e1), pack_bf16x2(e2, e3));
+  }
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    ks.x += __shfl_xor_sync(0xffffffffu, ks.x, o); ks.y += __shfl_xor_sync(0xffffffffu, ks.y, o);
+    ks.z += __shfl_xor_sync(0xffffffffu, ks.z, o); ks.w += __shfl_xor_sync(0xffffffffu, ks.w, o);
+  }
+  if (lane < 8) *reinterpret_cast<float4*>(&red[1][warp][q8 * 4]) = ks;
+  __syncthreads();   // qb, kb, vb and the per-warp sums are complete
+  if (tid < 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) t += red[1][w2][tid];
+    kinv[tid] = 1.f / t;
+  }
+  // ---- context: warp = tile (mi, ni) of ctx[d][e], d in [16 mi, +16), e in [8 ni, +8); K = all n positions
+  {
+    const int mi = warp >> 2, ni = warp & 3;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const int jm = lane >> 3, r = lane & 7;
+    const uint32_t kb_s = smem_addr(kb), vb_s = smem_addr(vb);
+#pragma unroll 4
+    for (int ks0 = 0; ks0 < n; ks0 += 16) {
+      uint32_t a[4], bfr[2];
+      // A[m = d][k = p] = kb[p][d] (stored [k][m]): matrices (k 0-7, m 0-7), (k 0-7, m 8-15), (k 8-15, m 0-7), (k 8-15, m 8-15)
+      ldsm_x4_t(kb_s + swz_off(ks0 + r + ((jm & 2) ? 8 : 0), 16 * mi + ((jm & 1) ? 8 : 0)), a);
+      // B[k = p][n = e] = vb[p][e] (stored [k][n]): matrices (k 0-7), (k 8-15) at columns 8 ni
+      ldsm_x2_t(vb_s + swz_off(ks0 + r + ((jm & 1) ? 8 : 0), 8 * ni), bfr);
+      mma_bf16_16816(c, a, bfr);
+    }
+    __syncthreads();   // kinv is visible (and every warp is past its reads of red[1])
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    const int d_lo = 16 * mi + g, d_hi = d_lo + 8, e = 8 * ni + t2;
+    *reinterpret_cast<uint32_t*>(cb + swz_off(d_lo, e)) = pack_bf16x2(c[0] * kinv[d_lo], c[1] * kinv[d_lo]);
+    *reinterpret_cast<uint32_t*>(cb + swz_off(d_hi, e)) = pack_bf16x2(c[2] * kinv[d_hi], c[3] * kinv[d_hi]);
+  }
+  __syncthreads();
+  // ---- out: warp = 16-row tiles mt = warp, warp + 8, ...; B fragments of the whole 32x32 context loaded once
+  {
+    const int jm = lane >> 3, r = lane & 7;
+    const uint32_t qb_s = smem_addr(qb), cb_s = smem_addr(cb);
+    uint32_t bf[2][4][2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) ldsm_x2_t(cb_s + swz_off(16 * kk + r + ((jm & 1) ? 8 : 0), 8 * ni), bf[kk][ni]);
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    for (int mt = warp; mt < n / 16; mt += 8) {
+      float c[4][4];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) { c[ni][0] = 0.f; c[ni][1] = 0.f; c[ni][2] = 0.f; c[ni][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t a[4];
+        // A[m = p][k = d] = qb[p][d] (row-major): matrices (m 0-7, k 0-7), (m 8-15, k 0-7), (m 0-7, k 8-15), (m 8-15, k 8-15)
+        ldsm_x4(qb_s + swz_off(16 * mt + r + ((jm & 1) ? 8 : 0), 16 * kk + ((jm & 2) ? 8 : 0)), a);
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) mma_bf16_16816(c[ni], a, bf[kk][ni]);
+      }
+      __syncwarp();   // all lanes have read this tile's qb rows: overwrite them with the output tile
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        *reinterpret_cast<uint32_t*>(qb + swz_off(16 * mt + g, 8 * ni + t2)) = pack_bf16x2(c[ni][0], c[ni][1]);
+        *reinterpret_cast<uint32_t*>(qb + swz_off(16 * mt + g + 8, 8 * ni + t2)) = pack_bf16x2(c[ni][2], c[ni][3]);
+      }
+      __syncwarp();
+      // 16 rows x 4 chunks of 16 bytes: two per lane, 4 consecutive lanes cover one 64-byte output row
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = lane + 32 * i, row = 16 * mt + (idx >> 2), ch = idx & 3;
+        const uint4 v = *reinterpret_cast<const uint4*>(qb + swz_off(row, ch * 8));
+        *reinterpret_cast<uint4*>(out + ((int64_t)b * n + row) * ldo + h * kHeadDim + ch * 8) = v;
+      }
+    }
+  }
+}
+
+// Small maps (n <= 16 positions: the 4x4, 2x2 and 1x1 levels).  One WARP per (head, sample), lane = channel; the
+// products broadcast their scalar operand with warp shuffles, nothing goes through shared memory.  The block-per-
+// (head, sample) kernels above spend 35-41 us per launch here on 4096 nearly empty blocks (ncu, round 2).
+template <int NMAX>
+__global__ void __launch_bounds__(256)
+linear_attn_small_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                         int n, int heads, int pairs, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int hb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (hb >= pairs) return;
+  const int b = hb / heads, h = hb - b * heads;
+  const int hid = heads * kHeadDim;
+  const float* base = qkv + (int64_t)b * n * ldq + h * kHeadDim + lane;
+  float q[NMAX], k[NMAX], v[NMAX];
+#pragma unroll
+  for (int p = 0; p < NMAX; ++p) {
+    const bool on = p < n;
+    q[p] = on ? __ldg(base + (int64_t)p * ldq) : 0.f;
+    k[p] = on ? __ldg(base + (int64_t)p * ldq + hid) : -INFINITY;
+    v[p] = on ? __ldg(base + (int64_t)p * ldq + 2 * hid) : 0.f;
+  }
+  // q: soft-max over the 32 channels of a row (across lanes), * scale
+#pragma unroll
+  for (int p = 0; p < NMAX; ++p) {
+    if (p >= n) break;
+    float m = q[p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = __expf(q[p] - m);
+    q[p] = e * (scale / warp_sum(e));
+  }
+  // k: soft-max over the positions of a channel (inside the lane)
+  float km = k[0];
+#pragma unroll
+  for (int p = 1; p < NMAX; ++p) km = fmaxf(km, k[p]);
+  float ksum = 0.f;
+#pragma unroll
+  for (int p = 0; p < NMAX; ++p) {
+    k[p] = __expf(k[p] - km);   // padded rows hold -inf -> 0
+    ksum += k[p];
+  }
+  const float kinv = 1.f / ksum;
+  // context[d][e] (lane = e): k~[p][d] comes from lane d
+  float ctx[kHeadDim];
+#pragma unroll
+  for (int d = 0; d < kHeadDim; ++d) ctx[d] = 0.f;
+#pragma unroll
+  for (int p = 0; p < NMAX; ++p) {
+    if (p >= n) break;
+    const float kp = k[p] * kinv;
+#pragma unroll
+    for (int d = 0; d < kHeadDim; ++d) ctx[d] = fmaf(__shfl_sync(0xffffffffu, kp, d), v[p], ctx[d]);
+  }
+  // out[p][e] = sum_d ctx[d][e] q~[p][d]
+  for (int p = 0; p < n; ++p) {
+    float qp = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < NMAX; ++pp) qp = (pp == p) ? q[pp] : qp;   // q[p] without dynamic register indexing
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < kHeadDim; ++d) acc = fmaf(ctx[d], __shfl_sync(0xffffffffu, qp, d), acc);
+    out[((int64_t)b * n + p) * ldo + h * kHeadDim + lane] = __float2bfloat16_rn(acc);
+  }
+}
+
 // ------------------------------------------------------------------------------ softmax attention core
 // qkv: fp32 [B, n, ldq]; layout selected by (q_off, k_off, v_off, head_stride): channel of (head, d) for q is
 // q_off + head*head_stride + d.   out[b, i, o_off + head*dh + d] = sum_j softmax_j(scale * q_i . k_j) v_j[d]
@@ -1320,6 +1574,36 @@ int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, i
                         float scale, void* stream) {
   SBM_CHECK_ARG(qkv && out && B > 0 && n > 0 && heads > 0, "sbm_linear_attn_fwd: bad args");
   dim3 grid(heads, B);
+  static const int use_mma = [] { const char* e = getenv("SBM_ATTN_MMA"); return e ? atoi(e) : 1; }();
+  if (use_mma && (n == 256 || n == 64) && ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+      ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const size_t sm = (size_t)3 * n * 64 + 32 * 64 + 2 * 8 * 32 * 4 + 32 * 4;
+    static bool configured = false;
+    if (!configured) {
+      SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       3 * 256 * 64 + 32 * 64 + 2 * 8 * 32 * 4 + 32 * 4));
+      configured = true;
+    }
+    if (n == 256)
+      linear_attn_mma_kernel<8><<<grid, 256, sm, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, heads, scale);
+    else
+      linear_attn_mma_kernel<2><<<grid, 256, sm, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, heads, scale);
+    SBM_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
+  if (use_mma && n <= 16) {
+    const int pairs = heads * B;
+    if (n <= 4)
+      linear_attn_small_kernel<4><<<(pairs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, n,
+                                                                                    heads, pairs, scale);
+    else
+      linear_attn_small_kernel<16><<<(pairs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo,
+                                                                                     n, heads, pairs, scale);
+    SBM_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const int n4 = (n + 3) & ~3;
   const size_t smem_t = ((size_t)n4 * 32 + std::max(n4 * 32, 4096) + (size_t)n4 * 32 + 1024 + 512) * sizeof(float);
   if (ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 && ldq % 4 == 0 &&
