@@ -10,7 +10,11 @@
  *
  * Conventions
  *  - all pointers are DEVICE pointers unless stated otherwise; no allocation, no
- *    ownership transfer, no hidden global state except immutable caches;
+ *    ownership transfer, no hidden global state except immutable caches -- and the
+ *    process-wide MEASUREMENT switches (sbm_conv_force_single_cta, sbm_conv_force_direct_epilogue,
+ *    sbm_conv_pixel_major, the SBM_* environment knobs read once at load), which select between
+ *    kernels that compute the same result (bit-identical or equal up to fp32 summation order)
+ *    and exist for A/B timing only: a production caller never touches them;
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and
  *    capturable into a CUDA graph;
  *  - return 0 on success; non-zero on error, message via sbm_last_error();

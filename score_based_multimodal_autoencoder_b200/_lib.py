@@ -123,3 +123,23 @@ class PackDesc(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("taps", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32),
                 ("cols_pad", C.c_int32), ("s_tap", C.c_int64), ("s_row", C.c_int64), ("s_col", C.c_int64),
                 ("tiles_c", C.c_int32), ("first_block", C.c_int32), ("taps_magic", C.c_uint32), ("reserved", C.c_int32)]
+
+
+# ------------------------------------------------------------------ NVTX ranges (opt-in: SBM_NVTX=1)
+import contextlib as _contextlib
+
+_NVTX = os.environ.get("SBM_NVTX", "0") == "1"
+
+
+@_contextlib.contextmanager
+def nvtx(name: str):
+    """Named range around a phase of the path (sampler step, score-net forward, training step) for Nsight timelines;
+    a no-op unless SBM_NVTX=1 (ranges cost a host call each)."""
+    if not _NVTX:
+        yield
+        return
+    torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        torch.cuda.nvtx.range_pop()

@@ -1058,7 +1058,12 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
     // CTA-pair kernel: 256 x BN tiles; worth it once the tile pairs cover ~40 % of the SM pairs (measured on the
     // 2x2-level layers: 64 pair tiles on 74 SM pairs run 1.3x faster than 128 single-CTA tiles -- half the weight
     // traffic per CTA).  A cout tail is fine: weight rows beyond cout are TMA zero fill, the epilogue clips the columns
-    return !g_force_single && (BN == 256 || BN == 128) && !a->out_nchw &&
+    // BN == 64 (cout <= 64: the PolyMNIST net's 42- and 64-channel layers): the persistent pair kernel only pays once
+    // the list is long -- a single-CTA launch of one tile per CTA has no epilogue / main-loop overlap, and at 64k
+    // latents these layers ran at a tenth of the tensor peak (round-1 sweep)
+    static const int kPair64 = [] { const char* e = getenv("SBM_PAIR_BN64"); return e ? atoi(e) : 1; }();
+    const bool bn_ok = BN == 256 || BN == 128 || (BN == 64 && kPair64 && a->cout > 32);
+    return !g_force_single && bn_ok && !a->out_nchw &&
            (int64_t)((m_tiles_ + 1) / 2) * ((a->cout + BN - 1) / BN) * nphase * 200 >= (int64_t)sm_count() * kPairPct;
   };
   // Pixel-major tiling (see ConvKernelParams::pm): a 'same' convolution computes taps on zero padding for every border
@@ -1146,11 +1151,13 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       for (int ph = 0; ph < nphase; ++ph)
         p.taps[ph].out_q = (a->kind == SBM_CONVT_4X4_S2) ? (int32_t)((ph >> 1) * OWf + (ph & 1)) : 0;
       if (BN == 256) return launch_conv_pair<256, 5, true>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
-      return launch_conv_pair<128, 6, true>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
+      if (BN == 128) return launch_conv_pair<128, 6, true>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
+      return launch_conv_pair<64, 8, true>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
     }
     memset(&em, 0, sizeof(em));
     if (BN == 256) return launch_conv_pair<256, 6, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
-    return launch_conv_pair<128, 8, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
+    if (BN == 128) return launch_conv_pair<128, 8, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
+    return launch_conv_pair<64, 10, false>(tmA, tmB, em, p, m_tiles, n_tiles_pair, nphase, stream);
   }
   dim3 grid((unsigned)m_tiles, (unsigned)((a->cout + BN - 1) / BN), (unsigned)nphase);
   g_last_variant = BN;

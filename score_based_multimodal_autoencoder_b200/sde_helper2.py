@@ -491,7 +491,8 @@ class _PCRun:
         self.n_draws = (0 if probability_flow else 1) + (n_steps if pc else 0)
 
     def _score(self, x):
-        s = _call_score(self.model, x, self.t_vec, self.z_cond)
+        with L.nvtx("sbm.score_net"):
+            s = _call_score(self.model, x, self.t_vec, self.z_cond)
         if self.guidance is not None:
             cl_g, cl_s, given, all_mods = self.guidance
             s = _guided(_f32c(s), x, self.t_vec, cl_g, cl_s, given, all_mods)
@@ -548,14 +549,15 @@ class _PCRun:
                                            noise_norm_done=side is not None)
             return x, xm
 
-        if self.predictor_first:
+        with L.nvtx(f"sbm.pc_step[{i}]"):
+            if self.predictor_first:
+                if self.pc:
+                    x, _ = predictor(x, None, False)
+                    return langevin(x, im, last)
+                return predictor(x, im, last)
             if self.pc:
-                x, _ = predictor(x, None, False)
-                return langevin(x, im, last)
+                x, _ = langevin(x, None, False)
             return predictor(x, im, last)
-        if self.pc:
-            x, _ = langevin(x, None, False)
-        return predictor(x, im, last)
 
 
 @torch.no_grad()

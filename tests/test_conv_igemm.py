@@ -59,6 +59,11 @@ CASES = [
     ("pair_down",    "s2", 4, 330, 16, 16, 64, 256),   # stride-2 view through the pair kernel
     ("pair_up",      "t",  4, 320, 4, 4, 64, 256),     # 4 output phases x 20 pairs... (80 pair tiles)
     ("pair_small2",  "s1", 3, 9000, 2, 2, 64, 128),    # 2x2 maps: 32 images per tile
+    # BN=64 pair variant (cout <= 64: the PolyMNIST net's narrow layers at large batch)
+    ("pair64_c3_8",  "s1", 3, 600, 8, 8, 64, 64),      # 300 m-tiles
+    ("pair64_c42",   "s1", 3, 330, 8, 8, 42, 42),      # cin and cout tails (init_dim = 42)
+    ("pair64_lin",   "s1", 1, 12000, 1, 1, 128, 64),
+    ("pair64_down",  "s2", 4, 500, 8, 8, 64, 64),
 ]
 
 

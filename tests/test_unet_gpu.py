@@ -96,7 +96,10 @@ def test_unet_pads_non_power_of_two_latents_like_the_reference(hw):
 
 def test_unet_large_batch_runs_in_slices_with_identical_results():
     """Batches beyond Unet.max_batch() (the 4k-64k sweep of BASELINE configs[4]) are walked in slices; the net has no
-    cross-sample coupling, so the result equals the one-shot forward bit for bit."""
+    cross-sample coupling, so the result equals the one-shot forward up to the GEMM variant a layer gets at the slice's
+    size (single-CTA vs CTA-pair tiles accumulate in another order: a last-bit fp32 difference can flip a bf16 rounding
+    downstream, cf. tests/test_full_size_gpu.py) -- far inside the net's bf16 error, and exactly 0 when the variants
+    coincide."""
     from score_based_multimodal_autoencoder_b200.unet_model import Unet
     torch.manual_seed(0)
     m = Unet(dim=32, channels=5, dim_mults=(1, 2)).cuda().eval()
@@ -107,4 +110,6 @@ def test_unet_large_batch_runs_in_slices_with_identical_results():
         m.max_chunk_elems = 300 * 8 * 8 * 64          # -> slices of 256 samples (whole 256-sample blocks)
         assert m.max_batch(8, 8) < 700
         y1 = m(x, t)
-    assert y1.shape == y0.shape and torch.equal(y0, y1)
+    err = rel_l2(y1, y0)
+    print(f"sliced vs one-shot forward: rel-L2 {err:.3e}")
+    assert y1.shape == y0.shape and err < 3e-3
