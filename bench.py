@@ -501,7 +501,9 @@ def conv_roofline(model, sde, x0, ops, L):
     dense_a = sum(r[4] for r in rec)
     top = max(rec, key=lambda r: r[2])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
         traffic = json.load(open(tpath)).get("conv_igemm_pair_kernel<256,5,staged>", {}).get("avg_dram_bytes_per_launch")
     return {"bound": "tensor", "kernel": "conv_igemm_pair_kernel<256,5,staged> (tcgen05 cta_group::2 implicit GEMM)",

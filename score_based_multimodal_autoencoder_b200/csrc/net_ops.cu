@@ -1252,25 +1252,45 @@ linear_attn_small_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat
     ksum += k[p];
   }
   const float kinv = 1.f / ksum;
-  // context[d][e] (lane = e): k~[p][d] comes from lane d
+  // the two products need a SCALAR of another lane per multiply-add (k~[p][d], q~[p][d] live in lane d): stage both in
+  // the warp's shared-memory rows and read them back as 16-byte broadcasts (a shuffle per multiply-add made the kernel
+  // SHFL-bound: 1 warp shuffle per clock and SM, 34 us at n = 16)
+  __shared__ __align__(16) float stage[8][2][NMAX][kHeadDim];
+  float (*sq)[kHeadDim] = stage[threadIdx.x >> 5][0];
+  float (*sk)[kHeadDim] = stage[threadIdx.x >> 5][1];
+#pragma unroll
+  for (int p = 0; p < NMAX; ++p) {
+    sq[p][lane] = q[p];
+    sk[p][lane] = k[p] * kinv;
+  }
+  __syncwarp();
+  // context[d][e] (lane = e)
   float ctx[kHeadDim];
 #pragma unroll
   for (int d = 0; d < kHeadDim; ++d) ctx[d] = 0.f;
 #pragma unroll
   for (int p = 0; p < NMAX; ++p) {
     if (p >= n) break;
-    const float kp = k[p] * kinv;
 #pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) ctx[d] = fmaf(__shfl_sync(0xffffffffu, kp, d), v[p], ctx[d]);
+    for (int d4 = 0; d4 < kHeadDim; d4 += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(&sk[p][d4]);
+      ctx[d4] = fmaf(kk.x, v[p], ctx[d4]);
+      ctx[d4 + 1] = fmaf(kk.y, v[p], ctx[d4 + 1]);
+      ctx[d4 + 2] = fmaf(kk.z, v[p], ctx[d4 + 2]);
+      ctx[d4 + 3] = fmaf(kk.w, v[p], ctx[d4 + 3]);
+    }
   }
   // out[p][e] = sum_d ctx[d][e] q~[p][d]
   for (int p = 0; p < n; ++p) {
-    float qp = 0.f;
-#pragma unroll
-    for (int pp = 0; pp < NMAX; ++pp) qp = (pp == p) ? q[pp] : qp;   // q[p] without dynamic register indexing
     float acc = 0.f;
 #pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) acc = fmaf(ctx[d], __shfl_sync(0xffffffffu, qp, d), acc);
+    for (int d4 = 0; d4 < kHeadDim; d4 += 4) {
+      const float4 qq = *reinterpret_cast<const float4*>(&sq[p][d4]);
+      acc = fmaf(ctx[d4], qq.x, acc);
+      acc = fmaf(ctx[d4 + 1], qq.y, acc);
+      acc = fmaf(ctx[d4 + 2], qq.z, acc);
+      acc = fmaf(ctx[d4 + 3], qq.w, acc);
+    }
     out[((int64_t)b * n + p) * ldo + h * kHeadDim + lane] = __float2bfloat16_rn(acc);
   }
 }

@@ -3,8 +3,8 @@
   * N-step drift of the conditional PC sampler with the bf16 score net and injected noise, against the fp32 CPU oracle:
     PolyMNIST net, VPSDE(1, 5), N = 100 (train_poly.sh:17, train_poly_unet_cont.py:843) and the CelebA SDE
     VPSDE(0.1, 20), N = 1000 (train_cel.sh:11) with a narrow net; the curve is printed at intermediate step counts.
-    STATED BOUND: rel-L2 of the sampler state <= 2e-2 after N = 100 steps, <= 5e-2 after N = 1000 steps
-    (SURVEY.md App. E: the reference's own autocast(bf16) run drifts 4.2e-3 after 100 steps);
+    STATED BOUND: rel-L2 of the sampler state <= 2e-2 after N = 100 steps and after N = 1000 steps (measured on B200:
+    5.0e-3 and 6.6e-3; SURVEY.md App. E: the reference's own autocast(bf16) run drifts 4.2e-3 after 100 steps);
   * `UNetModel` at the full z-conditioned CelebA configuration (train_lat_celebhq_unet_cont2_cond.py:648-653,
     model_channels 128, channel_mult (1,2,4,8), z_dim 512): rows of a 256-sample batch against the oracle;
   * `loss_fn(likelihood_weighting=True, im_sample=True)` (sde_helper2.py:129-150, 164-165, 177-179) against a golden of
@@ -78,7 +78,7 @@ def test_drift_after_1000_steps_celeba_sde():
                          (1, 10, 100, 500, 1000), seed=32)
     print("dim-32 three-level net on the CelebA latent, VPSDE(0.1,20), N=1000, B=2: drift (rel-L2 vs fp32 oracle) " +
           ", ".join(f"{k}: {v:.3e}" for k, v in curve.items()))
-    assert all(v < 5e-2 for v in curve.values()), curve
+    assert all(v < 2e-2 for v in curve.values()), curve
 
 
 def test_unetmodel_full_celeba_config_rows_vs_oracle():
