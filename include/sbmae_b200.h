@@ -111,6 +111,14 @@ int sbm_conv_wgrad(const sbm_wgrad_args* a, void* stream);
 int sbm_unpack_wgrad(const float* src, float* dst, int32_t taps, int32_t rows, int32_t cols, int32_t cols_pad,
                      int64_t s_tap, int64_t s_row, int64_t s_col, void* stream);
 
+/* Multi-tensor form of sbm_unpack_wgrad: every listed packed gradient -> its parameter layout in ONE launch.  Same
+ * descriptor as sbm_pack_weights_multi with the roles swapped: src = packed fp32 [taps][rows][cols_pad], dst = fp32
+ * parameter-gradient layout addressed by (s_tap, s_row, s_col); tensor k owns blocks [first_block, first_block +
+ * ceil(rows/32)*tiles_c), tiles_c = ceil(cols/32); sorted by first_block. */
+struct sbm_pack_desc;
+int sbm_unpack_wgrad_multi(const struct sbm_pack_desc* descs_dev, int32_t n_descs, int32_t n_blocks, int32_t max_taps,
+                           void* stream);
+
 /* GroupNorm(1,C) -> conv folding: dst = bf16 [kh*kw][rows][cols_pad] of w*gamma[col]; tab[0][cls][row] = sum over the
  * taps valid in border class cls of sum_col bf16(w*gamma), tab[1][cls][row] = same sum of w*beta, + bias[row].
  * cls bit0: tap row 0 valid (pixel row >= 1), bit1: tap row 2 valid, bit2 / bit3: same for columns. */

@@ -73,8 +73,14 @@ class _Plan:
     def _grad(self, p, g):
         sink = getattr(self.m, "_grad_sink", None)
         if sink is not None:  # data-parallel training: copy into the flat bucket buffer, all-reduce when a bucket fills
+            if sink.completes_bucket(p):
+                ops.unpack_flush()   # deferred weight-gradient unpacks of this bucket must land before it goes out
             g = sink.grad_ready(p, g)
-        self.pg[p] = g if p not in self.pg else self.pg[p] + g
+        if p in self.pg:
+            ops.unpack_flush()   # both contributions must be materialised before they are summed
+            self.pg[p] = self.pg[p] + g
+        else:
+            self.pg[p] = g
 
     # ------------------------------------------------------------------ generic conv backward pieces
     def _conv_s1_bwd(self, conv, x_b, dy_b, dy_f32_for_bias, cin, cout, k, want_dx=True, bias_grad=None):
@@ -402,11 +408,13 @@ class _Plan:
             sink.begin()
         # every zero-initialised accumulator of this pass comes out of ONE zeroed buffer (one fill launch)
         ops.arena_begin(getattr(self.m, "_zero_arena_words", 0), dout.device)
+        ops.unpack_begin()   # the ~100 weight-gradient unpacks of the pass leave as one launch (per bucket)
         try:
             self.bwd_last(dout.contiguous().float())
             for fn in reversed(self.tape):
                 fn()
         finally:
+            ops.unpack_end()
             self.m._zero_arena_words = ops.arena_end()
         self.tape = []
         if sink is not None:

@@ -1206,18 +1206,50 @@ __device__ __forceinline__ void pack_tile(const PackDesc& d, int tile, float* ti
   const int r0 = (tile / d.tiles_c) * 32, c0 = (tile % d.tiles_c) * 32;
   const bool col_inner = llabs(d.s_col) <= llabs(d.s_row);
   const int n = taps * 1024;
-  if (d.s_tap == 1 && d.s_col == taps && (taps & 1) && (d.s_row & 3) == 0 && c0 + 32 <= cols &&
-      (reinterpret_cast<uintptr_t>(d.src) & 15) == 0) {
-    // nn.Conv2d layout [O][I][taps] with odd taps: a tile row is ONE contiguous run of 32*taps floats that maps 1:1
-    // onto the shared-memory row (TP == taps) -> 16-byte loads
-    const int run4 = taps * 8;  // float4s per row
-    for (int e = threadIdx.x; e < 32 * run4; e += 256) {
-      const int rr = e / run4, j4 = e - rr * run4;
-      const int r = r0 + rr;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < rows) v = __ldg(reinterpret_cast<const float4*>(d.src + (int64_t)r * d.s_row + (int64_t)c0 * taps) + j4);
-      float* tp = tile_smem + rr * 33 * TP + j4 * 4;
-      tp[0] = v.x; tp[1] = v.y; tp[2] = v.z; tp[3] = v.w;
+  // Fast path: weights whose taps are contiguous in memory (|s_tap| == 1) and whose faster tensor index has stride
+  // `taps` -- the nn.Conv2d layout [O][I][taps] read as (rows = O, cols = I) for the forward operand, or as
+  // (rows = I, cols = O) with the taps walked backwards for the data-gradient operand.  For a fixed index of the slower
+  // ("major") dimension the 32 faster ("minor") indices x taps form ONE contiguous run of 32 * taps floats: 16-byte
+  // loads, issued in batches of up to 9 per thread before any is consumed (the kernel is memory-latency bound: ncu,
+  // round 2).  The generic path below reads the data-gradient operands (half of all packs of a training step) with
+  // one 4-byte load in flight per thread.
+  const bool tap_fwd = d.s_tap == 1, tap_rev = d.s_tap == -1;
+  const bool col_minor = d.s_col == taps, row_minor = !col_minor && d.s_row == taps;
+  const int64_t s_major = col_minor ? d.s_row : d.s_col;
+  const float* run0 = d.src - (tap_rev ? taps - 1 : 0);
+  if ((tap_fwd || tap_rev) && (col_minor || row_minor) && (taps & 1) && taps > 1 && (s_major & 3) == 0 &&
+      (col_minor ? c0 + 32 <= cols : r0 + 32 <= rows) && (reinterpret_cast<uintptr_t>(run0) & 15) == 0) {
+    const int run4 = taps * 8;  // float4s per run
+    const int minor0 = col_minor ? c0 : r0, major0 = col_minor ? r0 : c0, major_n = col_minor ? rows : cols;
+    for (int base = 0; base < 32 * run4; base += 9 * 256) {
+      float4 v[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int e = base + i * 256 + (int)threadIdx.x;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < 32 * run4) {
+          const int mj = e / run4, j4 = e - mj * run4;
+          if (major0 + mj < major_n)
+            v[i] = __ldg(reinterpret_cast<const float4*>(run0 + (int64_t)(major0 + mj) * s_major + (int64_t)minor0 * taps) + j4);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int e = base + i * 256 + (int)threadIdx.x;
+        if (e < 32 * run4) {
+          const int mj = e / run4, j4 = e - mj * run4;
+          const float vv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k = 4 * j4 + u;
+            const int mi = (int)__umulhi((uint32_t)k, d.taps_magic);   // k / taps
+            const int tt = k - mi * taps;
+            const int t = tap_rev ? taps - 1 - tt : tt;
+            const int rr = col_minor ? mj : mi, cc = col_minor ? mi : mj;
+            tile_smem[(rr * 33 + cc) * TP + t] = vv[u];
+          }
+        }
+      }
     }
   } else {
 #pragma unroll 4

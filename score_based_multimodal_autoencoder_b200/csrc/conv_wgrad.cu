@@ -411,9 +411,106 @@ unpack_wgrad_tiled_kernel(const float* __restrict__ src, float* __restrict__ dst
   }
 }
 
+// All weight-gradient unpacks of a backward pass (or of one gradient bucket) in ONE launch: block -> (descriptor, 32 x 32
+// tile) by binary search over first_block, then the tiled body above.  99 launches of 5-20 us each (one per GEMM weight:
+// 128-block grids, latency-bound at 0.3-0.7 TB/s, 1.2 ms of a CelebA training step) become one wave-filling launch.
+__global__ void __launch_bounds__(256)
+unpack_wgrad_multi_kernel(const sbm_pack_desc* __restrict__ descs, int n_descs) {
+  extern __shared__ float tile[];  // [32 rows][33][TP]
+  int lo = 0, hi = n_descs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const sbm_pack_desc d = descs[lo];
+  const int t_idx = (int)blockIdx.x - d.first_block;
+  const int taps = d.taps, rows = d.rows, cols = d.cols, cols_pad = d.cols_pad;
+  const int TP = taps | 1;
+  const int r0 = (t_idx / d.tiles_c) * 32, c0 = (t_idx % d.tiles_c) * 32;
+  const float* src = d.src;
+  float* dst = static_cast<float*>(d.dst);
+  const int n = taps * 1024;
+  // read side: 16-byte loads, issued in batches of up to 9 per thread BEFORE any of them is consumed (the kernel is
+  // bound by memory latency: with one 4-byte load in flight per thread it moved 1.5 TB/s, ncu round 2)
+  if ((cols_pad & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int n4 = taps * 256;   // (t, rr, c4): 8 float4 per 32-column row
+    for (int base = 0; base < n4; base += 9 * 256) {
+      float4 v[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int e = base + i * 256 + (int)threadIdx.x;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n4) {
+          const int c4 = e & 7, rr = (e >> 3) & 31, t = e >> 8;
+          const int r = r0 + rr, c = c0 + c4 * 4;
+          if (r < rows && c < cols_pad) v[i] = __ldcs(reinterpret_cast<const float4*>(src + ((int64_t)t * rows + r) * cols_pad + c));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int e = base + i * 256 + (int)threadIdx.x;
+        if (e < n4) {
+          const int c4 = e & 7, rr = (e >> 3) & 31, t = e >> 8;
+          float* tp = tile + (rr * 33 + c4 * 4) * TP + t;
+          tp[0] = v[i].x; tp[TP] = v[i].y; tp[2 * TP] = v[i].z; tp[3 * TP] = v[i].w;
+        }
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int cc = e & 31, rr = (e >> 5) & 31, t = e >> 10;
+      const int r = r0 + rr, c = c0 + cc;
+      tile[(rr * 33 + cc) * TP + t] = (r < rows && c < cols) ? src[((int64_t)t * rows + r) * cols_pad + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  const bool col_inner = llabs(d.s_col) <= llabs(d.s_row);
+  // write side, nn.Conv2d layout [rows][cols][taps] with odd taps: a tile row is ONE contiguous run of 32 * taps floats
+  // that maps 1:1 onto the shared-memory row (TP == taps) -> 16-byte stores
+  if (d.s_tap == 1 && d.s_col == taps && (taps & 1) && (d.s_row & 3) == 0 && c0 + 32 <= cols &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int run4 = taps * 8;
+    for (int e = threadIdx.x; e < 32 * run4; e += 256) {
+      const int rr = e / run4, j4 = e - rr * run4;
+      const int r = r0 + rr;
+      if (r < rows) {
+        const float* tp = tile + rr * 33 * TP + j4 * 4;
+        *reinterpret_cast<float4*>(dst + (int64_t)r * d.s_row + (int64_t)c0 * taps + j4 * 4) =
+            make_float4(tp[0], tp[1], tp[2], tp[3]);
+      }
+    }
+    return;
+  }
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int rc = taps == 1 ? e : (int)__umulhi((uint32_t)e, d.taps_magic);  // e / taps (exact for e < 2^16)
+    const int t = e - rc * taps;
+    const int inner = rc & 31, outer = rc >> 5;
+    const int rr = col_inner ? outer : inner, cc = col_inner ? inner : outer;
+    const int r = r0 + rr, c = c0 + cc;
+    if (r < rows && c < cols) dst[t * d.s_tap + (int64_t)r * d.s_row + (int64_t)c * d.s_col] = tile[(rr * 33 + cc) * TP + t];
+  }
+}
+
 }  // namespace sbm
 
 extern "C" {
+
+int sbm_unpack_wgrad_multi(const sbm_pack_desc* descs_dev, int32_t n_descs, int32_t n_blocks, int32_t max_taps,
+                           void* stream) {
+  SBM_CHECK_ARG(descs_dev && n_descs > 0 && n_blocks > 0 && max_taps > 0 && max_taps <= 16,
+                "sbm_unpack_wgrad_multi: bad args");
+  const size_t smem = (size_t)(max_taps | 1) * 32 * 33 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(sbm::unpack_wgrad_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    configured = smem;
+  }
+  sbm::unpack_wgrad_multi_kernel<<<n_blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(descs_dev, n_descs);
+  SBM_CUDA_OK(cudaGetLastError());
+  sbm::g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
 
 int sbm_conv_wgrad(const sbm_wgrad_args* a, void* stream) {
   return sbm::conv_wgrad_impl(a, static_cast<cudaStream_t>(stream));

@@ -126,6 +126,10 @@ class GradReducer:
         self._works = []
         self.launched = []  # bucket ids in launch order (introspection / tests)
 
+    def completes_bucket(self, p: torch.Tensor) -> bool:
+        """Whether reporting `p` next would launch its bucket's all-reduce (producers that defer writes flush first)."""
+        return self._pending[self.bucket_of[p]] == 1
+
     def grad_ready(self, p: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         """Called by the backward pass with the final gradient of `p`; returns the view that will hold the average."""
         off, n = self.slot[p]

@@ -311,13 +311,85 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, *, kind: int, kh: int, kw: int
     return dwpk
 
 
+class _UnpackBatch:
+    """Weight-gradient unpacks of one backward pass, deferred and issued as ONE `sbm_unpack_wgrad_multi` launch per
+    flush (end of the pass; data-parallel training: before a gradient bucket goes on the wire).  The descriptor table
+    of flush k lives in its own pinned staging buffer + device buffer, allocated outside CUDA-graph capture and refreshed
+    in place (a captured copy node re-reads the pinned buffer at every replay, like FusedAdam's tables)."""
+
+    def __init__(self):
+        self.items = []          # (dwpk, out, taps, rows, cols, cols_pad, s_tap, s_row, s_col): tensors kept alive
+        self.flushes = 0
+        self.stages = {}         # flush index -> [pinned bytes, device bytes, last signature]
+
+    def begin(self):
+        self.items, self.flushes = [], 0
+
+    def add(self, *item):
+        self.items.append(item)
+
+    def flush(self):
+        if not self.items:
+            return
+        items, self.items = self.items, []
+        k, self.flushes = self.flushes, self.flushes + 1
+        sig = tuple((it[0].data_ptr(), it[1].data_ptr()) + it[2:] for it in items)
+        nbytes = C.sizeof(L.PackDesc) * len(items)
+        st = self.stages.get(k)
+        dev = items[0][0].device
+        if st is None or st[0].numel() < nbytes or st[1].device != dev:
+            cap = max(nbytes, C.sizeof(L.PackDesc) * 256)
+            st = [torch.empty(cap, dtype=torch.uint8).pin_memory(), torch.empty(cap, dtype=torch.uint8, device=dev), None]
+            self.stages[k] = st
+        blocks, max_taps = 0, 1
+        arr = (L.PackDesc * len(items))()
+        for i, (dwpk, out, taps, rows, cols, cols_pad, s_tap, s_row, s_col) in enumerate(items):
+            tiles_c = (cols + 31) // 32
+            arr[i] = L.PackDesc(dwpk.data_ptr(), out.data_ptr(), taps, rows, cols, cols_pad, s_tap, s_row, s_col, tiles_c,
+                                blocks, ((1 << 32) + taps - 1) // taps if taps > 1 else 0, 0)
+            blocks += tiles_c * ((rows + 31) // 32)
+            max_taps = max(max_taps, taps)
+        if st[2] != sig:
+            st[0][:nbytes].copy_(torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8))
+            st[2] = sig
+        st[1][:nbytes].copy_(st[0][:nbytes], non_blocking=True)
+        L.check(L.lib().sbm_unpack_wgrad_multi(L.ptr(st[1]), C.c_int32(len(items)), C.c_int32(blocks),
+                                               C.c_int32(max_taps), L.stream_ptr()), "sbm_unpack_wgrad_multi")
+
+
+_unpack_batch = _UnpackBatch()
+_unpack_active = False
+
+
+def unpack_begin() -> None:
+    """Defer the large weight-gradient unpacks that follow until `unpack_flush()`."""
+    global _unpack_active
+    _unpack_batch.begin()
+    _unpack_active = True
+
+
+def unpack_flush() -> None:
+    _unpack_batch.flush()
+
+
+def unpack_end() -> None:
+    global _unpack_active
+    _unpack_batch.flush()
+    _unpack_active = False
+
+
 def unpack_wgrad(dwpk: torch.Tensor, like: torch.Tensor, cols: int, s_tap: int, s_row: int, s_col: int,
                  out: torch.Tensor | None = None) -> torch.Tensor:
     """Packed gradient -> a tensor shaped like the parameter `like` (strides as in pack_weight).  `out`: a contiguous
-    fp32 destination of that shape (data-parallel training: the parameter's slot in the flat bucket buffer)."""
+    fp32 destination of that shape (data-parallel training: the parameter's slot in the flat bucket buffer).  Inside
+    `unpack_begin()` ... `unpack_end()` the tiled unpacks are batched into one launch per flush: the returned tensor is
+    filled when the batch is flushed."""
     taps, rows, cols_pad = dwpk.shape
     if out is None:
         out = torch.empty_like(like, dtype=torch.float32, memory_format=torch.contiguous_format)
+    if _unpack_active and rows * cols >= 4096 and taps <= 16 and dwpk.is_contiguous():
+        _unpack_batch.add(dwpk, out, taps, rows, cols, cols_pad, s_tap, s_row, s_col)
+        return out
     L.check(L.lib().sbm_unpack_wgrad(L.ptr(dwpk), L.ptr(out), C.c_int32(taps), C.c_int32(rows), C.c_int32(cols),
                                      C.c_int32(cols_pad), C.c_int64(s_tap), C.c_int64(s_row), C.c_int64(s_col),
                                      L.stream_ptr()), "sbm_unpack_wgrad")
