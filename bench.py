@@ -365,7 +365,8 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
     # gradient all-reduce in bf16 (446 MB instead of 891 MB per step for the CelebA net); fp32 flat
     # buffer, parameters and Adam moments.  SBM_DSM_COMM=fp32 measures the exact-average variant
     comm = None if os.environ.get("SBM_DSM_COMM", "bf16") == "fp32" else torch.bfloat16
-    net = DataParallelScoreNet(model, bucket_mb=64.0, grad_comm_dtype=comm) if world > 1 else model
+    bucket_mb = float(os.environ.get("SBM_DSM_BUCKET_MB", "64"))   # A/B: bucket size of the overlapped all-reduce
+    net = DataParallelScoreNet(model, bucket_mb=bucket_mb, grad_comm_dtype=comm) if world > 1 else model
     opt = FusedAdam(model.parameters(), lr=lr)
     sh.manual_seed(777, sample_offset=rank * shape[0])
     z_host = torch.randn(*shape, generator=torch.Generator().manual_seed(1234 + rank)).pin_memory()
@@ -433,7 +434,8 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
             "gpu_launches_per_step": launches, "loss": loss_val, "cuda_graph": used_graph,
             "model_tflops_per_gpu": 3 * fwd_gf * 1e9 * shape[0] / (ms * 1e-3) / 1e12,
             "grad_allreduce": None if world == 1 else {
-                "backend": "nccl", "bucket_mb": 64, "dtype": "bf16" if comm is not None else "fp32",
+                "backend": "nccl", "bucket_mb": bucket_mb, "dtype": "bf16" if comm is not None else "fp32",
+                "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
                 "bytes_per_step": sum(p.numel() for p in model.parameters()) * (2 if comm is not None else 4),
                 "overlap": "buckets launched from inside the backward pass; weight gradients are written straight "
                            "into the flat bucket buffer"},

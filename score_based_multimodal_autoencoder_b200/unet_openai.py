@@ -500,4 +500,10 @@ class SuperResModel(UNetModel):  # unet_openai.py:578-592
         super().__init__(in_channels * 2, *args, **kwargs)
 
     def forward(self, x, timesteps, low_res=None, **kwargs):
-        raise NotImplementedError("SuperResModel is a pixel-space model outside the latent score path (SURVEY.md 2.1)")
+        """unet_openai.py:587-593: the low-resolution conditioning image is up-sampled (nearest) to x's extent and
+        concatenated along the channels; the net itself is UNetModel's kernel plan (2 * in_channels inputs).  No shipped
+        command of the reference instantiates this class; the input glue is two torch tensor ops."""
+        if low_res is not None:
+            up = torch.nn.functional.interpolate(low_res, tuple(x.shape[-2:]), mode="nearest")
+            x = torch.cat([x, up], dim=1)
+        return super().forward(x, timesteps, **kwargs)
