@@ -365,7 +365,7 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
     # gradient all-reduce in bf16 (446 MB instead of 891 MB per step for the CelebA net); fp32 flat
     # buffer, parameters and Adam moments.  SBM_DSM_COMM=fp32 measures the exact-average variant
     comm = None if os.environ.get("SBM_DSM_COMM", "bf16") == "fp32" else torch.bfloat16
-    bucket_mb = float(os.environ.get("SBM_DSM_BUCKET_MB", "64"))   # A/B: bucket size of the overlapped all-reduce
+    bucket_mb = float(os.environ.get("SBM_DSM_BUCKET_MB", "1024"))   # A/B knob; default = one bucket (measured best)
     net = DataParallelScoreNet(model, bucket_mb=bucket_mb, grad_comm_dtype=comm) if world > 1 else model
     opt = FusedAdam(model.parameters(), lr=lr)
     sh.manual_seed(777, sample_offset=rank * shape[0])
@@ -437,7 +437,8 @@ def dsm_train_bench(device, steps, warmup, which="poly", world=1, rank=0, use_gr
                 "backend": "nccl", "bucket_mb": bucket_mb, "dtype": "bf16" if comm is not None else "fp32",
                 "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"),
                 "bytes_per_step": sum(p.numel() for p in model.parameters()) * (2 if comm is not None else 4),
-                "overlap": "buckets launched from inside the backward pass; weight gradients are written straight "
+                "overlap": "a bucket is all-reduced as soon as the backward pass has produced its last gradient (one "
+                           "bucket by default: profiles/r2_dsm_dp_ab_n8.jsonl); weight gradients are written straight "
                            "into the flat bucket buffer"},
             "config": {"workload": f"{which}_dsm: Unet{tuple(kw.values())} DSM training, batch {shape[0]} per GPU x {world}, "
                                    f"latent {list(shape[1:])}, Adam lr {lr}, bf16 GEMM operands / fp32 master weights, "
