@@ -12,7 +12,7 @@
  *  - all pointers are DEVICE pointers unless stated otherwise; no allocation, no
  *    ownership transfer, no hidden global state except immutable caches -- and the
  *    process-wide MEASUREMENT switches (sbm_conv_force_single_cta, sbm_conv_force_direct_epilogue,
- *    sbm_conv_pixel_major, the SBM_* environment knobs read once at load), which select between
+ *    sbm_conv_epilogue_static, sbm_conv_pixel_major, the SBM_* environment knobs read once at load), which select between
  *    kernels that compute the same result (bit-identical or equal up to fp32 summation order)
  *    and exist for A/B timing only: a production caller never touches them;
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and
@@ -86,8 +86,11 @@ int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 int sbm_conv_force_single_cta(int32_t on);
 /* A/B switch: 1 = per-thread global stores in the CTA-pair kernel instead of the TMA-staged epilogue */
 int sbm_conv_force_direct_epilogue(int32_t on);
+/* A/B switch: 0 = always run the run-time tested epilogue loop of the CTA-pair kernel instead of the statically
+ * compiled loop of the call's flag set (same arithmetic in the same order: bit-identical results); default 1 */
+int sbm_conv_epilogue_static(int32_t on);
 /* which kernel the calling thread's last sbm_conv_igemm used: N tile | CTA-pair << 16 | staged epilogue << 17 |
- * pixel-major tiling << 18 */
+ * pixel-major tiling << 18 | statically compiled epilogue mode << 19 */
 int sbm_conv_last_variant(void);
 /* pixel-major tiling of stride-1 'same' convolutions (a tile = 128 samples at ONE output pixel, so taps that only read
  * zero padding there are skipped): -1 = decide by work estimate (default), 0 = never, 1 = whenever the CTA-pair kernel
