@@ -497,19 +497,19 @@ def conv_roofline(model, sde, x0, ops, L):
         fl = sum(r[2] for r in rows)
         return ms, fl
 
-    # same kernel template with or without pixel-major tiling (bit 18)
-    dom = [r for r in rec if (r[3] & ~(1 << 18)) == (256 | (1 << 16) | (1 << 17))] or rec
+    # same kernel family with or without pixel-major tiling (bit 18) and whichever epilogue loop was compiled in (bit 19:
+    # the 4th template argument of conv_igemm_pair_kernel selects the flag set of the epilogue, the main loop is one)
+    dom = [r for r in rec if (r[3] & ~((1 << 18) | (1 << 19))) == (256 | (1 << 16) | (1 << 17))] or rec
     ms_d, fl_d = agg(dom)
     ms_a, fl_a = agg(rec)
     dense_a = sum(r[4] for r in rec)
     top = max(rec, key=lambda r: r[2])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    if not os.path.exists(tpath):
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    tpath = next((q for q in (os.path.join(ROOT, "profiles", n) for n in ("r2b_traffic.json", "r2_traffic.json",
+                                                                          "r1_traffic.json")) if os.path.exists(q)), "")
+    if tpath:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
         traffic = json.load(open(tpath)).get("conv_igemm_pair_kernel<256,5,staged>", {}).get("avg_dram_bytes_per_launch")
-    return {"bound": "tensor", "kernel": "conv_igemm_pair_kernel<256,5,staged> (tcgen05 cta_group::2 implicit GEMM)",
+    return {"bound": "tensor", "kernel": "conv_igemm_pair_kernel<256,5,staged,MODE> (tcgen05 cta_group::2 implicit GEMM; MODE = compiled epilogue flag set)",
             "achieved": fl_d / (ms_d * 1e-3) / 1e12, "unit": "TFLOP/s", "launches": len(dom),
             "algorithmic_gflop_per_launch": fl_d / 1e9 / len(dom), "avg_launch_us": ms_d * 1e3 / len(dom),
             "share_of_forward_conv_time": ms_d / ms_a,

@@ -1427,10 +1427,18 @@ static int dwconv7_pipe_launch(const float* x, int64_t ldx, const float* w, cons
   return 0;
 }
 
+int dwconv7_mma_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
+                       void* out_bf16, int64_t ldo, double* stats, int B, int H, int W, int C, cudaStream_t st);
+
 static int dwconv7_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond,
                           int64_t ldc, void* out, int out_dtype, int64_t ldo, double* stats, int32_t B, int32_t H,
                           int32_t W, int32_t C, int flip, const float* addend, int64_t ldadd, cudaStream_t st) {
   SBM_CHECK_ARG(x && w && out && B > 0 && C > 0 && H > 0 && W > 0, "sbm_dwconv7: bad args");
+  // bf16 output on 16x16 / 8x8 / 4x4 maps: banded products on the tensor cores (dwconv_mma.cu)
+  if (out_dtype == SBM_BF16 && !flip && addend == nullptr) {
+    const int rc = dwconv7_mma_launch(x, ldx, w, bias, cond, ldc, out, ldo, stats, B, H, W, C, st);
+    if (rc >= 0) return rc;
+  }
   const bool aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (aligned && H == W && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16)) {
 #define SBM_DW_PIPE(WW)                                                                                              \
