@@ -181,6 +181,10 @@ int sbm_time_embed(const float* t, void* out_bf16, float* out_f32, int32_t B, in
 /* LinearAttention core (unet_model.py:162-177) on qkv fp32 [B,n,ldq] (channels q|k|v, heads x 32) -> bf16 [B,n,ldo] */
 int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
                         float scale, void* stream);
+/* the same on a bf16 qkv tensor (n = 64 or 256 positions): the to_qkv GEMM writes and the attention kernel reads half
+ * the bytes; the soft-max arithmetic stays fp32 */
+int sbm_linear_attn_fwd_bf16(const void* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
+                             float scale, void* stream);
 /* softmax attention core (unet_model.py:135-149; unet_openai.py:345-358): channel of (head,d) for q is
  * q_off + head*head_stride + d (k_off, v_off likewise); logits scaled by `scale`. */
 int sbm_softmax_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,

@@ -79,11 +79,11 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return 0;
 }
 
-// statically compiled epilogue modes live in conv_pair_modes{0..3}.cu (three modes each, compiled in parallel)
+// statically compiled epilogue modes live in conv_pair_modes{0..4}.cu (up to three modes each, compiled in parallel)
 #define SBM_DECL_GROUP(g)                                                                                              \
   int launch_pair_static_g##g(int mode_idx, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, \
                               const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream);
-SBM_DECL_GROUP(0) SBM_DECL_GROUP(1) SBM_DECL_GROUP(2) SBM_DECL_GROUP(3)
+SBM_DECL_GROUP(0) SBM_DECL_GROUP(1) SBM_DECL_GROUP(2) SBM_DECL_GROUP(3) SBM_DECL_GROUP(4)
 #undef SBM_DECL_GROUP
 int launch_pair_static(int mode_idx, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em,
                        const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream) {
@@ -92,6 +92,7 @@ int launch_pair_static(int mode_idx, int bn, const CUtensorMap& tmA, const CUten
     case 1: return launch_pair_static_g1(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 2: return launch_pair_static_g2(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 3: return launch_pair_static_g3(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
+    case 4: return launch_pair_static_g4(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     default: return -1;
   }
 }
@@ -385,11 +386,11 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       if (!a->out2) em.out2 = em.out;
       for (int ph = 0; ph < nphase; ++ph)
         p.taps[ph].out_q = (a->kind == SBM_CONVT_4X4_S2) ? (int32_t)((ph >> 1) * OWf + (ph & 1)) : 0;
-      // statically compiled epilogue loop when the flag set is one of SBM_EPI_MODES and there is no column tail
+      // statically compiled epilogue loop when the flag set is one of SBM_EPI_MODES
       int epi_mode = -1;
       const bool al16 = (a->bias == nullptr || p.bias_vec) &&
                         (a->gn_tab == nullptr || (reinterpret_cast<uintptr_t>(a->gn_tab) & 15) == 0);
-      if (g_epi_static && a->cout % 16 == 0 && al16 && a->rowbias == nullptr &&
+      if (g_epi_static && (a->gn_tab == nullptr || a->cout % 4 == 0) && al16 && a->rowbias == nullptr &&
           (a->act == SBM_ACT_NONE || a->act == SBM_ACT_GELU) && !(a->out2 != nullptr && a->out2_preact)) {
         uint32_t bits = 0;
         if (a->gn_tab) bits |= EM_GN;

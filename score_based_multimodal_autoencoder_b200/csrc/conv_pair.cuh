@@ -276,7 +276,7 @@ __device__ __forceinline__ uint32_t epi_flags(const ConvKernelParams& p) {
 template <uint32_t MODE>
 struct EpiMode {
   static constexpr bool dyn = (MODE & EM_DYN) != 0;
-  // static modes imply: cout % 16 == 0 (no column tail) and 16-byte aligned bias / table rows
+  // static modes imply 16-byte aligned bias / GroupNorm table rows (cout % 4 == 0 when a table is present)
   __device__ __forceinline__ static bool has(uint32_t fl, uint32_t bits) { return ((dyn ? fl : MODE) & bits) != 0; }
   __device__ __forceinline__ static bool gn(uint32_t fl) { return has(fl, EM_GN); }
   __device__ __forceinline__ static bool bias(uint32_t fl) { return has(fl, EM_BIAS); }
@@ -289,10 +289,11 @@ struct EpiMode {
   __device__ __forceinline__ static bool o2(uint32_t fl) { return has(fl, EM_O2 | EM_O2PRE); }
   __device__ __forceinline__ static bool o2pre(uint32_t fl) { return has(fl, EM_O2PRE); }
   __device__ __forceinline__ static bool stats(uint32_t fl) { return has(fl, EM_STATS); }
-  __device__ __forceinline__ static bool full(int n, int cout) { return dyn ? (n + 16 <= cout) : true; }
-  __device__ __forceinline__ static bool vec(int n, int cout) { return dyn ? (n + 16 <= cout && (cout & 3) == 0) : true; }
+  // a column tail (cout % 16 != 0: the 170-channel stem) takes the clamped scalar loads in its last chunk only
+  __device__ __forceinline__ static bool full(int n, int cout) { return n + 16 <= cout; }
+  __device__ __forceinline__ static bool vec(int n, int cout) { return n + 16 <= cout && (!dyn || (cout & 3) == 0); }
   __device__ __forceinline__ static bool biasvec(uint32_t fl, int n, int cout) {
-    return dyn ? ((fl & EM_BIASVEC) != 0 && n + 16 <= cout) : true;
+    return n + 16 <= cout && (!dyn || (fl & EM_BIASVEC) != 0);
   }
 };
 
@@ -589,7 +590,8 @@ struct EpiMaps {
   X(8, EM_BIAS | EM_O2)                        /* stem, down / up-sampling convs with a bf16 copy */ \
   X(9, EM_BIAS | EM_RES32)                     /* middle attention to_out + residual */           \
   X(10, EM_GN | EM_RES32 | EM_STATS)                                                             \
-  X(11, EM_BIAS | EM_GELU | EM_OBF16 | EM_STATS)
+  X(11, EM_BIAS | EM_GELU | EM_OBF16 | EM_STATS)                                                 \
+  X(12, EM_GN | EM_OBF16)                      /* to_qkv with bf16 output (16x16 / 8x8 attention) */
 inline int find_epi_mode(uint32_t bits) {
 #define SBM_EPI_FIND(idx, mode) if (bits == (uint32_t)(mode)) return idx;
   SBM_EPI_MODES(SBM_EPI_FIND)

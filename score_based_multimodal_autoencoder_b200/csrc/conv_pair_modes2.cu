@@ -19,6 +19,7 @@ int launch_pair_static_g2(int mode_idx, int bn, const CUtensorMap& tmA, const CU
 #define SBM_EPI_PICK_9(idx, mode) 
 #define SBM_EPI_PICK_10(idx, mode) 
 #define SBM_EPI_PICK_11(idx, mode) 
+#define SBM_EPI_PICK_12(idx, mode) 
     SBM_EPI_MODES(SBM_EPI_PICK)
 #undef SBM_EPI_PICK
     default: return -1;

@@ -62,7 +62,7 @@ struct DwCfg {
   static constexpr int PLW = NS * SPW + 2;                // words per channel plane (2 mod 8)
   static constexpr int RING = T < 8 ? T : 8;              // live accumulator tiles
   static constexpr int kChan = 16;
-  static constexpr size_t smem = (size_t)kChan * PLW * 4 + NS * 2 * sizeof(float);
+  static constexpr size_t smem = (size_t)kChan * PLW * 4 + 8 * NS * 2 * sizeof(float);   // + [warp][sample][2] sums
 };
 
 // tap of channel c that multiplies input position k of tile To + delta for output position m of tile To
@@ -141,7 +141,6 @@ dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
           dst[3 * PLW] = cq + 3 < C ? pack_bf16(v0[u].w, v1[u].w) : 0u;
         }
       }
-      if (tid < NS * 2) tstats[tid] = 0.f;
     }
     __syncthreads();
 
@@ -205,9 +204,10 @@ dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
           s1a += __shfl_xor_sync(0xffffffffu, s1a, o); s2a += __shfl_xor_sync(0xffffffffu, s2a, o);
           s1b += __shfl_xor_sync(0xffffffffu, s1b, o); s2b += __shfl_xor_sync(0xffffffffu, s2b, o);
         }
+        // one slot per (warp, sample): no floating-point atomics, so the sums do not depend on the order the warps finish
         if (g == 0) {
-          if (ok0) { atomicAdd(tstats + 2 * (nb + 2 * t), s1a); atomicAdd(tstats + 2 * (nb + 2 * t) + 1, s2a); }
-          if (ok1) { atomicAdd(tstats + 2 * (nb + 2 * t + 1), s1b); atomicAdd(tstats + 2 * (nb + 2 * t + 1) + 1, s2b); }
+          float* ws = tstats + (warp * NS + nb + 2 * t) * 2;
+          ws[0] = s1a; ws[1] = s2a; ws[2] = s1b; ws[3] = s2b;
         }
       }
     }
@@ -216,7 +216,12 @@ dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
     // ================= pass 3: planes -> channels-last bf16 rows (16-byte stores), statistics to global memory
     if (stats != nullptr && tid < NS * 2) {
       const int b = s_base + (tid >> 1);
-      if (b < B) atomicAdd(stats + 2 * (int64_t)b + (tid & 1), (double)tstats[tid]);
+      if (b < B) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) tsum += tstats[wq * NS * 2 + tid];   // fixed order
+        atomicAdd(stats + 2 * (int64_t)b + (tid & 1), (double)tsum);
+      }
     }
     {
       constexpr int kItems = NS * HW * 2;             // (sample, position, channel octet)
@@ -270,7 +275,9 @@ int launch_w(const float* x, int64_t ldx, const float* w, const float* bias, con
 int dwconv7_mma_launch(const float* x, int64_t ldx, const float* w, const float* bias, const float* cond, int64_t ldc,
                        void* out_bf16, int64_t ldo, double* stats, int B, int H, int W, int C, cudaStream_t st) {
   static const bool enabled = [] { const char* e = getenv("SBM_DWCONV_MMA"); return e ? atoi(e) != 0 : true; }();
-  if (!enabled || H != W || (W != 16 && W != 8 && W != 4)) return -1;
+  // 4x4 maps: 16 positions per sample leave the planes half padding; the FFMA2 kernel is faster there (36 vs 40 us)
+  static const bool w4 = [] { const char* e = getenv("SBM_DWCONV_MMA_W4"); return e ? atoi(e) != 0 : false; }();
+  if (!enabled || H != W || (W != 16 && W != 8 && !(W == 4 && w4))) return -1;
   if ((ldx & 3) || (ldo & 7) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out_bf16) & 15)) return -1;
   if (W == 16) return launch_w<16>(x, ldx, w, bias, cond, ldc, out_bf16, ldo, stats, B, C, st);
   if (W == 8) return launch_w<8>(x, ldx, w, bias, cond, ldc, out_bf16, ldo, stats, B, C, st);

@@ -117,6 +117,41 @@ dwconv7_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict
 }
 
 
+// 1x1 maps (the bottom level of the CelebA net): only the centre tap sees a pixel, so the "convolution" is
+// h[b][c] = x[b][c] * w[c][3][3] + bias[c] + cond[b][c].  One warp per sample; the tiled kernels spent 24 us per
+// launch on staging for it (64 blocks, one 32-channel chunk each).
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+dwconv7_point_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                     const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
+                     TOut* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float h = fmaf(__ldg(x + (int64_t)b * ldx + c), __ldg(w + (int64_t)c * 49 + 24), bias ? __ldg(bias + c) : 0.f);
+    if (cond != nullptr) h += __ldg(cond + (int64_t)b * ldc + c);
+    if constexpr (sizeof(TOut) == 2) {
+      const __nv_bfloat16 r = __float2bfloat16_rn(h);
+      out[(int64_t)b * ldo + c] = r;
+      h = __bfloat162float(r);   // the statistics describe the tensor the next GEMM reads
+    } else {
+      out[(int64_t)b * ldo + c] = h;
+    }
+    s1 += h;
+    s2 = fmaf(h, h, s2);
+  }
+  if (stats != nullptr) {
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+      atomicAdd(stats + 2 * (int64_t)b, (double)s1);
+      atomicAdd(stats + 2 * (int64_t)b + 1, (double)s2);
+    }
+  }
+}
+
 // Register-tiled variant for W in {1,2,4,8,16}: one thread = one (channel, output row); the 49 taps live in
 // registers and every staged input value is read from shared memory once per kernel row (7 LDS per input
 // instead of 49), so the kernel is FMA-bound instead of LDS-bound.
@@ -1060,9 +1095,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int R>  // rows per thread: n = 32 * R
+// 4 consecutive channels of a qkv row: fp32 (16 bytes) or bf16 (8 bytes; the to_qkv GEMM then writes and this kernel
+// reads half the bytes -- at 16x16 the pair is HBM-bound on exactly those)
+__device__ __forceinline__ float4 load_qkv4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load_qkv4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+
+template <int R, typename TIn>  // rows per thread: n = 32 * R
 __global__ void __launch_bounds__(256, 2)
-linear_attn_mma_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo,
+linear_attn_mma_kernel(const TIn* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ out, int64_t ldo,
                        int heads, float scale) {
   constexpr int n = 32 * R;
   extern __shared__ __align__(128) uint8_t attn_smem[];
@@ -1076,16 +1120,16 @@ linear_attn_mma_kernel(const float* __restrict__ qkv, int64_t ldq, __nv_bfloat16
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int hid = heads * kHeadDim;
   const int q8 = tid & 7, p0 = tid >> 3;        // 16-byte chunk (channels 4 q8 .. 4 q8 + 3) of rows p0 + 32 j
-  const float* src = qkv + ((int64_t)b * n + p0) * ldq + h * kHeadDim + q8 * 4;
+  const TIn* src = qkv + ((int64_t)b * n + p0) * ldq + h * kHeadDim + q8 * 4;
 
-  // ---- load: 3 R independent 16-byte loads per thread
+  // ---- load: 3 R independent 16-byte (fp32) / 8-byte (bf16) loads per thread
   float4 qv[R], kv[R], vv[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) {
-    const float* s = src + (int64_t)(32 * j) * ldq;
-    qv[j] = __ldg(reinterpret_cast<const float4*>(s));
-    kv[j] = __ldg(reinterpret_cast<const float4*>(s + hid));
-    vv[j] = __ldg(reinterpret_cast<const float4*>(s + 2 * hid));
+    const TIn* s = src + (int64_t)(32 * j) * ldq;
+    qv[j] = load_qkv4(s);
+    kv[j] = load_qkv4(s + hid);
+    vv[j] = load_qkv4(s + 2 * hid);
   }
   // ---- v -> bf16; q soft-max over d (8 lanes share a row); k column max over this thread's rows
   float4 kmax4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -1439,6 +1483,16 @@ static int dwconv7_launch(const float* x, int64_t ldx, const float* w, const flo
     const int rc = dwconv7_mma_launch(x, ldx, w, bias, cond, ldc, out, ldo, stats, B, H, W, C, st);
     if (rc >= 0) return rc;
   }
+  if (H == 1 && W == 1 && addend == nullptr) {
+    const int blocks = (B + 7) / 8;
+    if (out_dtype == SBM_BF16)
+      dwconv7_point_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, ldx, w, bias, cond, ldc, (__nv_bfloat16*)out, ldo, stats, B, C);
+    else
+      dwconv7_point_kernel<float><<<blocks, 256, 0, st>>>(x, ldx, w, bias, cond, ldc, (float*)out, ldo, stats, B, C);
+    SBM_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const bool aligned = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (aligned && H == W && (W == 1 || W == 2 || W == 4 || W == 8 || W == 16)) {
 #define SBM_DW_PIPE(WW)                                                                                              \
@@ -1481,6 +1535,26 @@ static int dwconv7_launch(const float* x, int64_t ldx, const float* w, const flo
     dwconv7_kernel<<<grid, 256, smem, st>>>(x, ldx, w, bias, cond, ldc, outf, ldo, stats, C, H, W);
   }
 #undef SBM_DW_ROWS
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <typename TIn>
+static int linear_attn_mma_launch(const TIn* qkv, int64_t ldq, void* out, int64_t ldo, int B, int n, int heads, float scale,
+                                  cudaStream_t st) {
+  const size_t sm = (size_t)3 * n * 64 + 32 * 64 + 2 * 8 * 32 * 4 + 32 * 4;
+  static bool configured = false;
+  if (!configured) {
+    SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_mma_kernel<8, TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     3 * 256 * 64 + 32 * 64 + 2 * 8 * 32 * 4 + 32 * 4));
+    configured = true;
+  }
+  dim3 grid(heads, B);
+  if (n == 256)
+    linear_attn_mma_kernel<8, TIn><<<grid, 256, sm, st>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, heads, scale);
+  else
+    linear_attn_mma_kernel<2, TIn><<<grid, 256, sm, st>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, heads, scale);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -1605,20 +1679,7 @@ int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, i
   static const int use_mma = [] { const char* e = getenv("SBM_ATTN_MMA"); return e ? atoi(e) : 1; }();
   if (use_mma && (n == 256 || n == 64) && ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
       ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    const size_t sm = (size_t)3 * n * 64 + 32 * 64 + 2 * 8 * 32 * 4 + 32 * 4;
-    static bool configured = false;
-    if (!configured) {
-      SBM_CUDA_OK(cudaFuncSetAttribute(linear_attn_mma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       3 * 256 * 64 + 32 * 64 + 2 * 8 * 32 * 4 + 32 * 4));
-      configured = true;
-    }
-    if (n == 256)
-      linear_attn_mma_kernel<8><<<grid, 256, sm, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, heads, scale);
-    else
-      linear_attn_mma_kernel<2><<<grid, 256, sm, (cudaStream_t)stream>>>(qkv, ldq, (__nv_bfloat16*)out, ldo, heads, scale);
-    SBM_CUDA_OK(cudaGetLastError());
-    count_launch();
-    return 0;
+    return linear_attn_mma_launch<float>(qkv, ldq, out, ldo, B, n, heads, scale, (cudaStream_t)stream);
   }
   if (use_mma && n <= 16) {
     const int pairs = heads * B;
@@ -1659,6 +1720,16 @@ int sbm_linear_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, i
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
+}
+
+int sbm_linear_attn_fwd_bf16(const void* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,
+                             float scale, void* stream) {
+  SBM_CHECK_ARG(qkv && out && B > 0 && heads > 0, "sbm_linear_attn_fwd_bf16: bad args");
+  SBM_CHECK_ARG(n == 256 || n == 64, "sbm_linear_attn_fwd_bf16: n = %d (the bf16-input kernel covers n = 64 and 256)", n);
+  SBM_CHECK_ARG(ldq % 4 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 7) == 0 && ldo % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0, "sbm_linear_attn_fwd_bf16: misaligned operands");
+  return linear_attn_mma_launch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(qkv), ldq, out, ldo, B, n, heads, scale,
+                                               (cudaStream_t)stream);
 }
 
 int sbm_softmax_attn_fwd(const float* qkv, int64_t ldq, void* out, int64_t ldo, int32_t B, int32_t n, int32_t heads,

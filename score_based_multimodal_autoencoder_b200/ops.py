@@ -277,6 +277,12 @@ def time_embed(t: torch.Tensor, dim: int, mode: int) -> torch.Tensor:
 def linear_attn(qkv: torch.Tensor, heads: int, scale: float) -> torch.Tensor:
     b, h, w, _ = qkv.shape
     out = torch.empty((b, h, w, heads * 32), dtype=torch.bfloat16, device=qkv.device)
+    if qkv.dtype == torch.bfloat16:
+        L.check(L.lib().sbm_linear_attn_fwd_bf16(L.ptr(qkv), C.c_int64(qkv.stride(2)), L.ptr(out),
+                                                 C.c_int64(out.stride(2)), C.c_int32(b), C.c_int32(h * w),
+                                                 C.c_int32(heads), C.c_float(scale), L.stream_ptr()),
+                "sbm_linear_attn_fwd_bf16")
+        return out
     L.check(L.lib().sbm_linear_attn_fwd(L.ptr(qkv), C.c_int64(qkv.stride(2)), L.ptr(out), C.c_int64(out.stride(2)),
                                         C.c_int32(b), C.c_int32(h * w), C.c_int32(heads), C.c_float(scale),
                                         L.stream_ptr()), "sbm_linear_attn_fwd")

@@ -13,6 +13,7 @@ GroupNorm statistics in fp64.  There is no CPU / eager fallback: a CPU tensor ra
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 
 import torch
@@ -166,6 +167,9 @@ class Unet(nn.Module):
         self.hidden_dtype = torch.bfloat16
         # inference: fold the block's first GroupNorm into its 3x3 convolution (depthwise output kept in bf16)
         self.fold_input_norm = True
+        # inference: the 16x16 / 8x8 linear-attention blocks pass q | k | v from the to_qkv GEMM to the attention kernel
+        # as bf16 (soft-max arithmetic stays fp32)
+        self.qkv_bf16 = os.environ.get("SBM_QKV_BF16", "1") != "0"
 
     # ------------------------------------------------------------------ packed-weight cache
     @staticmethod
@@ -308,20 +312,23 @@ class Unet(nn.Module):
                        **gn_kw)
         return _Act(c_out, bf16=ob, stats=st_out)
 
-    def _qkv(self, pre: PreNorm, att, x: _Act):
+    def _qkv(self, pre: PreNorm, att, x: _Act, bf16_out: bool = False):
         """PreNorm GroupNorm -> to_qkv (1x1, no bias).  With the bf16 copy of the residual stream at hand the norm is folded
-        into the GEMM (gamma in the weights, mean / rstd / beta in the epilogue); otherwise GroupNorm-apply + GEMM."""
+        into the GEMM (gamma in the weights, mean / rstd / beta in the epilogue); otherwise GroupNorm-apply + GEMM.
+        bf16_out: qkv leaves the GEMM as bf16 (the 16x16 / 8x8 linear-attention kernel reads it; at those map sizes the
+        GEMM and the attention kernel are bound by the HBM traffic of exactly this tensor)."""
         xf = x.f32
         b, h, w, _ = xf.shape
         c = x.c
         hid = att.heads * att.dim_head
+        od = torch.bfloat16 if bf16_out else torch.float32
         if self.fold_input_norm and x.bf16 is not None:
             wq, tabq = self._w_conv_gn(att.to_qkv, pre.norm)
             return ops.conv_igemm(x.bf16, wq, kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid, gn_stats=x.stats,
-                                  gn_tab=tabq, gn_eps=pre.norm.eps)
+                                  gn_tab=tabq, gn_eps=pre.norm.eps, out_dtype=od)
         a = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=xf.device)
         ops.groupnorm_apply(xf, c, x.stats, pre.norm.weight, pre.norm.bias, out=a)
-        return ops.conv_igemm(a, self._w_conv(att.to_qkv), kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid)
+        return ops.conv_igemm(a, self._w_conv(att.to_qkv), kind=L.CONV_S1, kh=1, kw=1, cin=c, cout=3 * hid, out_dtype=od)
 
     def _linear_attention(self, mod: Residual, x: _Act, *, out_f32=None, out_bf16=None, want_bf16=True) -> _Act:
         pre: PreNorm = mod.fn
@@ -331,7 +338,7 @@ class Unet(nn.Module):
         dev = xf.device
         c = x.c
         hid = att.heads * att.dim_head
-        qkv = self._qkv(pre, att, x)
+        qkv = self._qkv(pre, att, x, bf16_out=self.qkv_bf16 and h * w in (64, 256) and att.dim_head == 32)
         o = ops.linear_attn(qkv, att.heads, att.scale)
         st = self._stats(b, dev)
         y = ops.conv_igemm(o, self._w_conv(att.to_out[0]), kind=L.CONV_S1, kh=1, kw=1, cin=hid, cout=c,
