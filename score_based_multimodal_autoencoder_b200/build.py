@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "--compiler-options", "-fPIC",
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("SBM_NVCC_EXTRA", "").split()   # e.g. -DSBM_PAIR_TRACE for tools/trace_pair.py
 
 
 def _nvcc() -> str:

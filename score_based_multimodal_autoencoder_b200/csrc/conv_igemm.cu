@@ -41,6 +41,9 @@ static bool g_force_single = false;  // debugging / A-B timing switch (sbm_conv_
 static thread_local int g_last_variant = 0;  // BN | pair << 16 | staged << 17 of the last launch (bench bookkeeping)
 static int g_pixel_major = [] { const char* e = getenv("SBM_PIXEL_MAJOR"); return e ? atoi(e) : -1; }();       // -1: by work estimate, 0: never, 1: whenever the CTA-pair kernel runs the layer
 static bool g_force_direct = false;  // A-B switch: per-thread global stores instead of the TMA-staged epilogue
+#ifdef SBM_PAIR_TRACE
+static unsigned long long* g_trace = nullptr;
+#endif
 static bool g_epi_static = [] { const char* e = getenv("SBM_EPI_STATIC"); return e ? atoi(e) != 0 : true; }();  // A-B switch: statically compiled epilogue loops (sbm_conv_epilogue_static)
 
 
@@ -343,6 +346,9 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   const bool use_pair = pm ? true : choose(m_tiles);
   const int n_tiles_pair = (a->cout + BN - 1) / BN;
   p.pm = pm ? 1 : 0;
+#ifdef SBM_PAIR_TRACE
+  p.trace = g_trace;
+#endif
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -659,6 +665,13 @@ int sbm_conv_force_direct_epilogue(int32_t on) {
   sbm::g_force_direct = on != 0;
   return 0;
 }
+
+#ifdef SBM_PAIR_TRACE
+int sbm_debug_pair_trace(unsigned long long* buf) {
+  sbm::g_trace = buf;
+  return 0;
+}
+#endif
 
 int sbm_conv_epilogue_static(int32_t on) {
   sbm::g_epi_static = on != 0;

@@ -16,6 +16,19 @@ namespace sbm {
 
 extern std::atomic<unsigned long long> g_launches;
 
+// Pipeline trace of cluster 0 (compile with -DSBM_PAIR_TRACE, tools/trace_pair.py): one record per event
+#ifdef SBM_PAIR_TRACE
+#define SBM_TRACE(role, ev, round)                                                                              \
+  do {                                                                                                           \
+    if (p.trace != nullptr && blockIdx.x < 2) {                                                                  \
+      const unsigned long long i_ = atomicAdd(p.trace, 1ull);                                                    \
+      if (i_ < 60000) p.trace[1 + i_] = (ptx::globaltimer_ns() << 20) | ((unsigned long long)(blockIdx.x & 1) << 19) | ((unsigned long long)(role) << 16) | ((unsigned long long)(ev) << 12) | (unsigned long long)((round) & 0xFFF); \
+    }                                                                                                            \
+  } while (0)
+#else
+#define SBM_TRACE(role, ev, round) do {} while (0)
+#endif
+
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxTaps = 16;
@@ -57,6 +70,9 @@ struct ConvKernelParams {
   float gn_eps;
   // pixel-major tiling (stride-1 'same' convolutions at large batch): the 128 rows of a tile are 128 SAMPLES at ONE
   // output pixel, so the taps that read zero padding at that pixel are skipped for the whole tile
+#ifdef SBM_PAIR_TRACE
+  unsigned long long* trace;   // [0] = counter, then (globaltimer << 20 | role << 16 | event << 12 | round) records of cluster 0
+#endif
   int32_t pm;
   int32_t pm_blocks;        // 256-sample blocks in the batch
   int32_t pm_global;        // tile order: 1 = (pixel rank, block) -- cost-sorted over the whole list, for short lists;
@@ -612,13 +628,44 @@ struct StagedTileCtx {
   uint64_t* rbar;
   uint32_t res_bytes;
 };
+// Staging-buffer rotation of one epilogue warp (8 KB).  A chunk's buffer can be rewritten once the TMA store that
+// read it has finished READING shared memory; that takes ~1.2k cycles under load, so with the residual layout (three
+// main buffers, two chunks in flight) a warp could not stage faster than one chunk per ~600 cycles -- the pace of every
+// K-short layer after the epilogue code itself had been made straight-line (pipeline trace, tools/trace_pair.py).
+// Without a residual the 8 KB are cut into as many chunk buffers as fit: 4 (fp32 rows) or 8 (bf16 rows) in flight.
+template <uint32_t MODE>
+struct StageRing {
+  using M = EpiMode<MODE>;
+  static constexpr bool kDeep = !M::dyn && (MODE & (EM_RES32 | EM_RES16 | EM_O2 | EM_O2PRE)) == 0;
+  static constexpr int kBytes = (MODE & EM_OBF16) ? 1024 : 2048;     // one chunk: 32 rows x 16 columns
+  static constexpr int kDepth = kDeep ? (kStgPerWarp / kBytes) : 3;
+};
+
 template <uint32_t MODE>
 __device__ __forceinline__ void staged_step(const ConvKernelParams& p, const EpiMaps& em, const StagedTileCtx& t, int c,
                                             const uint32_t* cur, uint32_t* nxt, int lane, uint32_t& nchunk, float& s1,
                                             float& s2, const GnRow& gr, uint32_t fl) {
   using M = EpiMode<MODE>;
+  using R = StageRing<MODE>;
   const int col0 = t.ncol0 + c * kEC;
   __syncwarp();
+  if constexpr (R::kDeep) {
+    // buffer nchunk % kDepth was last read by the store of chunk nchunk - kDepth
+    if (lane == 0) ptx::bulk_wait_group_read<R::kDepth - 1>();
+    __syncwarp();
+    ptx::tmem_ld_wait();                                            // `cur` has arrived
+    if (c + 1 < t.nch) ptx::tmem_ld16(t.tacc + (c + 1) * kEC, nxt);  // next chunk streams in behind the math
+    const uint32_t off = (nchunk % R::kDepth) * R::kBytes;
+    epilogue_chunk_staged<MODE>(p, cur, col0, t.row_ok, t.b, lane, t.wst_u32 + off, 0u, s1, s2, gr, fl);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
+      ptx::bulk_commit_group();
+    }
+    ++nchunk;
+    return;
+  }
   // buffers of chunk nchunk+1 (main) / nchunk (bf16 copy) were last used by the stores of chunk nchunk-2
   if (lane == 0) {
     ptx::bulk_wait_group_read<1>();
@@ -779,10 +826,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tile_origin(t, ph, nt, b0, oh0, pj);
         const TapTable& tt = p.taps[ph];
         const int n0 = nt * BN + (int)rank * (BN / 2);
+        SBM_TRACE(0, 0, k);   // producer reaches tile k
         for (uint32_t tm = tap_mask(tt, oh0, pj); tm != 0; tm &= tm - 1) {
           const int tap = __ffs(tm) - 1;
           for (int cb = 0; cb < p.cblocks; ++cb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            SBM_TRACE(0, 1, k);   // got a free stage
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
@@ -806,11 +855,14 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int ph, nt, b0, oh0, pj;
         tile_origin(t, ph, nt, b0, oh0, pj);
         const int num_kb = __popc(tap_mask(p.taps[ph], oh0, pj)) * p.cblocks;
+        SBM_TRACE(1, 0, k);   // issuer reaches tile k
         ptx::mbar_wait(&tempty_bar[astage], aphase ^ 1);
+        SBM_TRACE(1, 1, k);   // accumulator stage free
         ptx::tc_fence_after_sync();
         const uint32_t tacc = tmem_base + (uint32_t)(astage * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
+          SBM_TRACE(1, 2, k);   // operands of a K block landed
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
           const uint64_t adesc = ptx::make_desc_k_sw128(sa);
@@ -822,6 +874,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit_2cta(&tfull_bar[astage], 3);
+        SBM_TRACE(1, 3, k);   // tile committed
         astage ^= 1;
         if (astage == 0) aphase ^= 1;
       }
@@ -871,7 +924,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           ptx::mbar_expect_tx(rb, res_bytes);
           ptx::tma_load_5d(wst + (nchunk % 3) * kStgMain, &em.res, rb, ncol0, cj, 0, ci, cb);
         }
+        if (e == 0 && lane == 0) SBM_TRACE(2, 0, k);   // epilogue warp 0 reaches tile k
         ptx::mbar_wait(&tfull_bar[astage], aphase);
+        if (e == 0 && lane == 0) SBM_TRACE(2, 1, k);   // accumulator complete
         ptx::tc_fence_after_sync();
         StagedTileCtx tc;
         tc.tacc = tmem_base + (uint32_t)(astage * BN) + (uint32_t(ew * 32) << 16) + (uint32_t)(hc * (BN / 2));
@@ -899,6 +954,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(lead_tempty0 + (uint32_t)astage * 8u);
+      if (e == 0 && lane == 0) SBM_TRACE(2, 2, k);   // accumulator stage released
       if (p.stats != nullptr) {
         if (!row_ok) { s1 = 0.f; s2 = 0.f; }
         const int seg = p.pm ? 1 : (log_ohw >= 5 ? 32 : (1 << log_ohw));   // rows of this warp that share a sample
