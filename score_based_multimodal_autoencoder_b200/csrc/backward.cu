@@ -439,6 +439,58 @@ dwconv7_wgrad_kernel(const float* __restrict__ x, int64_t ldx, const float* __re
   }
 }
 
+// Small maps (1x1, 2x2, 4x4: the lower levels of the nets).  The kernel above runs one block per (32-channel chunk,
+// sample) and ends every block with 49 x 32 global atomics: 13 M atomics for the 1x1 level of the CelebA net at batch
+// 256 (79 us per launch for 0.5 MFLOP).  Here a thread owns a channel and walks a slice of the BATCH with the whole
+// map of x and dy in registers (lanes = consecutive channels: coalesced rows), so the atomics are 49 per thread and
+// grid slice.  dw must be zero-initialised by the caller (as for the kernel above).
+template <int W>
+__global__ void __launch_bounds__(128)
+dwconv7_wgrad_small_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy, int64_t lddy,
+                           float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dcond, int64_t ldc,
+                           int B, int C) {
+  constexpr int HW = W * W;
+  constexpr int R = W < 4 ? W - 1 : 3;      // taps dh, dw in [-R, R] see a pixel pair
+  constexpr int NT = 2 * R + 1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc[NT * NT];
+#pragma unroll
+  for (int i = 0; i < NT * NT; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    float xv[HW], dv[HW];
+#pragma unroll
+    for (int pix = 0; pix < HW; ++pix) {
+      xv[pix] = __ldg(x + ((int64_t)b * HW + pix) * ldx + c);
+      dv[pix] = __ldg(dy + ((int64_t)b * HW + pix) * lddy + c);
+    }
+    float ds = 0.f;
+#pragma unroll
+    for (int pix = 0; pix < HW; ++pix) ds += dv[pix];
+    bsum += ds;
+    if (dcond) dcond[(int64_t)b * ldc + c] = ds;
+#pragma unroll
+    for (int oh = 0; oh < W; ++oh)
+#pragma unroll
+      for (int ow = 0; ow < W; ++ow)
+#pragma unroll
+        for (int ih = 0; ih < W; ++ih)
+#pragma unroll
+          for (int iw = 0; iw < W; ++iw) {
+            const int dh = ih - oh, dwi = iw - ow;
+            if (dh >= -R && dh <= R && dwi >= -R && dwi <= R)
+              acc[(dh + R) * NT + (dwi + R)] = fmaf(dv[oh * W + ow], xv[ih * W + iw], acc[(dh + R) * NT + (dwi + R)]);
+          }
+  }
+#pragma unroll
+  for (int a = 0; a < NT; ++a)
+#pragma unroll
+    for (int bb = 0; bb < NT; ++bb)
+      atomicAdd(dw + (int64_t)c * 49 + (a - R + 3) * 7 + (bb - R + 3), acc[a * NT + bb]);
+  if (db) atomicAdd(db + c, bsum);
+}
+
 // ------------------------------------------------------------------------------ linear attention backward
 // forward (unet_model.py:162-177): qs = softmax_d(q)*scale, ks = softmax_n(k), ctx[d][e] = sum_n ks v, out[n][e] = sum_d ctx qs
 __global__ void __launch_bounds__(256)
@@ -893,6 +945,19 @@ int sbm_dwconv7_wgrad(const float* x, int64_t ldx, const float* dy, int64_t lddy
     }                                                                                                              \
     dwconv7_wgrad_kernel<WW><<<grid, threads, smem, s>>>(x, ldx, dy, lddy, dw, db, dcond, ldc, C, H);               \
   } while (0)
+  static const bool small_env = [] { const char* e = getenv("SBM_DWWGRAD_SMALL"); return e ? atoi(e) != 0 : true; }();
+  if (small_env && H == W && W <= 4) {
+    // slices of the batch: enough blocks to fill the SMs, few enough that the final atomics stay cheap
+    const int cblocks = (C + 127) / 128;
+    const int gy = std::max(1, std::min((int)B, (2 * sm_count() + cblocks - 1) / cblocks));
+    dim3 g2(cblocks, gy);
+    if (W == 1) dwconv7_wgrad_small_kernel<1><<<g2, 128, 0, s>>>(x, ldx, dy, lddy, dw, db, dcond, ldc, B, C);
+    else if (W == 2) dwconv7_wgrad_small_kernel<2><<<g2, 128, 0, s>>>(x, ldx, dy, lddy, dw, db, dcond, ldc, B, C);
+    else dwconv7_wgrad_small_kernel<4><<<g2, 128, 0, s>>>(x, ldx, dy, lddy, dw, db, dcond, ldc, B, C);
+    SBM_CUDA_OK(cudaGetLastError());
+    count_launch_b();
+    return 0;
+  }
   if (W == 16) SBM_DWW(16);
   else if (W == 8) SBM_DWW(8);
   else if (W == 4) SBM_DWW(4);

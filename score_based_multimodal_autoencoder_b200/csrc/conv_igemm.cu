@@ -90,7 +90,7 @@ SBM_DECL_GROUP(0) SBM_DECL_GROUP(1) SBM_DECL_GROUP(2) SBM_DECL_GROUP(3) SBM_DECL
 #undef SBM_DECL_GROUP
 int launch_pair_static(int mode_idx, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em,
                        const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream) {
-  switch (mode_idx / 3) {
+  switch (mode_idx >= 12 ? 4 : mode_idx / 3) {
     case 0: return launch_pair_static_g0(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 1: return launch_pair_static_g1(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 2: return launch_pair_static_g2(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
@@ -397,14 +397,14 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       const bool al16 = (a->bias == nullptr || p.bias_vec) &&
                         (a->gn_tab == nullptr || (reinterpret_cast<uintptr_t>(a->gn_tab) & 15) == 0);
       if (g_epi_static && (a->gn_tab == nullptr || a->cout % 4 == 0) && al16 && a->rowbias == nullptr &&
-          (a->act == SBM_ACT_NONE || a->act == SBM_ACT_GELU) && !(a->out2 != nullptr && a->out2_preact)) {
+          (a->act == SBM_ACT_NONE || a->act == SBM_ACT_GELU)) {
         uint32_t bits = 0;
         if (a->gn_tab) bits |= EM_GN;
         if (a->bias) bits |= EM_BIAS;
         if (a->act == SBM_ACT_GELU) bits |= EM_GELU;
         if (a->residual) bits |= (a->res_dtype == SBM_F32) ? EM_RES32 : EM_RES16;
         if (a->out_dtype == SBM_BF16) bits |= EM_OBF16;
-        if (a->out2) bits |= EM_O2;
+        if (a->out2) bits |= a->out2_preact ? EM_O2PRE : EM_O2;
         if (a->stats) bits |= EM_STATS;
         epi_mode = find_epi_mode(bits);
       }

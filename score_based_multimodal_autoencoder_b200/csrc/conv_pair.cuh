@@ -607,7 +607,10 @@ struct EpiMaps {
   X(9, EM_BIAS | EM_RES32)                     /* middle attention to_out + residual */           \
   X(10, EM_GN | EM_RES32 | EM_STATS)                                                             \
   X(11, EM_BIAS | EM_GELU | EM_OBF16 | EM_STATS)                                                 \
-  X(12, EM_GN | EM_OBF16)                      /* to_qkv with bf16 output (16x16 / 8x8 attention) */
+  X(12, EM_GN | EM_OBF16)                      /* to_qkv with bf16 output (16x16 / 8x8 attention) */ \
+  X(13, 0u)                                    /* training: data-gradient GEMMs (plain fp32 output) */ \
+  X(14, EM_BIAS | EM_GELU | EM_OBF16 | EM_STATS | EM_O2PRE)  /* training: 3x3 #1 keeps its pre-activation */ \
+  X(15, EM_BIAS | EM_RES32 | EM_STATS)         /* training: 3x3 #2 + residual + statistics */
 inline int find_epi_mode(uint32_t bits) {
 #define SBM_EPI_FIND(idx, mode) if (bits == (uint32_t)(mode)) return idx;
   SBM_EPI_MODES(SBM_EPI_FIND)

@@ -20,6 +20,9 @@ int launch_pair_static_g0(int mode_idx, int bn, const CUtensorMap& tmA, const CU
 #define SBM_EPI_PICK_10(idx, mode) 
 #define SBM_EPI_PICK_11(idx, mode) 
 #define SBM_EPI_PICK_12(idx, mode) 
+#define SBM_EPI_PICK_13(idx, mode) 
+#define SBM_EPI_PICK_14(idx, mode) 
+#define SBM_EPI_PICK_15(idx, mode) 
     SBM_EPI_MODES(SBM_EPI_PICK)
 #undef SBM_EPI_PICK
     default: return -1;

@@ -1,4 +1,4 @@
-// Statically compiled epilogue modes [12] of the CTA-pair convolution kernel (see conv_pair.cuh: SBM_EPI_MODES).
+// Statically compiled epilogue modes [12, 13, 14, 15] of the CTA-pair convolution kernel (see conv_pair.cuh: SBM_EPI_MODES).
 #include "conv_pair.cuh"
 
 namespace sbm {
@@ -20,6 +20,9 @@ int launch_pair_static_g4(int mode_idx, int bn, const CUtensorMap& tmA, const CU
 #define SBM_EPI_PICK_10(idx, mode) 
 #define SBM_EPI_PICK_11(idx, mode) 
 #define SBM_EPI_PICK_12(idx, mode) SBM_EPI_LAUNCH_CASE(idx, mode)
+#define SBM_EPI_PICK_13(idx, mode) SBM_EPI_LAUNCH_CASE(idx, mode)
+#define SBM_EPI_PICK_14(idx, mode) SBM_EPI_LAUNCH_CASE(idx, mode)
+#define SBM_EPI_PICK_15(idx, mode) SBM_EPI_LAUNCH_CASE(idx, mode)
     SBM_EPI_MODES(SBM_EPI_PICK)
 #undef SBM_EPI_PICK
     default: return -1;

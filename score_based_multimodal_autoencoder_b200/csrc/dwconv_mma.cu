@@ -62,7 +62,7 @@ struct DwCfg {
   static constexpr int PLW = NS * SPW + 2;                // words per channel plane (2 mod 8)
   static constexpr int RING = T < 8 ? T : 8;              // live accumulator tiles
   static constexpr int kChan = 16;
-  static constexpr size_t smem = (size_t)kChan * PLW * 4 + 8 * NS * 2 * sizeof(float);   // + [warp][sample][2] sums
+  static constexpr size_t smem = 2 * ((size_t)kChan * PLW * 4 + 8 * NS * 2 * sizeof(float));   // two tiles: planes + [warp][sample][2] sums
 };
 
 // tap of channel c that multiplies input position k of tile To + delta for output position m of tile To
@@ -75,20 +75,113 @@ __device__ __forceinline__ float toeplitz_tap(const float* __restrict__ w, int c
   return __ldg(w + (int64_t)c * 49 + (dh + 3) * 7 + (dw + 3));
 }
 
+// 512 threads, one CTA per SM, two plane buffers.  Warps 0-7 run the products of tile j while warps 8-15 ("movers")
+// write tile j-1 back to global memory and then load tile j+1 into the buffer that frees: one __syncthreads per tile,
+// per-tile time = max(products, data movement) instead of their sum (the first version ran the three passes back to
+// back in every CTA: 41 % / 38 % / 20 % of the samples in load / products / store, ncu source view).
 template <int W>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(512, 1)
 dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                    const float* __restrict__ bias, const float* __restrict__ cond, int64_t ldc,
                    __nv_bfloat16* __restrict__ out, int64_t ldo, double* __restrict__ stats, int B, int C) {
   using K = DwCfg<W>;
   constexpr int HW = K::HW, T = K::T, DMAX = K::DMAX, ND = K::ND, G = K::G, NS = K::NS, SPW = K::SPW, PLW = K::PLW;
-  extern __shared__ __align__(16) uint32_t sm[];
-  float* tstats = reinterpret_cast<float*>(sm + K::kChan * PLW);
+  constexpr int kBufWords = K::kChan * PLW;
+  extern __shared__ __align__(16) uint32_t sm_all[];
+  float* tstats_all = reinterpret_cast<float*>(sm_all + 2 * kBufWords);   // [2][8 warps][NS][2]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
+  const bool mover = warp >= 8;
+  const int mtid = tid & 255;
   const int c0 = blockIdx.x * K::kChan;
+  const int ntiles = (B + NS - 1) / NS;
+  const int my_tiles = blockIdx.y < ntiles ? (ntiles - 1 - (int)blockIdx.y) / (int)gridDim.y + 1 : 0;
 
-  // ---- Toeplitz blocks of this warp's two channels as mma A fragments (a0:(g,2t) a1:(g+8,2t) a2:(g,2t+8) a3:(g+8,2t+8))
+  // ================= movers: fp32 channels-last -> bf16 channel planes (two positions per word)
+  auto load_tile = [&](int j) {
+    uint32_t* sm = sm_all + (j & 1) * kBufWords;
+    const int s_base = ((int)blockIdx.y + j * (int)gridDim.y) * NS;
+    constexpr int kItems = NS * (HW / 2) * 4;       // (sample, position pair, channel quad)
+    constexpr int kLogPairs = W == 16 ? 7 : (W == 8 ? 5 : 3);
+    constexpr int kBatch = 8;                       // 16 independent 16-byte loads in flight per mover thread
+    static_assert(kItems % (256 * kBatch) == 0, "tile must split into whole batches");
+#pragma unroll 1
+    for (int i0 = mtid; i0 < kItems; i0 += 256 * kBatch) {
+      float4 v0[kBatch], v1[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * 256;
+        const int q = i & 3, pair = (i >> 2) & (HW / 2 - 1), n = i >> (2 + kLogPairs);
+        const int b = s_base + n;
+        v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1[u] = v0[u];
+        if (b < B && c0 + 4 * q + 4 <= ldx) {
+          const float* px = x + ((int64_t)b * HW + 2 * pair) * ldx + c0 + 4 * q;
+          v0[u] = __ldg(reinterpret_cast<const float4*>(px));
+          v1[u] = __ldg(reinterpret_cast<const float4*>(px + ldx));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int i = i0 + u * 256;
+        const int q = i & 3, pair = (i >> 2) & (HW / 2 - 1), n = i >> (2 + kLogPairs);
+        const int cq = c0 + 4 * q;
+        uint32_t* dst = sm + (4 * q) * PLW + n * SPW + pair;
+        dst[0] = cq < C ? pack_bf16(v0[u].x, v1[u].x) : 0u;          // pad channels may hold anything: keep them zero
+        dst[PLW] = cq + 1 < C ? pack_bf16(v0[u].y, v1[u].y) : 0u;
+        dst[2 * PLW] = cq + 2 < C ? pack_bf16(v0[u].z, v1[u].z) : 0u;
+        dst[3 * PLW] = cq + 3 < C ? pack_bf16(v0[u].w, v1[u].w) : 0u;
+      }
+    }
+  };
+  // ================= movers: planes -> channels-last bf16 rows (16-byte stores), statistics to global memory
+  auto store_tile = [&](int j) {
+    const uint32_t* sm = sm_all + (j & 1) * kBufWords;
+    const float* tstats = tstats_all + (j & 1) * (8 * NS * 2);
+    const int s_base = ((int)blockIdx.y + j * (int)gridDim.y) * NS;
+    if (stats != nullptr && mtid < NS * 2) {
+      const int b = s_base + (mtid >> 1);
+      if (b < B) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 8; ++wq) tsum += tstats[wq * NS * 2 + mtid];   // fixed order
+        atomicAdd(stats + 2 * (int64_t)b + (mtid & 1), (double)tsum);
+      }
+    }
+    constexpr int kItems = NS * HW * 2;             // (sample, position, channel octet)
+    constexpr int kLogHW = W == 16 ? 8 : (W == 8 ? 6 : 4);
+    const uint16_t* hsm = reinterpret_cast<const uint16_t*>(sm);
+#pragma unroll 4
+    for (int i = mtid; i < kItems; i += 256) {
+      const int o = i & 1, pos = (i >> 1) & (HW - 1), n = i >> (1 + kLogHW);
+      const int b = s_base + n;
+      if (b < B && c0 + 8 * o + 8 <= ldo) {
+        const uint16_t* src = hsm + 2 * ((8 * o) * PLW + n * SPW) + pos;
+        uint32_t wv[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          wv[jj] = (uint32_t)src[2 * (2 * jj) * PLW] | ((uint32_t)src[2 * (2 * jj + 1) * PLW] << 16);
+        *reinterpret_cast<uint4*>(out + ((int64_t)b * HW + pos) * ldo + c0 + 8 * o) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+    }
+  };
+
+  if (mover) {
+    if (my_tiles > 0) load_tile(0);
+    __syncthreads();
+    for (int j = 0; j < my_tiles; ++j) {
+      if (j >= 1) store_tile(j - 1);
+      // every mover has finished reading buffer (j + 1) & 1 before anyone refills it (movers only: barrier 1)
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (j + 1 < my_tiles) load_tile(j + 1);
+      __syncthreads();
+    }
+    if (my_tiles > 0) store_tile(my_tiles - 1);
+    return;
+  }
+
+  // ================= warps 0-7: banded products, outputs written in place
+  const int g = lane >> 2, t = lane & 3;
+  // Toeplitz blocks of this warp's two channels as mma A fragments (a0:(g,2t) a1:(g+8,2t) a2:(g,2t+8) a3:(g+8,2t+8))
   uint32_t A[2][ND][4];
   float bias_c[2];
 #pragma unroll
@@ -104,47 +197,11 @@ dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
       }
     }
   }
-
-  const int ntiles = (B + NS - 1) / NS;
-  for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
-    const int s_base = tile * NS;
-    // ================= pass 1: fp32 channels-last -> bf16 channel planes (two positions per word)
-    {
-      constexpr int kItems = NS * (HW / 2) * 4;       // (sample, position pair, channel quad)
-      constexpr int kLogPairs = W == 16 ? 7 : (W == 8 ? 5 : 3);
-      static_assert(kItems % 1024 == 0, "tile must split into batches of 4 items per thread");
-#pragma unroll 1
-      for (int i0 = tid; i0 < kItems; i0 += 1024) {
-        float4 v0[4], v1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 256;
-          const int q = i & 3, pair = (i >> 2) & (HW / 2 - 1), n = i >> (2 + kLogPairs);
-          const int b = s_base + n;
-          v0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          v1[u] = v0[u];
-          if (b < B && c0 + 4 * q + 4 <= ldx) {
-            const float* px = x + ((int64_t)b * HW + 2 * pair) * ldx + c0 + 4 * q;
-            v0[u] = __ldg(reinterpret_cast<const float4*>(px));
-            v1[u] = __ldg(reinterpret_cast<const float4*>(px + ldx));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 256;
-          const int q = i & 3, pair = (i >> 2) & (HW / 2 - 1), n = i >> (2 + kLogPairs);
-          const int cq = c0 + 4 * q;
-          uint32_t* dst = sm + (4 * q) * PLW + n * SPW + pair;
-          dst[0] = cq < C ? pack_bf16(v0[u].x, v1[u].x) : 0u;          // pad channels may hold anything: keep them zero
-          dst[PLW] = cq + 1 < C ? pack_bf16(v0[u].y, v1[u].y) : 0u;
-          dst[2 * PLW] = cq + 2 < C ? pack_bf16(v0[u].z, v1[u].z) : 0u;
-          dst[3 * PLW] = cq + 3 < C ? pack_bf16(v0[u].w, v1[u].w) : 0u;
-        }
-      }
-    }
-    __syncthreads();
-
-    // ================= pass 2: banded products, outputs written in place
+  __syncthreads();   // tile 0 is in buffer 0
+  for (int j = 0; j < my_tiles; ++j) {
+    uint32_t* sm = sm_all + (j & 1) * kBufWords;
+    float* tstats = tstats_all + (j & 1) * (8 * NS * 2);
+    const int s_base = ((int)blockIdx.y + j * (int)gridDim.y) * NS;
 #pragma unroll 1
     for (int grp = 0; grp < G; ++grp) {
       const int nb = grp * 8;
@@ -167,7 +224,7 @@ dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
         __nv_bfloat16* o1 = o0 + 2 * SPW;                           // sample 2t + 1
         float acc[K::RING][4];
 #pragma unroll
-        for (int s = 0; s < K::RING; ++s) { acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f; }
+        for (int sl = 0; sl < K::RING; ++sl) { acc[sl][0] = 0.f; acc[sl][1] = 0.f; acc[sl][2] = 0.f; acc[sl][3] = 0.f; }
 
         auto emit = [&](int To, float (&a)[4]) {
           const __nv_bfloat16 h00 = __float2bfloat16_rn(a[0] + add0), h01 = __float2bfloat16_rn(a[1] + add1);
@@ -211,37 +268,7 @@ dwconv7_mma_kernel(const float* __restrict__ x, int64_t ldx, const float* __rest
         }
       }
     }
-    __syncthreads();
-
-    // ================= pass 3: planes -> channels-last bf16 rows (16-byte stores), statistics to global memory
-    if (stats != nullptr && tid < NS * 2) {
-      const int b = s_base + (tid >> 1);
-      if (b < B) {
-        float tsum = 0.f;
-#pragma unroll
-        for (int wq = 0; wq < 8; ++wq) tsum += tstats[wq * NS * 2 + tid];   // fixed order
-        atomicAdd(stats + 2 * (int64_t)b + (tid & 1), (double)tsum);
-      }
-    }
-    {
-      constexpr int kItems = NS * HW * 2;             // (sample, position, channel octet)
-      constexpr int kLogHW = W == 16 ? 8 : (W == 8 ? 6 : 4);
-      const uint16_t* hsm = reinterpret_cast<const uint16_t*>(sm);
-#pragma unroll 2
-      for (int i = tid; i < kItems; i += 256) {
-        const int o = i & 1, pos = (i >> 1) & (HW - 1), n = i >> (1 + kLogHW);
-        const int b = s_base + n;
-        if (b < B && c0 + 8 * o + 8 <= ldo) {
-          const uint16_t* src = hsm + 2 * ((8 * o) * PLW + n * SPW) + pos;
-          uint32_t wv[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            wv[j] = (uint32_t)src[2 * (2 * j) * PLW] | ((uint32_t)src[2 * (2 * j + 1) * PLW] << 16);
-          *reinterpret_cast<uint4*>(out + ((int64_t)b * HW + pos) * ldo + c0 + 8 * o) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-        }
-      }
-    }
-    __syncthreads();   // the planes are free for the next tile
+    __syncthreads();   // tile j is complete (the movers store it), tile j + 1 has landed in the other buffer
   }
 }
 
@@ -250,10 +277,10 @@ int launch_w(const float* x, int64_t ldx, const float* w, const float* bias, con
              int64_t ldo, double* stats, int B, int C, cudaStream_t st) {
   using K = DwCfg<W>;
   static bool configured = false;
-  static int per_sm = 2;
+  static int per_sm = 1;
   if (!configured) {
     SBM_CUDA_OK(cudaFuncSetAttribute(dwconv7_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::smem));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_mma_kernel<W>, 256, K::smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dwconv7_mma_kernel<W>, 512, K::smem) != cudaSuccess ||
         per_sm <= 0)
       per_sm = 1;
     configured = true;
@@ -262,7 +289,7 @@ int launch_w(const float* x, int64_t ldx, const float* w, const float* bias, con
   const int ntiles = (B + K::NS - 1) / K::NS;
   // one resident wave: every block walks several sample tiles with its Toeplitz fragments in registers
   const int gy = std::max(1, std::min(ntiles, per_sm * sm_count() / slabs));
-  dwconv7_mma_kernel<W><<<dim3(slabs, gy), 256, K::smem, st>>>(x, ldx, w, bias, cond, ldc, (__nv_bfloat16*)out, ldo, stats,
+  dwconv7_mma_kernel<W><<<dim3(slabs, gy), 512, K::smem, st>>>(x, ldx, w, bias, cond, ldc, (__nv_bfloat16*)out, ldo, stats,
                                                               B, C);
   SBM_CUDA_OK(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);

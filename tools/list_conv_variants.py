@@ -1,5 +1,6 @@
-"""Which kernel variant every convolution of one CelebA score-net forward runs (BN, CTA pair, staged epilogue,
-pixel-major tiling, statically compiled epilogue mode): python tools/list_conv_variants.py [batch]"""
+"""Which kernel variant every convolution of one CelebA score-net forward (or, with `train`, one DSM training step:
+forward + data gradients) runs (BN, CTA pair, staged epilogue, pixel-major tiling, statically compiled epilogue mode):
+python tools/list_conv_variants.py [batch] [train]"""
 import collections
 import os
 import sys
@@ -18,7 +19,7 @@ orig = ops.conv_igemm
 def traced(x, wpk, **kw):
     y = orig(x, wpk, **kw)
     v = L.lib().sbm_conv_last_variant()
-    flags = "+".join(k for k in ("bias", "act", "residual", "stats", "out2", "rowbias", "gn_tab") if kw.get(k) is not None and not (isinstance(kw.get(k), int) and kw.get(k) == 0))
+    flags = "+".join(k + ("(pre)" if k == "out2" and kw.get("out2_preact") else "") for k in ("bias", "act", "residual", "stats", "out2", "rowbias", "gn_tab") if kw.get(k) is not None and not (isinstance(kw.get(k), int) and kw.get(k) == 0))
     od = "bf16" if (kw.get("out") is not None and kw["out"].dtype == torch.bfloat16) or kw.get("out_dtype") == torch.bfloat16 else "f32"
     key = (x.shape[1], kw["cin"], kw["cout"], kw["kh"], flags, od, v & 0xFFFF, bool(v & (1 << 16)), bool(v & (1 << 17)),
            bool(v & (1 << 18)), bool(v & (1 << 19)))
@@ -32,8 +33,15 @@ torch.manual_seed(0)
 m = unet_model.Unet(dim=256, channels=3, dim_mults=(1, 2, 2, 2, 2)).cuda().eval()
 x = torch.randn(B, 3, 16, 16, device="cuda")
 t = torch.rand(B, device="cuda")
-with torch.no_grad():
-    m(x, t)
+if len(sys.argv) > 2 and sys.argv[2] == "train":
+    from score_based_multimodal_autoencoder_b200 import autograd, sde_helper2 as sh
+    autograd.ops.conv_igemm = traced
+    m.train()
+    loss = sh.loss_fn(x, m, sh.VPSDE(0.1, 20.0, 1000))
+    loss.backward()
+else:
+    with torch.no_grad():
+        m(x, t)
 torch.cuda.synchronize()
 print("H cin cout k flags out BN pair staged pixel-major static-epilogue count")
 for key, n in sorted(seen.items(), key=lambda kv: (-kv[0][0], kv[0][1:])):
