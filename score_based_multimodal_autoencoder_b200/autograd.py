@@ -73,8 +73,12 @@ class _Plan:
     def _grad(self, p, g):
         sink = getattr(self.m, "_grad_sink", None)
         if sink is not None:  # data-parallel training: copy into the flat bucket buffer, all-reduce when a bucket fills
-            if sink.completes_bucket(p):
-                ops.unpack_flush()   # deferred weight-gradient unpacks of this bucket must land before it goes out
+            # deferred weight-gradient unpacks must land (a) before their bucket goes out and (b) before grad_ready
+            # COPIES a gradient that was not produced in its slot: a deferred unpack into a private tensor is still
+            # unwritten at this point (round 2: the time-MLP / stem / last-conv weights went out as uninitialised memory,
+            # tools/check_multi_gpu.py: rank-averaged gradients 8e-2 off the single-GPU ones)
+            if sink.completes_bucket(p) or g.data_ptr() != sink.grad_view(p).data_ptr():
+                ops.unpack_flush()
             g = sink.grad_ready(p, g)
         if p in self.pg:
             ops.unpack_flush()   # both contributions must be materialised before they are summed
@@ -285,7 +289,7 @@ class _Plan:
             dt1 = ops.conv_igemm(d2b, self._dg_linear(lin3), kind=L.CONV_S1, kh=1, kw=1, cin=td, cout=td)
             d1f, d1b = ops.act_bwd(dt1, t1pre, td, L.ACT_GELU, want_f32=True, want_bf16=True)
             dw1 = ops.conv_wgrad(te, d1b, kind=L.CONV_S1, kh=1, kw=1, cin=m.dim, cout=td)
-            self._grad(lin1.weight, ops.unpack_linear_wgrad(dw1, lin1.weight))
+            self._grad(lin1.weight, ops.unpack_linear_wgrad(dw1, lin1.weight, self._slot(lin1.weight)))
             self._grad(lin1.bias, ops.colsum(d1f, td))
 
         self.tape.append(bwd_time)  # runs LAST in the backward (tape is replayed in reverse)
@@ -394,7 +398,7 @@ class _Plan:
         def bwd_last(dout):
             d_b, d_f = ops.nchw_to_nhwc(dout, want_f32=True)
             dw = ops.conv_wgrad(xf_node.bf16, d_b, kind=L.CONV_S1, kh=1, kw=1, cin=fin.dim_out, cout=m.out_dim)
-            self._grad(last.weight, ops.unpack_conv2d_wgrad(dw, last.weight))
+            self._grad(last.weight, ops.unpack_conv2d_wgrad(dw, last.weight, self._slot(last.weight)))
             self._grad(last.bias, ops.colsum(d_f, m.out_dim))
             xf_node.g = ops.conv_igemm(d_b, self._dg_conv_s1(last), kind=L.CONV_S1, kh=1, kw=1, cin=m.out_dim,
                                        cout=fin.dim_out)
