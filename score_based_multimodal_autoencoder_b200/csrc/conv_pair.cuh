@@ -834,7 +834,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const int tap = __ffs(tm) - 1;
           for (int cb = 0; cb < p.cblocks; ++cb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            SBM_TRACE(0, 1, k);   // got a free stage
+            if ((cb & 15) == 0) SBM_TRACE(0, 1, k);   // got a free stage (every 16th K block: the record itself costs ~0.4 us)
             uint8_t* sa = smem + stage * L::kStageBytes;
             uint8_t* sb = sa + L::kABytes;
             if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
@@ -865,7 +865,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint32_t tacc = tmem_base + (uint32_t)(astage * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
-          SBM_TRACE(1, 2, k);   // operands of a K block landed
+          if ((kb & 15) == 0) SBM_TRACE(1, 2, k);   // operands of a K block landed (every 16th)
           ptx::tc_fence_after_sync();
           const uint32_t sa = ptx::smem_u32(smem + stage * L::kStageBytes);
           const uint64_t adesc = ptx::make_desc_k_sw128(sa);

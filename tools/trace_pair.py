@@ -1,6 +1,6 @@
 """Pipeline trace of cluster 0 of the CTA-pair GEMM on a K-short layer (build the library with
 SBM_NVCC_EXTRA=-DSBM_PAIR_TRACE first; the production build has no trace code).
-python tools/trace_pair.py [cin] [cout] [k] [H]"""
+python tools/trace_pair.py [cin] [cout] [k] [H] [batch]"""
 import ctypes as C
 import os
 import sys
@@ -14,7 +14,7 @@ cin = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 cout = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 H = int(sys.argv[4]) if len(sys.argv) > 4 else 16
-B = 1024
+B = int(sys.argv[5]) if len(sys.argv) > 5 else 1024
 dev = torch.device("cuda")
 x = torch.randn(B, H, H, ops.pad8(cin), device=dev).to(torch.bfloat16)
 w = torch.randn(cout, cin, k, k, device=dev) / (cin * k * k) ** 0.5
@@ -43,5 +43,5 @@ names = {(0, 0): "prod tile", (0, 1): "prod stage", (1, 0): "mma tile", (1, 1): 
          (1, 3): "mma commit", (2, 0): "epi tile", (2, 1): "epi tfull", (2, 2): "epi release"}
 recs.sort()
 for t, cta, role, ev, rnd in recs:
-    if rnd <= 6 or rnd >= 12:
+    if rnd <= 6 or rnd >= 12 or True:
         print(f"{t - t0:8d} ns  cta{cta} round {rnd:3d}  {names.get((role, ev), (role, ev))}")
