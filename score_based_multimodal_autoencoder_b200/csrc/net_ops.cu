@@ -16,6 +16,16 @@ namespace sbm {
 extern std::atomic<unsigned long long> g_launches;
 static inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// 4 consecutive channels of a qkv row: fp32 (16 bytes) or bf16 (8 bytes; the to_qkv GEMM then writes and this kernel
+// reads half the bytes -- at 16x16 the pair is HBM-bound on exactly those)
+__device__ __forceinline__ float4 load_qkv4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load_qkv4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+}
+
+
 // ------------------------------------------------------------------------------ stem im2col
 // x: fp32 NCHW [B,C,H,W]  ->  a: bf16 [B*H*W, ldk], column k = (c*KH + kh)*KW + kw (matches weight.view(O,-1))
 __global__ void __launch_bounds__(256)
@@ -592,6 +602,48 @@ group_stats_kernel(const void* __restrict__ x, int in_dtype, int64_t ldx, int HW
   }
 }
 
+// Row-wise variant: a block walks whole pixel ROWS (all channels, 16-byte / 8-byte loads, coalesced) and keeps one
+// partial sum per thread -- a thread's 4 channels always fall into one group (channels per group % 4 == 0).  The
+// kernel above runs one block per (chunk, group, sample) over 16..128-byte pieces of every row with a division and a
+// modulo per element: 107 us per launch = 0.74 TB/s on the GroupNorm32 layers of `UNetModel`, 38 % of that net's
+// forward (launch list, round 2).  Partial sums meet in shared memory in a fixed order (deterministic per block).
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+group_stats_rows_kernel(const TIn* __restrict__ x, int64_t ldx, int HW, int C, int G, int pix_per_block,
+                        double* __restrict__ stats) {
+  __shared__ float red[2][8][64];            // [sum | sumsq][row of the block][group]
+  const int tpr = C >> 2;                    // threads per pixel row
+  const int rpb = 256 / tpr;                 // rows in flight per block
+  const int q = threadIdx.x % tpr, r = threadIdx.x / tpr;
+  const int b = blockIdx.y;
+  const int cpg4 = (C / G) >> 2;             // threads per group within a row (1, 2, 4, 8 ...)
+  float s1 = 0.f, s2 = 0.f;
+  if (r < rpb) {
+    const int p_end = min(HW, (int)(blockIdx.x + 1) * pix_per_block);
+    for (int pix = blockIdx.x * pix_per_block + r; pix < p_end; pix += rpb) {
+      const float4 v = load_qkv4(x + ((int64_t)b * HW + pix) * ldx + 4 * q);
+      s1 += (v.x + v.y) + (v.z + v.w);
+      s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+    }
+  }
+  // lanes of one group are consecutive (cpg4 <= 32 is a power of two: tpr is, G divides C)
+  for (int o = 1; o < cpg4 && o < 32; o <<= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (r < rpb && (q % cpg4) == 0 && cpg4 <= 32) {
+    red[0][r][q / cpg4] = s1;
+    red[1][r][q / cpg4] = s2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * G) {
+    const int which = threadIdx.x / G, g = threadIdx.x % G;
+    float t = 0.f;
+    for (int rr = 0; rr < rpb; ++rr) t += red[which][rr][g];
+    atomicAdd(stats + 2 * ((int64_t)b * G + g) + which, (double)t);
+  }
+}
+
 // ------------------------------------------------------------------------------ GroupNorm apply
 // y = act((x - mean)*rstd*gamma + beta) (+ residual).  grid = (chunks, B): a block streams a contiguous pixel range
 // of ONE sample, so mean / rstd of its groups are derived once (fp64 -> fp32) into shared memory; 8 channels per
@@ -1093,15 +1145,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
-}
-
-// 4 consecutive channels of a qkv row: fp32 (16 bytes) or bf16 (8 bytes; the to_qkv GEMM then writes and this kernel
-// reads half the bytes -- at 16x16 the pair is HBM-bound on exactly those)
-__device__ __forceinline__ float4 load_qkv4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 load_qkv4(const __nv_bfloat16* p) {
-  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
-  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
 }
 
 template <int R, typename TIn>  // rows per thread: n = 32 * R
@@ -1609,6 +1652,26 @@ int sbm_dwconv7_bwd_input(const float* dy, int64_t lddy, const float* w, const f
 int sbm_group_stats(const void* x, int32_t in_dtype, int64_t ldx, int32_t B, int32_t HW, int32_t C, int32_t G,
                     double* stats, void* stream) {
   SBM_CHECK_ARG(x && stats && B > 0 && G > 0 && C % G == 0, "sbm_group_stats: bad args");
+  // row-wise kernel: 4-channel vectors inside one group, a pixel row fits the block, groups fit its reduction buffer
+  const int cpg = C / G, tpr = C / 4;
+  const int esz = in_dtype == SBM_F32 ? 4 : 2;
+  static const bool rows_env = [] { const char* e = getenv("SBM_GROUP_STATS_ROWS"); return e ? atoi(e) != 0 : true; }();
+  if (rows_env && C % 4 == 0 && cpg % 4 == 0 && (cpg / 4 & (cpg / 4 - 1)) == 0 && cpg / 4 <= 32 && tpr <= 256 &&
+      256 % tpr == 0 && 256 / tpr <= 8 && G <= 64 && ldx % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & (4 * esz - 1)) == 0) {
+    // enough blocks for two waves when the batch is small, at least 32 pixels per block otherwise
+    int ppb = std::max(32, (int)(((int64_t)B * HW + 2 * sm_count() * 4 - 1) / (2 * sm_count() * 4)));
+    ppb = std::min(ppb, HW);
+    dim3 grid2((HW + ppb - 1) / ppb, B);
+    if (in_dtype == SBM_F32)
+      group_stats_rows_kernel<float><<<grid2, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, HW, C, G, ppb, stats);
+    else
+      group_stats_rows_kernel<__nv_bfloat16><<<grid2, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, HW, C, G,
+                                                                                    ppb, stats);
+    SBM_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   const int64_t n = (int64_t)HW * (C / G);
   int chunks = (int)std::min<int64_t>((n + 2047) / 2048, 64);
   if (chunks < 1) chunks = 1;
