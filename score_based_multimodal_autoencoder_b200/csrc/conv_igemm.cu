@@ -82,20 +82,21 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return 0;
 }
 
-// statically compiled epilogue modes live in conv_pair_modes{0..4}.cu (up to three modes each, compiled in parallel)
+// statically compiled epilogue modes live in conv_pair_modes{0..5}.cu (up to three modes each, compiled in parallel)
 #define SBM_DECL_GROUP(g)                                                                                              \
   int launch_pair_static_g##g(int mode_idx, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em, \
                               const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream);
-SBM_DECL_GROUP(0) SBM_DECL_GROUP(1) SBM_DECL_GROUP(2) SBM_DECL_GROUP(3) SBM_DECL_GROUP(4)
+SBM_DECL_GROUP(0) SBM_DECL_GROUP(1) SBM_DECL_GROUP(2) SBM_DECL_GROUP(3) SBM_DECL_GROUP(4) SBM_DECL_GROUP(5)
 #undef SBM_DECL_GROUP
 int launch_pair_static(int mode_idx, int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em,
                        const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream) {
-  switch (mode_idx >= 12 ? 4 : mode_idx / 3) {
+  switch (mode_idx >= 16 ? 5 : mode_idx >= 12 ? 4 : mode_idx / 3) {
     case 0: return launch_pair_static_g0(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 1: return launch_pair_static_g1(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 2: return launch_pair_static_g2(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 3: return launch_pair_static_g3(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     case 4: return launch_pair_static_g4(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
+    case 5: return launch_pair_static_g5(mode_idx, bn, tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream);
     default: return -1;
   }
 }
@@ -232,6 +233,7 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   p.out2_preact = (a->out2 != nullptr && a->out2_preact) ? 1 : 0;
   p.rowbias = a->rowbias; p.ld_rowbias = a->ld_rowbias;
   p.bias_vec = (a->bias != nullptr && (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) ? 1 : 0;
+  p.rowbias_vec = (a->rowbias != nullptr && (reinterpret_cast<uintptr_t>(a->rowbias) & 15) == 0 && a->ld_rowbias % 4 == 0) ? 1 : 0;
   if (a->gn_tab != nullptr) {
     SBM_CHECK_ARG(a->kind == SBM_CONV_S1 && (a->kh == 1 || a->kh == 3) && a->kh == a->kw,
                   "sbm_conv_igemm: GroupNorm folding supports 1x1 and 3x3 stride-1 convolutions");
@@ -396,11 +398,12 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       int epi_mode = -1;
       const bool al16 = (a->bias == nullptr || p.bias_vec) &&
                         (a->gn_tab == nullptr || (reinterpret_cast<uintptr_t>(a->gn_tab) & 15) == 0);
-      if (g_epi_static && (a->gn_tab == nullptr || a->cout % 4 == 0) && al16 && a->rowbias == nullptr &&
+      if (g_epi_static && (a->gn_tab == nullptr || a->cout % 4 == 0) && al16 &&
           (a->act == SBM_ACT_NONE || a->act == SBM_ACT_GELU)) {
         uint32_t bits = 0;
         if (a->gn_tab) bits |= EM_GN;
         if (a->bias) bits |= EM_BIAS;
+        if (a->rowbias) bits |= EM_ROWB;
         if (a->act == SBM_ACT_GELU) bits |= EM_GELU;
         if (a->residual) bits |= (a->res_dtype == SBM_F32) ? EM_RES32 : EM_RES16;
         if (a->out_dtype == SBM_BF16) bits |= EM_OBF16;

@@ -60,6 +60,7 @@ struct ConvKernelParams {
   double* stats;
   int32_t act, out_dtype, res_dtype, vec_ok;
   int32_t out2_preact, bias_vec;
+  int32_t rowbias_vec;      // rows of `rowbias` are 16-byte aligned
   const float* rowbias;     // optional per-sample bias [batch][ld_rowbias] added before the activation
   int64_t ld_rowbias;
   // GroupNorm(1, cin) of the INPUT folded into the convolution (weights carry gamma; see sbm_conv_fold_groupnorm):
@@ -357,8 +358,16 @@ __device__ __forceinline__ void epilogue_chunk_staged(const ConvKernelParams& p,
   }
   if (M::rowb(fl) && row_ok) {
     const float* rb = p.rowbias + (int64_t)b * p.ld_rowbias;
+    if (p.rowbias_vec && M::full(n, p.cout)) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) f[e] += __ldg(rb + min(n + e, cmax));
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(rb + n) + k);
+        f[4 * k] += t.x; f[4 * k + 1] += t.y; f[4 * k + 2] += t.z; f[4 * k + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] += __ldg(rb + min(n + e, cmax));
+    }
   }
   if (M::o2(fl) && M::o2pre(fl)) stg_store_bf16_row(stage2, lane, f);
   if (M::gelu(fl)) {
@@ -610,7 +619,9 @@ struct EpiMaps {
   X(12, EM_GN | EM_OBF16)                      /* to_qkv with bf16 output (16x16 / 8x8 attention) */ \
   X(13, 0u)                                    /* training: data-gradient GEMMs (plain fp32 output) */ \
   X(14, EM_BIAS | EM_GELU | EM_OBF16 | EM_STATS | EM_O2PRE)  /* training: 3x3 #1 keeps its pre-activation */ \
-  X(15, EM_BIAS | EM_RES32 | EM_STATS)         /* training: 3x3 #2 + residual + statistics */
+  X(15, EM_BIAS | EM_RES32 | EM_STATS)         /* training: 3x3 #2 + residual + statistics */     \
+  X(16, EM_BIAS | EM_ROWB)                     /* UNetModel ResBlock conv #1 + time / z embedding row bias */ \
+  X(17, EM_BIAS | EM_RES32 | EM_O2)            /* UNetModel ResBlock conv #2 + skip + bf16 copy */
 inline int find_epi_mode(uint32_t bits) {
 #define SBM_EPI_FIND(idx, mode) if (bits == (uint32_t)(mode)) return idx;
   SBM_EPI_MODES(SBM_EPI_FIND)

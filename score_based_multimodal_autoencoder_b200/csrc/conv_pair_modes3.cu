@@ -23,6 +23,8 @@ int launch_pair_static_g3(int mode_idx, int bn, const CUtensorMap& tmA, const CU
 #define SBM_EPI_PICK_13(idx, mode) 
 #define SBM_EPI_PICK_14(idx, mode) 
 #define SBM_EPI_PICK_15(idx, mode) 
+#define SBM_EPI_PICK_16(idx, mode) 
+#define SBM_EPI_PICK_17(idx, mode) 
     SBM_EPI_MODES(SBM_EPI_PICK)
 #undef SBM_EPI_PICK
     default: return -1;

@@ -1,6 +1,6 @@
 """Which kernel variant every convolution of one CelebA score-net forward (or, with `train`, one DSM training step:
 forward + data gradients) runs (BN, CTA pair, staged epilogue, pixel-major tiling, statically compiled epilogue mode):
-python tools/list_conv_variants.py [batch] [train]"""
+python tools/list_conv_variants.py [batch] [train|openai]"""
 import collections
 import os
 import sys
@@ -33,7 +33,14 @@ torch.manual_seed(0)
 m = unet_model.Unet(dim=256, channels=3, dim_mults=(1, 2, 2, 2, 2)).cuda().eval()
 x = torch.randn(B, 3, 16, 16, device="cuda")
 t = torch.rand(B, device="cuda")
-if len(sys.argv) > 2 and sys.argv[2] == "train":
+if len(sys.argv) > 2 and sys.argv[2] == "openai":
+    from score_based_multimodal_autoencoder_b200 import unet_openai
+    unet_openai.ops.conv_igemm = traced
+    mo = unet_openai.UNetModel(in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2, attention_resolutions=(),
+                               dropout=0.1, channel_mult=(1, 2, 4, 8), num_heads=1, use_z=True, z_dim=512).cuda().eval()
+    with torch.no_grad():
+        mo(x, t * 999, torch.randn(B, 512, device="cuda"))
+elif len(sys.argv) > 2 and sys.argv[2] == "train":
     from score_based_multimodal_autoencoder_b200 import autograd, sde_helper2 as sh
     autograd.ops.conv_igemm = traced
     m.train()
