@@ -487,6 +487,10 @@ def conv_roofline(model, sde, x0, ops, L):
         torch.cuda.synchronize()
         ops.conv_igemm = timed
         try:
+            # the events bracket each launch on the stream: give the host a head start (a spin kernel of ~30 ms) so that
+            # every launch of this eager forward is already queued when the GPU reaches it -- otherwise a slow host
+            # core adds its per-call overhead (tensor-map encodes, ctypes) to every measured launch
+            torch.cuda._sleep(60_000_000)
             model(x0, t)
         finally:
             ops.conv_igemm = orig

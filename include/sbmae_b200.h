@@ -79,9 +79,20 @@ typedef struct sbm_conv_args {
   const float* gn_tab;      /* [2][16][cout] */
   float gn_count;
   float gn_eps;
+  /* optional split-K workspace: fp32 [batch*oh*ow][ld_ws] (ld_ws >= cout, multiple of 4), ZEROED by the caller.  When
+   * given and sbm_conv_splitk_plan(a) > 1 (a stride-1 layer of a few 256 x 256 output tiles with a long K loop: the
+   * low-resolution levels at small batch), the K loop is cut across the SM pairs: partial accumulators are added into
+   * the workspace by TMA reduce-add, a second kernel applies the epilogue and hands the workspace back zeroed (so one
+   * buffer, zeroed once, serves every call on a stream).  NULL: never split. */
+  float* splitk_ws;
+  int64_t ld_ws;
 } sbm_conv_args;
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
+/* number of K slices sbm_conv_igemm would use for this call when given a workspace (1 = it would not split) */
+int sbm_conv_splitk_plan(const sbm_conv_args* a);
+/* A/B switch: 0 = never split along K (sbm_conv_splitk_plan then returns 1); default 1, also SBM_SPLITK */
+int sbm_conv_splitk(int32_t on);
 /* A/B switch for measurements: 1 = always use the single-CTA kernel instead of the CTA-pair (cta_group::2) one */
 int sbm_conv_force_single_cta(int32_t on);
 /* A/B switch: 1 = per-thread global stores in the CTA-pair kernel instead of the TMA-staged epilogue */
@@ -90,7 +101,7 @@ int sbm_conv_force_direct_epilogue(int32_t on);
  * compiled loop of the call's flag set (same arithmetic in the same order: bit-identical results); default 1 */
 int sbm_conv_epilogue_static(int32_t on);
 /* which kernel the calling thread's last sbm_conv_igemm used: N tile | CTA-pair << 16 | staged epilogue << 17 |
- * pixel-major tiling << 18 | statically compiled epilogue mode << 19 */
+ * pixel-major tiling << 18 | statically compiled epilogue mode << 19 | split-K << 20 | K slices << 24 */
 int sbm_conv_last_variant(void);
 /* pixel-major tiling of stride-1 'same' convolutions (a tile = 128 samples at ONE output pixel, so taps that only read
  * zero padding there are skipped): -1 = decide by work estimate (default), 0 = never, 1 = whenever the CTA-pair kernel

@@ -77,6 +77,7 @@ class ConvArgs(C.Structure):
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
         ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
         ("gn_stats", C.c_void_p), ("gn_tab", C.c_void_p), ("gn_count", C.c_float), ("gn_eps", C.c_float),
+        ("splitk_ws", C.c_void_p), ("ld_ws", C.c_int64),
     ]
 
 SDE_VP, SDE_SUBVP, SDE_VE = 0, 1, 2

@@ -127,6 +127,102 @@ static bool encode_rowbox_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensor
   return cr == CUDA_SUCCESS;
 }
 
+// ---------------------------------------------------------------- split-K for sub-wave, K-long layers
+// At 128 latents per GPU (the 8-GPU shard of the headline config) the 4x4 / 2x2 levels are GEMMs of 512..2048 rows with
+// K = 4608..9216: a handful of 256 x 256 tiles.  Narrow N tiles spread them over the SMs but re-read the activation
+// rows once per N tile and move 2.5 x the bytes per FLOP; an SM ingests ~40-50 B/clk, so those launches ran at 20 % of
+// the tensor pipe (pipeline trace, profiles/r2b_pair_pipeline_trace_small_batch.log).  With a caller-provided, zeroed
+// fp32 workspace the layer keeps 256-wide tiles and is cut along K instead: every (tile, K slice) work item ADDS its raw
+// accumulators into the workspace (TMA reduce-add boxes), then conv_splitk_epilogue_kernel applies the epilogue.
+static bool g_splitk = [] { const char* e = getenv("SBM_SPLITK"); return e ? atoi(e) != 0 : true; }();
+
+// number of K slices sbm_conv_igemm would use for this call if it is given a workspace (1 = no split)
+static int splitk_plan(const sbm_conv_args* a) {
+  if (!g_splitk || g_force_single || a->kind != SBM_CONV_S1 || a->out_nchw || a->cout <= 128) return 1;
+  const int ph = a->kh / 2, pw = a->kw / 2;
+  int ntaps = 0;
+  for (int kh = 0; kh < a->kh; ++kh)
+    for (int kw = 0; kw < a->kw; ++kw)
+      if (abs(kh - ph) < a->h && abs(kw - pw) < a->w) ++ntaps;
+  const int num_kb = ntaps * ((a->cin + kBK - 1) / kBK);
+  const int64_t M = (int64_t)a->batch * a->h * a->w;
+  if (M < 128 || num_kb < 32) return 1;
+  const int64_t tiles = ((M + 255) / 256) * ((a->cout + 255) / 256);
+  const int npairs = sm_count() / 2;
+  if (tiles * 2 > npairs) return 1;
+  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(8, npairs / tiles), num_kb / 8));
+  // split-K runs the standard tiling, which also multiplies the taps that only read zero padding.  Where the
+  // pixel-major tiling would skip them (conv_igemm_impl: 56 % of a 3x3 at 2x2, 31 % at 4x4, batch in 256-sample blocks),
+  // the split has to win that work back: at 1024 latents the 2x2 level is 32 tiles, 2 slices of 9 taps lose to 1 slice
+  // of 4 (measured: forward 9.16 -> 9.29 ms with the split on)
+  int64_t valid = 0;
+  for (int i = 0; i < a->h; ++i)
+    for (int j = 0; j < a->w; ++j)
+      for (int kh = 0; kh < a->kh; ++kh)
+        for (int kw = 0; kw < a->kw; ++kw)
+          valid += (i + kh - ph >= 0 && i + kh - ph < a->h && j + kw - pw >= 0 && j + kw - pw < a->w) ? 1 : 0;
+  const double work_pm = (double)((a->batch + 255) / 256) * 256 * valid;
+  const double work_std = (double)((M + kBM - 1) / kBM) * kBM * ntaps;
+  if (g_pixel_major != 0 && a->h * a->w <= 256 && work_pm < 0.97 * work_std && splits * work_pm < 1.25 * work_std)
+    return 1;
+  return splits;
+}
+
+// epilogue of a split-K convolution: thread = (output row, 16-column chunk), chunk index fastest, so a warp reads and
+// writes contiguous pieces of one row (or of a few consecutive rows when the row has fewer than 32 chunks).  The
+// workspace is handed back ZEROED (every thread clears what it has read): the caller's buffer is ready for the next call.
+__global__ void __launch_bounds__(256)
+conv_splitk_epilogue_kernel(const __grid_constant__ ConvKernelParams p, float* __restrict__ ws, int64_t ldw,
+                            int chunks, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t idx = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
+  const int64_t r = idx / chunks;
+  const int chunk = (int)(idx - r * chunks);
+  const int log_ohw = p.log_oh + p.log_ow;
+  const bool row_ok = r < rows;
+  const int64_t rr = row_ok ? r : 0;
+  const int b = (int)(rr >> log_ohw);
+  const int rem = (int)(rr & ((1 << log_ohw) - 1));
+  const int oh = rem >> p.log_ow, j = rem & ((1 << p.log_ow) - 1);
+  const int n = chunk * 16;
+  uint32_t v[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = 0u;
+  if (row_ok) {
+    float* src = ws + rr * ldw + n;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (n + 4 * k + 4 <= ldw) {
+        const float4 t = *(reinterpret_cast<const float4*>(src) + k);
+        *(reinterpret_cast<float4*>(src) + k) = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * k] = __float_as_uint(t.x); v[4 * k + 1] = __float_as_uint(t.y);
+        v[4 * k + 2] = __float_as_uint(t.z); v[4 * k + 3] = __float_as_uint(t.w);
+      }
+  }
+  const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw;
+  const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
+  const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw;
+  float s1 = 0.f, s2 = 0.f;
+  const GnRow gr = gn_row(p, b, oh, j, row_ok);
+  epilogue16(p, v, n, row_ok, b, o_base, r_base, o2_base, s1, s2, gr);
+  if (p.stats != nullptr) {
+    if (!row_ok) { s1 = 0.f; s2 = 0.f; }
+    // a warp covers 32 / chunks consecutive rows: almost always one sample
+    const int b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, b == b0 || !row_ok)) {
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0 && __shfl_sync(0xffffffffu, (int)row_ok, 0)) {
+        atomicAdd(p.stats + 2 * (int64_t)b0, (double)s1);
+        atomicAdd(p.stats + 2 * (int64_t)b0 + 1, (double)s2);
+      }
+    } else if (row_ok) {
+      atomicAdd(p.stats + 2 * (int64_t)b, (double)s1);
+      atomicAdd(p.stats + 2 * (int64_t)b + 1, (double)s2);
+    }
+  }
+}
+
 static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   SBM_CHECK_ARG(a != nullptr, "sbm_conv_igemm: null args");
   SBM_CHECK_ARG(a->x && a->wpk && a->out, "sbm_conv_igemm: null operand pointer");
@@ -345,7 +441,16 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
       }
     }
   }
-  const bool use_pair = pm ? true : choose(m_tiles);
+  bool use_pair = pm ? true : choose(m_tiles);
+  // split-K (see splitk_plan): standard tiling, 256-wide tiles, raw accumulators into the caller's zeroed workspace
+  const int splits = (a->splitk_ws != nullptr && a->ld_ws >= a->cout && a->ld_ws % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(a->splitk_ws) & 15) == 0 && M >= 128) ? splitk_plan(a) : 1;
+  if (splits > 1) {
+    pm = false;
+    m_tiles = (int)((M + kBM - 1) / kBM);
+    BN = 256;
+    use_pair = true;
+  }
   const int n_tiles_pair = (a->cout + BN - 1) / BN;
   p.pm = pm ? 1 : 0;
 #ifdef SBM_PAIR_TRACE
@@ -373,6 +478,28 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SBM_CHECK_ARG(cr == CUDA_SUCCESS, "sbm_conv_igemm: weight tensor map encode failed (CUresult %d)", (int)cr);
 
+  if (splits > 1) {
+    EpiMaps em;
+    SBM_CHECK_ARG(encode_rowbox_map(encode, &em.out, a->splitk_ws, SBM_F32, a->ld_ws, a->cout, ow, oh, a->batch, 1, log_ow,
+                                    log_th, false),
+                  "sbm_conv_igemm: split-K workspace tensor map encode failed");
+    em.res = em.out;
+    em.out2 = em.out;
+    ConvKernelParams q = p;   // the GEMM pass has no epilogue arithmetic
+    q.bias = nullptr; q.residual = nullptr; q.out = a->splitk_ws; q.out2 = nullptr; q.stats = nullptr; q.rowbias = nullptr;
+    q.gn_stats = nullptr; q.gn_tab = nullptr; q.act = SBM_ACT_NONE; q.out_dtype = SBM_F32; q.out2_preact = 0;
+    q.bias_vec = 0; q.rowbias_vec = 0;
+    q.taps[0].out_q = 0;
+    g_last_variant = BN | (1 << 16) | (1 << 17) | (1 << 20) | (splits << 24);
+    const int rc = launch_conv_pair<256, 5, true, EM_SPLITK>(tmA, tmB, em, q, m_tiles, n_tiles_pair, nphase, stream, splits);
+    if (rc != 0) return rc;
+    const int chunks = (a->cout + 15) / 16;
+    const int64_t items = M * chunks;
+    conv_splitk_epilogue_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(p, a->splitk_ws, a->ld_ws, chunks, M);
+    SBM_CUDA_OK(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
   if (use_pair) {
     // staged epilogue: TMA box stores / residual loads; needs 16-byte aligned rows (vec) and at least one full warp box
     EpiMaps em;
@@ -678,6 +805,12 @@ int sbm_debug_pair_trace(unsigned long long* buf) {
 
 int sbm_conv_epilogue_static(int32_t on) {
   sbm::g_epi_static = on != 0;
+  return 0;
+}
+
+int sbm_conv_splitk_plan(const sbm_conv_args* a) { return a ? sbm::splitk_plan(a) : 1; }
+int sbm_conv_splitk(int32_t on) {
+  sbm::g_splitk = on != 0;
   return 0;
 }
 

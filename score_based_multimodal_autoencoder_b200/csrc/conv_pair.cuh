@@ -271,7 +271,10 @@ __device__ __forceinline__ void stg_store_bf16_row(uint32_t buf, int r, const fl
 // old run-time tested loop.
 enum : uint32_t {
   EM_GN = 1u, EM_BIAS = 2u, EM_ROWB = 4u, EM_GELU = 8u, EM_SILU = 16u, EM_RES32 = 32u, EM_RES16 = 64u, EM_OBF16 = 128u,
-  EM_O2 = 256u, EM_O2PRE = 512u, EM_STATS = 1024u, EM_DYN = 1u << 31
+  EM_O2 = 256u, EM_O2PRE = 512u, EM_STATS = 1024u, EM_DYN = 1u << 31,
+  // split-K work items: no epilogue arithmetic, the raw fp32 accumulators are ADDED into a zeroed workspace by TMA
+  // reduce-add boxes (a second kernel applies the epilogue); the tile list carries a K-slice index
+  EM_SPLITK = 1u << 17
 };
 // EM_DYN: the same bits, computed from the kernel parameters ONCE per tile into a register (`fl`), so that the chunk
 // loop tests register predicates instead of re-loading and comparing constant-bank parameters.
@@ -674,7 +677,8 @@ __device__ __forceinline__ void staged_step(const ConvKernelParams& p, const Epi
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      ptx::tma_store_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
+      if constexpr ((MODE & EM_SPLITK) != 0) ptx::tma_reduce_add_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
+      else ptx::tma_store_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
       ptx::bulk_commit_group();
     }
     ++nchunk;
@@ -730,6 +734,7 @@ struct Smem2Layout {
 
 struct PairSchedule {
   int32_t m_tiles, m_pairs, n_tiles, nphase, total;
+  int32_t splits;   // K slices per output tile (EM_SPLITK kernels; 1 otherwise); `total` counts (tile, slice) items
 };
 
 template <int BN, int STAGES, bool kStaged, uint32_t MODE>
@@ -754,6 +759,16 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int npairs = gridDim.x >> 1;
   const int log_ohw = p.log_oh + p.log_ow;
   const int per_phase = sch.m_pairs * sch.n_tiles;
+  constexpr bool kSplit = (MODE & EM_SPLITK) != 0;
+  // work item -> (output tile, K slice): consecutive items are the slices of one tile
+  auto split_of = [&](int& t) -> int {
+    if constexpr (kSplit) {
+      const int s = t % sch.splits;
+      t /= sch.splits;
+      return s;
+    }
+    return 0;
+  };
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -834,25 +849,33 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int k = 0; k * npairs < sch.total; ++k) {
-        const int t = tile_of_round(k);
+        int t = tile_of_round(k);
         if (t >= sch.total) continue;
+        const int sp = split_of(t);
         int ph, nt, b0, oh0, pj;
         tile_origin(t, ph, nt, b0, oh0, pj);
         const TapTable& tt = p.taps[ph];
         const int n0 = nt * BN + (int)rank * (BN / 2);
         SBM_TRACE(0, 0, k);   // producer reaches tile k
-        for (uint32_t tm = tap_mask(tt, oh0, pj); tm != 0; tm &= tm - 1) {
-          const int tap = __ffs(tm) - 1;
-          for (int cb = 0; cb < p.cblocks; ++cb) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if ((cb & 15) == 0) SBM_TRACE(0, 1, k);   // got a free stage (every 16th K block: the record itself costs ~0.4 us)
-            uint8_t* sa = smem + stage * L::kStageBytes;
-            uint8_t* sb = sa + L::kABytes;
-            if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
-            const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
-            ptx::tma_load_5d_2sm(sa, &tmA, lead_bar, cb * kBK, pj + tt.dw[tap], tt.q[tap], oh0 + tt.dh[tap], b0);
-            ptx::tma_load_3d_2sm(sb, &tmB, lead_bar, cb * kBK, n0, tt.wtap[tap]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        auto issue = [&](int tap, int cb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          if ((cb & 15) == 0) SBM_TRACE(0, 1, k);   // got a free stage (every 16th K block: the record itself costs ~0.4 us)
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          const uint32_t lead_bar = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+          ptx::tma_load_5d_2sm(sa, &tmA, lead_bar, cb * kBK, pj + tt.dw[tap], tt.q[tap], oh0 + tt.dh[tap], b0);
+          ptx::tma_load_3d_2sm(sb, &tmB, lead_bar, cb * kBK, n0, tt.wtap[tap]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+        if constexpr (kSplit) {   // standard tiling only: every tap of the table is valid, K block kb = tap * cblocks + cb
+          const int nkb = tt.ntaps * p.cblocks;
+          const int lo = sp * nkb / sch.splits, hi = (sp + 1) * nkb / sch.splits;
+          for (int kb = lo; kb < hi; ++kb) issue(kb / p.cblocks, kb % p.cblocks);
+        } else {
+          for (uint32_t tm = tap_mask(tt, oh0, pj); tm != 0; tm &= tm - 1) {
+            const int tap = __ffs(tm) - 1;
+            for (int cb = 0; cb < p.cblocks; ++cb) issue(tap, cb);
           }
         }
       }
@@ -864,11 +887,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0, astage = 0;
       uint32_t phase = 0, aphase = 0;
       for (int k = 0; k * npairs < sch.total; ++k) {
-        const int t = tile_of_round(k);
+        int t = tile_of_round(k);
         if (t >= sch.total) continue;
+        const int sp = split_of(t);
         int ph, nt, b0, oh0, pj;
         tile_origin(t, ph, nt, b0, oh0, pj);
-        const int num_kb = __popc(tap_mask(p.taps[ph], oh0, pj)) * p.cblocks;
+        int num_kb = __popc(tap_mask(p.taps[ph], oh0, pj)) * p.cblocks;
+        if constexpr (kSplit) num_kb = (sp + 1) * num_kb / sch.splits - sp * num_kb / sch.splits;
         SBM_TRACE(1, 0, k);   // issuer reaches tile k
         ptx::mbar_wait(&tempty_bar[astage], aphase ^ 1);
         SBM_TRACE(1, 1, k);   // accumulator stage free
@@ -917,8 +942,9 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int astage = 0;
     uint32_t aphase = 0;
     for (int k = 0; k * npairs < sch.total; ++k) {
-        const int t = tile_of_round(k);
-        if (t >= sch.total) continue;
+      int t = tile_of_round(k);
+      if (t >= sch.total) continue;
+      split_of(t);
       int ph, nt, b0, oh0, pj;
       tile_origin(t, ph, nt, b0, oh0, pj);
       const TapTable& tt = p.taps[ph];
@@ -995,7 +1021,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 template <int BN, int STAGES, bool kStaged, uint32_t MODE>
 inline int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em,
-                            const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream) {
+                            const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream,
+                            int splits = 1) {
   using L = Smem2Layout<BN, STAGES, kStaged>;
   static_assert(L::kTotal <= 232448, "shared-memory budget of one CTA exceeded");
   static bool configured = false;
@@ -1009,7 +1036,8 @@ inline int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   sch.m_pairs = (m_tiles + 1) / 2;
   sch.n_tiles = n_tiles;
   sch.nphase = nphase;
-  sch.total = nphase * sch.m_pairs * n_tiles;
+  sch.splits = splits;
+  sch.total = nphase * sch.m_pairs * n_tiles * splits;
   const int pairs = std::min(sch.total, sm_count() / 2);
   conv_igemm_pair_kernel<BN, STAGES, kStaged, MODE><<<dim3(2 * pairs), 384, L::kTotal, stream>>>(tmA, tmB, em, p, sch);
   SBM_CUDA_OK(cudaGetLastError());

@@ -159,6 +159,24 @@ def pack_linear_weight(w: torch.Tensor, out=None) -> torch.Tensor:
     return pack_weight(w, 1, o, i, 0, i, 1, out)
 
 
+_splitk_ws: dict = {}
+
+
+def _splitk_workspace(dev: torch.device, rows: int, ld: int) -> torch.Tensor:
+    """Zeroed fp32 workspace of a split-K convolution.  The library hands it back zeroed, so ONE buffer per device is
+    zeroed once and then serves every call in stream order (no memset per layer; the address is stable, so it can be
+    replayed from a CUDA graph).  Like the packed-weight caches it assumes that one device's score-net calls are
+    issued in order (one stream at a time, or streams that are joined between calls)."""
+    key = dev.index
+    ws = _splitk_ws.get(key)
+    if ws is None or ws.numel() < rows * ld:
+        if torch.cuda.is_current_stream_capturing():
+            # growing inside a capture would put the buffer into the graph's private pool: size it beforehand
+            raise L.SbmError("split-K workspace too small inside CUDA-graph capture (run the call once eagerly first)")
+        ws = _splitk_ws[key] = torch.zeros(max(rows * ld, 1 << 22), dtype=torch.float32, device=dev)
+    return ws
+
+
 def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: int, cin: int, cout: int,
                bias: torch.Tensor | None = None, act: int = L.ACT_NONE, residual: torch.Tensor | None = None,
                out: torch.Tensor | None = None, out_dtype: torch.dtype = torch.float32, nchw: bool = False,
@@ -205,6 +223,11 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
     if gn_tab is not None:  # GroupNorm(1, cin) of x folded into the weights (fold_groupnorm_conv)
         a.gn_stats, a.gn_tab = gn_stats.data_ptr(), gn_tab.data_ptr()
         a.gn_count, a.gn_eps = float(h * w * cin), gn_eps
+    # sub-wave K-long layers (low-resolution levels at small batch): split-K needs a zeroed fp32 workspace; the plan
+    # lives in the library (one source of truth), the allocation here (memset node under CUDA-graph capture)
+    if kind == L.CONV_S1 and not nchw and L.lib().sbm_conv_splitk_plan(C.byref(a)) > 1:
+        ws = _splitk_workspace(x.device, b * oh * ow, pad8(cout))
+        a.splitk_ws, a.ld_ws = ws.data_ptr(), pad8(cout)
     L.check(L.lib().sbm_conv_igemm(C.byref(a), L.stream_ptr()), "sbm_conv_igemm")
     return out
 

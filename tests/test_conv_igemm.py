@@ -424,3 +424,54 @@ def test_conv_pixel_major_tiling(case):
         L.lib().sbm_conv_pixel_major(-1)
         assert (v & (1 << 18)) and not (v & (1 << 17))
         assert torch.equal(o3[..., :cout], outs[0][0])
+
+
+@pytest.mark.parametrize("opt", ["gn_gelu_bf16_stats", "gn_res_f32_out2_stats", "bias_f32", "bias_res_bf16out"])
+@pytest.mark.parametrize("shape", [(4, 128, 1024, 512, 3), (2, 100, 512, 1024, 3), (8, 96, 640, 256, 3)])
+def test_conv_split_k_matches_unsplit(opt, shape):
+    """Sub-wave K-long layers (low-resolution levels at small batch) are cut along K across the SM pairs: partial sums
+    meet in an fp32 workspace by TMA reduce-add, a second kernel applies the epilogue.  Same result as the unsplit
+    launch up to fp32 summation order, every epilogue flag honoured, and the workspace comes back zeroed."""
+    from score_based_multimodal_autoencoder_b200 import _lib as L, ops
+    H, B, cin, cout, k = shape
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(H * 7 + cin)
+    xb = (torch.randn(B, H, H, ops.pad8(cin), generator=g)).to(dev).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    bias = torch.randn(cout, generator=g).to(dev)
+    res = torch.randn(B, H, H, ops.pad8(cout), generator=g).to(dev)
+    kw = dict(kind=L.CONV_S1, kh=k, kw=k, cin=cin, cout=cout)
+    gamma = (1 + 0.3 * torch.randn(cin, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(cin, generator=g)).to(dev)
+    outs = []
+    for split in (1, 0):
+        L.lib().sbm_conv_splitk(split)
+        stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
+        out2 = None
+        if opt.startswith("gn_"):
+            wg, tab = ops.fold_groupnorm_conv(w, bias, gamma, beta)
+            xs = xb[..., :cin].double()
+            gst = torch.stack([xs.sum(dim=(1, 2, 3)), (xs * xs).sum(dim=(1, 2, 3))], dim=1).contiguous()
+            gkw = dict(gn_stats=gst, gn_tab=tab, gn_eps=1e-5)
+            if opt == "gn_gelu_bf16_stats":
+                out = ops.conv_igemm(xb, wg, act=L.ACT_GELU, out_dtype=torch.bfloat16, stats=stats, **gkw, **kw)
+            else:
+                out2 = torch.empty(B, H, H, ops.pad8(cout), dtype=torch.bfloat16, device=dev)
+                out = ops.conv_igemm(xb, wg, residual=res, stats=stats, out2=out2, **gkw, **kw)
+        elif opt == "bias_f32":
+            out = ops.conv_igemm(xb, ops.pack_conv2d_weight(w), bias=bias, **kw)
+        else:
+            out = ops.conv_igemm(xb, ops.pack_conv2d_weight(w), bias=bias, residual=res, out_dtype=torch.bfloat16, **kw)
+        torch.cuda.synchronize()
+        v = L.lib().sbm_conv_last_variant()
+        assert bool(v & (1 << 20)) == bool(split), (split, hex(v))
+        outs.append((out[..., :cout].float().clone(), None if out2 is None else out2[..., :cout].float().clone(), stats.clone()))
+    L.lib().sbm_conv_splitk(1)
+    ws = ops._splitk_ws[dev.index if dev.index is not None else torch.cuda.current_device()]
+    assert not ws.any()   # handed back zeroed
+    a, b_ = outs
+    tol = 2e-2 if "bf16" in opt else 1e-4   # bf16 outputs: one rounding step of either result
+    assert (a[0] - b_[0]).abs().max().item() <= tol * b_[0].abs().max().item()
+    if a[1] is not None:
+        assert (a[1] - b_[1]).abs().max().item() <= 2e-2 * b_[1].abs().max().item()
+    assert torch.allclose(a[2], b_[2], rtol=1e-4, atol=1e-2)
