@@ -183,6 +183,15 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
                         const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
                         int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
                         float eps, int32_t act, void* stream);
+/* the same with per-sample modulation: y = act(GroupNorm(x) * (1 + mod_scale[b][c]) + mod_shift[b][c]) +
+ * post_add[b][c] (+ residual).  mod_scale / mod_shift (fp32 [B][ld_mod], both or neither): `use_scale_shift_norm` of
+ * unet_openai.py:296-300; post_add (fp32 [B][ld_post]): the time embedding added AFTER the SiLU of Block 1 in
+ * ResnetBlock (unet_model.py:82-87).  Null pointers: plain sbm_groupnorm_apply. */
+int sbm_groupnorm_apply_mod(const void* x, int32_t in_dtype, int64_t ldx, const double* stats, const float* gamma,
+                            const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
+                            int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
+                            float eps, int32_t act, const float* mod_scale, const float* mod_shift, int64_t ld_mod,
+                            const float* post_add, int64_t ld_post, void* stream);
 /* nearest-neighbour 2x upsampling of a bf16 channels-last map (unet_openai.py:185) */
 int sbm_upsample_nearest2x(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t B, int32_t H, int32_t W,
                            int32_t C, void* stream);
@@ -301,6 +310,12 @@ int sbm_groupnorm_bwd(const void* x, int32_t x_dtype, int64_t ldx, const void* d
 /* out[b][c] = sum over the pixels of sample b of x[b][p][c]: gradient of a per-sample row bias (unet_openai.py:303) */
 int sbm_colsum_per_sample(const void* x, int32_t dtype, int64_t ld, int32_t B, int32_t HW, int32_t C, float* out,
                           int64_t ldo, void* stream);
+/* backward of y = act(n * (1 + scale[b][c]) + shift[b][c]) (ResBlock(use_scale_shift_norm=True), unet_openai.py:296-300;
+ * n = GroupNorm32 output, fp32 channels-last): dn = dy * act'(u) * (1 + scale); dscale[b][c] += sum_pix dy * act'(u) * n;
+ * dshift[b][c] += sum_pix dy * act'(u)  (fp32 [B][ld_dmod], caller zeroes). */
+int sbm_scale_shift_bwd(const float* n, int64_t ldn, const float* dy, int64_t lddy, const float* scale,
+                        const float* shift, int64_t ld_mod, int32_t act, float* dn, int64_t lddn, float* dscale,
+                        float* dshift, int64_t ld_dmod, int32_t B, int32_t HW, int32_t C, void* stream);
 /* backward of sbm_upsample_nearest2x: out[b,i,j,c] = sum of the 2x2 block of dy (fp32 [B,2H,2W,lddy]) */
 int sbm_upsample_nearest2x_bwd(const float* dy, int64_t lddy, float* out, int64_t ldo, void* out_bf16, int64_t ldb,
                                int32_t B, int32_t H, int32_t W, int32_t C, void* stream);

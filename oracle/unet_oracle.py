@@ -47,6 +47,20 @@ def convnext_block(sd, p, x, t_emb):
     return h + res
 
 
+def resnet_block(sd, p, x, t_emb, groups=8):
+    """unet_model.py:49-65, 67-90 (`Unet(use_convnext=False)`): Block = conv3x3 -> GroupNorm(groups) -> SiLU; the time
+    projection (SiLU -> Linear) is added to Block 1's OUTPUT."""
+    h = F.silu(_gn(F.conv2d(x, sd[p + ".block1.proj.weight"], sd[p + ".block1.proj.bias"], padding=1), sd,
+                   p + ".block1.norm", groups))
+    if (p + ".mlp.1.weight") in sd and t_emb is not None:
+        h = F.linear(F.silu(t_emb), sd[p + ".mlp.1.weight"], sd[p + ".mlp.1.bias"])[:, :, None, None] + h
+    h = F.silu(_gn(F.conv2d(h, sd[p + ".block2.proj.weight"], sd[p + ".block2.proj.bias"], padding=1), sd,
+                   p + ".block2.norm", groups))
+    if (p + ".res_conv.weight") in sd:
+        return h + F.conv2d(x, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
+    return h + x
+
+
 def linear_attention(sd, p, x, heads=4):
     """unet_model.py:162-177 (p = prefix of the LinearAttention module)."""
     b, c, hh, ww = x.shape
@@ -83,14 +97,17 @@ def _residual_prenorm(sd, p, x, fn):
     return fn(sd, p + ".fn.fn", _gn(x, sd, p + ".fn.norm")) + x
 
 
-def unet_forward(sd: dict, x: torch.Tensor, time: torch.Tensor, *, dim: int, dim_mults=(1, 2, 4, 8)) -> torch.Tensor:
+def unet_forward(sd: dict, x: torch.Tensor, time: torch.Tensor, *, dim: int, dim_mults=(1, 2, 4, 8),
+                 use_convnext: bool = True, groups: int = 8) -> torch.Tensor:
     """unet_model.py:275-323, including the zero padding of non-power-of-two extents (:276-284) and the final crop
-    (:318-322)."""
+    (:318-322).  use_convnext=False: ResnetBlock(groups) in place of every ConvNextBlock (unet_model.py:214-217)."""
+    block = convnext_block if use_convnext else (lambda sd_, p, x_, t_: resnet_block(sd_, p, x_, t_, groups))
     n_levels = len(dim_mults)
     pw = int((2 ** math.ceil(math.log2(x.shape[-1])) - x.shape[-1]) // 2)
     ph = int((2 ** math.ceil(math.log2(x.shape[-2])) - x.shape[-2]) // 2)
     if pw or ph:
-        y = unet_forward(sd, F.pad(x, (pw, pw, ph, ph)), time, dim=dim, dim_mults=dim_mults)
+        y = unet_forward(sd, F.pad(x, (pw, pw, ph, ph)), time, dim=dim, dim_mults=dim_mults,
+                         use_convnext=use_convnext, groups=groups)
         y = y[..., pw:-pw] if pw else y
         return y[..., ph:-ph, :] if ph else y
     x = F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
@@ -100,23 +117,23 @@ def unet_forward(sd: dict, x: torch.Tensor, time: torch.Tensor, *, dim: int, dim
     t = F.linear(t, sd["time_mlp.3.weight"], sd["time_mlp.3.bias"])
     skips = []
     for lv in range(n_levels):
-        x = convnext_block(sd, f"downs.{lv}.0", x, t)
-        x = convnext_block(sd, f"downs.{lv}.1", x, t)
+        x = block(sd, f"downs.{lv}.0", x, t)
+        x = block(sd, f"downs.{lv}.1", x, t)
         x = _residual_prenorm(sd, f"downs.{lv}.2", x, linear_attention)
         skips.append(x)
         if lv < n_levels - 1:
             x = F.conv2d(x, sd[f"downs.{lv}.3.weight"], sd[f"downs.{lv}.3.bias"], stride=2, padding=1)
-    x = convnext_block(sd, "mid_block1", x, t)
+    x = block(sd, "mid_block1", x, t)
     x = _residual_prenorm(sd, "mid_attn", x, softmax_attention)
-    x = convnext_block(sd, "mid_block2", x, t)
+    x = block(sd, "mid_block2", x, t)
     for u in range(n_levels - 1):
         x = torch.cat((x, skips.pop()), dim=1)
-        x = convnext_block(sd, f"ups.{u}.0", x, t)
-        x = convnext_block(sd, f"ups.{u}.1", x, t)
+        x = block(sd, f"ups.{u}.0", x, t)
+        x = block(sd, f"ups.{u}.1", x, t)
         x = _residual_prenorm(sd, f"ups.{u}.2", x, linear_attention)
         # `is_last` at unet_model.py:257 is never true -> every up level upsamples
         x = F.conv_transpose2d(x, sd[f"ups.{u}.3.weight"], sd[f"ups.{u}.3.bias"], stride=2, padding=1)
-    x = convnext_block(sd, "final_conv.0", x, None)
+    x = block(sd, "final_conv.0", x, None)
     return F.conv2d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"])
 
 
@@ -137,13 +154,17 @@ def _gn32(x, sd, key):
 
 
 def res_block(sd, p, x, emb):
-    """unet_openai.py:291-305 (use_scale_shift_norm=False, eval mode: dropout is the identity)."""
+    """unet_openai.py:291-305 (eval mode: dropout is the identity).  use_scale_shift_norm (:296-300) shows in the
+    width of the embedding projection: 2 * out_channels = [scale | shift]."""
     h = F.conv2d(F.silu(_gn32(x, sd, p + ".in_layers.0")), sd[p + ".in_layers.2.weight"], sd[p + ".in_layers.2.bias"],
                  padding=1)
     e = F.linear(F.silu(emb), sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
-    h = h + e[:, :, None, None]
-    h = F.conv2d(F.silu(_gn32(h, sd, p + ".out_layers.0")), sd[p + ".out_layers.3.weight"],
-                 sd[p + ".out_layers.3.bias"], padding=1)
+    if e.shape[1] == 2 * h.shape[1]:
+        scale, shift = torch.chunk(e[:, :, None, None], 2, dim=1)
+        h = F.silu(_gn32(h, sd, p + ".out_layers.0") * (1 + scale) + shift)
+    else:
+        h = F.silu(_gn32(h + e[:, :, None, None], sd, p + ".out_layers.0"))
+    h = F.conv2d(h, sd[p + ".out_layers.3.weight"], sd[p + ".out_layers.3.bias"], padding=1)
     if (p + ".skip_connection.weight") in sd:
         w = sd[p + ".skip_connection.weight"]
         x = F.conv2d(x, w, sd[p + ".skip_connection.bias"], padding=w.shape[-1] // 2)
@@ -167,8 +188,8 @@ def attention_block(sd, p, x, num_heads):
 
 
 def unet_openai_forward(sd: dict, x, timesteps, *, model_channels, num_res_blocks, attention_resolutions,
-                        channel_mult=(1, 2, 4, 8), num_heads=1, z=None):
-    """unet_openai.py:538-575 (dims=2, conv_resample=True, no class conditioning)."""
+                        channel_mult=(1, 2, 4, 8), num_heads=1, z=None, y=None):
+    """unet_openai.py:538-575 (dims=2, conv_resample=True; y: class labels when the net has a `label_emb`)."""
     emb = timestep_embedding(timesteps, model_channels)
     emb = F.linear(F.silu(F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])),
                    sd["time_embed.2.weight"], sd["time_embed.2.bias"])
@@ -176,6 +197,8 @@ def unet_openai_forward(sd: dict, x, timesteps, *, model_channels, num_res_block
         zp = F.linear(F.silu(F.linear(z, sd["proj.0.weight"], sd["proj.0.bias"])), sd["proj.2.weight"],
                       sd["proj.2.bias"])
         emb = emb + zp
+    if y is not None:
+        emb = emb + sd["label_emb.weight"][y]   # unet_openai.py:561-564
     hs = []
     h = F.conv2d(x, sd["input_blocks.0.0.weight"], sd["input_blocks.0.0.bias"], padding=1)
     hs.append(h)

@@ -168,6 +168,74 @@ class _Plan:
         self.tape.append(bwd)
         return out
 
+    # ------------------------------------------------------------------ ResnetBlock (unet_model.py:67-90)
+    def resnet(self, blk, xin: _Node, cond, cond_off, ldc, dcond, *, want_f32=True, want_bf16=False,
+               want_stats=False, out_f32=None, out_bf16=None) -> _Node:
+        """Block 1 = conv3x3 -> GroupNorm(groups) -> SiLU, + time projection, Block 2 the same, + res_conv(x)
+        (`Unet(use_convnext=False)`).  Same signature as `convnext`; the bf16 operand copy of the output is always
+        written (the next block's convolution reads it)."""
+        m = self.m
+        xf = xin.f32
+        b, h, w, _ = xf.shape
+        dev = xf.device
+        c_in, c_out, G = blk.dim, blk.dim_out, blk.groups
+        has_t = cond is not None and blk.mlp is not None
+        x_b = xin.bf16
+        if x_b is None:
+            _, x_b = ops.add(xf, None, c_in, want_bf16=True)
+        p1, n1, p2, n2 = blk.block1.proj, blk.block1.norm, blk.block2.proj, blk.block2.norm
+        h1 = ops.conv_igemm(x_b, m._w_conv(p1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out, bias=p1.bias)
+        st1 = torch.zeros((b, G, 2), dtype=torch.float64, device=dev)
+        ops.group_stats(h1, c_out, G, st1)
+        a1 = torch.empty((b, h, w, pad8(c_out)), dtype=torch.bfloat16, device=dev)
+        ops.groupnorm_apply(h1, c_out, st1, n1.weight, n1.bias, groups=G, act=L.ACT_SILU, out=a1, eps=n1.eps,
+                            post_add=cond[:, 0, 0, cond_off:cond_off + c_out] if has_t else None)
+        h2 = ops.conv_igemm(a1, m._w_conv(p2), kind=L.CONV_S1, kh=3, kw=3, cin=c_out, cout=c_out, bias=p2.bias)
+        st2 = torch.zeros((b, G, 2), dtype=torch.float64, device=dev)
+        ops.group_stats(h2, c_out, G, st2)
+        has_res = isinstance(blk.res_conv, nn.Conv2d)
+        if has_res:
+            res = ops.conv_igemm(x_b, m._w_conv(blk.res_conv), kind=L.CONV_S1, kh=1, kw=1, cin=c_in, cout=c_out,
+                                 bias=blk.res_conv.bias)
+        else:
+            res = xf
+        of = None
+        if want_f32 or want_stats:
+            of = out_f32 if out_f32 is not None else torch.empty((b, h, w, pad8(c_out)), dtype=torch.float32, device=dev)
+        ob = out_bf16 if out_bf16 is not None else torch.empty((b, h, w, pad8(c_out)), dtype=torch.bfloat16, device=dev)
+        ops.groupnorm_apply(h2, c_out, st2, n2.weight, n2.bias, groups=G, act=L.ACT_SILU, residual=res, out=ob,
+                            out_f32=of, eps=n2.eps)
+        st_out = None
+        if want_stats:   # statistics of the PreNorm GroupNorm(1, C) that follows (the ConvNeXt path gets them from the
+            st_out = m._stats(b, dev)   # last convolution's epilogue; here the block ends in a norm, not a GEMM)
+            ops.group_stats(of, c_out, 1, st_out)
+        out = _Node(c_out, f32=of, bf16=ob, stats=st_out)
+
+        def bwd():
+            g = out.g
+            dh2, dh2_b, dg2, db2 = ops.groupnorm_bwd(h2, g, c_out, st2, n2.weight, groups=G, want_f32=True,
+                                                     want_bf16=True, eps=n2.eps, beta=n2.bias, out_act=L.ACT_SILU)
+            self._grad(n2.weight, dg2)
+            self._grad(n2.bias, db2)
+            da1 = self._conv_s1_bwd(p2, a1, dh2_b, dh2, c_out, c_out, 3)
+            if has_t:
+                ops.colsum_per_sample(da1, c_out, dcond[:, 0, 0, cond_off:cond_off + c_out])
+            dh1, dh1_b, dg1, db1 = ops.groupnorm_bwd(h1, da1, c_out, st1, n1.weight, groups=G, want_f32=True,
+                                                     want_bf16=True, eps=n1.eps, beta=n1.bias, out_act=L.ACT_SILU)
+            self._grad(n1.weight, dg1)
+            self._grad(n1.bias, db1)
+            dx = self._conv_s1_bwd(p1, x_b, dh1_b, dh1, c_in, c_out, 3)
+            if has_res:
+                _, g_b = ops.add(g, None, c_out, want_bf16=True)
+                dres = self._conv_s1_bwd(blk.res_conv, x_b, g_b, g, c_in, c_out, 1)
+            else:
+                dres = g
+            ops.add(dx, dres, c_in, out=dx)
+            _acc(xin, dx)
+
+        self.tape.append(bwd)
+        return out
+
     # ------------------------------------------------------------------ Residual(PreNorm(LinearAttention))
     def linear_attention(self, mod, x: _Node, *, out_f32=None, out_bf16=None, want_bf16=True) -> _Node:
         m = self.m
@@ -246,6 +314,7 @@ class _Plan:
         b, mch, hh, ww = x.shape
         dev = x.device
         n_levels = len(m.downs)
+        block = self.convnext if m.use_convnext else self.resnet
         m._arena = torch.zeros((3 * len(m._time_blocks) + 2 * n_levels + 12, b, 2), dtype=torch.float64, device=dev)
         m._arena_next = 0
         # ---- time path
@@ -255,8 +324,9 @@ class _Plan:
         t1 = ops.conv_igemm(te, m._w_linear(lin1), kind=L.CONV_S1, kh=1, kw=1, cin=m.dim, cout=m.time_dim,
                             bias=lin1.bias, act=L.ACT_GELU, out_dtype=torch.bfloat16, out2=t1pre, out2_preact=True)
         t2pre = torch.empty((b, 1, 1, pad8(m.time_dim)), dtype=torch.bfloat16, device=dev)
+        cond_act = m._cond_act   # GELU (ConvNextBlock.mlp) / SiLU (ResnetBlock.mlp) in front of the time projections
         tg = ops.conv_igemm(t1, m._w_linear(lin3), kind=L.CONV_S1, kh=1, kw=1, cin=m.time_dim, cout=m.time_dim,
-                            bias=lin3.bias, act=L.ACT_GELU, out_dtype=torch.bfloat16, out2=t2pre, out2_preact=True)
+                            bias=lin3.bias, act=cond_act, out_dtype=torch.bfloat16, out2=t2pre, out2_preact=True)
         wc, bc, offs, total = m._w_cond()
         cond = ops.conv_igemm(tg, wc, kind=L.CONV_S1, kh=1, kw=1, cin=m.time_dim, cout=total, bias=bc)
         ldc = cond.stride(2)
@@ -270,8 +340,8 @@ class _Plan:
             for blk in m._time_blocks:
                 o = offs[id(blk)]
                 lin = blk.mlp[1]
-                self._grad(lin.weight, ops.unpack_linear_wgrad(dwc[:, o:o + blk.dim], lin.weight))
-                self._grad(lin.bias, dbc[o:o + blk.dim].clone())
+                self._grad(lin.weight, ops.unpack_linear_wgrad(dwc[:, o:o + blk.cond_channels], lin.weight))
+                self._grad(lin.bias, dbc[o:o + blk.cond_channels].clone())
 
             # pack W_cat^T once per parameter version: [1][td][sum(C)]
             params = tuple(blk.mlp[1].weight for blk in m._time_blocks)
@@ -282,7 +352,7 @@ class _Plan:
 
             wct = m._cached("cond_dg", params, build_t)
             dtg = ops.conv_igemm(dc_b, wct, kind=L.CONV_S1, kh=1, kw=1, cin=total, cout=td)
-            d2f, d2b = ops.act_bwd(dtg, t2pre, td, L.ACT_GELU, want_f32=True, want_bf16=True)
+            d2f, d2b = ops.act_bwd(dtg, t2pre, td, cond_act, want_f32=True, want_bf16=True)
             dw3 = ops.conv_wgrad(t1, d2b, kind=L.CONV_S1, kh=1, kw=1, cin=td, cout=td)
             self._grad(lin3.weight, ops.unpack_linear_wgrad(dw3, lin3.weight, self._slot(lin3.weight)))
             self._grad(lin3.bias, ops.colsum(d2f, td))
@@ -316,8 +386,8 @@ class _Plan:
 
         skips = []
         for lv, (block1, block2, attn, down) in enumerate(m.downs):
-            cur = self.convnext(block1, cur, cond, offs[id(block1)], ldc, dcond)
-            cur = self.convnext(block2, cur, cond, offs[id(block2)], ldc, dcond, want_stats=True)
+            cur = block(block1, cur, cond, offs[id(block1)], ldc, dcond)
+            cur = block(block2, cur, cond, offs[id(block2)], ldc, dcond, want_stats=True)
             c = cur.c
             h, w = cur.f32.shape[1:3]
             if lv >= 1:
@@ -346,10 +416,10 @@ class _Plan:
 
                 self.tape.append(bwd_down)
 
-        cur = self.convnext(m.mid_block1, cur, cond, offs[id(m.mid_block1)], ldc, dcond, want_stats=True)
+        cur = block(m.mid_block1, cur, cond, offs[id(m.mid_block1)], ldc, dcond, want_stats=True)
         cur = self.mid_attention(m.mid_attn, cur)
         cat_f, cat_b, c, skip_node = skips.pop()
-        cur = self.convnext(m.mid_block2, cur, cond, offs[id(m.mid_block2)], ldc, dcond, want_bf16=True,
+        cur = block(m.mid_block2, cur, cond, offs[id(m.mid_block2)], ldc, dcond, want_bf16=True,
                             out_f32=cat_f[..., :c], out_bf16=cat_b[..., :c])
         first_half = cur
         for u, (block1, block2, attn, up) in enumerate(m.ups):
@@ -361,8 +431,8 @@ class _Plan:
                 _acc(skip, g[..., c:])
 
             self.tape.append(bwd_cat)
-            cur = self.convnext(block1, cat_node, cond, offs[id(block1)], ldc, dcond)
-            cur = self.convnext(block2, cur, cond, offs[id(block2)], ldc, dcond, want_stats=True)
+            cur = block(block1, cat_node, cond, offs[id(block1)], ldc, dcond)
+            cur = block(block2, cur, cond, offs[id(block2)], ldc, dcond, want_stats=True)
             cur = self.linear_attention(attn, cur)
             cu = cur.c
             xin = cur
@@ -389,7 +459,7 @@ class _Plan:
             self.tape.append(bwd_up)
 
         fin = m.final_conv[0]
-        cur = self.convnext(fin, cur, None, 0, 0, None, want_f32=False)
+        cur = block(fin, cur, None, 0, 0, None, want_f32=False)
         last = m.final_conv[1]
         xf_node = cur
         out = ops.conv_igemm(cur.bf16, m._w_conv(last), kind=L.CONV_S1, kh=1, kw=1, cin=fin.dim_out, cout=m.out_dim,

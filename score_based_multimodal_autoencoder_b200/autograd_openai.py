@@ -83,9 +83,19 @@ class _OPlan(_Plan):
         gn1, conv1 = blk.in_layers[0], blk.in_layers[2]
         gn2, conv2 = blk.out_layers[0], blk.out_layers[3]
         a, st1 = self._gn32(x.f32, c_in, gn1, L.ACT_SILU)
-        h = ops.conv_igemm(a, m._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out, bias=conv1.bias,
-                           rowbias=cond[:, :, :, off:off + c_out])
-        a2, st2 = self._gn32(h, c_out, gn2, L.ACT_SILU)
+        ssn = blk.use_scale_shift_norm
+        if ssn:   # out_norm(h) * (1 + scale) + shift -> SiLU (unet_openai.py:296-300)
+            sc, sh = cond[:, 0, 0, off:off + c_out], cond[:, 0, 0, off + c_out:off + 2 * c_out]
+            h = ops.conv_igemm(a, m._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out, bias=conv1.bias)
+            st2 = torch.zeros((h.shape[0], gn2.num_groups, 2), dtype=torch.float64, device=h.device)
+            ops.group_stats(h, c_out, gn2.num_groups, st2)
+            a2 = torch.empty((*h.shape[:3], pad8(c_out)), dtype=torch.bfloat16, device=h.device)
+            ops.groupnorm_apply(h, c_out, st2, gn2.weight, gn2.bias, groups=gn2.num_groups, act=L.ACT_SILU, out=a2,
+                                eps=gn2.eps, mod_scale=sc, mod_shift=sh)
+        else:
+            h = ops.conv_igemm(a, m._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out, bias=conv1.bias,
+                               rowbias=cond[:, :, :, off:off + c_out])
+            a2, st2 = self._gn32(h, c_out, gn2, L.ACT_SILU)
         drop = self.drop
         p_drop = float(blk.dropout) if drop is not None else 0.0
         layer_id = m._res_index[id(blk)]
@@ -111,8 +121,18 @@ class _OPlan(_Plan):
             da2 = self._conv2d_bwd(conv2, a2, g_b, g, c_out, c_out, 3)
             if p_drop > 0:
                 ops.dropout_(da2, c_out, p_drop, drop[0], layer_id, drop[1])
-            dh, dh_b = self._gn32_bwd(gn2, h, da2, c_out, st2, L.ACT_SILU, want_bf16=True)
-            ops.colsum_per_sample(dh, c_out, dcond[:, 0, 0, off:off + c_out])   # d emb_out = sum over the pixels
+            if ssn:
+                # the normalised tensor n = out_norm(h) is recomputed (fp32), the modulation + SiLU back-propagate in
+                # one kernel (dn, per-sample dscale / dshift), then the plain GroupNorm32 backward
+                nrm = torch.empty((*h.shape[:3], pad8(c_out)), dtype=torch.float32, device=h.device)
+                ops.groupnorm_apply(h, c_out, st2, gn2.weight, gn2.bias, groups=gn2.num_groups, act=L.ACT_NONE,
+                                    out_f32=nrm, eps=gn2.eps)
+                dn = ops.scale_shift_bwd(nrm, da2, c_out, sc, sh, L.ACT_SILU, dcond[:, 0, 0, off:off + c_out],
+                                         dcond[:, 0, 0, off + c_out:off + 2 * c_out])
+                dh, dh_b = self._gn32_bwd(gn2, h, dn, c_out, st2, L.ACT_NONE, want_bf16=True)
+            else:
+                dh, dh_b = self._gn32_bwd(gn2, h, da2, c_out, st2, L.ACT_SILU, want_bf16=True)
+                ops.colsum_per_sample(dh, c_out, dcond[:, 0, 0, off:off + c_out])   # d emb_out = sum over the pixels
             da = self._conv2d_bwd(conv1, a, dh_b, dh, c_in, c_out, 3)
             dskip = self._conv2d_bwd(sk, x_b, g_b, g, c_in, c_out, ksk) if has_skip else g
             dx, _ = self._gn32_bwd(gn1, x_f, da, c_in, st1, L.ACT_SILU, addend=dskip)
@@ -149,13 +169,14 @@ class _OPlan(_Plan):
         return out
 
     # ------------------------------------------------------------------ whole network
-    def forward(self, x, timesteps, z):
+    def forward(self, x, timesteps, z, y=None):
         from .unet_openai import AttentionBlock, ResBlock
         m = self.m
         b, mch, hh, ww = x.shape
         dev = x.device
         ted, mc = m.time_embed_dim, m.model_channels
         with_z = z is not None
+        labels = y   # class labels (UNetModel(num_classes=K)); `y` is rebound to the network output further down
         self.drop = m._dropout_draw() if (m.training and m.dropout > 0) else None
 
         # ---- embedding path (pre-activations kept for the SiLU backward)
@@ -175,7 +196,8 @@ class _OPlan(_Plan):
         w2, b2 = m._w_emb2(with_z)
         epre = torch.empty((b, 1, 1, pad8(ted)), dtype=torch.bfloat16, device=dev)
         emb_act = ops.conv_igemm(hcat, w2, kind=L.CONV_S1, kh=1, kw=1, cin=width, cout=ted, bias=b2, act=L.ACT_SILU,
-                                 out_dtype=torch.bfloat16, out2=epre, out2_preact=True)
+                                 out_dtype=torch.bfloat16, out2=epre, out2_preact=True,
+                                 rowbias=m._label_rows(labels, b) if labels is not None else None)
         wc, bc, offs, total = m._w_cond()
         cond = ops.conv_igemm(emb_act, wc, kind=L.CONV_S1, kh=1, kw=1, cin=ted, cout=total, bias=bc)
         dcond = torch.zeros_like(cond)
@@ -186,8 +208,8 @@ class _OPlan(_Plan):
             dwc = ops.conv_wgrad(emb_act, dc_b, kind=L.CONV_S1, kh=1, kw=1, cin=ted, cout=total)
             for blk in m._res_blocks:
                 o, lin = offs[id(blk)], blk.emb_layers[1]
-                self._grad(lin.weight, ops.unpack_linear_wgrad(dwc[:, o:o + blk.out_channels], lin.weight))
-                self._grad(lin.bias, dbc[o:o + blk.out_channels].clone())
+                self._grad(lin.weight, ops.unpack_linear_wgrad(dwc[:, o:o + blk.cond_channels], lin.weight))
+                self._grad(lin.bias, dbc[o:o + blk.cond_channels].clone())
             params = tuple(blk.emb_layers[1].weight for blk in m._res_blocks)
 
             def build_t():  # W_cat^T: [1][ted][sum(C_out)]
@@ -199,6 +221,10 @@ class _OPlan(_Plan):
             de_f, de_b = ops.act_bwd(de_act, epre, ted, L.ACT_SILU, want_f32=True, want_bf16=True)
             lt2 = m.time_embed[2]
             db2 = ops.colsum(de_f, ted)
+            if labels is not None:   # d label_emb.weight[k] = sum of d emb over the samples labelled k (row scatter: torch)
+                dlab = torch.zeros_like(m.label_emb.weight, dtype=torch.float32)
+                dlab.index_add_(0, labels.long(), de_f.view(b, -1)[:, :ted])
+                self._grad(m.label_emb.weight, dlab)
             dwt = ops.conv_wgrad(hcat[..., :ted], de_b, kind=L.CONV_S1, kh=1, kw=1, cin=ted, cout=ted)
             self._grad(lt2.weight, ops.unpack_linear_wgrad(dwt, lt2.weight))
             self._grad(lt2.bias, db2)
@@ -253,10 +279,10 @@ class _OPlan(_Plan):
             h_, w_ = cur.bf16.shape[1:3]
             c = cur.c
             of, ob = dst(c, (b, h_ // 2, w_ // 2))
+            xin = cur
             ops.conv_igemm(cur.bf16, m._w_conv(layer.op), kind=L.CONV_S2, kh=3, kw=3, cin=c, cout=c, bias=layer.op.bias,
                            out=of, out2=ob)
             out = _Node(c, f32=of, bf16=ob)
-            xin = cur
 
             def bwd():
                 g = out.g
@@ -268,12 +294,12 @@ class _OPlan(_Plan):
 
         def upsample(layer, cur, dst):
             c = cur.c
+            xin = cur
             up = ops.upsample_nearest2x(cur.bf16, c)
             of, ob = dst(c, up.shape)
             ops.conv_igemm(up, m._w_conv(layer.conv), kind=L.CONV_S1, kh=3, kw=3, cin=c, cout=c, bias=layer.conv.bias,
                            out=of, out2=ob)
             out = _Node(c, f32=of, bf16=ob)
-            xin = cur
 
             def bwd():
                 g = out.g
@@ -360,14 +386,14 @@ class _OPlan(_Plan):
 
 class UNetModelFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, x, timesteps, z, *params):
+    def forward(ctx, model, x, timesteps, z, y, *params):
         if x.requires_grad or timesteps.requires_grad or (z is not None and z.requires_grad):
             raise L.SbmError("UNetModel: gradients w.r.t. the input latent / timesteps / conditioning code z are not "
                              "implemented on the B200 path (detach them, or differentiate the parameters only)")
         plan = _OPlan(model)
         with torch.no_grad():
             out = plan.forward(x.contiguous().float(), timesteps.contiguous().float(),
-                               None if z is None else z.contiguous().float())
+                               None if z is None else z.contiguous().float(), y)
         ctx.plan = plan
         ctx.params = params
         return out
@@ -382,9 +408,9 @@ class UNetModelFn(torch.autograd.Function):
             plan.backward(dout)
         grads = tuple(plan.pg.get(p) for p in ctx.params)
         ctx.plan = None
-        return (None, None, None, None) + grads
+        return (None, None, None, None, None) + grads
 
 
-def unet_openai_forward_train(model, x, timesteps, z=None):
+def unet_openai_forward_train(model, x, timesteps, z=None, y=None):
     params = tuple(p for p in model.parameters() if p.requires_grad)
-    return UNetModelFn.apply(model, x, timesteps, z, *params)
+    return UNetModelFn.apply(model, x, timesteps, z, y, *params)

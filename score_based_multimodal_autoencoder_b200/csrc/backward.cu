@@ -834,6 +834,34 @@ static int egrid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8));
 }
 
+// ------------------------------------------------------------------------------ scale-shift modulation, backward
+// y = act(u), u = n * (1 + scale[b][c]) + shift[b][c]  (ResBlock(use_scale_shift_norm=True), unet_openai.py:296-300; n
+// = GroupNorm32(h)).  Given dy:  du = dy * act'(u);  dn = du * (1 + scale);  dscale[b][c] += sum_pix du * n;
+// dshift[b][c] += sum_pix du.  Block = (pixel chunk, sample); thread = channel (consecutive threads -> consecutive
+// channels), sums over the chunk's pixels in registers, one global atomic pair per (thread, channel).
+__global__ void __launch_bounds__(256)
+scale_shift_bwd_kernel(const float* __restrict__ n, int64_t ldn, const float* __restrict__ dy, int64_t lddy,
+                       const float* __restrict__ scale, const float* __restrict__ shift, int64_t ld_mod, int act,
+                       float* __restrict__ dn, int64_t lddn, float* __restrict__ dscale, float* __restrict__ dshift,
+                       int64_t ld_dmod, int HW, int C, int ppb) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * ppb, p1 = min(p0 + ppb, HW);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s1 = 1.f + __ldg(scale + (int64_t)b * ld_mod + c), t = __ldg(shift + (int64_t)b * ld_mod + c);
+    float as = 0.f, at = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const int64_t pix = (int64_t)b * HW + p;
+      const float nv = n[pix * ldn + c];
+      const float du = dy[pix * lddy + c] * act_grad(fmaf(nv, s1, t), act);
+      dn[pix * lddn + c] = du * s1;
+      as = fmaf(du, nv, as);
+      at += du;
+    }
+    atomicAdd(dscale + (int64_t)b * ld_dmod + c, as);
+    atomicAdd(dshift + (int64_t)b * ld_dmod + c, at);
+  }
+}
+
 }  // namespace sbm
 
 using namespace sbm;
@@ -859,6 +887,22 @@ int sbm_colsum_per_sample(const void* x, int32_t dtype, int64_t ld, int32_t B, i
   else
     colsum_per_sample_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, HW, C,
                                                                                     out, ldo);
+  SBM_CUDA_OK(cudaGetLastError());
+  count_launch_b();
+  return 0;
+}
+
+int sbm_scale_shift_bwd(const float* n, int64_t ldn, const float* dy, int64_t lddy, const float* scale,
+                        const float* shift, int64_t ld_mod, int32_t act, float* dn, int64_t lddn, float* dscale,
+                        float* dshift, int64_t ld_dmod, int32_t B, int32_t HW, int32_t C, void* stream) {
+  SBM_CHECK_ARG(n && dy && scale && shift && dn && dscale && dshift && B > 0 && HW > 0 && C > 0,
+                "sbm_scale_shift_bwd: bad args");
+  // enough blocks for ~4 per SM, at least 8 pixels each
+  const int want = std::max(1, sm_count() * 4 / B);
+  const int ppb = std::max(8, (HW + want - 1) / want);
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  scale_shift_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, ldn, dy, lddy, scale, shift, ld_mod, act, dn, lddn,
+                                                                 dscale, dshift, ld_dmod, HW, C, ppb);
   SBM_CUDA_OK(cudaGetLastError());
   count_launch_b();
   return 0;

@@ -692,7 +692,8 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        const float* __restrict__ residual, int64_t ldr, TOut* __restrict__ out, int64_t ldo,
                        float* __restrict__ out_f32, int64_t ldo_f32, int HW, int C, int G, float eps, int act,
-                       int vec_ok) {
+                       int vec_ok, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
+                       int64_t ld_mod, const float* __restrict__ post_add, int64_t ld_post) {
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.y;
   const int cpg = C / G;
@@ -715,14 +716,21 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
   for (int q = threadIdx.x - pl * tq; q < co; q += tq) {
     const int c = q * 8;
     const bool full = vec_ok && (c + 8 <= C);
-    float sc[8], sh[8];  // y = x * sc + sh
+    float sc[8], sh[8], pa[8];  // y = act(x * sc + sh) + pa
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int ce = min(c + e, C - 1);
       const int g = (G == 1) ? 0 : ce / cpg;
-      const float a = s_rstd[g] * __ldg(gamma + ce);
+      float a = s_rstd[g] * __ldg(gamma + ce);
+      float o = __ldg(beta + ce) - s_mean[g] * a;
+      if (mod_scale != nullptr) {  // per-sample modulation of the normalised value: n * (1 + scale) + shift
+        const float m1 = 1.f + __ldg(mod_scale + (int64_t)b * ld_mod + ce);
+        a *= m1;
+        o = fmaf(o, m1, __ldg(mod_shift + (int64_t)b * ld_mod + ce));
+      }
       sc[e] = a;
-      sh[e] = __ldg(beta + ce) - s_mean[g] * a;
+      sh[e] = o;
+      pa[e] = (post_add != nullptr) ? __ldg(post_add + (int64_t)b * ld_post + ce) : 0.f;
     }
     auto one = [&](int pix_in_sample, const float* v_in) {
       const int64_t pix = (int64_t)b * HW + pix_in_sample;
@@ -732,7 +740,7 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
         float y = fmaf(v_in[e], sc[e], sh[e]);
         if (act == SBM_ACT_SILU) y = silu(y);
         else if (act == SBM_ACT_GELU) y = gelu_exact(y);
-        v[e] = y;
+        v[e] = y + pa[e];
       }
       if (residual != nullptr) {
         const float* rp = residual + pix * ldr + c;
@@ -1686,8 +1694,20 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
                         const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
                         int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
                         float eps, int32_t act, void* stream) {
+  return sbm_groupnorm_apply_mod(x, in_dtype, ldx, stats, gamma, beta, residual, ldr, out, out_dtype, ldo, out_f32,
+                                 ldo_f32, B, HW, C, G, eps, act, nullptr, nullptr, 0, nullptr, 0, stream);
+}
+
+int sbm_groupnorm_apply_mod(const void* x, int32_t in_dtype, int64_t ldx, const double* stats, const float* gamma,
+                            const float* beta, const float* residual, int64_t ldr, void* out, int32_t out_dtype,
+                            int64_t ldo, float* out_f32, int64_t ldo_f32, int32_t B, int32_t HW, int32_t C, int32_t G,
+                            float eps, int32_t act, const float* mod_scale, const float* mod_shift, int64_t ld_mod,
+                            const float* post_add, int64_t ld_post, void* stream) {
   SBM_CHECK_ARG(x && stats && gamma && beta && (out || out_f32) && B > 0 && G > 0 && C % G == 0,
                 "sbm_groupnorm_apply: bad args");
+  SBM_CHECK_ARG((mod_scale == nullptr) == (mod_shift == nullptr), "sbm_groupnorm_apply_mod: scale and shift come together");
+  SBM_CHECK_ARG((mod_scale == nullptr || ld_mod >= C) && (post_add == nullptr || ld_post >= C),
+                "sbm_groupnorm_apply_mod: per-sample row stride < C");
   SBM_CHECK_ARG(G <= 64, "sbm_groupnorm_apply: at most 64 groups");
   const int isz = in_dtype == SBM_F32 ? 4 : 2, osz = out_dtype == SBM_F32 ? 4 : 2;
   auto al16 = [](const void* p, int64_t ld, int esz) {
@@ -1703,7 +1723,8 @@ int sbm_groupnorm_apply(const void* x, int32_t in_dtype, int64_t ldx, const doub
   cudaStream_t s = (cudaStream_t)stream;
 #define SBM_GN_LAUNCH(TI, TO)                                                                                   \
   groupnorm_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x, ldx, stats, gamma, beta, residual, ldr,      \
-                                                      (TO*)out, ldo, out_f32, ldo_f32, HW, C, G, eps, act, vec_ok)
+                                                      (TO*)out, ldo, out_f32, ldo_f32, HW, C, G, eps, act, vec_ok,   \
+                                                      mod_scale, mod_shift, ld_mod, post_add, ld_post)
   if (in_dtype == SBM_F32 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(float, __nv_bfloat16);
   else if (in_dtype == SBM_F32 && out_dtype == SBM_F32) SBM_GN_LAUNCH(float, float);
   else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16);

@@ -266,16 +266,23 @@ def group_stats(x: torch.Tensor, c: int, groups: int, stats: torch.Tensor) -> No
 
 
 def groupnorm_apply(x: torch.Tensor, c: int, stats: torch.Tensor, gamma, beta, *, groups: int = 1, act: int = 0,
-                    residual=None, out=None, out_f32=None, eps: float = 1e-5) -> None:
+                    residual=None, out=None, out_f32=None, eps: float = 1e-5, mod_scale=None, mod_shift=None,
+                    post_add=None) -> None:
+    """y = act(GroupNorm(x) [* (1 + mod_scale[b]) + mod_shift[b]]) [+ post_add[b]] [+ residual]; the per-sample
+    operands are fp32 [B, >=c] views (row stride = stride(0))."""
     b, h, w, _ = x.shape
-    L.check(L.lib().sbm_groupnorm_apply(
+    if mod_scale is not None:
+        assert mod_shift is not None and mod_scale.stride(0) == mod_shift.stride(0)
+    L.check(L.lib().sbm_groupnorm_apply_mod(
         L.ptr(x), C.c_int32(_dt(x)), C.c_int64(x.stride(2)), L.ptr(stats), L.ptr(gamma), L.ptr(beta),
         L.ptr(residual), C.c_int64(residual.stride(2) if residual is not None else 0),
         L.ptr(out), C.c_int32(_dt(out) if out is not None else L.BF16),
         C.c_int64(out.stride(2) if out is not None else 4),
         L.ptr(out_f32), C.c_int64(out_f32.stride(2) if out_f32 is not None else 0),
         C.c_int32(b), C.c_int32(h * w), C.c_int32(c), C.c_int32(groups), C.c_float(eps), C.c_int32(act),
-        L.stream_ptr()), "sbm_groupnorm_apply")
+        L.ptr(mod_scale), L.ptr(mod_shift), C.c_int64(mod_scale.stride(0) if mod_scale is not None else 0),
+        L.ptr(post_add), C.c_int64(post_add.stride(0) if post_add is not None else 0),
+        L.stream_ptr()), "sbm_groupnorm_apply_mod")
 
 
 def dropout_(x: torch.Tensor, c: int, p: float, seed: int, draw: int, draw_dev=None) -> torch.Tensor:
@@ -569,3 +576,18 @@ def upsample_nearest2x_bwd(dy: torch.Tensor, c: int) -> torch.Tensor:
                                                None, C.c_int64(0), C.c_int32(b), C.c_int32(h2 // 2), C.c_int32(w2 // 2),
                                                C.c_int32(c), L.stream_ptr()), "sbm_upsample_nearest2x_bwd")
     return out
+
+
+def scale_shift_bwd(n: torch.Tensor, dy: torch.Tensor, c: int, scale: torch.Tensor, shift: torch.Tensor, act: int,
+                    dscale: torch.Tensor, dshift: torch.Tensor) -> torch.Tensor:
+    """Backward of act(n * (1 + scale[b]) + shift[b]): returns dn (fp32, shaped like n); accumulates the per-sample
+    dscale / dshift ([B, >=c] fp32 views sharing one row stride, zeroed by the caller)."""
+    b, h, w, _ = n.shape
+    assert scale.stride(0) == shift.stride(0) and dscale.stride(0) == dshift.stride(0)
+    dn = torch.empty((b, h, w, pad8(c)), dtype=torch.float32, device=n.device)
+    L.check(L.lib().sbm_scale_shift_bwd(L.ptr(n), C.c_int64(n.stride(2)), L.ptr(dy), C.c_int64(dy.stride(2)),
+                                        L.ptr(scale), L.ptr(shift), C.c_int64(scale.stride(0)), C.c_int32(act),
+                                        L.ptr(dn), C.c_int64(dn.stride(2)), L.ptr(dscale), L.ptr(dshift),
+                                        C.c_int64(dscale.stride(0)), C.c_int32(b), C.c_int32(h * w), C.c_int32(c),
+                                        L.stream_ptr()), "sbm_scale_shift_bwd")
+    return dn

@@ -66,6 +66,25 @@ class SinusoidalPositionEmbeddings(_Container):  # unet_model.py:35-47
         self.dim = dim
 
 
+class Block(_Container):  # unet_model.py:49-65
+    def __init__(self, dim, dim_out, groups=8):
+        super().__init__()
+        self.proj = nn.Conv2d(dim, dim_out, 3, padding=1)
+        self.norm = nn.GroupNorm(groups, dim_out)
+        self.act = nn.SiLU()
+
+
+class ResnetBlock(_Container):  # unet_model.py:67-90 (`Unet(use_convnext=False)`; no shipped command builds it)
+    def __init__(self, dim, dim_out, *, time_emb_dim=None, groups=8):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, dim_out)) if exists(time_emb_dim) else None
+        self.block1 = Block(dim, dim_out, groups=groups)
+        self.block2 = Block(dim_out, dim_out, groups=groups)
+        self.res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+        self.dim, self.dim_out, self.hidden, self.groups = dim, dim_out, dim_out, groups
+        self.cond_channels = dim_out   # the time projection is added to Block 1's OUTPUT (unet_model.py:84-87)
+
+
 class ConvNextBlock(_Container):  # unet_model.py:92-124
     def __init__(self, dim, dim_out, *, time_emb_dim=None, mult=2, norm=True):
         super().__init__()
@@ -80,6 +99,7 @@ class ConvNextBlock(_Container):  # unet_model.py:92-124
         )
         self.res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
         self.dim, self.dim_out, self.hidden = dim, dim_out, dim_out * mult
+        self.cond_channels = dim   # the time projection is added to the depthwise output (unet_model.py:118-121)
 
 
 class Attention(_Container):  # unet_model.py:126-149
@@ -113,13 +133,13 @@ class _Act:
 
 
 class Unet(nn.Module):
-    """unet_model.py:189-323 (ConvNeXt variant; `use_convnext=False` is not used by any shipped command)."""
+    """unet_model.py:189-323.  `use_convnext=True` (every shipped command) runs the tuned inference plan below;
+    `use_convnext=False` (ResnetBlock, unet_model.py:67-90) runs on the same kernels through the tape plan of
+    autograd.py (`_Plan.resnet`), for inference and training alike."""
 
     def __init__(self, dim, init_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=3, with_time_emb=True,
                  resnet_block_groups=8, use_convnext=True, convnext_mult=2):
         super().__init__()
-        if not use_convnext:
-            raise NotImplementedError("only the ConvNeXt score net (the reference's shipped configuration) is built")
         if not with_time_emb:
             raise NotImplementedError("the score net is always time-conditioned (forward(x, t))")
         self.channels = channels
@@ -130,7 +150,14 @@ class Unet(nn.Module):
         self.dim_mults = dim_mults
         dims = [init_dim, *map(lambda m: dim * m, dim_mults)]
         in_out = list(zip(dims[:-1], dims[1:]))
-        block_klass = partial(ConvNextBlock, mult=convnext_mult)
+        self.use_convnext = bool(use_convnext)
+        if use_convnext:
+            block_klass = partial(ConvNextBlock, mult=convnext_mult)
+        else:
+            block_klass = partial(ResnetBlock, groups=resnet_block_groups)
+        # activation in front of every block's time projection (unet_model.py:98 GELU / :73 SiLU): applied ONCE to the
+        # time-MLP output, all projections are one GEMM
+        self._cond_act = L.ACT_GELU if use_convnext else L.ACT_SILU
         time_dim = dim * 4
         self.time_dim = time_dim
         self.time_mlp = nn.Sequential(SinusoidalPositionEmbeddings(dim), nn.Linear(dim, time_dim), nn.GELU(),
@@ -162,7 +189,8 @@ class Unet(nn.Module):
         self.out_dim = out_dim
         self.final_conv = nn.Sequential(block_klass(dim, dim), nn.Conv2d(dim, out_dim, 1))
         self._packed: dict = {}
-        self._time_blocks = [m for m in self.modules() if isinstance(m, ConvNextBlock) and m.mlp is not None]
+        self._time_blocks = [m for m in self.modules() if isinstance(m, (ConvNextBlock, ResnetBlock))
+                             and m.mlp is not None]
         # bf16 storage for the GELU'd hidden activation between the two 3x3 convolutions of a block
         self.hidden_dtype = torch.bfloat16
         # inference: fold the block's first GroupNorm into its 3x3 convolution (depthwise output kept in bf16)
@@ -238,15 +266,15 @@ class Unet(nn.Module):
         params = tuple(b.mlp[1].weight for b in blocks) + tuple(b.mlp[1].bias for b in blocks)
 
         def build():
-            total = sum(b.dim for b in blocks)
+            total = sum(b.cond_channels for b in blocks)
             wpk = torch.empty((1, total, pad8(self.time_dim)), dtype=torch.bfloat16, device=params[0].device)
             off = 0
             offsets = {}
             subpacks = []
             for b in blocks:
-                subpacks.append(ops.pack_linear_weight(b.mlp[1].weight, out=wpk[:, off:off + b.dim]))
+                subpacks.append(ops.pack_linear_weight(b.mlp[1].weight, out=wpk[:, off:off + b.cond_channels]))
                 offsets[id(b)] = off
-                off += b.dim
+                off += b.cond_channels
             bias = torch.cat([b.mlp[1].bias.detach().float() for b in blocks]).contiguous()
             wpk._subpacks = subpacks                      # for the in-place multi-tensor refresh
             wpk._bias_sources = [b.mlp[1].bias for b in blocks]
@@ -392,7 +420,7 @@ class Unet(nn.Module):
         return max(1, self.max_chunk_elems // widest)
 
     def _convnext_blocks(self):
-        return [mod for mod in self.modules() if isinstance(mod, ConvNextBlock)]
+        return [mod for mod in self.modules() if isinstance(mod, (ConvNextBlock, ResnetBlock))]
 
     @torch.no_grad()
     def _forward_chunked(self, x, time):
@@ -421,6 +449,10 @@ class Unet(nn.Module):
         dev = x.device
         x = x.contiguous().float()
         time = time.contiguous().float()
+        if not self.use_convnext:
+            # ResnetBlock variant: the tape plan's forward (same kernels); the tape is dropped with the plan
+            from .autograd import _Plan
+            return _Plan(self).forward(x, time)
         n_levels = len(self.downs)
         self._arena = torch.zeros((3 * len(self._time_blocks) + 2 * n_levels + 12, b, 2), dtype=torch.float64,
                                   device=dev)

@@ -95,7 +95,11 @@ class Downsample(_Container):  # unet_openai.py:191-213
         super().__init__()
         self.channels, self.use_conv, self.dims = channels, use_conv, dims
         if not use_conv:
-            raise NotImplementedError("conv_resample=False (average-pool downsampling) is not used by the reference")
+            # unet_openai.py:209 calls `avg_pool_nd(stride)`: the stride lands in the `dims` parameter and
+            # nn.AvgPool2d() is built without a kernel size -- the reference raises this TypeError for every
+            # UNetModel(conv_resample=False) with more than one resolution level, so there is no behaviour to match
+            raise TypeError("AvgPool2d.__init__() missing 1 required positional argument: 'kernel_size' "
+                            "(conv_resample=False cannot be constructed in the reference either: unet_openai.py:209)")
         self.op = conv_nd(dims, channels, channels, 3, stride=2, padding=1)
 
 
@@ -103,14 +107,16 @@ class ResBlock(_Container):  # unet_openai.py:216-305
     def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
                  use_scale_shift_norm=False, dims=2, use_checkpoint=False):
         super().__init__()
-        if use_scale_shift_norm:
-            raise NotImplementedError("use_scale_shift_norm=True is not used by any reference configuration")
         self.channels, self.emb_channels, self.dropout = channels, emb_channels, dropout
         self.out_channels = out_channels or channels
         self.use_conv, self.use_checkpoint, self.use_scale_shift_norm = use_conv, use_checkpoint, use_scale_shift_norm
         self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
                                        conv_nd(dims, channels, self.out_channels, 3, padding=1))
-        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, self.out_channels))
+        # use_scale_shift_norm (unet_openai.py:257-260, 296-300; no shipped command sets it): the projection yields
+        # [scale | shift], applied to the second GroupNorm's output instead of being added to conv #1's output
+        self.emb_layers = nn.Sequential(nn.SiLU(), linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm
+                                                          else self.out_channels))
+        self.cond_channels = self.emb_layers[1].out_features
         self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
                                         zero_module(conv_nd(dims, self.out_channels, self.out_channels, 3, padding=1)))
         if self.out_channels == channels:
@@ -271,13 +277,13 @@ class UNetModel(nn.Module):
         params = tuple(b.emb_layers[1].weight for b in blocks) + tuple(b.emb_layers[1].bias for b in blocks)
 
         def build():
-            total = sum(b.out_channels for b in blocks)
+            total = sum(b.cond_channels for b in blocks)
             wpk = torch.empty((1, total, pad8(self.time_embed_dim)), dtype=torch.bfloat16, device=params[0].device)
             off, offsets = 0, {}
             for b in blocks:
-                ops.pack_linear_weight(b.emb_layers[1].weight, out=wpk[:, off:off + b.out_channels])
+                ops.pack_linear_weight(b.emb_layers[1].weight, out=wpk[:, off:off + b.cond_channels])
                 offsets[id(b)] = off
-                off += b.out_channels
+                off += b.cond_channels
             bias = torch.cat([b.emb_layers[1].bias.detach().float() for b in blocks]).contiguous()
             return wpk, bias, offsets, total
 
@@ -285,12 +291,13 @@ class UNetModel(nn.Module):
 
     # ------------------------------------------------------------------ building blocks
     @staticmethod
-    def _gn32_silu(x_f32, c, gn, act):
+    def _gn32_silu(x_f32, c, gn, act, mod_scale=None, mod_shift=None):
         b, h, w, _ = x_f32.shape
         st = torch.zeros((b, gn.num_groups, 2), dtype=torch.float64, device=x_f32.device)
         ops.group_stats(x_f32, c, gn.num_groups, st)
         a = torch.empty((b, h, w, pad8(c)), dtype=torch.bfloat16, device=x_f32.device)
-        ops.groupnorm_apply(x_f32, c, st, gn.weight, gn.bias, groups=gn.num_groups, act=act, out=a, eps=gn.eps)
+        ops.groupnorm_apply(x_f32, c, st, gn.weight, gn.bias, groups=gn.num_groups, act=act, out=a, eps=gn.eps,
+                            mod_scale=mod_scale, mod_shift=mod_shift)
         return a
 
     def _res_block(self, blk: ResBlock, x: _Act, cond, off, dst) -> _Act:
@@ -298,9 +305,15 @@ class UNetModel(nn.Module):
         c_in, c_out = blk.channels, blk.out_channels
         a = self._gn32_silu(x.f32, c_in, blk.in_layers[0], L.ACT_SILU)
         conv1 = blk.in_layers[2]
-        h = ops.conv_igemm(a, self._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out, bias=conv1.bias,
-                           rowbias=cond[:, :, :, off:off + c_out])
-        a2 = self._gn32_silu(h, c_out, blk.out_layers[0], L.ACT_SILU)
+        if blk.use_scale_shift_norm:   # out_norm(h) * (1 + scale) + shift, then SiLU (unet_openai.py:296-300)
+            h = ops.conv_igemm(a, self._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out,
+                               bias=conv1.bias)
+            a2 = self._gn32_silu(h, c_out, blk.out_layers[0], L.ACT_SILU, mod_scale=cond[:, 0, 0, off:off + c_out],
+                                 mod_shift=cond[:, 0, 0, off + c_out:off + 2 * c_out])
+        else:
+            h = ops.conv_igemm(a, self._w_conv(conv1), kind=L.CONV_S1, kh=3, kw=3, cin=c_in, cout=c_out,
+                               bias=conv1.bias, rowbias=cond[:, :, :, off:off + c_out])
+            a2 = self._gn32_silu(h, c_out, blk.out_layers[0], L.ACT_SILU)
         sk = blk.skip_connection
         if isinstance(sk, nn.Conv2d):
             k = sk.kernel_size[0]
@@ -331,26 +344,25 @@ class UNetModel(nn.Module):
     def forward(self, x, timesteps, z=None, y=None, **kwargs):
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
-        if self.num_classes is not None:
-            raise NotImplementedError("class-conditional embedding is not used by any reference score-net command")
         if not x.is_cuda:
             raise L.SbmError("UNetModel.forward needs CUDA tensors: the B200 path has no CPU fallback")
         # train() mode with dropout > 0 always takes the training plan (it owns the mask kernel), also under no_grad
         if (self.training and self.dropout > 0) or (torch.is_grad_enabled()
                                                     and any(p.requires_grad for p in self.parameters())):
             from .autograd_openai import unet_openai_forward_train
-            return unet_openai_forward_train(self, x, timesteps, z)
+            return unet_openai_forward_train(self, x, timesteps, z, y)
         with torch.no_grad():
             # large batches run in slices (exact: GroupNorm32 and the attention are per-sample)
             b = x.shape[0]
             widest = x.shape[-2] * x.shape[-1] * self.model_channels * max(self.channel_mult) * 2
             mb = max(1, self.max_chunk_elems // widest)
             if b <= mb:
-                return self._forward_infer(x, timesteps, z)
+                return self._forward_infer(x, timesteps, z, y)
             out = torch.empty((b, self.out_channels, x.shape[-2], x.shape[-1]), dtype=torch.float32, device=x.device)
             for lo in range(0, b, mb):
                 out[lo:lo + mb] = self._forward_infer(x[lo:lo + mb], timesteps[lo:lo + mb],
-                                                      None if z is None else z[lo:lo + mb])
+                                                      None if z is None else z[lo:lo + mb],
+                                                      None if y is None else y[lo:lo + mb])
             return out
 
     max_chunk_elems = 1 << 29
@@ -377,7 +389,14 @@ class UNetModel(nn.Module):
                 "sbm_train_tick")
         return self._dropout_seed, snap
 
-    def _forward_infer(self, x, timesteps, z):
+    def _label_rows(self, y, b):
+        """`emb + self.label_emb(y)` (unet_openai.py:561-564): the looked-up rows enter the second time-MLP GEMM as a
+        per-sample row bias (added before its SiLU).  The row gather itself is a torch index op."""
+        if y.shape != (b,):
+            raise ValueError(f"y must have shape ({b},), got {tuple(y.shape)}")
+        return self.label_emb.weight.detach().float()[y.long()].contiguous().view(b, 1, 1, self.time_embed_dim)
+
+    def _forward_infer(self, x, timesteps, z, y=None):
         b, m, hh, ww = x.shape
         if m != self.in_channels:
             raise ValueError(f"expected {self.in_channels} input channels, got {m}")
@@ -401,7 +420,8 @@ class UNetModel(nn.Module):
                            act=L.ACT_SILU, out=hcat[..., ted:])
         w2, b2 = self._w_emb2(with_z)
         emb_act = ops.conv_igemm(hcat, w2, kind=L.CONV_S1, kh=1, kw=1, cin=hcat.shape[-1], cout=ted, bias=b2,
-                                 act=L.ACT_SILU, out_dtype=torch.bfloat16)
+                                 act=L.ACT_SILU, out_dtype=torch.bfloat16,
+                                 rowbias=self._label_rows(y, b) if y is not None else None)
         wc, bc, offs, total = self._w_cond()
         cond = ops.conv_igemm(emb_act, wc, kind=L.CONV_S1, kh=1, kw=1, cin=ted, cout=total, bias=bc)
 
@@ -478,14 +498,12 @@ class UNetModel(nn.Module):
                     cur = self._res_block(layer, cur, cond, offs[id(layer)], dst)
                 elif isinstance(layer, AttentionBlock):
                     cur = self._attention(layer, cur, dst)
-                else:  # Upsample: nearest 2x + 3x3 conv (unet_openai.py:185-187)
+                else:  # Upsample: nearest 2x + 3x3 conv (unet_openai.py:185-187; a UNetModel with conv_resample=False
+                    # never gets here: its Downsample cannot be constructed, see above)
                     up = ops.upsample_nearest2x(cur.bf16, cur.c)
                     of, ob = dst(cur.c, up.shape)
-                    if layer.use_conv:
-                        ops.conv_igemm(up, self._w_conv(layer.conv), kind=L.CONV_S1, kh=3, kw=3, cin=cur.c, cout=cur.c,
-                                       bias=layer.conv.bias, out=of, out2=ob)
-                    else:
-                        raise NotImplementedError("conv_resample=False is not used by the reference")
+                    ops.conv_igemm(up, self._w_conv(layer.conv), kind=L.CONV_S1, kh=3, kw=3, cin=cur.c, cout=cur.c,
+                                   bias=layer.conv.bias, out=of, out2=ob)
                     cur = _Act(cur.c, f32=of, bf16=ob)
 
         # --- out: GroupNorm32 -> SiLU -> conv3x3 -> NCHW fp32 (unet_openai.py:525-529)

@@ -348,3 +348,42 @@ def test_checkpoint_container_round_trip_and_reference_compatibility(tmp_path):
         _, um, _ = import_reference()
         ref = um.Unet(dim=32, channels=3, dim_mults=(1, 2))
         ref.load_state_dict(ck["model_state_dict"], strict=True)
+
+
+def test_oracle_variants_match_reference_golden():
+    """Oracle restatements of the constructor paths no shipped command uses (ResnetBlock Unet, class-conditional and
+    scale-shift-norm UNetModel) against tests/golden/unet_variants.pt (the unmodified reference, run by
+    oracle/gen_golden_variants.py)."""
+    from oracle import unet_oracle as uo
+    from oracle.det_weights import fill_state_dict
+    fix = torch.load(os.path.join(ROOT, "tests", "golden", "unet_variants.pt"))
+    for name, c in fix.items():
+        kw, sd = c["kwargs"], fill_state_dict(c["shapes"])
+        with torch.no_grad():
+            if name == "unet_resnet_blocks":
+                y = uo.unet_forward(sd, c["x"], c["t"], dim=kw["dim"], dim_mults=kw["dim_mults"], use_convnext=False,
+                                    groups=kw["resnet_block_groups"])
+            else:
+                y = uo.unet_openai_forward(sd, c["x"], c["t"], model_channels=kw["model_channels"],
+                                           num_res_blocks=kw["num_res_blocks"],
+                                           attention_resolutions=kw["attention_resolutions"],
+                                           channel_mult=kw["channel_mult"], num_heads=kw["num_heads"],
+                                           z=c["zc"] if kw.get("use_z") else None,
+                                           y=c["y"] if kw.get("num_classes") is not None else None)
+        assert ((y - c["out"]).norm() / c["out"].norm()).item() < 1e-5, name
+
+
+def test_variant_modules_mirror_the_reference_state_dict_and_errors():
+    """Parameter names / shapes of the variant nets equal the reference's (fixture `shapes`), and
+    UNetModel(conv_resample=False) raises the reference's own TypeError (unet_openai.py:209 builds nn.AvgPool2d()
+    without a kernel size: the reference cannot construct that net either)."""
+    import pytest
+    from score_based_multimodal_autoencoder_b200.unet_model import Unet
+    from score_based_multimodal_autoencoder_b200.unet_openai import UNetModel
+    fix = torch.load(os.path.join(ROOT, "tests", "golden", "unet_variants.pt"))
+    for name, c in fix.items():
+        m = (Unet if name == "unet_resnet_blocks" else UNetModel)(**c["kwargs"])
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == c["shapes"], name
+    with pytest.raises(TypeError, match="kernel_size"):
+        UNetModel(in_channels=3, model_channels=32, out_channels=3, num_res_blocks=1, attention_resolutions=(),
+                  channel_mult=(1, 2), conv_resample=False)
