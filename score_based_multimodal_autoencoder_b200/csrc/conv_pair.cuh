@@ -1056,6 +1056,7 @@ int launch_pair_static(int mode_idx, int bn, const CUtensorMap& tmA, const CUten
   case idx:                                                                                                             \
     if (bn == 256) return launch_conv_pair<256, 5, true, (uint32_t)(mode)>(tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream); \
     if (bn == 128) return launch_conv_pair<128, 6, true, (uint32_t)(mode)>(tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream); \
+    if (bn == 64) return launch_conv_pair<64, 8, true, (uint32_t)(mode)>(tmA, tmB, em, p, m_tiles, n_tiles, nphase, stream); \
     return -1;
 
 }  // namespace sbm

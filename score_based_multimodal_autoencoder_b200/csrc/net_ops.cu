@@ -686,6 +686,9 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
 
 // A thread owns ONE channel octet (its gamma/beta/mean/rstd live in registers) and walks the pixels of the block's
 // pixel range with 4 independent 16-byte loads in flight; consecutive threads = consecutive octets of one pixel.
+// A block serves SB consecutive samples (SB > 1 when a sample is only a few hundred octets -- the 8x8 / 4x4 maps of the
+// PolyMNIST net at 32k latents ran one block per sample for two pixels per thread: the fp64 mean / rstd prologue and
+// the block turnover, not HBM, set the pace (1.4 TB/s, ncu); the statistics of all SB samples are reduced up front.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __restrict__ stats,
@@ -693,13 +696,15 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
                        const float* __restrict__ residual, int64_t ldr, TOut* __restrict__ out, int64_t ldo,
                        float* __restrict__ out_f32, int64_t ldo_f32, int HW, int C, int G, float eps, int act,
                        int vec_ok, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
-                       int64_t ld_mod, const float* __restrict__ post_add, int64_t ld_post) {
-  __shared__ float s_mean[64], s_rstd[64];
-  const int b = blockIdx.y;
+                       int64_t ld_mod, const float* __restrict__ post_add, int64_t ld_post, int B, int SB) {
+  __shared__ float s_mean[256], s_rstd[256];   // [SB][G], SB * G <= 256
+  const int b_first = blockIdx.y * SB;
+  const int nb = min(SB, B - b_first);
   const int cpg = C / G;
-  if (threadIdx.x < G) {
+  if ((int)threadIdx.x < nb * G) {
     const double inv_n = 1.0 / ((double)HW * cpg);
-    const double s1 = stats[2 * ((int64_t)b * G + threadIdx.x)], s2 = stats[2 * ((int64_t)b * G + threadIdx.x) + 1];
+    const int64_t slot = (int64_t)b_first * G + threadIdx.x;   // stats is [B][G][2]: the block's slots are contiguous
+    const double s1 = stats[2 * slot], s2 = stats[2 * slot + 1];
     const double mean = s1 * inv_n;
     const double var = fmax(s2 * inv_n - mean * mean, 0.0);
     s_mean[threadIdx.x] = (float)mean;
@@ -716,86 +721,96 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
   for (int q = threadIdx.x - pl * tq; q < co; q += tq) {
     const int c = q * 8;
     const bool full = vec_ok && (c + 8 <= C);
-    float sc[8], sh[8], pa[8];  // y = act(x * sc + sh) + pa
+    float gm[8], bt[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int ce = min(c + e, C - 1);
-      const int g = (G == 1) ? 0 : ce / cpg;
-      float a = s_rstd[g] * __ldg(gamma + ce);
-      float o = __ldg(beta + ce) - s_mean[g] * a;
-      if (mod_scale != nullptr) {  // per-sample modulation of the normalised value: n * (1 + scale) + shift
-        const float m1 = 1.f + __ldg(mod_scale + (int64_t)b * ld_mod + ce);
-        a *= m1;
-        o = fmaf(o, m1, __ldg(mod_shift + (int64_t)b * ld_mod + ce));
-      }
-      sc[e] = a;
-      sh[e] = o;
-      pa[e] = (post_add != nullptr) ? __ldg(post_add + (int64_t)b * ld_post + ce) : 0.f;
+      gm[e] = __ldg(gamma + ce);
+      bt[e] = __ldg(beta + ce);
     }
-    auto one = [&](int pix_in_sample, const float* v_in) {
-      const int64_t pix = (int64_t)b * HW + pix_in_sample;
-      float v[8];
+    for (int sb = 0; sb < nb; ++sb) {
+      const int b = b_first + sb;
+      float sc[8], sh[8], pa[8];  // y = act(x * sc + sh) + pa
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float y = fmaf(v_in[e], sc[e], sh[e]);
-        if (act == SBM_ACT_SILU) y = silu(y);
-        else if (act == SBM_ACT_GELU) y = gelu_exact(y);
-        v[e] = y + pa[e];
-      }
-      if (residual != nullptr) {
-        const float* rp = residual + pix * ldr + c;
-        if (full) {
-          float r[8];
-          load8<float>(rp, r);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] += r[e];
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (c + e < C) v[e] += rp[e];
+        const int ce = min(c + e, C - 1);
+        const int g = sb * G + ((G == 1) ? 0 : ce / cpg);
+        float a = s_rstd[g] * gm[e];
+        float o = bt[e] - s_mean[g] * a;
+        if (mod_scale != nullptr) {  // per-sample modulation of the normalised value: n * (1 + scale) + shift
+          const float m1 = 1.f + __ldg(mod_scale + (int64_t)b * ld_mod + ce);
+          a *= m1;
+          o = fmaf(o, m1, __ldg(mod_shift + (int64_t)b * ld_mod + ce));
         }
+        sc[e] = a;
+        sh[e] = o;
+        pa[e] = (post_add != nullptr) ? __ldg(post_add + (int64_t)b * ld_post + ce) : 0.f;
       }
-      if (out != nullptr) {
-        TOut* op = out + pix * ldo + c;
-        if (full) {
-          store8<TOut>(op, v);
-        } else {
+      auto one = [&](int pix_in_sample, const float* v_in) {
+        const int64_t pix = (int64_t)b * HW + pix_in_sample;
+        float v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (c + e < C) op[e] = (TOut)v[e];
+        for (int e = 0; e < 8; ++e) {
+          float y = fmaf(v_in[e], sc[e], sh[e]);
+          if (act == SBM_ACT_SILU) y = silu(y);
+          else if (act == SBM_ACT_GELU) y = gelu_exact(y);
+          v[e] = y + pa[e];
         }
-      }
-      if (out_f32 != nullptr) {
-        float* op = out_f32 + pix * ldo_f32 + c;
-        if (full) {
-          store8<float>(op, v);
-        } else {
+        if (residual != nullptr) {
+          const float* rp = residual + pix * ldr + c;
+          if (full) {
+            float r[8];
+            load8<float>(rp, r);
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            if (c + e < C) op[e] = v[e];
+            for (int e = 0; e < 8; ++e) v[e] += r[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (c + e < C) v[e] += rp[e];
+          }
         }
-      }
-    };
-    int p = p0;
-    if (full) {
-      for (; p + 3 * pstride < HW; p += 4 * pstride) {
-        float v[4][8];
+        if (out != nullptr) {
+          TOut* op = out + pix * ldo + c;
+          if (full) {
+            store8<TOut>(op, v);
+          } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) load8<TIn>(x + ((int64_t)b * HW + p + u * pstride) * ldx + c, v[u]);
+            for (int e = 0; e < 8; ++e)
+              if (c + e < C) op[e] = (TOut)v[e];
+          }
+        }
+        if (out_f32 != nullptr) {
+          float* op = out_f32 + pix * ldo_f32 + c;
+          if (full) {
+            store8<float>(op, v);
+          } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) one(p + u * pstride, v[u]);
-      }
-    }
-    for (; p < HW; p += pstride) {
-      float v[8];
-      const TIn* xp = x + ((int64_t)b * HW + p) * ldx + c;
+            for (int e = 0; e < 8; ++e)
+              if (c + e < C) op[e] = v[e];
+          }
+        }
+      };
+      int p = p0;
       if (full) {
-        load8<TIn>(xp, v);
-      } else {
+        for (; p + 3 * pstride < HW; p += 4 * pstride) {
+          float v[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
+          for (int u = 0; u < 4; ++u) load8<TIn>(x + ((int64_t)b * HW + p + u * pstride) * ldx + c, v[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) one(p + u * pstride, v[u]);
+        }
       }
-      one(p, v);
+      for (; p < HW; p += pstride) {
+        float v[8];
+        const TIn* xp = x + ((int64_t)b * HW + p) * ldx + c;
+        if (full) {
+          load8<TIn>(xp, v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (c + e < C) ? (float)xp[e] : 0.f;
+        }
+        one(p, v);
+      }
     }
   }
 }
@@ -1719,12 +1734,21 @@ int sbm_groupnorm_apply_mod(const void* x, int32_t in_dtype, int64_t ldx, const 
   const int lanes = std::max(1, 256 / std::min(co, 256));
   int chunks = (int)std::min<int64_t>((HW + lanes - 1) / lanes, std::max<int64_t>(1, (int64_t)sm_count() * 8 / B));
   if (chunks < 1) chunks = 1;
-  dim3 grid(chunks, B);
+  // samples per block: small maps at large batch (one chunk per sample, only a few pixels per thread) are walked SB
+  // samples at a time -- at least ~8 pixels per thread, the machine still covered 4 x, SB * G statistics slots <= 256
+  int SB = 1;
+  if (chunks == 1) {
+    const int64_t per_sample = (int64_t)HW * std::min(co, 256);
+    SB = (int)std::min<int64_t>((8 * 256 + per_sample - 1) / per_sample, 16);
+    SB = std::min(SB, std::max(1, B / (sm_count() * 4)));
+    SB = std::max(1, std::min(SB, 256 / G));
+  }
+  dim3 grid(chunks, (B + SB - 1) / SB);
   cudaStream_t s = (cudaStream_t)stream;
 #define SBM_GN_LAUNCH(TI, TO)                                                                                   \
   groupnorm_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x, ldx, stats, gamma, beta, residual, ldr,      \
                                                       (TO*)out, ldo, out_f32, ldo_f32, HW, C, G, eps, act, vec_ok,   \
-                                                      mod_scale, mod_shift, ld_mod, post_add, ld_post)
+                                                      mod_scale, mod_shift, ld_mod, post_add, ld_post, B, SB)
   if (in_dtype == SBM_F32 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(float, __nv_bfloat16);
   else if (in_dtype == SBM_F32 && out_dtype == SBM_F32) SBM_GN_LAUNCH(float, float);
   else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
