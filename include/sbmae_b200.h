@@ -79,18 +79,22 @@ typedef struct sbm_conv_args {
   const float* gn_tab;      /* [2][16][cout] */
   float gn_count;
   float gn_eps;
-  /* optional split-K workspace: fp32 [batch*oh*ow][ld_ws] (ld_ws >= cout, multiple of 4), ZEROED by the caller.  When
-   * given and sbm_conv_splitk_plan(a) > 1 (a stride-1 layer of a few 256 x 256 output tiles with a long K loop: the
-   * low-resolution levels at small batch), the K loop is cut across the SM pairs: partial accumulators are added into
-   * the workspace by TMA reduce-add, a second kernel applies the epilogue and hands the workspace back zeroed (so one
-   * buffer, zeroed once, serves every call on a stream).  NULL: never split. */
+  /* optional split-K workspace: ws_elems floats (16-byte aligned), rows of ld_ws >= cout floats (multiple of 4), need
+   * not be initialised.  When given and sbm_conv_splitk_plan(a) > 1 (a stride-1 or stride-2 layer of a few 256 x 256
+   * output tiles with a long K loop: the low-resolution levels at small batch), the K loop is cut across the SM pairs:
+   * slice s stores its partial accumulators into slab s of the workspace, a second kernel sums the slabs in slice order
+   * (deterministic) and applies the epilogue.  Size: sbm_conv_splitk_ws_elems(a).  NULL: never split.  One buffer can
+   * serve every call issued in stream order. */
   float* splitk_ws;
   int64_t ld_ws;
+  int64_t ws_elems;
 } sbm_conv_args;
 
 int sbm_conv_igemm(const sbm_conv_args* a, void* stream);
 /* number of K slices sbm_conv_igemm would use for this call when given a workspace (1 = it would not split) */
 int sbm_conv_splitk_plan(const sbm_conv_args* a);
+/* floats the split-K workspace of this call needs with rows of a->ld_ws floats (0 = the call would not split) */
+int64_t sbm_conv_splitk_ws_elems(const sbm_conv_args* a);
 /* A/B switch: 0 = never split along K (sbm_conv_splitk_plan then returns 1); default 1, also SBM_SPLITK */
 int sbm_conv_splitk(int32_t on);
 /* A/B switch for measurements: 1 = always use the single-CTA kernel instead of the CTA-pair (cta_group::2) one */

@@ -31,6 +31,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.sbm_last_error.restype = C.c_char_p
         _lib.sbm_launch_count.restype = C.c_ulonglong
+        _lib.sbm_conv_splitk_ws_elems.restype = C.c_int64
     return _lib
 
 
@@ -77,7 +78,7 @@ class ConvArgs(C.Structure):
         ("out2", C.c_void_p), ("ldo2", C.c_int64),
         ("rowbias", C.c_void_p), ("ld_rowbias", C.c_int64),
         ("gn_stats", C.c_void_p), ("gn_tab", C.c_void_p), ("gn_count", C.c_float), ("gn_eps", C.c_float),
-        ("splitk_ws", C.c_void_p), ("ld_ws", C.c_int64),
+        ("splitk_ws", C.c_void_p), ("ld_ws", C.c_int64), ("ws_elems", C.c_int64),
     ]
 
 SDE_VP, SDE_SUBVP, SDE_VE = 0, 1, 2

@@ -131,21 +131,40 @@ static bool encode_rowbox_map(PFN_cuTensorMapEncodeTiled_v12000 encode, CUtensor
 // At 128 latents per GPU (the 8-GPU shard of the headline config) the 4x4 / 2x2 levels are GEMMs of 512..2048 rows with
 // K = 4608..9216: a handful of 256 x 256 tiles.  Narrow N tiles spread them over the SMs but re-read the activation
 // rows once per N tile and move 2.5 x the bytes per FLOP; an SM ingests ~40-50 B/clk, so those launches ran at 20 % of
-// the tensor pipe (pipeline trace, profiles/r2b_pair_pipeline_trace_small_batch.log).  With a caller-provided, zeroed
-// fp32 workspace the layer keeps 256-wide tiles and is cut along K instead: every (tile, K slice) work item ADDS its raw
-// accumulators into the workspace (TMA reduce-add boxes), then conv_splitk_epilogue_kernel applies the epilogue.
+// the tensor pipe (pipeline trace, profiles/r2b_pair_pipeline_trace_small_batch.log).  With a caller-provided fp32
+// workspace the layer keeps 256-wide tiles and is cut along K instead: every (tile, K slice) work item stores its raw
+// accumulators into slab `slice` of the workspace (TMA box stores), then conv_splitk_epilogue_kernel sums the slabs in
+// slice order and applies the epilogue.  Deterministic (no atomics: a first version met in ONE zeroed slab through TMA
+// reduce-adds, whose order made graph replays differ from the eager run in the last fp32 bits), no zeroing needed.
 static bool g_splitk = [] { const char* e = getenv("SBM_SPLITK"); return e ? atoi(e) != 0 : true; }();
 
 // number of K slices sbm_conv_igemm would use for this call if it is given a workspace (1 = no split)
 static int splitk_plan(const sbm_conv_args* a) {
-  if (!g_splitk || g_force_single || a->kind != SBM_CONV_S1 || a->out_nchw || a->cout <= 128) return 1;
+  if (!g_splitk || g_force_single || (a->kind != SBM_CONV_S1 && a->kind != SBM_CONV_S2) || a->out_nchw || a->cout <= 128)
+    return 1;
   const int ph = a->kh / 2, pw = a->kw / 2;
   int ntaps = 0;
-  for (int kh = 0; kh < a->kh; ++kh)
-    for (int kw = 0; kw < a->kw; ++kw)
-      if (abs(kh - ph) < a->h && abs(kw - pw) < a->w) ++ntaps;
+  int64_t M;
+  if (a->kind == SBM_CONV_S1) {
+    for (int kh = 0; kh < a->kh; ++kh)
+      for (int kw = 0; kw < a->kw; ++kw)
+        if (abs(kh - ph) < a->h && abs(kw - pw) < a->w) ++ntaps;
+    M = (int64_t)a->batch * a->h * a->w;
+  } else {
+    // stride-2 down-sampling convolution (4x4 / 3x3, padding 1): same tap rule as the table in conv_igemm_impl.  16 taps
+    // of up to 512 channels on a quarter of the pixels: at 128 latents the 8x8 -> 4x4 and 4x4 -> 2x2 layers were one
+    // 128-deep K loop on 32 (or 128 narrow) CTAs, 49 us each
+    const int oh = a->h / 2, ow = a->w / 2;
+    for (int kh = 0; kh < a->kh; ++kh)
+      for (int kw = 0; kw < a->kw; ++kw) {
+        const int rh = kh - 1, rw = kw - 1;
+        const int dh = (rh < 0) ? -1 : rh / 2, dw = (rw < 0) ? -1 : rw / 2;
+        if ((abs(dh) >= oh && dh != 0) || (abs(dw) >= ow && dw != 0)) continue;
+        ++ntaps;
+      }
+    M = (int64_t)a->batch * oh * ow;
+  }
   const int num_kb = ntaps * ((a->cin + kBK - 1) / kBK);
-  const int64_t M = (int64_t)a->batch * a->h * a->w;
   if (M < 128 || num_kb < 32) return 1;
   const int64_t tiles = ((M + 255) / 256) * ((a->cout + 255) / 256);
   const int npairs = sm_count() / 2;
@@ -163,17 +182,21 @@ static int splitk_plan(const sbm_conv_args* a) {
           valid += (i + kh - ph >= 0 && i + kh - ph < a->h && j + kw - pw >= 0 && j + kw - pw < a->w) ? 1 : 0;
   const double work_pm = (double)((a->batch + 255) / 256) * 256 * valid;
   const double work_std = (double)((M + kBM - 1) / kBM) * kBM * ntaps;
-  if (g_pixel_major != 0 && a->h * a->w <= 256 && work_pm < 0.97 * work_std && splits * work_pm < 1.25 * work_std)
+  if (a->kind == SBM_CONV_S1 && g_pixel_major != 0 && a->h * a->w <= 256 && work_pm < 0.97 * work_std &&
+      splits * work_pm < 1.25 * work_std)
     return 1;
   return splits;
 }
 
+// samples per workspace slab: the rows of whole 256-row tile pairs (a tail tile stores its padding rows inside its own slab)
+static int64_t splitk_slab_samples(int64_t M, int64_t ohw) { return ((M + 255) / 256 * 256 + ohw - 1) / ohw; }
+
 // epilogue of a split-K convolution: thread = (output row, 16-column chunk), chunk index fastest, so a warp reads and
-// writes contiguous pieces of one row (or of a few consecutive rows when the row has fewer than 32 chunks).  The
-// workspace is handed back ZEROED (every thread clears what it has read): the caller's buffer is ready for the next call.
+// writes contiguous pieces of one row (or of a few consecutive rows when the row has fewer than 32 chunks).  The K
+// slices are summed in slice order: the result does not depend on which SM pair finished first.
 __global__ void __launch_bounds__(256)
-conv_splitk_epilogue_kernel(const __grid_constant__ ConvKernelParams p, float* __restrict__ ws, int64_t ldw,
-                            int chunks, int64_t rows) {
+conv_splitk_epilogue_kernel(const __grid_constant__ ConvKernelParams p, const float* __restrict__ ws, int64_t ldw,
+                            int chunks, int64_t rows, int splits, int64_t slab) {
   const int lane = threadIdx.x & 31;
   const int64_t idx = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;
   const int64_t r = idx / chunks;
@@ -185,20 +208,23 @@ conv_splitk_epilogue_kernel(const __grid_constant__ ConvKernelParams p, float* _
   const int rem = (int)(rr & ((1 << log_ohw) - 1));
   const int oh = rem >> p.log_ow, j = rem & ((1 << p.log_ow) - 1);
   const int n = chunk * 16;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  if (row_ok) {
+    const float* src = ws + rr * ldw + n;
+    for (int s = 0; s < splits; ++s, src += slab) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (n + 4 * k + 4 <= ldw) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(src) + k);
+          acc[4 * k] += t.x; acc[4 * k + 1] += t.y; acc[4 * k + 2] += t.z; acc[4 * k + 3] += t.w;
+        }
+    }
+  }
   uint32_t v[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = 0u;
-  if (row_ok) {
-    float* src = ws + rr * ldw + n;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (n + 4 * k + 4 <= ldw) {
-        const float4 t = *(reinterpret_cast<const float4*>(src) + k);
-        *(reinterpret_cast<float4*>(src) + k) = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[4 * k] = __float_as_uint(t.x); v[4 * k + 1] = __float_as_uint(t.y);
-        v[4 * k + 2] = __float_as_uint(t.z); v[4 * k + 3] = __float_as_uint(t.w);
-      }
-  }
+  for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(acc[e]);
   const int64_t o_base = (int64_t)b * p.o_sb + (int64_t)oh * p.o_sh + (int64_t)j * p.o_sw;
   const int64_t r_base = (int64_t)b * p.r_sb + (int64_t)oh * p.r_sh + (int64_t)j * p.r_sw;
   const int64_t o2_base = (int64_t)b * p.o2_sb + (int64_t)oh * p.o2_sh + (int64_t)j * p.o2_sw;
@@ -445,7 +471,11 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
   // split-K (see splitk_plan): standard tiling, 256-wide tiles, raw accumulators into the caller's zeroed workspace
   const int splits = (a->splitk_ws != nullptr && a->ld_ws >= a->cout && a->ld_ws % 4 == 0 &&
                       (reinterpret_cast<uintptr_t>(a->splitk_ws) & 15) == 0 && M >= 128) ? splitk_plan(a) : 1;
+  const int64_t slab_samples = splitk_slab_samples(M, (int64_t)1 << log_ohw);
   if (splits > 1) {
+    SBM_CHECK_ARG(a->ws_elems >= (int64_t)splits * slab_samples * ((int64_t)1 << log_ohw) * a->ld_ws,
+                  "sbm_conv_igemm: split-K workspace of %lld floats is too small (sbm_conv_splitk_ws_elems)",
+                  (long long)a->ws_elems);
     pm = false;
     m_tiles = (int)((M + kBM - 1) / kBM);
     BN = 256;
@@ -480,8 +510,9 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
 
   if (splits > 1) {
     EpiMaps em;
-    SBM_CHECK_ARG(encode_rowbox_map(encode, &em.out, a->splitk_ws, SBM_F32, a->ld_ws, a->cout, ow, oh, a->batch, 1, log_ow,
-                                    log_th, false),
+    // workspace = [splits][slab_samples][oh][ow][ld_ws]: one tensor map, slice s stores at sample coordinate b + s * slab
+    SBM_CHECK_ARG(encode_rowbox_map(encode, &em.out, a->splitk_ws, SBM_F32, a->ld_ws, a->cout, ow, oh,
+                                    (int)(splits * slab_samples), 1, log_ow, log_th, false),
                   "sbm_conv_igemm: split-K workspace tensor map encode failed");
     em.res = em.out;
     em.out2 = em.out;
@@ -491,11 +522,13 @@ static int conv_igemm_impl(const sbm_conv_args* a, cudaStream_t stream) {
     q.bias_vec = 0; q.rowbias_vec = 0;
     q.taps[0].out_q = 0;
     g_last_variant = BN | (1 << 16) | (1 << 17) | (1 << 20) | (splits << 24);
-    const int rc = launch_conv_pair<256, 5, true, EM_SPLITK>(tmA, tmB, em, q, m_tiles, n_tiles_pair, nphase, stream, splits);
+    const int rc = launch_conv_pair<256, 5, true, EM_SPLITK>(tmA, tmB, em, q, m_tiles, n_tiles_pair, nphase, stream, splits,
+                                                             (int)slab_samples);
     if (rc != 0) return rc;
     const int chunks = (a->cout + 15) / 16;
     const int64_t items = M * chunks;
-    conv_splitk_epilogue_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(p, a->splitk_ws, a->ld_ws, chunks, M);
+    conv_splitk_epilogue_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(
+        p, a->splitk_ws, a->ld_ws, chunks, M, splits, slab_samples * ((int64_t)1 << log_ohw) * a->ld_ws);
     SBM_CUDA_OK(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -811,6 +844,13 @@ int sbm_conv_epilogue_static(int32_t on) {
 }
 
 int sbm_conv_splitk_plan(const sbm_conv_args* a) { return a ? sbm::splitk_plan(a) : 1; }
+int64_t sbm_conv_splitk_ws_elems(const sbm_conv_args* a) {
+  if (a == nullptr) return 0;
+  const int splits = sbm::splitk_plan(a);
+  if (splits <= 1) return 0;
+  const int64_t ohw = (a->kind == SBM_CONV_S2) ? (int64_t)(a->h / 2) * (a->w / 2) : (int64_t)a->h * a->w;
+  return (int64_t)splits * sbm::splitk_slab_samples((int64_t)a->batch * ohw, ohw) * ohw * a->ld_ws;
+}
 int sbm_conv_splitk(int32_t on) {
   sbm::g_splitk = on != 0;
   return 0;

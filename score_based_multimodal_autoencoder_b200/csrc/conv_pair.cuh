@@ -272,8 +272,9 @@ __device__ __forceinline__ void stg_store_bf16_row(uint32_t buf, int r, const fl
 enum : uint32_t {
   EM_GN = 1u, EM_BIAS = 2u, EM_ROWB = 4u, EM_GELU = 8u, EM_SILU = 16u, EM_RES32 = 32u, EM_RES16 = 64u, EM_OBF16 = 128u,
   EM_O2 = 256u, EM_O2PRE = 512u, EM_STATS = 1024u, EM_DYN = 1u << 31,
-  // split-K work items: no epilogue arithmetic, the raw fp32 accumulators are ADDED into a zeroed workspace by TMA
-  // reduce-add boxes (a second kernel applies the epilogue); the tile list carries a K-slice index
+  // split-K work items: no epilogue arithmetic, the raw fp32 accumulators of K slice s go to slab s of a workspace by
+  // TMA box stores (a second kernel sums the slabs in slice order and applies the epilogue: deterministic); the tile
+  // list carries a K-slice index
   EM_SPLITK = 1u << 17
 };
 // EM_DYN: the same bits, computed from the kernel parameters ONCE per tile into a register (`fl`), so that the chunk
@@ -677,8 +678,7 @@ __device__ __forceinline__ void staged_step(const ConvKernelParams& p, const Epi
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      if constexpr ((MODE & EM_SPLITK) != 0) ptx::tma_reduce_add_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
-      else ptx::tma_store_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
+      ptx::tma_store_5d(&em.out, t.wst + off, col0, t.cj, t.cq, t.ci, t.cb);
       ptx::bulk_commit_group();
     }
     ++nchunk;
@@ -735,6 +735,7 @@ struct Smem2Layout {
 struct PairSchedule {
   int32_t m_tiles, m_pairs, n_tiles, nphase, total;
   int32_t splits;   // K slices per output tile (EM_SPLITK kernels; 1 otherwise); `total` counts (tile, slice) items
+  int32_t split_bstride;   // samples per workspace slab: slice s stores at sample coordinate b + s * split_bstride
 };
 
 template <int BN, int STAGES, bool kStaged, uint32_t MODE>
@@ -944,7 +945,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int k = 0; k * npairs < sch.total; ++k) {
       int t = tile_of_round(k);
       if (t >= sch.total) continue;
-      split_of(t);
+      const int sp = split_of(t);
       int ph, nt, b0, oh0, pj;
       tile_origin(t, ph, nt, b0, oh0, pj);
       const TapTable& tt = p.taps[ph];
@@ -955,7 +956,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       float s1 = 0.f, s2 = 0.f;
       const GnRow gr = gn_row(p, b, oh, j, row_ok);
       if constexpr (kStaged) {
-        const int cj = pj + sub_j, ci = oh0 + sub_i, cb = b0 + sub_b, cq = tt.out_q;
+        const int cj = pj + sub_j, ci = oh0 + sub_i, cq = tt.out_q;
+        const int cb = b0 + sub_b + (kSplit ? sp * sch.split_bstride : 0);
         const int ncol0 = nt * BN + hc * (BN / 2);
         const int nch = min((BN / 2) / kEC, max(0, (p.cout - ncol0 + kEC - 1) / kEC));
         if (has_res && nch > 0 && lane == 0) {
@@ -1022,7 +1024,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 template <int BN, int STAGES, bool kStaged, uint32_t MODE>
 inline int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiMaps& em,
                             const ConvKernelParams& p, int m_tiles, int n_tiles, int nphase, cudaStream_t stream,
-                            int splits = 1) {
+                            int splits = 1, int split_bstride = 0) {
   using L = Smem2Layout<BN, STAGES, kStaged>;
   static_assert(L::kTotal <= 232448, "shared-memory budget of one CTA exceeded");
   static bool configured = false;
@@ -1037,6 +1039,7 @@ inline int launch_conv_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, cons
   sch.n_tiles = n_tiles;
   sch.nphase = nphase;
   sch.splits = splits;
+  sch.split_bstride = split_bstride;
   sch.total = nphase * sch.m_pairs * n_tiles * splits;
   const int pairs = std::min(sch.total, sm_count() / 2);
   conv_igemm_pair_kernel<BN, STAGES, kStaged, MODE><<<dim3(2 * pairs), 384, L::kTotal, stream>>>(tmA, tmB, em, p, sch);

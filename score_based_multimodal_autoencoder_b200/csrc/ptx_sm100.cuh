@@ -113,14 +113,6 @@ __device__ __forceinline__ void tma_reduce_add_3d(const void* tmap, const void* 
       ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// the same as a 5-D box (split-K partial accumulators meeting in an fp32 workspace)
-__device__ __forceinline__ void tma_reduce_add_5d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3,
-                                                  int c4) {
-  asm volatile(
-      "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-      ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N>

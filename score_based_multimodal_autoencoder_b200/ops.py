@@ -162,18 +162,18 @@ def pack_linear_weight(w: torch.Tensor, out=None) -> torch.Tensor:
 _splitk_ws: dict = {}
 
 
-def _splitk_workspace(dev: torch.device, rows: int, ld: int) -> torch.Tensor:
-    """Zeroed fp32 workspace of a split-K convolution.  The library hands it back zeroed, so ONE buffer per device is
-    zeroed once and then serves every call in stream order (no memset per layer; the address is stable, so it can be
-    replayed from a CUDA graph).  Like the packed-weight caches it assumes that one device's score-net calls are
-    issued in order (one stream at a time, or streams that are joined between calls)."""
-    key = dev.index
+def _splitk_workspace(dev: torch.device, elems: int) -> torch.Tensor:
+    """fp32 workspace of a split-K convolution (per-slice slabs, summed by the library's second kernel; no zeroing
+    needed).  ONE buffer per device serves every call in stream order; the address is stable, so the calls can be
+    replayed from a CUDA graph.  Like the packed-weight caches it assumes that one device's score-net calls are issued
+    in order (one stream at a time, or streams that are joined between calls)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
     ws = _splitk_ws.get(key)
-    if ws is None or ws.numel() < rows * ld:
+    if ws is None or ws.numel() < elems:
         if torch.cuda.is_current_stream_capturing():
             # growing inside a capture would put the buffer into the graph's private pool: size it beforehand
             raise L.SbmError("split-K workspace too small inside CUDA-graph capture (run the call once eagerly first)")
-        ws = _splitk_ws[key] = torch.zeros(max(rows * ld, 1 << 22), dtype=torch.float32, device=dev)
+        ws = _splitk_ws[key] = torch.empty(max(elems, 1 << 24), dtype=torch.float32, device=dev)
     return ws
 
 
@@ -225,9 +225,12 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
         a.gn_count, a.gn_eps = float(h * w * cin), gn_eps
     # sub-wave K-long layers (low-resolution levels at small batch): split-K needs a zeroed fp32 workspace; the plan
     # lives in the library (one source of truth), the allocation here (memset node under CUDA-graph capture)
-    if kind == L.CONV_S1 and not nchw and L.lib().sbm_conv_splitk_plan(C.byref(a)) > 1:
-        ws = _splitk_workspace(x.device, b * oh * ow, pad8(cout))
-        a.splitk_ws, a.ld_ws = ws.data_ptr(), pad8(cout)
+    if kind in (L.CONV_S1, L.CONV_S2) and not nchw:
+        a.ld_ws = pad8(cout)
+        need = L.lib().sbm_conv_splitk_ws_elems(C.byref(a))
+        if need > 0:
+            ws = _splitk_workspace(x.device, need)
+            a.splitk_ws, a.ws_elems = ws.data_ptr(), ws.numel()
     L.check(L.lib().sbm_conv_igemm(C.byref(a), L.stream_ptr()), "sbm_conv_igemm")
     return out
 
