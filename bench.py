@@ -543,8 +543,8 @@ def sampler_kernel_roofline(sh, sde, device, batch=65536):
         r_pred, r_corr = rng.next(), rng.next()
         side = sh._fork_noise_norm(x, r_corr, acc)
         x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
-        torch.cuda.current_stream().wait_stream(side)
-        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True)
+        sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True,
+                              join=side)
 
     for _ in range(3):
         pc_kernels()

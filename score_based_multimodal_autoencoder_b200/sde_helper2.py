@@ -347,11 +347,12 @@ def _fork_noise_norm(x, rng, acc):
 
 
 def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, impute=None, want_mean=True,
-                       global_batch=None, reduce_fn=None, acc=None, out=None, noise_norm_done=False):
+                       global_batch=None, reduce_fn=None, acc=None, out=None, noise_norm_done=False, join=None):
     """norms kernel -> (optional cross-rank sum of the two batch norms) -> update kernel.  `acc` is a zeroed buffer of
     3 doubles (2 sums + a completion ticket); the update kernel re-zeroes it, so a reused `acc` never needs a memset.
-    `noise_norm_done`: acc[1] already holds the Philox noise norm (`_fork_noise_norm`), the norms kernel reads the
-    score only."""
+    `noise_norm_done`: acc[1] gets the Philox noise norm from `_fork_noise_norm`, the norms kernel reads the score only;
+    `join` = that side stream: it is joined AFTER the score-norm kernel has been issued (the two kernels add into
+    different slots of `acc`), so the noise kernel can also run beside it -- only the update kernel needs both sums."""
     ls = _latent_shape(x)
     if acc is None:
         acc = torch.zeros(3, dtype=torch.float64, device=x.device)
@@ -360,6 +361,8 @@ def _corrector_kernels(sde, x, grad, t, target_snr, *, noise=None, rng=None, imp
     rp = C.byref(rng) if rng is not None else None
     L.check(L.lib().sbm_corrector_norms(C.byref(ls), L.ptr(grad), L.ptr(noise), None if noise_norm_done else rp,
                                         L.ptr(acc), L.stream_ptr()), "sbm_corrector_norms")
+    if join is not None:
+        torch.cuda.current_stream().wait_stream(join)
     if reduce_fn is not None:  # multi-GPU exact mode: sum the two batch norms over ranks
         reduce_fn(acc[:2])
     x_new = out if out is not None else torch.empty_like(x)
@@ -447,10 +450,8 @@ def corrector(x, t, score_fn, sde, n_steps, target_snr, cl_g=None, cl_s=None, ta
         grad = _guided(grad, x, t, cl_g, cl_s, given, all_mods)
         if nz is None and r is None:
             nz = torch.randn_like(x)
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)
         x, x_mean = _corrector_kernels(sde, x, grad, t, target_snr, noise=nz, rng=r, global_batch=global_batch,
-                                       reduce_fn=reduce_fn, acc=acc, noise_norm_done=side is not None)
+                                       reduce_fn=reduce_fn, acc=acc, noise_norm_done=side is not None, join=side)
     return x, x_mean
 
 
@@ -540,13 +541,11 @@ class _PCRun:
                 grad = self._score(x)
                 if torch_rng:
                     nz = torch.randn_like(x)  # reference order: drawn AFTER the net call (sde_helper2.py:96)
-                if side is not None:
-                    torch.cuda.current_stream().wait_stream(side)
                 final_k = k == self.n_steps - 1
                 x, xm = _corrector_kernels(sde, x, grad, t_vec, self.target_snr, noise=nz, rng=r,
                                            impute=impute if final_k else None, want_mean=want_mean and final_k,
                                            global_batch=self.global_batch, reduce_fn=self.reduce_fn, acc=self.acc,
-                                           noise_norm_done=side is not None)
+                                           noise_norm_done=side is not None, join=side)
             return x, xm
 
         with L.nvtx(f"sbm.pc_step[{i}]"):

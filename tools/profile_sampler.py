@@ -30,8 +30,8 @@ def pc_kernels():
         return
     side = sh._fork_noise_norm(x, r_corr, acc)
     x1, _ = sh._predictor_kernel(sde, x, s, t, rng=r_pred, want_mean=False, out=out)
-    torch.cuda.current_stream().wait_stream(side)
-    sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True)
+    sh._corrector_kernels(sde, x1, s, t, 0.16, rng=r_corr, want_mean=False, acc=acc, out=out, noise_norm_done=True,
+                          join=side)
 
 
 def dsm():
