@@ -509,7 +509,7 @@ def conv_roofline(model, sde, x0, ops, L):
     dense_a = sum(r[4] for r in rec)
     top = max(rec, key=lambda r: r[2])
     traffic = None
-    tpath = next((q for q in (os.path.join(ROOT, "profiles", n) for n in ("r2c_traffic.json", "r2b_traffic.json", "r2_traffic.json",
+    tpath = next((q for q in (os.path.join(ROOT, "profiles", n) for n in ("r2d_traffic.json", "r2c_traffic.json", "r2b_traffic.json", "r2_traffic.json",
                                                                           "r1_traffic.json")) if os.path.exists(q)), "")
     if tpath:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
         traffic = json.load(open(tpath)).get("conv_igemm_pair_kernel<256,5,staged>", {}).get("avg_dram_bytes_per_launch")

@@ -689,7 +689,11 @@ __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const fl
 // A block serves SB consecutive samples (SB > 1 when a sample is only a few hundred octets -- the 8x8 / 4x4 maps of the
 // PolyMNIST net at 32k latents ran one block per sample for two pixels per thread: the fp64 mean / rstd prologue and
 // the block turnover, not HBM, set the pace (1.4 TB/s, ncu); the statistics of all SB samples are reduced up front.
-template <typename TIn, typename TOut>
+// MULTI = false is the one-sample-per-block kernel with the sample loop compiled away (the loop and the hoisted
+// gamma / beta registers cost 30 registers and 15 % of the large-map launches when they were unconditional).
+// MOD = false compiles the per-sample modulation / addend operands out (they cost 20 registers: 74 -> 94, i.e. the
+// third resident block per SM and 15 % of the bandwidth of every plain GroupNorm-apply launch).
+template <typename TIn, typename TOut, bool MULTI, bool MOD>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __restrict__ stats,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -697,9 +701,9 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
                        float* __restrict__ out_f32, int64_t ldo_f32, int HW, int C, int G, float eps, int act,
                        int vec_ok, const float* __restrict__ mod_scale, const float* __restrict__ mod_shift,
                        int64_t ld_mod, const float* __restrict__ post_add, int64_t ld_post, int B, int SB) {
-  __shared__ float s_mean[256], s_rstd[256];   // [SB][G], SB * G <= 256
-  const int b_first = blockIdx.y * SB;
-  const int nb = min(SB, B - b_first);
+  __shared__ float s_mean[MULTI ? 256 : 64], s_rstd[MULTI ? 256 : 64];   // [SB][G], SB * G <= 256
+  const int b_first = MULTI ? blockIdx.y * SB : blockIdx.y;
+  const int nb = MULTI ? min(SB, B - b_first) : 1;
   const int cpg = C / G;
   if ((int)threadIdx.x < nb * G) {
     const double inv_n = 1.0 / ((double)HW * cpg);
@@ -721,30 +725,32 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
   for (int q = threadIdx.x - pl * tq; q < co; q += tq) {
     const int c = q * 8;
     const bool full = vec_ok && (c + 8 <= C);
-    float gm[8], bt[8];
+    float gm[MULTI ? 8 : 1], bt[MULTI ? 8 : 1];   // gamma / beta of the octet, loaded once for the block's samples
+    if constexpr (MULTI) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int ce = min(c + e, C - 1);
-      gm[e] = __ldg(gamma + ce);
-      bt[e] = __ldg(beta + ce);
+      for (int e = 0; e < 8; ++e) {
+        const int ce = min(c + e, C - 1);
+        gm[e] = __ldg(gamma + ce);
+        bt[e] = __ldg(beta + ce);
+      }
     }
     for (int sb = 0; sb < nb; ++sb) {
       const int b = b_first + sb;
-      float sc[8], sh[8], pa[8];  // y = act(x * sc + sh) + pa
+      float sc[8], sh[8], pa[MOD ? 8 : 1];  // y = act(x * sc + sh) + pa
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ce = min(c + e, C - 1);
         const int g = sb * G + ((G == 1) ? 0 : ce / cpg);
-        float a = s_rstd[g] * gm[e];
-        float o = bt[e] - s_mean[g] * a;
-        if (mod_scale != nullptr) {  // per-sample modulation of the normalised value: n * (1 + scale) + shift
+        float a = s_rstd[g] * (MULTI ? gm[MULTI ? e : 0] : __ldg(gamma + ce));
+        float o = (MULTI ? bt[MULTI ? e : 0] : __ldg(beta + ce)) - s_mean[g] * a;
+        if (MOD && mod_scale != nullptr) {  // per-sample modulation of the normalised value: n * (1 + scale) + shift
           const float m1 = 1.f + __ldg(mod_scale + (int64_t)b * ld_mod + ce);
           a *= m1;
           o = fmaf(o, m1, __ldg(mod_shift + (int64_t)b * ld_mod + ce));
         }
         sc[e] = a;
         sh[e] = o;
-        pa[e] = (post_add != nullptr) ? __ldg(post_add + (int64_t)b * ld_post + ce) : 0.f;
+        if constexpr (MOD) pa[e] = (post_add != nullptr) ? __ldg(post_add + (int64_t)b * ld_post + ce) : 0.f;
       }
       auto one = [&](int pix_in_sample, const float* v_in) {
         const int64_t pix = (int64_t)b * HW + pix_in_sample;
@@ -754,7 +760,7 @@ groupnorm_apply_kernel(const TIn* __restrict__ x, int64_t ldx, const double* __r
           float y = fmaf(v_in[e], sc[e], sh[e]);
           if (act == SBM_ACT_SILU) y = silu(y);
           else if (act == SBM_ACT_GELU) y = gelu_exact(y);
-          v[e] = y + pa[e];
+          v[e] = MOD ? y + pa[MOD ? e : 0] : y;
         }
         if (residual != nullptr) {
           const float* rp = residual + pix * ldr + c;
@@ -1745,15 +1751,21 @@ int sbm_groupnorm_apply_mod(const void* x, int32_t in_dtype, int64_t ldx, const 
   }
   dim3 grid(chunks, (B + SB - 1) / SB);
   cudaStream_t s = (cudaStream_t)stream;
-#define SBM_GN_LAUNCH(TI, TO)                                                                                   \
-  groupnorm_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)x, ldx, stats, gamma, beta, residual, ldr,      \
-                                                      (TO*)out, ldo, out_f32, ldo_f32, HW, C, G, eps, act, vec_ok,   \
-                                                      mod_scale, mod_shift, ld_mod, post_add, ld_post, B, SB)
-  if (in_dtype == SBM_F32 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(float, __nv_bfloat16);
-  else if (in_dtype == SBM_F32 && out_dtype == SBM_F32) SBM_GN_LAUNCH(float, float);
-  else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16);
-  else SBM_GN_LAUNCH(__nv_bfloat16, float);
+#define SBM_GN_ARGS(TI, TO)                                                                                       \
+  (const TI*)x, ldx, stats, gamma, beta, residual, ldr, (TO*)out, ldo, out_f32, ldo_f32, HW, C, G, eps, act, vec_ok,    \
+      mod_scale, mod_shift, ld_mod, post_add, ld_post, B, SB
+#define SBM_GN_LAUNCH(TI, TO)                                                                                     \
+  if (SB > 1 && mod) groupnorm_apply_kernel<TI, TO, true, true><<<grid, 256, 0, s>>>(SBM_GN_ARGS(TI, TO));            \
+  else if (SB > 1) groupnorm_apply_kernel<TI, TO, true, false><<<grid, 256, 0, s>>>(SBM_GN_ARGS(TI, TO));             \
+  else if (mod) groupnorm_apply_kernel<TI, TO, false, true><<<grid, 256, 0, s>>>(SBM_GN_ARGS(TI, TO));                \
+  else groupnorm_apply_kernel<TI, TO, false, false><<<grid, 256, 0, s>>>(SBM_GN_ARGS(TI, TO))
+  const bool mod = mod_scale != nullptr || post_add != nullptr;
+  if (in_dtype == SBM_F32 && out_dtype == SBM_BF16) { SBM_GN_LAUNCH(float, __nv_bfloat16); }
+  else if (in_dtype == SBM_F32 && out_dtype == SBM_F32) { SBM_GN_LAUNCH(float, float); }
+  else if (in_dtype == SBM_BF16 && out_dtype == SBM_BF16) { SBM_GN_LAUNCH(__nv_bfloat16, __nv_bfloat16); }
+  else { SBM_GN_LAUNCH(__nv_bfloat16, float); }
 #undef SBM_GN_LAUNCH
+#undef SBM_GN_ARGS
   SBM_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -223,9 +223,11 @@ def conv_igemm(x: torch.Tensor, wpk: torch.Tensor, *, kind: int, kh: int, kw: in
     if gn_tab is not None:  # GroupNorm(1, cin) of x folded into the weights (fold_groupnorm_conv)
         a.gn_stats, a.gn_tab = gn_stats.data_ptr(), gn_tab.data_ptr()
         a.gn_count, a.gn_eps = float(h * w * cin), gn_eps
-    # sub-wave K-long layers (low-resolution levels at small batch): split-K needs a zeroed fp32 workspace; the plan
-    # lives in the library (one source of truth), the allocation here (memset node under CUDA-graph capture)
-    if kind in (L.CONV_S1, L.CONV_S2) and not nchw:
+    # sub-wave K-long layers (low-resolution levels at small batch): split-K needs an fp32 workspace; the plan lives in
+    # the library (one source of truth), the allocation here
+    # (cheap host-side screen first: the library only splits layers of a few 256 x 256 tiles -- at most half the SM pairs
+    # of the largest part, 128 -- with more than 128 output channels; every other call skips the extra ABI round trip)
+    if kind in (L.CONV_S1, L.CONV_S2) and not nchw and cout > 128 and 128 <= b * oh * ow <= 64 * 256:
         a.ld_ws = pad8(cout)
         need = L.lib().sbm_conv_splitk_ws_elems(C.byref(a))
         if need > 0:

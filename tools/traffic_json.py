@@ -30,7 +30,9 @@ def summarise(items):
 per = collections.OrderedDict()
 for d in launch.values():
     per.setdefault(d["k"], []).append(d)
-dom = [d for d in launch.values() if re.search(r"conv_igemm_pair_kernel<256, 5, (1|true)", d["k"])]
+# (the split-K GEMM passes -- epilogue mode 131072 = EM_SPLITK -- are left out like in bench.py's dominant-kernel filter)
+dom = [d for d in launch.values() if re.search(r"conv_igemm_pair_kernel<256, 5, (1|true)", d["k"])
+       and not re.search(r", 131072u?>", d["k"])]
 out = {"conv_igemm_pair_kernel<256,5,staged>": summarise(dom), "source": f"{src} (ncu, one forward, batch 1024)",
        "forward_ms_serialised": sum(d.get("gpu__time_duration.sum", 0.0) for d in launch.values()) / 1e6,
        "per_kernel": {k: summarise(v) for k, v in sorted(per.items(), key=lambda kv: -sum(x.get("gpu__time_duration.sum", 0) for x in kv[1]))}}
