@@ -4,7 +4,10 @@ activity; then the longest launches.  Usage: python tools/launch_table.py <launc
 import collections
 import csv
 import re
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)   # `| head` closes the pipe early
 
 path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 12
