@@ -444,7 +444,7 @@ def test_conv_split_k_matches_unsplit(opt, shape):
     gamma = (1 + 0.3 * torch.randn(cin, generator=g)).to(dev)
     beta = (0.2 * torch.randn(cin, generator=g)).to(dev)
     outs = []
-    for split in (1, 0):
+    for split in (1, 1, 1, 0):   # the split launch three times: slabs summed in slice order -> bit-identical outputs
         L.lib().sbm_conv_splitk(split)
         stats = torch.zeros(B, 2, dtype=torch.float64, device=dev)
         out2 = None
@@ -467,7 +467,10 @@ def test_conv_split_k_matches_unsplit(opt, shape):
         assert bool(v & (1 << 20)) == bool(split), (split, hex(v))
         outs.append((out[..., :cout].float().clone(), None if out2 is None else out2[..., :cout].float().clone(), stats.clone()))
     L.lib().sbm_conv_splitk(1)
-    a, b_ = outs
+    a, a1, a2_, b_ = outs
+    for again in (a1, a2_):
+        assert torch.equal(a[0], again[0]) and (a[1] is None or torch.equal(a[1], again[1]))
+        assert torch.allclose(a[2], again[2], rtol=1e-12, atol=1e-9)   # fp64 statistics: atomics, order-dependent last bits
     tol = 2e-2 if "bf16" in opt else 1e-4   # bf16 outputs: one rounding step of either result
     assert (a[0] - b_[0]).abs().max().item() <= tol * b_[0].abs().max().item()
     if a[1] is not None:
@@ -489,7 +492,7 @@ def test_conv_split_k_stride2_matches_unsplit(shape):
     bias = torch.randn(cout, generator=g).to(dev)
     wpk = ops.pack_conv2d_weight(w)
     outs = []
-    for split in (1, 1, 0):   # the split launch twice: the slabs are summed in slice order -> bit-identical
+    for split in (1, 1, 1, 0):   # the split launch three times: the slabs are summed in slice order -> bit-identical
         L.lib().sbm_conv_splitk(split)
         o2 = torch.empty(B, H // 2, H // 2, ops.pad8(cout), dtype=torch.bfloat16, device=dev)
         out = ops.conv_igemm(xb, wpk, kind=L.CONV_S2, kh=k, kw=k, cin=cin, cout=cout, bias=bias, out2=o2)
@@ -500,8 +503,8 @@ def test_conv_split_k_stride2_matches_unsplit(shape):
     L.lib().sbm_conv_splitk(1)
     ref = torch.nn.functional.conv2d(xb[..., :cin].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), bias,
                                      stride=2, padding=1).permute(0, 2, 3, 1)
-    (a, a2), (a_again, a2_again), (b_, b2) = outs
-    assert torch.equal(a, a_again) and torch.equal(a2, a2_again)
+    (a, a2), (a_again, a2_again), (a_third, a2_third), (b_, b2) = outs
+    assert torch.equal(a, a_again) and torch.equal(a2, a2_again) and torch.equal(a, a_third) and torch.equal(a2, a2_third)
     scale = ref.abs().max().item()
     assert (a - b_).abs().max().item() <= 1e-4 * scale
     assert (a - ref).abs().max().item() <= 2e-3 * scale
