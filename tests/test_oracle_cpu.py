@@ -387,3 +387,28 @@ def test_variant_modules_mirror_the_reference_state_dict_and_errors():
     with pytest.raises(TypeError, match="kernel_size"):
         UNetModel(in_channels=3, model_channels=32, out_channels=3, num_res_blocks=1, attention_resolutions=(),
                   channel_mult=(1, 2), conv_resample=False)
+
+
+def test_ctypes_struct_mirrors_match_the_header(tmp_path):
+    """The `ctypes.Structure` mirrors in `_lib.py` are written by hand: compile a probe against include/sbmae_b200.h with
+    gcc and compare sizeof and the offset of every field (an ABI drift here corrupts kernel arguments silently)."""
+    import subprocess
+    from score_based_multimodal_autoencoder_b200 import _lib as L
+    pairs = {"sbm_conv_args": L.ConvArgs, "sbm_wgrad_args": L.WgradArgs, "sbm_pack_desc": L.PackDesc,
+             "sbm_latent_shape": L.LatentShape, "sbm_sde": L.SdeC, "sbm_rng": L.Rng, "sbm_impute": L.Impute,
+             "sbm_adam_tensor": L.AdamTensor, "sbm_ema_tensor": L.EmaTensor}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "sbmae_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
