@@ -412,3 +412,47 @@ def test_ctypes_struct_mirrors_match_the_header(tmp_path):
         assert int(got[cname]) == ctypes.sizeof(cls), (cname, got[cname], ctypes.sizeof(cls))
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_split_k_plan_host_logic():
+    """Host-side plan of the split-K convolution (no kernel launch; without a device the library assumes the B200's 148
+    SMs): which layers of the headline net are cut along K at which per-GPU batch, that the plan yields to the
+    pixel-major tiling where that skips more work, and the workspace size it asks for."""
+    from score_based_multimodal_autoencoder_b200 import _lib as L
+    lib = L.lib()
+    lib.sbm_conv_splitk(1)
+
+    def plan(kind, k, b, h, cin, cout, nchw=0):
+        a = L.ConvArgs()
+        a.kind, a.kh, a.kw = kind, k, k
+        a.batch, a.h, a.w = b, h, h
+        a.cin, a.cout = cin, cout
+        a.out_nchw = nchw
+        a.ld_ws = (cout + 7) // 8 * 8
+        return lib.sbm_conv_splitk_plan(ctypes.byref(a)), lib.sbm_conv_splitk_ws_elems(ctypes.byref(a))
+
+    S1, S2 = L.CONV_S1, L.CONV_S2
+    # 128 latents per GPU (the 8-GPU shard): 4x4 and 2x2 levels, both 3x3 convolutions of a ConvNeXt block
+    assert plan(S1, 3, 128, 4, 512, 1024)[0] == 2      # 8 x 4 = 32 tiles on 74 SM pairs
+    assert plan(S1, 3, 128, 4, 1024, 512)[0] == 4      # 16 tiles
+    assert plan(S1, 3, 128, 2, 1024, 512)[0] == 8      # 4 tiles: capped at 8 slices
+    # the stride-2 down-sampling convolutions (4x4 kernel): 8x8 -> 4x4 and 2x2 -> 1x1 (4 of 16 taps see real pixels)
+    assert plan(S2, 4, 128, 8, 512, 512)[0] == 4
+    assert plan(S2, 4, 256, 2, 512, 512)[0] == 4       # 32 K blocks / 8
+    assert plan(S2, 4, 256, 2, 256, 512)[0] == 1       # 16 K blocks: too short to cut
+    # 1024 latents: the 2x2 level would be 2 slices of 9 taps against 1 slice of 4 valid taps -> pixel-major wins
+    assert plan(S1, 3, 1024, 2, 1024, 512)[0] == 1
+    assert plan(S1, 3, 1024, 16, 256, 512)[0] == 1     # large layers: more tiles than SM pairs
+    assert plan(S1, 1, 128, 4, 512, 1024)[0] == 1      # 1x1: K too short
+    assert plan(S1, 3, 128, 4, 512, 128)[0] == 1       # narrow outputs run other tile shapes
+    assert plan(S1, 3, 128, 4, 512, 1024, nchw=1)[0] == 1
+    # workspace: slices x rows rounded up to whole 256-row tile pairs x row stride
+    n, elems = plan(S1, 3, 100, 2, 512, 1024)          # M = 400 rows -> 512 per slab
+    assert n == 8 and elems == 8 * 512 * 1024
+    n, elems = plan(S2, 4, 128, 8, 512, 512)           # M = 2048
+    assert elems == n * 2048 * 512
+    lib.sbm_conv_splitk(0)
+    try:
+        assert plan(S1, 3, 128, 4, 512, 1024) == (1, 0)
+    finally:
+        lib.sbm_conv_splitk(1)
